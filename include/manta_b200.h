@@ -1,0 +1,267 @@
+/*
+ * manta_b200.h -- C ABI of the B200-native GenerateSVCandidates hot path.
+ *
+ * This is the drop-in boundary ("B2 -- in-process C++ seams"):
+ * each entry point below is the batched replacement of one synchronous C++ call in
+ * Illumina/manta.  Citations are path:line under the reference tree
+ * (src/c++/lib/ abbreviated lib/, lib/applications/GenerateSVCandidates/ abbreviated GSC/).
+ *
+ *   mb200_jump_align_batch   <- GlobalJumpAligner<int>::align        lib/alignment/GlobalJumpAligner.hpp:45-53
+ *                                called from GSC/SVCandidateAssemblyRefiner.cpp:1668,1706
+ *   mb200_indel_align_batch  <- GlobalLargeIndelAligner<int>::align  lib/alignment/GlobalLargeIndelAligner.hpp:48-54
+ *                                called from GSC/SVCandidateAssemblyRefiner.cpp:2032
+ *   mb200_global_align_batch <- GlobalAligner<int>::align            lib/alignment/GlobalAligner.hpp (same shape)
+ *                                called from GSC/SVCandidateAssemblyRefiner.cpp:933, GSC/SVScorePairAltProcessor.cpp:211
+ *   mb200_split_align_batch  <- splitReadAligner                     GSC/SplitReadAlignment.hpp:63-70
+ *                                called from GSC/SVScorerSplit.cpp:190-226
+ *   mb200_assemble_batch     <- runIterativeAssembler                lib/assembly/IterativeAssembler.hpp:43-47
+ *                                called from lib/manta/SVCandidateAssembler.cpp:674,697
+ *   mb200_candidates_batch   <- the assemble -> align-every-contig composition of
+ *                                GSC/SVCandidateAssemblyRefiner.cpp:1422-1743 (spanning) and :1925-2039 (complex),
+ *                                kept resident on the device (BASELINE.json metric "candidates assembled+aligned").
+ *
+ * Conventions
+ *   - plain C types only; all pointers are HOST pointers unless the name ends in _dev.
+ *   - every call returns an int status (MB200_OK == 0).  On failure mb200_last_error(ctx)
+ *     returns a message; the C++ shim (include/manta_b200_shim.hpp) turns it into the same
+ *     exception type the reference throws.
+ *   - caller owns host buffers, the library owns device memory.  Calls on one ctx must be
+ *     serialised by the caller (one ctx per host driver thread), no global state.
+ *   - there is NO CPU fallback: if the CUDA device or kernels are unavailable, mb200_create fails.
+ *   - sequences are ASCII bytes in a caller-provided pool, addressed by (offset,length) views.
+ *     Aligners compare raw bytes (any alphabet; N==N is a match in the DP, lib/alignment/GlobalJumpAlignerImpl.hpp:132).
+ *
+ * Alignment paths (CIGARs) are returned run-length encoded, one uint32 per segment:
+ *      segment = (length << 4) | type,   type = ALIGNPATH::align_t  (lib/blt_util/align_path.hpp:34)
+ */
+#ifndef MANTA_B200_H
+#define MANTA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_API __attribute__((visibility("default")))
+
+/* ---- status codes ---------------------------------------------------------------------- */
+enum {
+  MB200_OK                = 0,
+  MB200_ERR_CUDA          = 1,  /* CUDA runtime / launch failure (fatal, like any exception in the reference) */
+  MB200_ERR_NO_DEVICE     = 2,  /* no usable sm_100 device -- there is no CPU fallback */
+  MB200_ERR_EMPTY_QUERY   = 3,  /* "Unexpected empty query sequence"      GlobalJumpAlignerImpl.hpp:50 */
+  MB200_ERR_EMPTY_REF     = 4,  /* "Unexpected empty reference sequence"  GlobalAlignerImpl.hpp:47 */
+  MB200_ERR_EMPTY_REF1    = 5,  /* "Unexpected empty reference1 sequence" GlobalJumpAlignerImpl.hpp:53 */
+  MB200_ERR_EMPTY_REF2    = 6,  /* "Unexpected empty reference2 sequence" GlobalJumpAlignerImpl.hpp:56 */
+  MB200_ERR_SPLIT_INPUT   = 7,  /* querySize >= targetSize                SplitReadAlignment.cpp:236 */
+  MB200_ERR_SPLIT_SCAN    = 8,  /* scanEnd < scanStart                    SplitReadAlignment.cpp:264 */
+  MB200_ERR_SPLIT_OUTCOME = 9,  /* leftSize > querySize                   SplitReadAlignment.cpp:305 */
+  MB200_ERR_BAD_QUAL      = 10, /* basecall quality > 70 or < 0           lib/blt_util/qscore_cache.hpp:48-52 */
+  MB200_ERR_POOL_OVERFLOW = 11, /* caller-provided output pool too small (call again with a larger pool) */
+  MB200_ERR_BAD_ARG       = 12,
+  MB200_ERR_BAD_BASE      = 13, /* assembler input byte outside {A,C,G,T,N} (documented restriction) */
+  MB200_ERR_ASM_OVERFLOW  = 14, /* assembler workspace cap exceeded for some locus */
+  MB200_ERR_UNSUPPORTED   = 15
+};
+
+/* ---- alignment path segment types == ALIGNPATH::align_t -------------------------------- */
+enum {
+  MB200_SEG_NONE = 0,
+  MB200_SEG_MATCH = 1,
+  MB200_SEG_INSERT = 2,
+  MB200_SEG_DELETE = 3,
+  MB200_SEG_SKIP = 4,
+  MB200_SEG_SOFT_CLIP = 5,
+  MB200_SEG_HARD_CLIP = 6,
+  MB200_SEG_PAD = 7,
+  MB200_SEG_SEQ_MATCH = 8,
+  MB200_SEG_SEQ_MISMATCH = 9
+};
+#define MB200_SEG_TYPE(s) ((uint32_t)(s) & 0xFu)
+#define MB200_SEG_LEN(s) ((uint32_t)(s) >> 4)
+#define MB200_SEG_MAKE(len, type) ((((uint32_t)(len)) << 4) | ((uint32_t)(type)))
+
+/* ---- common structs -------------------------------------------------------------------- */
+
+/* AlignmentScores<int>  lib/alignment/AlignmentScores.hpp:23-57 */
+typedef struct mb200_scores {
+  int32_t match;
+  int32_t mismatch;
+  int32_t open;
+  int32_t extend;
+  int32_t offEdge;
+  int32_t isAllowEdgeInsertion; /* must be 0 for the jump aligner (GlobalJumpAligner.hpp:41) */
+} mb200_scores;
+
+/* a byte range of the caller's sequence pool */
+typedef struct mb200_seqview {
+  uint64_t off;
+  uint32_t len;
+  uint32_t reserved;
+} mb200_seqview;
+
+/* AlignmentResult<int>  lib/alignment/SingleRefAlignerShared.hpp:34-47 */
+typedef struct mb200_aln_result {
+  int32_t  score;
+  int32_t  beginPos;
+  uint32_t isJumped;
+  uint32_t cigarLen; /* number of path segments */
+  uint64_t cigarOff; /* first segment, in uint32 units, inside the caller's cigar pool */
+} mb200_aln_result;
+
+/* JumpAlignmentResult<int>  lib/alignment/JumpAlignerBase.hpp:37-56 */
+typedef struct mb200_jump_result {
+  int32_t  score;
+  uint32_t jumpInsertSize;
+  uint32_t jumpRange;
+  int32_t  beginPos1;
+  int32_t  beginPos2;
+  uint32_t cigarLen1;
+  uint32_t cigarLen2;
+  uint32_t reserved;
+  uint64_t cigarOff1;
+  uint64_t cigarOff2;
+} mb200_jump_result;
+
+/* SRAlignmentInfo  GSC/SplitReadAlignment.hpp:35-49 */
+typedef struct mb200_sr_result {
+  uint32_t alignPos;
+  uint32_t leftSize;
+  uint32_t homSize;
+  uint32_t rightSize;
+  uint32_t leftMismatches;
+  uint32_t homMismatches;
+  uint32_t rightMismatches;
+  uint32_t alignScore;
+  float    alignLnLhood;
+  uint32_t isEvidence;
+  uint32_t isTier2Evidence;
+  float    evidence;
+  int32_t  status; /* MB200_OK or the MB200_ERR_SPLIT_* / MB200_ERR_BAD_QUAL the reference would have thrown for this item */
+  uint32_t reserved;
+} mb200_sr_result;
+
+/* one (read, target) split-read job  GSC/SVScorerSplit.cpp:190-226 */
+typedef struct mb200_sr_job {
+  mb200_seqview query;   /* read bases (ASCII) in the pool */
+  uint64_t      qualOff; /* query.len basecall qualities (raw phred bytes) in the pool */
+  mb200_seqview target;  /* target sequence in the pool */
+  int32_t       bpBegin; /* targetBpOffsetRange.begin_pos() */
+  int32_t       bpEnd;   /* targetBpOffsetRange.end_pos()   */
+  uint32_t      table;   /* which qscore_snp table pair: 0 or 1 (ref allele / alt allele, GSC/SVScorer.hpp:46-51) */
+  uint32_t      reserved;
+} mb200_sr_job;
+
+/* qscore_snp tables  lib/blt_util/qscore_snp.hpp:43-53 (71 doubles each, index = phred) */
+#define MB200_MAX_QSCORE 70
+typedef struct mb200_qscore_tables {
+  double lnComp[2][MB200_MAX_QSCORE + 1]; /* qphred_to_ln_comp_error_prob */
+  double lnErr[2][MB200_MAX_QSCORE + 1];  /* qphred_to_ln_error_prob      */
+} mb200_qscore_tables;
+
+/* IterativeAssemblerOptions  lib/options/IterativeAssemblerOptions.hpp:26-59
+ * (alphabet is fixed to "ACGT"; minContigLength/maxError are never read by the reference) */
+typedef struct mb200_asm_opts {
+  uint32_t minWordLength;           /* 41 */
+  uint32_t maxWordLength;           /* 76 */
+  uint32_t wordStepSize;            /* 5  */
+  uint32_t minCoverage;             /* 1  */
+  uint32_t minConservativeCoverage; /* 2  */
+  uint32_t maxAssemblyCount;        /* 10 */
+  uint32_t minUnusedReads;          /* 3  */
+  uint32_t minSupportReads;         /* 2  */
+} mb200_asm_opts;
+
+/* AssembledContig  lib/assembly/AssembledContig.hpp:38-50 ; read sets are bitsets of
+ * setWords uint32 words (bit r of word r/32 == read index r, pseudo reads included). */
+typedef struct mb200_contig {
+  uint64_t seqOff; /* contig bases (ASCII) inside the caller's contig byte pool */
+  uint32_t seqLen;
+  uint32_t seedReadCount;
+  int32_t  conservativeBegin;
+  int32_t  conservativeEnd;
+  uint64_t supportOff; /* first uint32 word of supportReads inside the caller's set pool */
+  uint64_t rejectOff;  /* first uint32 word of rejectReads  */
+} mb200_contig;
+
+/* per-locus assembly output (Assembly + the mutated AssemblyReadInput/AssemblyReadOutput) */
+typedef struct mb200_asm_locus {
+  uint32_t firstContig; /* index into the contig array */
+  uint32_t nContigs;    /* <= maxAssemblyCount */
+  uint32_t firstPseudo; /* index into the pseudo-read array (reads appended by the reference, IterativeAssembler.cpp:895-905) */
+  uint32_t nPseudo;
+  uint32_t setWords;    /* uint32 words per read set for this locus */
+  uint32_t lastWordLength; /* k of the last buildContigs iteration */
+  int32_t  status;
+  uint32_t reserved;
+} mb200_asm_locus;
+
+typedef struct mb200_config {
+  uint32_t ctasPerSm;        /* 0 = library default */
+  uint32_t maxContigLen;     /* assembler workspace cap per contig, 0 = default */
+  uint64_t scratchBytes;     /* device scratch budget for DP back-pointers, 0 = default */
+  uint32_t reserved[4];
+} mb200_config;
+
+typedef struct mb200_ctx mb200_ctx;
+
+/* kernel timing of the last call on this ctx (CUDA events on the launching stream) */
+typedef struct mb200_timing {
+  float    h2dMs;
+  float    kernelMs;
+  float    d2hMs;
+  uint32_t launches; /* kernels launched by the last call */
+  uint64_t cells;    /* DP cells filled (aligners) / base comparisons (split) / k-mer windows (assembler) */
+  uint64_t algoBytes; /* algorithmic HBM bytes of the dominant kernel */
+} mb200_timing;
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+MB200_API int         mb200_create(int device, const mb200_config* cfg, mb200_ctx** out);
+MB200_API void        mb200_destroy(mb200_ctx* ctx);
+MB200_API const char* mb200_last_error(const mb200_ctx* ctx);
+MB200_API const char* mb200_version(void);
+MB200_API int         mb200_get_timing(const mb200_ctx* ctx, mb200_timing* out);
+
+/* ---- aligners ------------------------------------------------------------------------------
+ * n independent alignments.  cigarPool receives the path segments; *cigarUsed returns the
+ * number of uint32 written (MB200_ERR_POOL_OVERFLOW if cigarCap was too small; *cigarUsed then
+ * holds the required size). */
+MB200_API int mb200_jump_align_batch(mb200_ctx* ctx, const mb200_scores* scores, int32_t jumpScore, uint32_t n,
+                                     const uint8_t* pool, uint64_t poolBytes, const mb200_seqview* query,
+                                     const mb200_seqview* ref1, const mb200_seqview* ref2,
+                                     mb200_jump_result* results, uint32_t* cigarPool, uint64_t cigarCap,
+                                     uint64_t* cigarUsed);
+
+MB200_API int mb200_indel_align_batch(mb200_ctx* ctx, const mb200_scores* scores, int32_t largeIndelScore,
+                                      uint32_t n, const uint8_t* pool, uint64_t poolBytes,
+                                      const mb200_seqview* query, const mb200_seqview* ref,
+                                      mb200_aln_result* results, uint32_t* cigarPool, uint64_t cigarCap,
+                                      uint64_t* cigarUsed);
+
+MB200_API int mb200_global_align_batch(mb200_ctx* ctx, const mb200_scores* scores, uint32_t n,
+                                       const uint8_t* pool, uint64_t poolBytes, const mb200_seqview* query,
+                                       const mb200_seqview* ref, mb200_aln_result* results,
+                                       uint32_t* cigarPool, uint64_t cigarCap, uint64_t* cigarUsed);
+
+/* ---- split-read scan ----------------------------------------------------------------------- */
+MB200_API int mb200_split_align_batch(mb200_ctx* ctx, const mb200_qscore_tables* tables,
+                                      uint32_t flankScoreSize, uint32_t n, const uint8_t* pool,
+                                      uint64_t poolBytes, const mb200_sr_job* jobs, mb200_sr_result* results);
+
+/* ---- assembler ------------------------------------------------------------------------------
+ * nLoci independent read sets.  reads of locus i are readViews[readOff[i] .. readOff[i+1]).
+ * Outputs: loci[nLoci]; contigs[contigCap]; pseudoReads[pseudoCap] (views into contigPool);
+ * contigPool (bytes) and setPool (uint32 words) are bump-allocated output pools. */
+MB200_API int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci,
+                                   const uint64_t* readOff, const mb200_seqview* readViews,
+                                   const uint8_t* pool, uint64_t poolBytes, mb200_asm_locus* loci,
+                                   mb200_contig* contigs, uint64_t contigCap, mb200_seqview* pseudoReads,
+                                   uint64_t pseudoCap, uint8_t* contigPool, uint64_t contigPoolCap,
+                                   uint32_t* setPool, uint64_t setPoolCap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANTA_B200_H */

@@ -1,0 +1,426 @@
+"""ctypes mirror of include/manta_b200.h plus batch marshalling helpers.
+
+The helpers are parametrised by (library handle, symbol prefix, optional ctx) so the very same
+marshalling drives the product library (prefix ``mb200_``, with a ctx) and -- from tests/ and
+bench.py only -- the reference / oracle checker libraries (prefixes ``ref_`` / ``orc_``, no ctx).
+Nothing in this module loads a library by itself.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# ---- status codes (include/manta_b200.h) ---------------------------------------------------
+MB200_OK = 0
+MB200_ERR_CUDA = 1
+MB200_ERR_NO_DEVICE = 2
+MB200_ERR_EMPTY_QUERY = 3
+MB200_ERR_EMPTY_REF = 4
+MB200_ERR_EMPTY_REF1 = 5
+MB200_ERR_EMPTY_REF2 = 6
+MB200_ERR_SPLIT_INPUT = 7
+MB200_ERR_SPLIT_SCAN = 8
+MB200_ERR_SPLIT_OUTCOME = 9
+MB200_ERR_BAD_QUAL = 10
+MB200_ERR_POOL_OVERFLOW = 11
+MB200_ERR_BAD_ARG = 12
+MB200_ERR_BAD_BASE = 13
+MB200_ERR_ASM_OVERFLOW = 14
+MB200_ERR_UNSUPPORTED = 15
+
+# messages the reference throws for the same conditions (GlobalJumpAlignerImpl.hpp:50-58 etc.)
+ERROR_MESSAGES = {
+    MB200_ERR_EMPTY_QUERY: "Unexpected empty query sequence",
+    MB200_ERR_EMPTY_REF: "Unexpected empty reference sequence",
+    MB200_ERR_EMPTY_REF1: "Unexpected empty reference1 sequence",
+    MB200_ERR_EMPTY_REF2: "Unexpected empty reference2 sequence",
+    MB200_ERR_SPLIT_INPUT: "Unexpected split read alignment input.",
+    MB200_ERR_SPLIT_SCAN: "Unexpected split read alignment input condition: scanEnd < scanStart.",
+    MB200_ERR_SPLIT_OUTCOME: "Unexpected split read alignment outcome.",
+    MB200_ERR_BAD_QUAL: "basecall quality out of range",
+}
+
+# ALIGNPATH::align_t -> CIGAR character (lib/blt_util/align_path.hpp:36-61)
+SEG_CODES = "?MIDNSHP=X"
+
+MAX_QSCORE = 70
+
+
+class Scores(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("open", C.c_int32), ("extend", C.c_int32),
+                ("offEdge", C.c_int32), ("isAllowEdgeInsertion", C.c_int32)]
+
+
+SEQVIEW_DT = np.dtype([("off", "<u8"), ("len", "<u4"), ("reserved", "<u4")], align=True)
+ALN_RESULT_DT = np.dtype([("score", "<i4"), ("beginPos", "<i4"), ("isJumped", "<u4"), ("cigarLen", "<u4"),
+                          ("cigarOff", "<u8")], align=True)
+JUMP_RESULT_DT = np.dtype([("score", "<i4"), ("jumpInsertSize", "<u4"), ("jumpRange", "<u4"),
+                           ("beginPos1", "<i4"), ("beginPos2", "<i4"), ("cigarLen1", "<u4"),
+                           ("cigarLen2", "<u4"), ("reserved", "<u4"), ("cigarOff1", "<u8"),
+                           ("cigarOff2", "<u8")], align=True)
+SR_RESULT_DT = np.dtype([("alignPos", "<u4"), ("leftSize", "<u4"), ("homSize", "<u4"), ("rightSize", "<u4"),
+                         ("leftMismatches", "<u4"), ("homMismatches", "<u4"), ("rightMismatches", "<u4"),
+                         ("alignScore", "<u4"), ("alignLnLhood", "<f4"), ("isEvidence", "<u4"),
+                         ("isTier2Evidence", "<u4"), ("evidence", "<f4"), ("status", "<i4"),
+                         ("reserved", "<u4")], align=True)
+SR_JOB_DT = np.dtype([("q_off", "<u8"), ("q_len", "<u4"), ("q_res", "<u4"), ("qualOff", "<u8"),
+                      ("t_off", "<u8"), ("t_len", "<u4"), ("t_res", "<u4"), ("bpBegin", "<i4"),
+                      ("bpEnd", "<i4"), ("table", "<u4"), ("reserved", "<u4")], align=True)
+ASM_OPTS_DT = np.dtype([("minWordLength", "<u4"), ("maxWordLength", "<u4"), ("wordStepSize", "<u4"),
+                        ("minCoverage", "<u4"), ("minConservativeCoverage", "<u4"),
+                        ("maxAssemblyCount", "<u4"), ("minUnusedReads", "<u4"), ("minSupportReads", "<u4")],
+                       align=True)
+CONTIG_DT = np.dtype([("seqOff", "<u8"), ("seqLen", "<u4"), ("seedReadCount", "<u4"),
+                      ("conservativeBegin", "<i4"), ("conservativeEnd", "<i4"), ("supportOff", "<u8"),
+                      ("rejectOff", "<u8")], align=True)
+ASM_LOCUS_DT = np.dtype([("firstContig", "<u4"), ("nContigs", "<u4"), ("firstPseudo", "<u4"),
+                         ("nPseudo", "<u4"), ("setWords", "<u4"), ("lastWordLength", "<u4"),
+                         ("status", "<i4"), ("reserved", "<u4")], align=True)
+QSCORE_TABLES_DT = np.dtype([("lnComp", "<f8", (2, MAX_QSCORE + 1)), ("lnErr", "<f8", (2, MAX_QSCORE + 1))])
+TIMING_DT = np.dtype([("h2dMs", "<f4"), ("kernelMs", "<f4"), ("d2hMs", "<f4"), ("launches", "<u4"),
+                      ("cells", "<u8"), ("algoBytes", "<u8")], align=True)
+CONFIG_DT = np.dtype([("ctasPerSm", "<u4"), ("maxContigLen", "<u4"), ("scratchBytes", "<u8"),
+                      ("reserved", "<u4", (4,))], align=True)
+
+assert SEQVIEW_DT.itemsize == 16 and ALN_RESULT_DT.itemsize == 24 and JUMP_RESULT_DT.itemsize == 48
+assert SR_RESULT_DT.itemsize == 56 and SR_JOB_DT.itemsize == 56 and CONTIG_DT.itemsize == 40
+assert ASM_LOCUS_DT.itemsize == 32 and TIMING_DT.itemsize == 32 and CONFIG_DT.itemsize == 32
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- python-side result objects (field names follow the reference structs) -----------------
+@dataclass
+class Alignment:  # lib/alignment/Alignment.hpp:28-41
+    beginPos: int = 0
+    cigar: str = ""  # apath_to_cigar(apath)
+
+    def isAligned(self) -> bool:
+        return self.cigar != ""
+
+
+@dataclass
+class AlignmentResult:  # lib/alignment/SingleRefAlignerShared.hpp:34-47
+    score: int = 0
+    isJumped: bool = False
+    align: Alignment = field(default_factory=Alignment)
+
+
+@dataclass
+class JumpAlignmentResult:  # lib/alignment/JumpAlignerBase.hpp:37-56
+    score: int = 0
+    jumpInsertSize: int = 0
+    jumpRange: int = 0
+    align1: Alignment = field(default_factory=Alignment)
+    align2: Alignment = field(default_factory=Alignment)
+
+
+@dataclass
+class SRAlignmentInfo:  # GSC/SplitReadAlignment.hpp:35-49
+    alignPos: int = 0
+    leftSize: int = 0
+    homSize: int = 0
+    rightSize: int = 0
+    leftMismatches: int = 0
+    homMismatches: int = 0
+    rightMismatches: int = 0
+    alignScore: int = 0
+    alignLnLhood: float = 0.0
+    isEvidence: bool = False
+    isTier2Evidence: bool = False
+    evidence: float = 0.0
+
+
+@dataclass
+class AssembledContig:  # lib/assembly/AssembledContig.hpp:38-50
+    seq: str = ""
+    seedReadCount: int = 0
+    supportReads: Tuple[int, ...] = ()
+    rejectReads: Tuple[int, ...] = ()
+    conservativeRange: Tuple[int, int] = (0, 0)
+
+
+@dataclass
+class AssemblyReadInfo:  # lib/assembly/AssemblyReadInfo.hpp:29-41
+    isUsed: bool = False
+    isFiltered: bool = False
+    isPseudo: bool = False
+    contigIds: List[int] = field(default_factory=list)
+
+
+def cigar_from_segments(segs: np.ndarray) -> str:
+    return "".join("%d%s" % (int(s) >> 4, SEG_CODES[int(s) & 0xF]) for s in segs)
+
+
+class Mb200Error(RuntimeError):
+    """Raised for a non-zero status; mirrors illumina::common::GeneralException for the input checks."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(message)
+        self.status = status
+
+
+# ---- sequence pool builder ------------------------------------------------------------------
+class SeqPool:
+    """Concatenates byte strings into one pool with 16-byte aligned starts (TMA bulk-copy friendly)."""
+
+    ALIGN = 16
+
+    def __init__(self):
+        self._chunks: List[bytes] = []
+        self._size = 0
+
+    def add(self, s) -> Tuple[int, int]:
+        b = s.encode("latin-1") if isinstance(s, str) else bytes(s)
+        off = self._size
+        padded = (len(b) + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self._chunks.append(b + b"\0" * (padded - len(b)))
+        self._size += padded
+        return off, len(b)
+
+    def views(self, items: Sequence) -> np.ndarray:
+        v = np.zeros(len(items), dtype=SEQVIEW_DT)
+        for i, s in enumerate(items):
+            v["off"][i], v["len"][i] = self.add(s)
+        return v
+
+    def finish(self) -> np.ndarray:
+        data = b"".join(self._chunks) + b"\0" * 64
+        return np.frombuffer(data, dtype=np.uint8).copy()
+
+
+class Binding:
+    """Function table for one implementation of the ABI (product, reference shim or C oracle)."""
+
+    def __init__(self, lib: C.CDLL, prefix: str, ctx: Optional[C.c_void_p] = None):
+        self.lib = lib
+        self.prefix = prefix
+        self.ctx = ctx
+
+    def _fn(self, name):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = C.c_int
+        return f
+
+    def _call(self, name, *args):
+        f = self._fn(name)
+        if self.ctx is not None:
+            st = f(self.ctx, *args)
+        else:
+            st = f(*args)
+        return st
+
+    def _raise(self, st):
+        msg = ERROR_MESSAGES.get(st)
+        if self.ctx is not None:
+            self.lib.mb200_last_error.restype = C.c_char_p
+            detail = self.lib.mb200_last_error(self.ctx)
+            if detail:
+                msg = detail.decode()
+        raise Mb200Error(st, msg or ("status %d" % st))
+
+    # -- aligners -----------------------------------------------------------------------------
+    def _with_cigar_pool(self, n, call, guess):
+        cap = max(64, guess)
+        for _ in range(8):
+            cig = np.zeros(cap, dtype=np.uint32)
+            used = C.c_uint64(0)
+            st = call(cig, cap, used)
+            if st == MB200_ERR_POOL_OVERFLOW:
+                cap = max(int(used.value), cap * 2)
+                continue
+            if st != MB200_OK:
+                self._raise(st)
+            return cig, int(used.value)
+        raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "cigar pool overflow")
+
+    def jump_align_raw(self, scores: Scores, jumpScore: int, pool: np.ndarray, q: np.ndarray, r1: np.ndarray,
+                       r2: np.ndarray):
+        n = len(q)
+        res = np.zeros(n, dtype=JUMP_RESULT_DT)
+
+        def call(cig, cap, used):
+            args = [C.byref(scores), C.c_int32(jumpScore), C.c_uint32(n), _ptr(pool)]
+            if self.ctx is not None:
+                args.append(C.c_uint64(pool.size))
+            args += [_ptr(q), _ptr(r1), _ptr(r2), _ptr(res), _ptr(cig), C.c_uint64(cap), C.byref(used)]
+            return self._call("jump_align_batch", *args)
+
+        cig, used = self._with_cigar_pool(n, call, 32 * n)
+        return res, cig[:used]
+
+    def single_align_raw(self, kind: str, scores: Scores, largeIndelScore: int, pool: np.ndarray,
+                         q: np.ndarray, r: np.ndarray):
+        n = len(q)
+        res = np.zeros(n, dtype=ALN_RESULT_DT)
+
+        def call(cig, cap, used):
+            args = [C.byref(scores)]
+            if kind == "indel":
+                args.append(C.c_int32(largeIndelScore))
+            args += [C.c_uint32(n), _ptr(pool)]
+            if self.ctx is not None:
+                args.append(C.c_uint64(pool.size))
+            args += [_ptr(q), _ptr(r), _ptr(res), _ptr(cig), C.c_uint64(cap), C.byref(used)]
+            return self._call("indel_align_batch" if kind == "indel" else "global_align_batch", *args)
+
+        cig, used = self._with_cigar_pool(n, call, 32 * n)
+        return res, cig[:used]
+
+    def jump_align(self, scores: Scores, jumpScore: int, triples: Sequence[Tuple]) -> List[JumpAlignmentResult]:
+        sp = SeqPool()
+        q = sp.views([t[0] for t in triples])
+        r1 = sp.views([t[1] for t in triples])
+        r2 = sp.views([t[2] for t in triples])
+        res, cig = self.jump_align_raw(scores, jumpScore, sp.finish(), q, r1, r2)
+        return [decode_jump(res[i], cig) for i in range(len(triples))]
+
+    def single_align(self, kind: str, scores: Scores, largeIndelScore: int,
+                     pairs: Sequence[Tuple]) -> List[AlignmentResult]:
+        sp = SeqPool()
+        q = sp.views([t[0] for t in pairs])
+        r = sp.views([t[1] for t in pairs])
+        res, cig = self.single_align_raw(kind, scores, largeIndelScore, sp.finish(), q, r)
+        return [decode_aln(res[i], cig) for i in range(len(pairs))]
+
+    # -- split read ---------------------------------------------------------------------------
+    def split_align_raw(self, tables: np.ndarray, priors: Tuple[float, float], flank: int, pool: np.ndarray,
+                        jobs: np.ndarray) -> np.ndarray:
+        n = len(jobs)
+        res = np.zeros(n, dtype=SR_RESULT_DT)
+        if self.prefix == "ref_":
+            st = self._call("split_align_batch", C.c_double(priors[0]), C.c_double(priors[1]),
+                            C.c_uint32(flank), C.c_uint32(n), _ptr(pool), _ptr(jobs), _ptr(res))
+        else:
+            args = [_ptr(tables), C.c_uint32(flank), C.c_uint32(n), _ptr(pool)]
+            if self.ctx is not None:
+                args.append(C.c_uint64(pool.size))
+            args += [_ptr(jobs), _ptr(res)]
+            st = self._call("split_align_batch", *args)
+        if st != MB200_OK:
+            self._raise(st)
+        return res
+
+    # -- assembler ----------------------------------------------------------------------------
+    def assemble_raw(self, opts: np.ndarray, readOff: np.ndarray, views: np.ndarray, pool: np.ndarray):
+        nLoci = len(readOff) - 1
+        maxAsm = int(opts["maxAssemblyCount"][0])
+        contigCap = nLoci * maxAsm
+        pseudoCap = nLoci * 2 * maxAsm
+        nReadsMax = int(np.max(np.diff(readOff))) if nLoci else 0
+        totalBases = int(views["len"].sum()) if len(views) else 0
+        poolCap = max(1 << 16, 4 * totalBases)
+        setCap = max(1024, contigCap * 2 * ((nReadsMax + 2 * maxAsm + 31) // 32))
+        for _ in range(6):
+            loci = np.zeros(nLoci, dtype=ASM_LOCUS_DT)
+            contigs = np.zeros(contigCap, dtype=CONTIG_DT)
+            pseudo = np.zeros(pseudoCap, dtype=SEQVIEW_DT)
+            cpool = np.zeros(poolCap, dtype=np.uint8)
+            spool = np.zeros(setCap, dtype=np.uint32)
+            args = [_ptr(opts), C.c_uint32(nLoci), _ptr(readOff), _ptr(views), _ptr(pool)]
+            if self.ctx is not None:
+                args.append(C.c_uint64(pool.size))
+            args += [_ptr(loci), _ptr(contigs), C.c_uint64(contigCap), _ptr(pseudo), C.c_uint64(pseudoCap),
+                     _ptr(cpool), C.c_uint64(poolCap), _ptr(spool), C.c_uint64(setCap)]
+            st = self._call("assemble_batch", *args)
+            if st == MB200_ERR_POOL_OVERFLOW:
+                poolCap *= 4
+                setCap *= 2
+                continue
+            if st != MB200_OK:
+                self._raise(st)
+            return loci, contigs, pseudo, cpool, spool
+        raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "assembler output pool overflow")
+
+    def assemble(self, opts: np.ndarray, loci_reads: Sequence[Sequence]):
+        """returns per locus (contigs, pseudoReads, readInfo) like runIterativeAssembler's outputs"""
+        sp = SeqPool()
+        readOff = np.zeros(len(loci_reads) + 1, dtype=np.uint64)
+        allReads = []
+        for i, reads in enumerate(loci_reads):
+            allReads.extend(reads)
+            readOff[i + 1] = len(allReads)
+        views = sp.views(allReads)
+        loci, contigs, pseudo, cpool, spool = self.assemble_raw(opts, readOff, views, sp.finish())
+        out = []
+        for i, reads in enumerate(loci_reads):
+            out.append(decode_locus(loci[i], contigs, pseudo, cpool, spool, len(reads)))
+        return out
+
+
+def default_asm_opts(**kw) -> np.ndarray:
+    o = np.zeros(1, dtype=ASM_OPTS_DT)
+    o["minWordLength"] = 41
+    o["maxWordLength"] = 76
+    o["wordStepSize"] = 5
+    o["minCoverage"] = 1
+    o["minConservativeCoverage"] = 2
+    o["maxAssemblyCount"] = 10
+    o["minUnusedReads"] = 3
+    o["minSupportReads"] = 2
+    for k, v in kw.items():
+        o[k] = v
+    return o
+
+
+def _segs(cig, off, ln):
+    return cigar_from_segments(cig[int(off):int(off) + int(ln)])
+
+
+def decode_aln(r, cig) -> AlignmentResult:
+    return AlignmentResult(int(r["score"]), bool(r["isJumped"]),
+                           Alignment(int(r["beginPos"]), _segs(cig, r["cigarOff"], r["cigarLen"])))
+
+
+def decode_jump(r, cig) -> JumpAlignmentResult:
+    return JumpAlignmentResult(int(r["score"]), int(r["jumpInsertSize"]), int(r["jumpRange"]),
+                               Alignment(int(r["beginPos1"]), _segs(cig, r["cigarOff1"], r["cigarLen1"])),
+                               Alignment(int(r["beginPos2"]), _segs(cig, r["cigarOff2"], r["cigarLen2"])))
+
+
+def decode_sr(r) -> SRAlignmentInfo:
+    return SRAlignmentInfo(int(r["alignPos"]), int(r["leftSize"]), int(r["homSize"]), int(r["rightSize"]),
+                           int(r["leftMismatches"]), int(r["homMismatches"]), int(r["rightMismatches"]),
+                           int(r["alignScore"]), float(r["alignLnLhood"]), bool(r["isEvidence"]),
+                           bool(r["isTier2Evidence"]), float(r["evidence"]))
+
+
+def _set_from_words(words: np.ndarray) -> Tuple[int, ...]:
+    out = []
+    for w, v in enumerate(words):
+        v = int(v)
+        while v:
+            b = (v & -v).bit_length() - 1
+            out.append(w * 32 + b)
+            v &= v - 1
+    return tuple(out)
+
+
+def decode_locus(L, contigs, pseudo, cpool, spool, nNormalReads: int):
+    sw = int(L["setWords"])
+    cs = []
+    for ci in range(int(L["firstContig"]), int(L["firstContig"]) + int(L["nContigs"])):
+        c = contigs[ci]
+        seq = bytes(cpool[int(c["seqOff"]):int(c["seqOff"]) + int(c["seqLen"])]).decode("latin-1")
+        sup = _set_from_words(spool[int(c["supportOff"]):int(c["supportOff"]) + sw])
+        rej = _set_from_words(spool[int(c["rejectOff"]):int(c["rejectOff"]) + sw])
+        cs.append(AssembledContig(seq, int(c["seedReadCount"]), sup, rej,
+                                  (int(c["conservativeBegin"]), int(c["conservativeEnd"]))))
+    ps = []
+    for pi in range(int(L["firstPseudo"]), int(L["firstPseudo"]) + int(L["nPseudo"])):
+        v = pseudo[pi]
+        ps.append(bytes(cpool[int(v["off"]):int(v["off"]) + int(v["len"])]).decode("latin-1"))
+    # AssemblyReadOutput as selectContigs leaves it (IterativeAssembler.cpp:822-831)
+    info = [AssemblyReadInfo() for _ in range(nNormalReads + len(ps))]
+    for r in range(nNormalReads, len(info)):
+        info[r].isPseudo = True
+    for cid, c in enumerate(cs):
+        for rd in c.supportReads:
+            info[rd].isUsed = True
+            info[rd].contigIds.append(cid)
+    return cs, ps, info
