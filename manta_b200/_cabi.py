@@ -421,6 +421,12 @@ def decode_locus(L, contigs, pseudo, cpool, spool, nNormalReads: int):
         info[r].isPseudo = True
     for cid, c in enumerate(cs):
         for rd in c.supportReads:
+            # When the LAST word length fails, the reference replaces the pseudo reads after the contigs were
+            # built (IterativeAssembler.cpp:882-910), so a contig can name a pseudo read index past the end of
+            # the final read list (the reference indexes its vector out of bounds there, :765,:826).  Such
+            # indices are >= the normal read count and are treated as pseudo reads.
+            while rd >= len(info):
+                info.append(AssemblyReadInfo(isPseudo=True))
             info[rd].isUsed = True
             info[rd].contigIds.append(cid)
     return cs, ps, info

@@ -1,0 +1,254 @@
+"""Seeded synthetic workloads shared by tests/, tests/golden/make_golden.py and bench.py.
+
+All generators are deterministic functions of their seed.  Nothing here touches a GPU or any library.
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTN", b"TGCAN"):
+    COMP[_a] = _b
+
+
+# ---------------------------------------------------------------------------------------------
+# small python-level generators for parity tests / golden vectors
+def _rseq(rng: random.Random, n: int, alpha: str = "ACGT") -> str:
+    return "".join(rng.choice(alpha) for _ in range(n))
+
+
+def _mutate(rng: random.Random, s: str, rate: float, alpha: str = "ACGT") -> str:
+    out = []
+    for ch in s:
+        r = rng.random()
+        if r < rate / 3:
+            continue
+        if r < 2 * rate / 3:
+            out.append(rng.choice(alpha))
+            out.append(ch)
+            continue
+        if r < rate:
+            out.append(rng.choice(alpha))
+            continue
+        out.append(ch)
+    return "".join(out)
+
+
+def random_alignment_cases(seed: int, n: int, kind: str, maxq: int = 260, maxr: int = 700) -> List[Tuple[str, ...]]:
+    """contig-vs-reference shaped cases: deletions, insertions, jumps, soft-clips, N's, tiny inputs"""
+    rng = random.Random(seed)
+    cases = []
+    for i in range(n):
+        alpha = "ACGTN" if rng.random() < 0.25 else ("AC" if rng.random() < 0.1 else "ACGT")
+        r1 = _rseq(rng, rng.randint(1, maxr), alpha)
+        r2 = _rseq(rng, rng.randint(1, maxr), alpha)
+        mode = rng.random()
+        a = rng.randint(0, len(r1) - 1)
+        left = r1[a:a + rng.randint(1, maxq // 2)]
+        if kind == "jump":
+            b = rng.randint(0, len(r2) - 1)
+            right = r2[b:b + rng.randint(1, maxq // 2)]
+            ins = _rseq(rng, rng.randint(0, 12)) if mode < 0.3 else ""
+            q = left + ins + right
+            if mode > 0.85:
+                q = left  # aligns to one reference only
+            elif mode > 0.8:
+                q = _rseq(rng, 8) + q + _rseq(rng, 8)  # off-edge soft clips
+            q = _mutate(rng, q, 0.04, alpha) or "A"
+            cases.append((q[:maxq], r1, r2))
+        else:
+            # large deletion / insertion inside one reference
+            gap = rng.randint(0, max(0, len(r1) - a - len(left) - 1))
+            b = min(len(r1) - 1, a + len(left) + gap)
+            right = r1[b:b + rng.randint(1, maxq // 2)]
+            ins = _rseq(rng, rng.randint(20, 120)) if mode < 0.25 else ""
+            q = left + ins + right
+            if mode > 0.9:
+                q = _rseq(rng, 6) + q + _rseq(rng, 6)
+            q = _mutate(rng, q, 0.04, alpha) or "A"
+            cases.append((q[:maxq], r1))
+    # degenerate sizes
+    if kind == "jump":
+        cases += [("A", "A", "A"), ("ACGT", "T", "G"), ("A" * 40, "A" * 3, "A" * 50), ("ACGTACGTAC", "ACGTA", "CGTAC")]
+    else:
+        cases += [("A", "A"), ("ACGT", "T"), ("A" * 40, "A" * 7), ("T", "ACGTACGT" * 12)]
+    return cases
+
+
+def random_assembly_reads(rng: random.Random, nreads: int, rl: int, with_repeat: bool, n_rate: float = 0.02,
+                          err: float = 0.005) -> List[str]:
+    reflen = 1200
+    refw = _rseq(rng, reflen)
+    bp = reflen // 2
+    kind = rng.random()
+    if kind < 0.4:
+        alt = refw[:bp] + refw[bp + rng.randint(50, 400):]
+    elif kind < 0.6:
+        alt = refw[:bp] + _rseq(rng, rng.randint(50, 300)) + refw[bp:]
+    else:
+        alt = refw[:bp] + _rseq(rng, 600)
+    if with_repeat:
+        per = rng.randint(1, 30)
+        unit = _rseq(rng, per)
+        rep = (unit * (200 // per + 2))[:rng.randint(60, 200)]
+        alt = alt[:bp] + rep + alt[bp:]
+    reads = []
+    for i in range(nreads):
+        src = alt if i < nreads * 3 // 4 else refw
+        st = rng.randint(max(0, bp - rl + 10), max(0, min(len(src) - rl, bp - 10))) if len(src) > rl else 0
+        r = list(src[st:st + rl])
+        for j in range(len(r)):
+            x = rng.random()
+            if x < err:
+                r[j] = rng.choice("ACGT")
+            elif x < err + n_rate:
+                r[j] = "N"
+        reads.append("".join(r))
+    return reads
+
+
+def random_assembly_cases(seed: int, n: int) -> List[Tuple[Dict[str, int], List[str]]]:
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        opts: Dict[str, int] = {}
+        m = rng.random()
+        if m < 0.35:
+            opts = dict(minWordLength=rng.choice([8, 12, 21]), maxWordLength=rng.choice([21, 31, 41]),
+                        wordStepSize=rng.choice([3, 5, 10]))
+        if rng.random() < 0.3:
+            opts["minCoverage"] = rng.choice([2, 3])
+        reads = random_assembly_reads(rng, rng.choice([6, 20, 64, 90]), rng.choice([50, 100, 150]),
+                                      with_repeat=rng.random() < 0.4)
+        if i == 0:
+            reads = reads[:3] + ["", "ACGT", "N" * 60] + reads[3:]  # empty / short / all-N reads
+        out.append((opts, reads))
+    return out
+
+
+def random_split_cases(seed: int, n: int) -> List[dict]:
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        T = rng.randint(160, 1300)
+        tgt = _rseq(rng, T, "ACGTN" if rng.random() < 0.2 else "ACGT")
+        Q = rng.randint(20, min(150, T - 1))
+        bp = rng.randint(0, T - 1)
+        hom = rng.randint(0, 10)
+        st = max(0, min(T - Q, bp - rng.randint(0, Q)))
+        q = list(tgt[st:st + Q])
+        for j in range(Q):
+            if rng.random() < 0.03:
+                q[j] = rng.choice("ACGTN")
+        if rng.random() < 0.3:
+            q[Q // 2:] = list(_rseq(rng, Q - Q // 2))
+        qual = [rng.choice([2, 2, 5, 20, 30, 37, 40, 41, 0, 70]) for _ in range(Q)]
+        bpr = [bp, bp + hom]
+        if rng.random() < 0.03:
+            bpr = [T + 5, T + 6]
+        out.append(dict(test="seeded-random-%d" % i, query="".join(q), qual=qual, target=tgt, bp=bpr,
+                        table=rng.randint(0, 1)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[1]: "synthetic 50k candidate loci x 64 reads x 150 bp, assembly + 5 kb DP"
+@dataclass
+class CandidateBatch:
+    """One batch of candidate loci laid out for the C ABI (all numpy, host memory)."""
+    nLoci: int
+    readsPerLocus: int
+    readLen: int
+    pool: np.ndarray         # uint8: all reads, then all reference windows (16-byte aligned starts)
+    readOff: np.ndarray      # uint64 [nLoci+1] into readViews
+    readViews: np.ndarray    # SEQVIEW_DT [nLoci*readsPerLocus]
+    isJump: np.ndarray       # uint8 [nLoci]: 1 -> spanning candidate (GlobalJumpAligner), 0 -> complex (large-indel aligner)
+    ref1: np.ndarray         # SEQVIEW_DT [nLoci]: reference window (complex) or ref1 (spanning)
+    ref2: np.ndarray         # SEQVIEW_DT [nLoci]: ref2 for spanning candidates (len 0 otherwise)
+
+
+def make_candidate_batch(n_loci: int, seed: int = 20260923, reads_per_locus: int = 64, read_len: int = 150,
+                         window: int = 5000, seqview_dtype=None) -> CandidateBatch:
+    """SURVEY.md 8(d) config 2.  Per locus: a `window`-bp iid reference; an SV at a breakpoint
+    (40 % deletion 50-2000 bp, 20 % novel insertion 50-300 bp, 20 % inversion, 20 % translocation to a second
+    window); 48 reads from the alt haplotype tiling the breakpoint (start in [bp-140, bp-10]) + 16 from the
+    reference; 0.5 % substitutions; 2 % of bases low quality -> 'N' (minQval 5, SVCandidateAssembler.cpp:102-136);
+    10 % of loci carry a tandem repeat (period 2-30, >= 100 bp) at the breakpoint.
+    Deletion/insertion loci are 'complex' candidates aligned with the large-indel aligner against the whole
+    window; inversion/translocation loci are 'spanning' candidates aligned with the jump aligner against two
+    window/2 references (R1 + R2 = window)."""
+    from ._cabi import SEQVIEW_DT
+    rng = np.random.default_rng(seed)
+    n_alt = reads_per_locus * 3 // 4
+    read_stride = read_len
+    reads_bytes = n_loci * reads_per_locus * read_stride
+    ref_stride = (window + 15) // 16 * 16
+    half = window // 2
+    half_stride = (half + 15) // 16 * 16
+    reads_bytes_al = (reads_bytes + 15) // 16 * 16
+    pool = np.zeros(reads_bytes_al + n_loci * (ref_stride + 2 * half_stride) + 64, dtype=np.uint8)
+
+    readViews = np.zeros(n_loci * reads_per_locus, dtype=SEQVIEW_DT)
+    readViews["off"] = np.arange(n_loci * reads_per_locus, dtype=np.uint64) * read_stride
+    readViews["len"] = read_len
+    readOff = np.arange(n_loci + 1, dtype=np.uint64) * reads_per_locus
+    isJump = np.zeros(n_loci, dtype=np.uint8)
+    ref1 = np.zeros(n_loci, dtype=SEQVIEW_DT)
+    ref2 = np.zeros(n_loci, dtype=SEQVIEW_DT)
+
+    col = np.arange(read_len)
+    ref_base = reads_bytes_al
+    for li in range(n_loci):
+        w1 = ACGT[rng.integers(0, 4, window)]
+        kind = rng.random()
+        bp = int(rng.integers(1000, 2500))
+        if kind < 0.4:  # deletion
+            dl = int(rng.integers(50, 2001))
+            alt = np.concatenate([w1[:bp], w1[bp + dl:]])
+        elif kind < 0.6:  # novel insertion
+            il = int(rng.integers(50, 301))
+            alt = np.concatenate([w1[:bp], ACGT[rng.integers(0, 4, il)], w1[bp:]])
+        else:
+            w2 = ACGT[rng.integers(0, 4, window)]
+            bp2 = int(rng.integers(1000, 2500))
+            if kind < 0.8:  # inversion: continue on the reverse complement of a second segment
+                seg = COMP[w2[::-1]]
+            else:  # translocation
+                seg = w2
+            alt = np.concatenate([w1[:bp], seg[bp2:]])
+            isJump[li] = 1
+        if rng.random() < 0.10:
+            per = int(rng.integers(2, 31))
+            ln = int(rng.integers(100, 181))
+            rep = np.tile(ACGT[rng.integers(0, 4, per)], ln // per + 1)[:ln]
+            alt = np.concatenate([alt[:bp], rep, alt[bp:]])
+        # reads
+        st_alt = rng.integers(bp - 140, bp - 9, n_alt)
+        st_ref = rng.integers(bp - 140, bp - 9, reads_per_locus - n_alt)
+        rd = np.empty((reads_per_locus, read_len), dtype=np.uint8)
+        rd[:n_alt] = alt[st_alt[:, None] + col[None, :]]
+        rd[n_alt:] = w1[st_ref[:, None] + col[None, :]]
+        u = rng.random((reads_per_locus, read_len))
+        sub = u < 0.005
+        rd[sub] = ACGT[rng.integers(0, 4, int(sub.sum()))]
+        rd[(u >= 0.005) & (u < 0.025)] = ord("N")
+        o = li * reads_per_locus * read_stride
+        pool[o:o + reads_per_locus * read_len] = rd.reshape(-1)
+        # references
+        rb = ref_base + li * (ref_stride + 2 * half_stride)
+        if isJump[li]:
+            a0 = max(0, min(window - half, bp - half // 2))
+            b0 = max(0, min(window - half, bp2 - half // 2))
+            pool[rb + ref_stride:rb + ref_stride + half] = w1[a0:a0 + half]
+            pool[rb + ref_stride + half_stride:rb + ref_stride + half_stride + half] = seg[b0:b0 + half]
+            ref1["off"][li], ref1["len"][li] = rb + ref_stride, half
+            ref2["off"][li], ref2["len"][li] = rb + ref_stride + half_stride, half
+        else:
+            pool[rb:rb + window] = w1
+            ref1["off"][li], ref1["len"][li] = rb, window
+    return CandidateBatch(n_loci, reads_per_locus, read_len, pool, readOff, readViews, isJump, ref1, ref2)

@@ -29,7 +29,9 @@ if [ ! -d "$OUT/htslib-1.9/htslib" ]; then
   tar -xjf "$REF/redist/htslib-1.9.tar.bz2" -C "$OUT" htslib-1.9/htslib
 fi
 
-CXX="${CXX:-g++}"
+# the image exports CXX=/opt/gcc/bin/g++, a wrapper that links libstdc++ statically (exceptions thrown inside a
+# dlopen()ed library then crash); use the distribution compiler and the shared libstdc++ instead.
+if [ -x /usr/bin/g++ ]; then CXX=/usr/bin/g++; else CXX=g++; fi
 # Release flags of the reference: -O3 -fomit-frame-pointer, asserts ON (src/cmake/cxxConfigure.cmake:452-454)
 CXXFLAGS="-std=c++11 -O3 -fomit-frame-pointer -fPIC -fvisibility=hidden -ffunction-sections -fdata-sections -w \
   -I$LIB -I$OUT/boost_1_58_0 -I$OUT/htslib-1.9 -I$HERE/../include"

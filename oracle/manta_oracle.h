@@ -1,0 +1,60 @@
+/*
+ * manta_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C CPU restatement of the reference algorithms on the hot path, one function per seam of
+ * include/manta_b200.h, same argument meaning (no ctx, no poolBytes).  It exists so the CUDA path can
+ * be checked bit-for-bit on the GPU box, where /root/reference (and therefore oracle/_ref) may be
+ * absent.  Parity of THIS file is pinned in tests/ against (a) the golden vectors transcribed from the
+ * reference's own unit tests (tests/golden/) and (b) oracle/_ref/libmanta_ref.so, the unmodified
+ * reference compiled by oracle/build_ref.sh, on seeded random inputs.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * compile, link, load or call anything declared here.  The product never does.
+ */
+#ifndef MANTA_ORACLE_H
+#define MANTA_ORACLE_H
+
+#include "manta_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+ORC_API int orc_jump_align_batch(const mb200_scores* scores, int32_t jumpScore, uint32_t n, const uint8_t* pool,
+                                 const mb200_seqview* query, const mb200_seqview* ref1,
+                                 const mb200_seqview* ref2, mb200_jump_result* results, uint32_t* cigarPool,
+                                 uint64_t cigarCap, uint64_t* cigarUsed);
+
+ORC_API int orc_indel_align_batch(const mb200_scores* scores, int32_t largeIndelScore, uint32_t n,
+                                  const uint8_t* pool, const mb200_seqview* query, const mb200_seqview* ref,
+                                  mb200_aln_result* results, uint32_t* cigarPool, uint64_t cigarCap,
+                                  uint64_t* cigarUsed);
+
+ORC_API int orc_global_align_batch(const mb200_scores* scores, uint32_t n, const uint8_t* pool,
+                                   const mb200_seqview* query, const mb200_seqview* ref,
+                                   mb200_aln_result* results, uint32_t* cigarPool, uint64_t cigarCap,
+                                   uint64_t* cigarUsed);
+
+/* qscore_snp(snpPrior) tables, lib/blt_util/qscore_snp.cpp:29-41 */
+ORC_API void orc_qscore_tables(double snpPrior0, double snpPrior1, mb200_qscore_tables* out);
+
+ORC_API int orc_split_align_batch(const mb200_qscore_tables* tables, uint32_t flankScoreSize, uint32_t n,
+                                  const uint8_t* pool, const mb200_sr_job* jobs, mb200_sr_result* results);
+
+ORC_API int orc_assemble_batch(const mb200_asm_opts* opts, uint32_t nLoci, const uint64_t* readOff,
+                               const mb200_seqview* readViews, const uint8_t* pool, mb200_asm_locus* loci,
+                               mb200_contig* contigs, uint64_t contigCap, mb200_seqview* pseudoReads,
+                               uint64_t pseudoCap, uint8_t* contigPool, uint64_t contigPoolCap,
+                               uint32_t* setPool, uint64_t setPoolCap);
+
+/* libstdc++ std::unordered_map<std::string,T> iteration-order emulation (exported for its own test) */
+ORC_API void orc_unordered_order(uint32_t n, const uint8_t* keys, uint32_t keyLen, uint32_t* order);
+
+ORC_API const char* orc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

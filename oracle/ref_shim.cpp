@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "alignment/GlobalAligner.hpp"
@@ -277,6 +278,18 @@ REF_API int ref_assemble_batch(const mb200_asm_opts* opts, uint32_t nLoci, const
   }
   ok = (nContig <= contigCap) && (nPseudo <= pseudoCap) && (poolUsed <= contigPoolCap) && (setUsed <= setPoolCap);
   return ok ? MB200_OK : MB200_ERR_POOL_OVERFLOW;
+}
+
+/// iteration order of a real std::unordered_map<std::string,unsigned> filled with operator[] in the given
+/// key order (pins the libstdc++ emulation of oracle/orc_assemble.c)
+REF_API void ref_unordered_order(uint32_t n, const uint8_t* keys, uint32_t keyLen, uint32_t* order)
+{
+  std::unordered_map<std::string, unsigned> m;
+  for (uint32_t i(0); i < n; ++i) {
+    m[std::string(reinterpret_cast<const char*>(keys + static_cast<size_t>(i) * keyLen), keyLen)] = i;
+  }
+  uint32_t k(0);
+  for (const auto& kv : m) order[k++] = kv.second;
 }
 
 REF_API const char* ref_version()

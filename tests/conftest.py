@@ -1,0 +1,49 @@
+"""pytest wiring: the `gpu` marker and the three library fixtures.
+
+  orc  -- oracle/_build/libmanta_oracle.so, the C restatement (built on demand with `make -C oracle`)
+  ref  -- oracle/_ref/libmanta_ref.so, the unmodified reference compiled by oracle/build_ref.sh
+          (present in the build container; tests that need it are skipped where it is absent)
+  gpu  -- manta_b200.Context on cuda:0 through the C ABI of libmanta_b200.so (tests marked @pytest.mark.gpu)
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from manta_b200 import _cabi as cb  # noqa: E402
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    lib = os.path.join(ROOT, "oracle", "_build", "libmanta_oracle.so")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    return cb.Binding(C.CDLL(lib), "orc_")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    lib = os.path.join(ROOT, "oracle", "_ref", "libmanta_ref.so")
+    if not os.path.exists(lib):
+        if os.path.isdir("/root/reference/src"):
+            subprocess.check_call([os.path.join(ROOT, "oracle", "build_ref.sh")])
+        else:
+            pytest.skip("oracle/_ref/libmanta_ref.so not built (no reference tree on this box)")
+    return cb.Binding(C.CDLL(lib), "ref_")
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    import manta_b200
+    ctx = manta_b200.Context(0)
+    yield ctx
+    ctx.close()

@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.json from the reference (run in the BUILD container only).
+
+Two sources are combined per vector:
+  * ``expected``  -- values asserted by the reference's own unit tests, transcribed by parsing the test
+                     sources under /root/reference (alignment suites) or by hand (assembler, split-read
+                     suites, whose cases are few and irregular);
+  * ``reference`` -- the full result produced here by the UNMODIFIED reference compiled into
+                     oracle/_ref/libmanta_ref.so (oracle/build_ref.sh), for the same inputs plus seeded
+                     random inputs, so that fields the unit tests do not assert (score, jumpRange,
+                     support/reject read sets, ...) are pinned too.
+
+Usage:  python tests/golden/make_golden.py          (writes the json files next to this script)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import random
+import re
+import sys
+from dataclasses import asdict
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from manta_b200 import _cabi as cb  # noqa: E402
+from manta_b200 import synth as workloads  # noqa: E402
+
+REF_SRC = os.environ.get("MANTA_REF", "/root/reference")
+ALN_TESTS = os.path.join(REF_SRC, "src/c++/lib/alignment/test")
+
+
+def load_ref():
+    path = os.path.join(ROOT, "oracle", "_ref", "libmanta_ref.so")
+    return cb.Binding(C.CDLL(path), "ref_")
+
+
+# --------------------------------------------------------------------------------------------
+# alignment suites: parse BOOST_AUTO_TEST_CASE bodies
+HELPERS = {
+    # file -> helper name -> (kind, scores(match,mismatch,open,extend,offEdge), extra)
+    "GlobalJumpAlignerTest.cpp": {
+        "testAlign": ("jump", (2, -4, -5, -1, -1), -3),      # GlobalJumpAlignerTest.cpp:32-42
+        "testAlign2": ("jump", (2, -4, -10, -1, -1), -20),   # :44-54
+        "testAlign3": ("jump", (2, -4, -2, 0, -1), -20),     # :56-66
+    },
+    "GlobalLargeIndelAlignerTest.cpp": {
+        "testAlign": ("indel", (2, -4, -5, -1, -4), -10),    # GlobalLargeIndelAlignerTest.cpp:32-40
+    },
+    "GlobalAlignerTest.cpp": {
+        "testAlign": ("global", (2, -4, -5, -1, None), 0),   # GlobalAlignerTest.cpp:32-44 (offEdge, edgeIns are args)
+    },
+}
+
+
+def parse_alignment_tests(fname):
+    src = open(os.path.join(ALN_TESTS, fname)).read()
+    helpers = HELPERS[fname]
+    cases = []
+    for m in re.finditer(r"BOOST_AUTO_TEST_CASE\((\w+)\)\s*\{(.*?)\n\}", src, re.S):
+        name, body = m.group(1), m.group(2)
+        strings = {}
+        calls = {}
+        for line in re.split(r";\s*\n", body):
+            line = " ".join(line.split())
+            sm = re.search(r"std::string\s+(\w+)\s*\(\s*\"(.*)\"\s*\)$", line) or re.search(
+                r"std::string\s+(\w+)\s*=\s*\"(.*)\"$", line)
+            if sm:
+                strings[sm.group(1)] = sm.group(2).replace('" "', "")
+                continue
+            cm = re.search(r"(\w+)\s*=\s*(testAlign\d?)\((.*)\)$", line)
+            if cm and cm.group(2) in helpers:
+                args = [a.strip() for a in cm.group(3).split(",")]
+                kind, sc, extra = helpers[cm.group(2)]
+                nseq = 3 if kind == "jump" else 2
+                seqs = [strings[a] for a in args[:nseq]]
+                sc = list(sc)
+                edge = 0
+                if kind == "global":
+                    sc[4] = int(args[2]) if len(args) > 2 else -4
+                    edge = 1 if (len(args) > 3 and args[3] == "true") else 0
+                calls[cm.group(1)] = dict(test=fname + ":" + name, kind=kind, scores=sc + [edge], extra=extra,
+                                          seqs=seqs, expected={})
+                continue
+            em = re.search(r"BOOST_REQUIRE_EQUAL\((.*)\)$", line)
+            if em:
+                lhs, rhs = [x.strip() for x in em.group(1).rsplit(",", 1)]
+                rhs = rhs.rstrip("u")
+                cg = re.match(r"apath_to_cigar\((\w+)\.(align\d?)\.apath\)", lhs)
+                if cg and cg.group(1) in calls:
+                    calls[cg.group(1)]["expected"][cg.group(2) + ".cigar"] = rhs.strip('"')
+                    continue
+                fm = re.match(r"(\w+)\.([\w\.]+)$", lhs)
+                if fm and fm.group(1) in calls:
+                    val = rhs
+                    val = {"true": 1, "false": 0}.get(val, val)
+                    calls[fm.group(1)]["expected"][fm.group(2)] = int(val)
+        cases.extend(calls.values())
+    return cases
+
+
+def run_alignment(ref, case):
+    S = cb.Scores(*case["scores"])
+    if case["kind"] == "jump":
+        r = ref.jump_align(S, case["extra"], [tuple(case["seqs"])])[0]
+    else:
+        r = ref.single_align(case["kind"], S, case["extra"], [tuple(case["seqs"])])[0]
+    return asdict(r)
+
+
+def check_expected(case):
+    ref = case["reference"]
+    for key, val in case["expected"].items():
+        cur = ref
+        for part in key.split("."):
+            cur = cur[part]
+        if isinstance(cur, bool):
+            cur = int(cur)
+        assert cur == val, (case["test"], key, cur, val)
+
+
+# --------------------------------------------------------------------------------------------
+# assembler suite (lib/assembly/test/IterativeAssemblerTest.cpp), transcribed by hand
+ASM_CASES = [
+    dict(test="IterativeAssemblerTest.cpp:test_BasicAssembler(:66-98)",
+         opts=dict(minWordLength=6, maxWordLength=6, minCoverage=2),
+         reads=["ACGTGTATTACC", "GTGTATTACCTA", "ATTACCTAGTAC", "TACCTAGTACTC", "123456789123"],
+         expected=dict(contigs=["GTGTATTACCTAGTAC"], used=[True, True, True, True, False],
+                       contigIds=[[0], [0], [0], [0], []])),
+    dict(test="IterativeAssemblerTest.cpp:test_IterativeKmer(:100-130)",
+         opts=dict(minWordLength=3, maxWordLength=9, wordStepSize=3, minCoverage=1),
+         reads=["ACACACACGATG", "GATGTCTCTCTC", "123456789123"],
+         expected=dict(contigs=["ACACACACGATGTCTCTCTC"], used=[True, True, False], contigIds=[[0], [0], []])),
+    dict(test="IterativeAssemblerTest.cpp:test_branching_basic(:132-170)",
+         opts=dict(minWordLength=6, maxWordLength=6, minCoverage=1, minSupportReads=1, minUnusedReads=1),
+         reads=["ATATAGACGATG", "ACGATGTCTATCTT", "ACGATGTTGGCCTT"],
+         expected=dict(contigs=["ATATAGACGATGTCTATCTT", "ATATAGACGATGTTGGCCTT"], used=[True, True, True],
+                       contigIds=[[0, 1], [0], [1]])),
+    dict(test="IterativeAssemblerTest.cpp:test_branching_iterative(:172-210)",
+         opts=dict(minWordLength=3, maxWordLength=9, wordStepSize=3, minCoverage=1, minSupportReads=1,
+                   minUnusedReads=1),
+         reads=["ACACACACGATG", "GATGGCCCCCCC", "GATGTCTCTCTC"],
+         expected=dict(contigs=["ACACACACGATGGCCCCCCC", "ACACACACGATGTCTCTCTC"], used=[True, True, True],
+                       contigIds=[[0, 1], [0], [1]])),
+    # same cases with the non-ACGTN read replaced by N's (the CUDA path accepts {A,C,G,T,N} only)
+    dict(test="variant-of:test_BasicAssembler", opts=dict(minWordLength=6, maxWordLength=6, minCoverage=2),
+         reads=["ACGTGTATTACC", "GTGTATTACCTA", "ATTACCTAGTAC", "TACCTAGTACTC", "NNNNNNNNNNNN"], expected={}),
+    dict(test="variant-of:test_IterativeKmer",
+         opts=dict(minWordLength=3, maxWordLength=9, wordStepSize=3, minCoverage=1),
+         reads=["ACACACACGATG", "GATGTCTCTCTC", "NNNNNNNNNNNN"], expected={}),
+    # the 8 words of test_CircleDetector (:30-64) presented as reads of length k=5
+    dict(test="variant-of:test_CircleDetector", opts=dict(minWordLength=5, maxWordLength=5, minCoverage=1,
+                                                          minSupportReads=1, minUnusedReads=1),
+         reads=["TACCA", "CCACC", "CACCA", "ACCAC", "CCACA", "CACAC", "ACACA", "AAAAA"] * 2, expected={}),
+]
+
+
+def asm_to_json(res):
+    contigs, pseudo, info = res
+    return dict(contigs=[asdict(c) for c in contigs], pseudoReads=pseudo,
+                readInfo=[dict(isUsed=i.isUsed, isPseudo=i.isPseudo, contigIds=i.contigIds) for i in info])
+
+
+def run_asm(ref, case):
+    opts = cb.default_asm_opts(**case["opts"])
+    return asm_to_json(ref.assemble(opts, [case["reads"]])[0])
+
+
+# --------------------------------------------------------------------------------------------
+# split-read suite (GSC/test/SplitReadAlignmentTest.cpp:386-428 test_Exception), transcribed by hand
+SR_TARGET2 = ("GATCACAGGTCTATCACCCTATTAACCACTCACGGGAGCTCTCCATGCATTTGGT"
+              "ATTTTCGTCTGGGGGGTGTGCACGCGATAGCATTGCGAGACGCTGGA")
+SR_QUERY1 = "TCTATCACCCATCGTACCACTCACGGGAGCTCTCC"
+SR_CASES = [
+    dict(test="SplitReadAlignmentTest.cpp:test_Exception(:401) query>=target", flank=2, query=SR_QUERY1,
+         qual=[30] * 35, target="GATCACAGGTCTAT", bp=[8, 50], table=0, expected=dict(status=cb.MB200_ERR_SPLIT_INPUT)),
+    dict(test="SplitReadAlignmentTest.cpp:test_Exception(:413) scanEnd<scanStart", flank=2, query=SR_QUERY1,
+         qual=[30] * 35, target=SR_TARGET2, bp=[1000, 1050], table=0, expected=dict(status=cb.MB200_ERR_SPLIT_SCAN)),
+    dict(test="SplitReadAlignmentTest.cpp:test_Exception(:420-427)", flank=2, query=SR_QUERY1, qual=[30] * 35,
+         target=SR_TARGET2, bp=[8, 50], table=0,
+         expected=dict(status=0, leftSize=0, leftMismatches=0, rightSize=34, rightMismatches=27, homSize=1,
+                       homMismatches=1, alignScore=7)),
+]
+SNP_PRIORS = (1e-3, 0.0)  # ref alleles / alt alleles, GSC/SVScorer.hpp:46-51, lib/options/CallOptionsShared.hpp:30
+
+
+def sr_jobs(cases):
+    sp = cb.SeqPool()
+    jobs = np.zeros(len(cases), dtype=cb.SR_JOB_DT)
+    for i, c in enumerate(cases):
+        jobs["q_off"][i], jobs["q_len"][i] = sp.add(c["query"])
+        jobs["qualOff"][i], _ = sp.add(bytes(c["qual"]))
+        jobs["t_off"][i], jobs["t_len"][i] = sp.add(c["target"])
+        jobs["bpBegin"][i], jobs["bpEnd"][i] = c["bp"]
+        jobs["table"][i] = c["table"]
+    return sp.finish(), jobs
+
+
+def sr_to_json(r):
+    d = {k: (float(r[k]) if r[k].dtype.kind == "f" else int(r[k])) for k in r.dtype.names if k != "reserved"}
+    # floats are stored as their exact bit patterns too
+    d["alignLnLhood_bits"] = int(np.float32(r["alignLnLhood"]).view(np.uint32))
+    d["evidence_bits"] = int(np.float32(r["evidence"]).view(np.uint32))
+    return d
+
+
+def main():
+    ref = load_ref()
+    out = {}
+
+    # ---- alignment
+    aln = []
+    for fname in HELPERS:
+        aln.extend(parse_alignment_tests(fname))
+    for c in aln:
+        c["reference"] = run_alignment(ref, c)
+        check_expected(c)
+    # seeded random cases at production score sets (SVRefinerOptions.hpp:40-45)
+    rnd = []
+    for kind, sc, extra in [("jump", (2, -8, -12, -1, -1, 0), -100), ("indel", (2, -8, -24, -1, -1, 0), -100),
+                            ("global", (2, -8, -12, -1, -1, 0), 0), ("global", (2, -8, -12, -1, -1, 1), 0),
+                            ("indel", (2, -8, -24, -1, -1, 1), -100)]:
+        for seqs in workloads.random_alignment_cases(seed=1234 + len(rnd), n=12, kind=kind):
+            c = dict(test="seeded-random", kind=kind, scores=list(sc), extra=extra, seqs=list(seqs), expected={})
+            c["reference"] = run_alignment(ref, c)
+            rnd.append(c)
+    json.dump(dict(source="lib/alignment/test/*.cpp + oracle/_ref", cases=aln + rnd),
+              open(os.path.join(HERE, "alignment.json"), "w"), indent=1)
+    out["alignment"] = len(aln) + len(rnd)
+
+    # ---- assembler
+    asm = []
+    for c in ASM_CASES:
+        c = dict(c)
+        c["reference"] = run_asm(ref, c)
+        if c["expected"]:
+            assert [x["seq"] for x in c["reference"]["contigs"]] == c["expected"]["contigs"], c["test"]
+            n = len(c["expected"]["used"])
+            assert [i["isUsed"] for i in c["reference"]["readInfo"][:n]] == c["expected"]["used"], c["test"]
+            assert [i["contigIds"] for i in c["reference"]["readInfo"][:n]] == c["expected"]["contigIds"]
+        asm.append(c)
+    for i, (opts, reads) in enumerate(workloads.random_assembly_cases(seed=77, n=24)):
+        c = dict(test="seeded-random-%d" % i, opts=opts, reads=reads, expected={})
+        c["reference"] = run_asm(ref, c)
+        asm.append(c)
+    json.dump(dict(source="lib/assembly/test/IterativeAssemblerTest.cpp + oracle/_ref", cases=asm),
+              open(os.path.join(HERE, "assembly.json"), "w"), indent=1)
+    out["assembly"] = len(asm)
+
+    # ---- split read
+    tables = np.zeros(1, dtype=cb.QSCORE_TABLES_DT)
+    ref.lib.ref_qscore_tables(C.c_double(SNP_PRIORS[0]), C.c_double(SNP_PRIORS[1]), tables.ctypes.data_as(C.c_void_p))
+    cases = [dict(c) for c in SR_CASES] + workloads.random_split_cases(seed=5, n=60)
+    pool, jobs = sr_jobs(cases)
+    res = ref.split_align_raw(tables, SNP_PRIORS, 50, pool, jobs)
+    # the unit-test cases use flankScoreSize=2
+    res2 = ref.split_align_raw(tables, SNP_PRIORS, 2, pool, jobs)
+    for i, c in enumerate(cases):
+        r = res2[i] if c.get("flank", 50) == 2 else res[i]
+        c["flank"] = c.get("flank", 50)
+        c.setdefault("expected", {})
+        c["reference"] = sr_to_json(r)
+        for k, v in c["expected"].items():
+            assert c["reference"][k] == v, (c["test"], k, c["reference"][k], v)
+    json.dump(dict(source="GSC/test/SplitReadAlignmentTest.cpp + oracle/_ref", snpPriors=SNP_PRIORS,
+                   lnComp=[[float.hex(float(x)) for x in row] for row in tables["lnComp"][0]],
+                   lnErr=[[float.hex(float(x)) for x in row] for row in tables["lnErr"][0]], cases=cases),
+              open(os.path.join(HERE, "splitread.json"), "w"), indent=1)
+    out["splitread"] = len(cases)
+
+    # ---- libstdc++ unordered_map iteration order
+    rng = random.Random(99)
+    uo = []
+    for n, k in [(0, 5), (1, 5), (13, 5), (14, 8), (30, 41), (200, 46), (1500, 76)]:
+        keys = set()
+        while len(keys) < n:
+            keys.add("".join(rng.choice("ACGT") for _ in range(k)))
+        keys = sorted(keys)
+        rng.shuffle(keys)
+        buf = np.frombuffer(("".join(keys)).encode() + b"\0", dtype=np.uint8).copy()
+        order = np.zeros(max(n, 1), dtype=np.uint32)
+        ref.lib.ref_unordered_order(C.c_uint32(n), buf.ctypes.data_as(C.c_void_p), C.c_uint32(k),
+                                    order.ctypes.data_as(C.c_void_p))
+        uo.append(dict(k=k, keys=keys, order=[int(x) for x in order[:n]]))
+    json.dump(dict(source="std::unordered_map<std::string,unsigned> of this image's libstdc++ via oracle/_ref",
+                   cases=uo), open(os.path.join(HERE, "unordered_order.json"), "w"))
+    out["unordered_order"] = len(uo)
+    print("golden vectors written:", out)
+
+
+if __name__ == "__main__":
+    main()

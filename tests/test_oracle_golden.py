@@ -1,0 +1,114 @@
+"""The C restatement (oracle/) against the committed golden vectors (tests/golden/*.json):
+values asserted by the reference's own unit tests plus full results recorded from the reference build."""
+import ctypes as C
+import json
+import os
+from dataclasses import asdict
+
+import numpy as np
+import pytest
+
+from manta_b200 import _cabi as cb
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return json.load(open(os.path.join(GOLD, name)))
+
+
+def run_alignment(b, case):
+    S = cb.Scores(*case["scores"])
+    if case["kind"] == "jump":
+        return asdict(b.jump_align(S, case["extra"], [tuple(case["seqs"])])[0])
+    return asdict(b.single_align(case["kind"], S, case["extra"], [tuple(case["seqs"])])[0])
+
+
+def lookup(d, dotted):
+    for part in dotted.split("."):
+        d = d[part]
+    return int(d) if isinstance(d, bool) else d
+
+
+def test_alignment_golden(orc):
+    cases = load("alignment.json")["cases"]
+    assert len([c for c in cases if c["expected"]]) >= 40
+    for c in cases:
+        got = run_alignment(orc, c)
+        for k, v in c["expected"].items():
+            assert lookup(got, k) == v, (c["test"], k)
+        assert got == c["reference"], c["test"]
+
+
+def asm_to_json(res):
+    contigs, pseudo, info = res
+    return dict(contigs=[json.loads(json.dumps(asdict(c))) for c in contigs], pseudoReads=pseudo,
+                readInfo=[dict(isUsed=i.isUsed, isPseudo=i.isPseudo, contigIds=i.contigIds) for i in info])
+
+
+def test_assembly_golden(orc):
+    for c in load("assembly.json")["cases"]:
+        got = asm_to_json(orc.assemble(cb.default_asm_opts(**c["opts"]), [c["reads"]])[0])
+        if c["expected"]:
+            assert [x["seq"] for x in got["contigs"]] == c["expected"]["contigs"], c["test"]
+        assert got == c["reference"], c["test"]
+
+
+def test_qscore_tables_golden(orc):
+    g = load("splitread.json")
+    t = np.zeros(1, dtype=cb.QSCORE_TABLES_DT)
+    orc.lib.orc_qscore_tables(C.c_double(g["snpPriors"][0]), C.c_double(g["snpPriors"][1]), t.ctypes.data_as(C.c_void_p))
+    for name in ("lnComp", "lnErr"):
+        want = np.array([[float.fromhex(x) for x in row] for row in g[name]])
+        assert t[name][0].tobytes() == want.tobytes(), name
+
+
+def split_jobs(cases):
+    sp = cb.SeqPool()
+    jobs = np.zeros(len(cases), dtype=cb.SR_JOB_DT)
+    for i, c in enumerate(cases):
+        jobs["q_off"][i], jobs["q_len"][i] = sp.add(c["query"])
+        jobs["qualOff"][i], _ = sp.add(bytes(c["qual"]))
+        jobs["t_off"][i], jobs["t_len"][i] = sp.add(c["target"])
+        jobs["bpBegin"][i], jobs["bpEnd"][i] = c["bp"]
+        jobs["table"][i] = c["table"]
+    return sp.finish(), jobs
+
+
+def check_split(binding, tables, g):
+    cases = g["cases"]
+    pool, jobs = split_jobs(cases)
+    res = {f: binding.split_align_raw(tables, tuple(g["snpPriors"]), f, pool, jobs) for f in (2, 50)}
+    for i, c in enumerate(cases):
+        r = res[c["flank"]][i]
+        want = c["reference"]
+        for k in r.dtype.names:
+            if k == "reserved":
+                continue
+            if k in ("alignLnLhood", "evidence"):
+                assert int(np.float32(r[k]).view(np.uint32)) == want[k + "_bits"], (c["test"], k)
+            else:
+                assert int(r[k]) == want[k], (c["test"], k)
+
+
+def golden_tables(g):
+    t = np.zeros(1, dtype=cb.QSCORE_TABLES_DT)
+    for name in ("lnComp", "lnErr"):
+        t[name][0] = np.array([[float.fromhex(x) for x in row] for row in g[name]])
+    return t
+
+
+def test_splitread_golden(orc):
+    g = load("splitread.json")
+    check_split(orc, golden_tables(g), g)
+
+
+def test_unordered_order_golden(orc):
+    """libstdc++ std::unordered_map<std::string,T> iteration order"""
+    for c in load("unordered_order.json")["cases"]:
+        n = len(c["keys"])
+        buf = np.frombuffer("".join(c["keys"]).encode() + b"\0", dtype=np.uint8).copy()
+        order = np.zeros(max(n, 1), dtype=np.uint32)
+        orc.lib.orc_unordered_order(C.c_uint32(n), buf.ctypes.data_as(C.c_void_p), C.c_uint32(c["k"]),
+                                    order.ctypes.data_as(C.c_void_p))
+        assert [int(x) for x in order[:n]] == c["order"]

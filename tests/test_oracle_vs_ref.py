@@ -1,0 +1,84 @@
+"""The C restatement against the UNMODIFIED reference (oracle/_ref, built by oracle/build_ref.sh) on seeded
+random inputs.  Skipped where the reference library has not been built."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from manta_b200 import _cabi as cb
+from manta_b200 import synth
+from test_oracle_golden import split_jobs
+
+SCORE_SETS = [((2, -4, -5, -1, -1, 0), -3), ((2, -8, -12, -1, -1, 0), -100), ((2, -8, -24, -1, -1, 0), -100),
+              ((2, -8, -18, 0, -1, 1), -50), ((1, -4, -5, -1, -2, 1), -10)]
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_aligners_vs_ref(orc, ref, seed):
+    for si, (sc, extra) in enumerate(SCORE_SETS):
+        S = cb.Scores(*sc)
+        if not sc[5]:
+            cases = synth.random_alignment_cases(seed * 100 + si, 25, "jump")
+            assert orc.jump_align(S, extra, cases) == ref.jump_align(S, extra, cases)
+        cases = synth.random_alignment_cases(seed * 100 + si + 50, 25, "indel")
+        assert orc.single_align("indel", S, extra, cases) == ref.single_align("indel", S, extra, cases)
+        assert orc.single_align("global", S, 0, cases) == ref.single_align("global", S, 0, cases)
+
+
+def test_long_query_sentinel_regime(orc, ref):
+    """q > ~1250: scores fall below badVal=-10000 and the sentinel can win a max"""
+    rng = random.Random(5)
+    q = "".join(rng.choice("ACGT") for _ in range(1600))
+    r = "".join(rng.choice("ACGT") for _ in range(300))
+    S = cb.Scores(2, -8, -24, -1, -1, 0)
+    assert orc.single_align("indel", S, -100, [(q, r)]) == ref.single_align("indel", S, -100, [(q, r)])
+    S = cb.Scores(2, -8, -12, -1, -1, 0)
+    assert orc.jump_align(S, -100, [(q, r, r[::-1])]) == ref.jump_align(S, -100, [(q, r, r[::-1])])
+
+
+def test_empty_input_errors(orc, ref):
+    S = cb.Scores(2, -8, -12, -1, -1, 0)
+    for b in (orc, ref):
+        for triple, st in [(("", "A", "A"), cb.MB200_ERR_EMPTY_QUERY), (("A", "", "A"), cb.MB200_ERR_EMPTY_REF1),
+                           (("A", "A", ""), cb.MB200_ERR_EMPTY_REF2)]:
+            with pytest.raises(cb.Mb200Error) as e:
+                b.jump_align(S, -100, [triple])
+            assert e.value.status == st
+        with pytest.raises(cb.Mb200Error) as e:
+            b.single_align("global", S, 0, [("A", "")])
+        assert e.value.status == cb.MB200_ERR_EMPTY_REF
+
+
+def test_split_vs_ref(orc, ref):
+    cases = synth.random_split_cases(seed=21, n=1500)
+    pool, jobs = split_jobs(cases)
+    t = np.zeros(1, dtype=cb.QSCORE_TABLES_DT)
+    ref.lib.ref_qscore_tables(C.c_double(1e-3), C.c_double(0.0), t.ctypes.data_as(C.c_void_p))
+    a = ref.split_align_raw(t, (1e-3, 0.0), 50, pool, jobs)
+    b = orc.split_align_raw(t, (1e-3, 0.0), 50, pool, jobs)
+    assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_assembler_vs_ref(orc, ref, seed):
+    for opts, reads in synth.random_assembly_cases(seed, 40):
+        o = cb.default_asm_opts(**opts)
+        assert orc.assemble(o, [reads]) == ref.assemble(o, [reads])
+
+
+def test_unordered_order_vs_ref(orc, ref):
+    rng = random.Random(7)
+    for n in [0, 1, 13, 14, 29, 30, 59, 60, 127, 128, 1000, 5087, 5088, 30000]:
+        k = rng.choice([5, 8, 41, 46, 76]) if n <= 128 else rng.choice([12, 41, 46, 76])
+        keys = set()
+        while len(keys) < n:
+            keys.add("".join(rng.choice("ACGT") for _ in range(k)))
+        keys = sorted(keys)
+        rng.shuffle(keys)
+        buf = np.frombuffer("".join(keys).encode() + b"\0", dtype=np.uint8).copy()
+        o1 = np.zeros(max(n, 1), dtype=np.uint32)
+        o2 = np.zeros(max(n, 1), dtype=np.uint32)
+        ref.lib.ref_unordered_order(C.c_uint32(n), buf.ctypes.data_as(C.c_void_p), C.c_uint32(k), o1.ctypes.data_as(C.c_void_p))
+        orc.lib.orc_unordered_order(C.c_uint32(n), buf.ctypes.data_as(C.c_void_p), C.c_uint32(k), o2.ctypes.data_as(C.c_void_p))
+        assert (o1 == o2).all(), n
