@@ -1,0 +1,1019 @@
+// dp_align.cu -- batched contig-to-reference affine-gap aligners for sm_100a.
+//
+// Replaces (bit-exactly) the three full-matrix aligners of the reference:
+//   GlobalAligner<int>::align            lib/alignment/GlobalAlignerImpl.hpp:29-181            (3 states, KIND_GLOBAL)
+//   GlobalJumpAligner<int>::align        lib/alignment/GlobalJumpAlignerImpl.hpp:33-333        (4 states, KIND_JUMP)
+//   GlobalLargeIndelAligner<int>::align  lib/alignment/GlobalLargeIndelAlignerImpl.hpp:35-225  (5 states, KIND_INDEL)
+// and their back-traces (SingleRefAlignerSharedImpl.hpp:75-168, JumpAlignerBaseImpl.hpp:86-242) including
+// apath_add_seqmatch (lib/blt_util/align_path_impl.hpp:33-75) and the jumpRange scan.
+//
+// Mapping to the machine (DESIGN.md "DP kernel"):
+//   * one WARP per alignment, persistent warps pulling tasks from a global counter (longest first);
+//   * query rows live in registers: thread `lane` owns RT consecutive rows, the warp covers a strip of
+//     32*RT rows; queries longer than one strip are swept in passes with the strip-boundary row kept in a
+//     per-warp L2-resident buffer;
+//   * columns are processed as a skewed (anti-diagonal) wavefront: at step t lane l works on column
+//     t-l; the values of its last row reach lane l+1 with one __shfl_up per state per step;
+//   * the reference window is staged through shared memory in 2 KiB tiles by TMA bulk copies
+//     (cp.async.bulk + mbarrier), double buffered ahead of the wavefront;
+//   * back-pointers (2 or 3 bits per state, 1 or 2 bytes per cell, same information as the reference's
+//     PtrVal) are written in the skewed [step][lane] order, so every store instruction of a warp covers
+//     one contiguous 128..512-byte line -- this stream is the algorithmic HBM traffic of the kernel;
+//   * the best back-trace start is tracked as a 64-bit (score, -sequence) key so that the reference's
+//     first-strict-maximum rule (updateBacktrace, AlignerUtil.hpp:53-67) is order independent;
+//   * the same warp then walks the pointers back (lane 0), emits the run-length path, splits M runs
+//     into '='/'X', computes jumpRange and appends the segments to the caller's pool.
+//
+// Scores are int32 with the finite sentinel badVal = -10000 exactly as in the reference (no saturation).
+#include <algorithm>
+#include <cstdint>
+
+#include "mb200_internal.h"
+
+#ifndef MB200_USE_TMA
+#define MB200_USE_TMA 1
+#endif
+
+namespace {
+
+constexpr int BADVAL = -10000;
+
+enum { KIND_GLOBAL = 0, KIND_JUMP = 1, KIND_INDEL = 2 };
+enum { ST_MATCH = 0, ST_DELETE = 1, ST_INSERT = 2, ST_JUMP = 3, ST_JUMPINS = 4 };
+
+constexpr int REF_TILE  = 2048;            // bytes per staged reference tile
+constexpr int REF_RING  = 2 * REF_TILE;    // two tiles resident per warp
+constexpr int WARPS_PER_CTA = 4;
+
+struct DpTask {
+  uint64_t qOff, r1Off, r2Off;  // byte offsets into the device pool
+  uint32_t Q, R1, R2;
+  uint32_t outIndex;            // index of the result record
+};
+
+struct DpParams {
+  int match, mismatch, open, extend, offEdge, allowEdgeIns;
+  int extra;  // jumpScore (KIND_JUMP) or largeIndelScore (KIND_INDEL)
+  const uint8_t* pool;
+  const DpTask*  tasks;
+  uint32_t       nTasks;
+  uint32_t*      workCounter;
+  uint8_t*       ptrScratch;
+  size_t         ptrStride;  // bytes per warp slot
+  uint32_t*      segScratch;
+  size_t         segStride;  // uint32 per warp slot
+  int*           bndScratch;
+  size_t         bndStride;  // ints per warp slot
+  void*          results;
+  uint32_t*      cigarPool;
+  unsigned long long cigarCap;
+  unsigned long long* cigarUsed;
+  int*           errFlag;
+};
+
+template <int KIND> struct KindTraits;
+template <> struct KindTraits<KIND_GLOBAL> { static constexpr int NS = 3, BITS = 2, CELLB = 1; };
+template <> struct KindTraits<KIND_JUMP>   { static constexpr int NS = 4, BITS = 2, CELLB = 1; };
+template <> struct KindTraits<KIND_INDEL>  { static constexpr int NS = 5, BITS = 3, CELLB = 2; };
+
+// ---- first-maximum-wins scans (AlignerBase.hpp:46-59, JumpAlignerBase.hpp:93-111, GlobalLargeIndelAligner.hpp:124-151)
+__device__ __forceinline__ int max3p(int& m, int v0, int v1, int v2)
+{
+  int p = 0;
+  m     = v0;
+  if (v1 > m) { m = v1; p = 1; }
+  if (v2 > m) { m = v2; p = 2; }
+  return p;
+}
+__device__ __forceinline__ int max4p(int& m, int v0, int v1, int v2, int v3)
+{
+  int p = 0;
+  m     = v0;
+  if (v1 > m) { m = v1; p = 1; }
+  if (v2 > m) { m = v2; p = 2; }
+  if (v3 > m) { m = v3; p = 3; }
+  return p;
+}
+__device__ __forceinline__ int max5p(int& m, int v0, int v1, int v2, int v3, int v4)
+{
+  int p = 0;
+  m     = v0;
+  if (v1 > m) { m = v1; p = 1; }
+  if (v2 > m) { m = v2; p = 2; }
+  if (v3 > m) { m = v3; p = 3; }
+  if (v4 > m) { m = v4; p = 4; }
+  return p;
+}
+
+__device__ __forceinline__ long long makeKey(int val, uint32_t seq)
+{
+  return (long long)val * 4294967296LL + (long long)(0x7fffffffu - seq);
+}
+
+// ---- shared-memory staging of the reference window ---------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+struct RefStage {
+  // staged coordinates: ref1 occupies [shift1, shift1+R1), ref2 [base2+shift2, base2+shift2+R2)
+  const uint8_t* src1;  // 16-byte aligned-down global address of ref1
+  const uint8_t* src2;
+  uint32_t       shift1, shift2, base2, total;  // total = staged bytes (multiple of 16)
+  uint8_t*       ring;                           // REF_RING bytes of shared memory
+  uint64_t*      bar;                            // two mbarriers (one per ring slot)
+  uint32_t       nTiles;
+};
+
+__device__ __forceinline__ void stageIssue(const RefStage& st, uint32_t tile, int lane)
+{
+  const uint32_t a = tile * REF_TILE;
+  uint32_t       b = a + REF_TILE;
+  if (b > st.total) b = st.total;
+  uint8_t* dst = st.ring + (tile & 1) * REF_TILE;
+#if MB200_USE_TMA
+  if (lane == 0) {
+    const uint32_t barAddr = smemAddr(&st.bar[tile & 1]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(b - a) : "memory");
+    // part inside ref1's staged range
+    uint32_t e1 = b < st.base2 ? b : st.base2;
+    if (a < e1) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smemAddr(dst)),
+                   "l"(st.src1 + a), "r"(e1 - a), "r"(barAddr)
+                   : "memory");
+    }
+    uint32_t s2 = a > st.base2 ? a : st.base2;
+    if (s2 < b) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smemAddr(dst + (s2 - a))),
+                   "l"(st.src2 + (s2 - st.base2)), "r"(b - s2), "r"(barAddr)
+                   : "memory");
+    }
+  }
+#else
+  for (uint32_t o = a + lane * 16; o < b; o += 32 * 16) {
+    const uint8_t* src = (o < st.base2) ? (st.src1 + o) : (st.src2 + (o - st.base2));
+    *reinterpret_cast<uint4*>(dst + (o - a)) = *reinterpret_cast<const uint4*>(src);
+  }
+#endif
+}
+
+// ---- back-pointer addressing in the skewed layout --------------------------------------------------
+template <int RT, int CELLB> struct PtrLayout {
+  static constexpr int BYTES_PER_THREAD = RT * CELLB;                                // per step
+  static constexpr int CHUNK_BYTES      = BYTES_PER_THREAD < 16 ? BYTES_PER_THREAD : 16;
+  static constexpr int NCHUNK           = BYTES_PER_THREAD / CHUNK_BYTES;
+  static constexpr int STEP_BYTES       = 32 * BYTES_PER_THREAD;
+  __device__ static __forceinline__ size_t passBytes(uint32_t rtot) { return (size_t)(rtot + 31) * STEP_BYTES; }
+  // cell (q>=1, c>=1) -> byte offset
+  __device__ static __forceinline__ size_t cellOffset(uint32_t q, uint32_t c, uint32_t rtot)
+  {
+    const uint32_t row    = q - 1;
+    const uint32_t pass   = row / (32 * RT);
+    const uint32_t within = row % (32 * RT);
+    const uint32_t lane   = within / RT;
+    const uint32_t rr     = within % RT;
+    const uint32_t t      = c - 1 + lane;
+    const uint32_t boff   = rr * CELLB;
+    const uint32_t chunk  = boff / CHUNK_BYTES;
+    const uint32_t inner  = boff % CHUNK_BYTES;
+    return (size_t)pass * passBytes(rtot) + ((size_t)(t * NCHUNK + chunk) * 32 + lane) * CHUNK_BYTES + inner;
+  }
+};
+
+// ---- path emission helpers (lane 0 only) -------------------------------------------------------------
+struct SegWriter {
+  uint32_t* buf;  // raw segments in back-trace (reverse) order
+  uint32_t  n;
+  uint32_t  type, length;  // the open segment `ps`
+  __device__ void updatePath(uint32_t atype)
+  {  // AlignerUtil::updatePath
+    if (type == atype) return;
+    if (type != MB200_SEG_NONE) buf[n++] = MB200_SEG_MAKE(length, type);
+    type   = atype;
+    length = 0;
+  }
+  __device__ void push(uint32_t t, uint32_t len) { buf[n++] = MB200_SEG_MAKE(len, t); }
+};
+
+__device__ __forceinline__ bool segIsReadLen(uint32_t t)
+{
+  return t == MB200_SEG_MATCH || t == MB200_SEG_INSERT || t == MB200_SEG_SOFT_CLIP;
+}
+__device__ __forceinline__ bool segIsRefLen(uint32_t t) { return t == MB200_SEG_MATCH || t == MB200_SEG_DELETE; }
+
+// Expand a raw path (given in REVERSE order in raw[first..first+n)) into the final '='/'X' form
+// (apath_add_seqmatch).  If out == nullptr only counts.  q/r point at the first query/ref base the path covers.
+__device__ uint32_t expandPath(const uint32_t* raw, uint32_t n, const uint8_t* q, const uint8_t* r, uint32_t* out)
+{
+  uint32_t count = 0;
+  uint32_t curT = MB200_SEG_NONE, curL = 0;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t seg  = raw[n - 1 - k];
+    const uint32_t type = MB200_SEG_TYPE(seg);
+    const uint32_t len  = MB200_SEG_LEN(seg);
+    if (type == MB200_SEG_MATCH) {
+      for (uint32_t i = 0; i < len; ++i) {
+        const uint8_t qc = q[i], rc = r[i];
+        const bool isMatch = (qc == rc) && (qc != 'N') && (rc != 'N');
+        const uint32_t t   = isMatch ? MB200_SEG_SEQ_MATCH : MB200_SEG_SEQ_MISMATCH;
+        if (t == curT) {
+          curL++;
+        } else {
+          if (curT != MB200_SEG_NONE) {
+            if (out) out[count] = MB200_SEG_MAKE(curL, curT);
+            count++;
+          }
+          curT = t;
+          curL = 1;
+        }
+      }
+      q += len;
+      r += len;
+    } else {
+      if (curT != MB200_SEG_NONE) {
+        if (out) out[count] = MB200_SEG_MAKE(curL, curT);
+        count++;
+        curT = MB200_SEG_NONE;
+        curL = 0;
+      }
+      if (out) out[count] = seg;
+      count++;
+      if (segIsReadLen(type)) q += len;
+      if (segIsRefLen(type)) r += len;
+    }
+  }
+  if (curT != MB200_SEG_NONE) {
+    if (out) out[count] = MB200_SEG_MAKE(curL, curT);
+    count++;
+  }
+  return count;
+}
+
+__device__ void rawLengths(const uint32_t* raw, uint32_t n, uint32_t& readLen, uint32_t& refLen)
+{
+  readLen = refLen = 0;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t type = MB200_SEG_TYPE(raw[k]);
+    const uint32_t len  = MB200_SEG_LEN(raw[k]);
+    if (segIsReadLen(type)) readLen += len;
+    if (segIsRefLen(type)) refLen += len;
+  }
+}
+
+// ======================================================================================================
+template <int KIND, int RT>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpAlignKernel(const DpParams P)
+{
+  using KT               = KindTraits<KIND>;
+  using PL               = PtrLayout<RT, KT::CELLB>;
+  constexpr int NS       = KT::NS;
+  constexpr int BITS     = KT::BITS;
+  constexpr int STRIP    = 32 * RT;
+  constexpr int PTRWORDS = RT * KT::CELLB / 4;  // uint32 words of pointers per thread per step
+  static_assert(RT % 4 == 0, "RT must be a multiple of 4");
+
+  __shared__ __align__(128) uint8_t sRing[WARPS_PER_CTA][REF_RING];
+  __shared__ __align__(8) uint64_t sBar[WARPS_PER_CTA][2];
+  __shared__ uint32_t sTask[WARPS_PER_CTA];
+
+  const int      lane   = threadIdx.x & 31;
+  const int      warp   = threadIdx.x >> 5;
+  const uint32_t slot   = blockIdx.x * WARPS_PER_CTA + warp;
+  uint8_t*       ptrBuf = P.ptrScratch + (size_t)slot * P.ptrStride;
+  uint32_t*      segBuf = P.segScratch + (size_t)slot * P.segStride;
+  int*           bndBuf = P.bndScratch + (size_t)slot * P.bndStride;
+
+#if MB200_USE_TMA
+  uint32_t tilesUsed[2] = {0, 0};  // completed phases per ring slot (mbarrier parity bookkeeping)
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&sBar[warp][0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&sBar[warp][1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+#endif
+
+  const int open = P.open, extend = P.extend, offEdge = P.offEdge, match = P.match, mismatch = P.mismatch;
+  const int extra = P.extra;
+
+  for (;;) {
+    if (lane == 0) sTask[warp] = atomicAdd(P.workCounter, 1u);
+    __syncwarp();
+    const uint32_t taskIdx = sTask[warp];
+    __syncwarp();
+    if (taskIdx >= P.nTasks) break;
+    const DpTask   task = P.tasks[taskIdx];
+    const uint32_t Q = task.Q, R1 = task.R1;
+    const uint32_t R2   = (KIND == KIND_JUMP) ? task.R2 : 0u;
+    const uint32_t RTOT = R1 + R2;
+    const uint8_t* qSeq = P.pool + task.qOff;
+    const uint8_t* ref1 = P.pool + task.r1Off;
+    const uint8_t* ref2 = P.pool + task.r2Off;
+
+    // ---- reference staging geometry
+    RefStage st;
+    st.shift1 = (uint32_t)(reinterpret_cast<uintptr_t>(ref1) & 15);
+    st.src1   = ref1 - st.shift1;
+    st.base2  = (st.shift1 + R1 + 15) & ~15u;
+    if (KIND == KIND_JUMP) {
+      st.shift2 = (uint32_t)(reinterpret_cast<uintptr_t>(ref2) & 15);
+      st.src2   = ref2 - st.shift2;
+      st.total  = st.base2 + ((st.shift2 + R2 + 15) & ~15u);
+    } else {
+      st.shift2 = 0;
+      st.src2   = st.src1;
+      st.total  = st.base2;
+    }
+    st.ring   = sRing[warp];
+    st.bar    = sBar[warp];
+    st.nTiles = (st.total + REF_TILE - 1) / REF_TILE;
+
+    long long bestKey = (long long)0x8000000000000000LL;
+    bool      stageOk = true;
+
+    const uint32_t nPass = (Q + STRIP - 1) / STRIP;
+    for (uint32_t pass = 0; pass < nPass; ++pass) {
+      const uint32_t q0 = pass * STRIP + lane * RT;  // rows q0+1 .. q0+RT (1-based)
+      // query characters of my rows (0 where beyond the query: such rows never influence valid rows)
+      uint32_t qch[RT / 4];
+#pragma unroll
+      for (int w = 0; w < RT / 4; ++w) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const uint32_t row = q0 + w * 4 + b;  // 0-based query index
+          const uint32_t ch  = (row < Q) ? (uint32_t)__ldg(qSeq + row) : 0u;
+          v |= ch << (8 * b);
+        }
+        qch[w] = v;
+      }
+
+      // restart the reference stream for this pass
+#if MB200_USE_TMA
+      // (mbarrier phases continue across passes and tasks: parity = number of completed uses of the slot)
+#endif
+      uint32_t nextIssue = 0;
+      __syncwarp();
+      // tiles 0 and 1
+      {
+        stageIssue(st, 0, lane);
+        nextIssue = 1;
+        if (st.nTiles > 1) {
+          stageIssue(st, 1, lane);
+          nextIssue = 2;
+        }
+      }
+
+      int pM[RT], pD[RT], pI[RT], pJ[RT], pK[RT];
+      int lastM = 0, lastD = BADVAL, lastI = BADVAL, lastJ = BADVAL, lastK = BADVAL;
+      int dgM = 0, dgD = BADVAL, dgI = BADVAL, dgJ = BADVAL, dgK = BADVAL;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) { pM[r] = 0; pD[r] = pI[r] = pJ[r] = pK[r] = BADVAL; }
+
+      const uint32_t nSteps   = RTOT + 31;
+      uint8_t*       passPtr  = ptrBuf + (size_t)pass * PL::passBytes(RTOT);
+      uint32_t       waitTile = 0;  // next tile lane 0 has to wait for
+
+      for (uint32_t t = 0; t < nSteps; ++t) {
+        // ---- reference tiles: wait when the head of the wavefront enters a tile, refill behind the tail
+        {
+          // highest staged coordinate touched this step is that of lane 0 (or of the last column)
+          uint32_t cz0 = t < RTOT ? t : RTOT - 1;
+          uint32_t s0  = (KIND == KIND_JUMP && cz0 >= R1) ? (st.base2 + st.shift2 + (cz0 - R1)) : (st.shift1 + cz0);
+          const uint32_t needTile = s0 / REF_TILE;
+          while (waitTile <= needTile) {
+#if MB200_USE_TMA
+            const uint32_t barAddr = smemAddr(&st.bar[waitTile & 1]);
+            const uint32_t parity  = tilesUsed[waitTile & 1] & 1;
+            uint32_t       ok      = 0;
+            for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+              asm volatile(
+                  "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                  : "=r"(ok)
+                  : "r"(barAddr), "r"(parity)
+                  : "memory");
+              if (ok) break;
+            }
+            if (!ok) stageOk = false;
+            tilesUsed[waitTile & 1]++;
+#else
+            __syncwarp();
+#endif
+            waitTile++;
+          }
+          // lowest staged coordinate still needed is that of lane 31 (column t-31)
+          if (nextIssue < st.nTiles) {
+            const uint32_t czT = t >= 31 ? t - 31 : 0;
+            uint32_t sT = (KIND == KIND_JUMP && czT >= R1) ? (st.base2 + st.shift2 + (czT - R1)) : (st.shift1 + czT);
+            // tile (nextIssue) reuses the ring slot of tile (nextIssue-2): free once the tail has left it
+            if (sT / REF_TILE >= nextIssue - 1) {
+              __syncwarp();
+              stageIssue(st, nextIssue, lane);
+              nextIssue++;
+            }
+          }
+        }
+
+        // ---- values of the row above (row q0) for this step's column
+        int upM = __shfl_up_sync(0xffffffffu, lastM, 1);
+        int upD = __shfl_up_sync(0xffffffffu, lastD, 1);
+        int upI = __shfl_up_sync(0xffffffffu, lastI, 1);
+        int upJ = (NS >= 4) ? __shfl_up_sync(0xffffffffu, lastJ, 1) : BADVAL;
+        int upK = (NS >= 5) ? __shfl_up_sync(0xffffffffu, lastK, 1) : BADVAL;
+
+        const int  c      = (int)t - lane + 1;  // 1-based combined column
+        const bool active = (c >= 1) && (c <= (int)RTOT);
+        if (lane == 0) {
+          if (pass == 0) {
+            upM = 0;
+            upD = upI = upJ = upK = BADVAL;  // row 0 of every column >= 1
+          } else if (active) {
+            const int* b = bndBuf + (size_t)c * 5;
+            upM = b[0]; upD = b[1]; upI = b[2]; upJ = b[3]; upK = b[4];
+          }
+        }
+
+        if (active) {
+          const bool phase2 = (KIND == KIND_JUMP) && ((uint32_t)c > R1);
+          const uint32_t cz = (uint32_t)c - 1;
+          const uint32_t sidx = phase2 ? (st.base2 + st.shift2 + (cz - R1)) : (st.shift1 + cz);
+          const uint32_t refch = st.ring[sidx & (REF_RING - 1)];
+
+          if (c == 1) {
+            // column 0: M=q*offEdge, D=bad, I=(allowEdgeIns ? open+q*extend : bad), others bad
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              const int q = (int)q0 + r + 1;
+              pM[r] = q * offEdge;
+              pD[r] = BADVAL;
+              pI[r] = (KIND != KIND_JUMP && P.allowEdgeIns) ? (open + q * extend) : BADVAL;
+              pJ[r] = BADVAL;
+              pK[r] = BADVAL;
+            }
+            dgM = (int)q0 * offEdge;
+            dgD = BADVAL;
+            dgI = (KIND != KIND_JUMP && P.allowEdgeIns) ? (open + (int)q0 * extend) : BADVAL;
+            dgJ = dgK = BADVAL;
+          }
+          if (KIND == KIND_JUMP && (uint32_t)c == R1 + 1) {
+            // re-initialisation between ref1 and ref2 (GlobalJumpAlignerImpl.hpp:197-204): jump is preserved
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              pM[r] = ((int)q0 + r + 1) * offEdge;
+              pD[r] = pI[r] = BADVAL;
+            }
+            dgM = (int)q0 * offEdge;
+            dgD = dgI = BADVAL;
+            if (q0 == 0) dgJ = BADVAL;
+          }
+
+          int dM = dgM, dD = dgD, dI = dgI, dJ = dgJ, dK = dgK;   // row above, previous column
+          int vM = upM, vI = upI, vJ = upJ, vK = upK;             // row above, this column
+          uint32_t ptrw[PTRWORDS];
+#pragma unroll
+          for (int w = 0; w < PTRWORDS; ++w) ptrw[w] = 0;
+
+          const bool isLastCol1 = (KIND == KIND_JUMP) && ((uint32_t)c == R1);
+          const bool isLastCol  = ((uint32_t)c == RTOT);
+
+#pragma unroll
+          for (int r = 0; r < RT; ++r) {
+            const uint32_t q   = q0 + r + 1;  // 1-based row
+            const uint32_t qc  = (qch[r / 4] >> (8 * (r % 4))) & 0xffu;
+            const int      s   = (qc == refch) ? match : mismatch;
+            const bool     row1 = (r == 0) && (q0 == 0);
+            int nM, nD, nI, nJ = BADVAL, nK = BADVAL;
+            int pm, pd, pi, pj = 0, pk = 0;
+            if (KIND == KIND_GLOBAL) {
+              pm = max3p(nM, dM, dD, dI);
+              nM += s;
+              pd = max3p(nD, pM[r] + open, pD[r], pI[r]);
+              nD += extend;
+              if (row1) nD = BADVAL;
+              pi = max3p(nI, vM + open, BADVAL, vI);
+              nI += extend;
+              if (row1) nI = BADVAL;
+            } else if (KIND == KIND_INDEL) {
+              pm = max5p(nM, dM, dD, dI, dJ, dK);
+              nM += s;
+              pd = max5p(nD, pM[r] + open, pD[r], pI[r], BADVAL, pK[r]);
+              nD += extend;
+              if (row1) nD = BADVAL;
+              pi = max5p(nI, vM + open, BADVAL, vI, BADVAL, BADVAL);
+              nI += extend;
+              if (row1) nI = BADVAL;
+              pj = max5p(nJ, pM[r] + extra, BADVAL, pI[r] + extra - open, pJ[r], pK[r] + extra);
+              if (row1) nJ = BADVAL;
+              pk = max5p(nK, vM + extra, BADVAL, BADVAL, BADVAL, vK);
+              if (row1) nK = BADVAL;
+            } else {  // KIND_JUMP
+              if (!phase2) {
+                pm = max3p(nM, dM, dD, dI);
+                nM += s;
+                pd = max3p(nD, pM[r] + open, pD[r], pI[r]);
+                nD += extend;
+                if (row1) nD = BADVAL;
+                pi = max3p(nI, vM + open, BADVAL, vI);
+                nI += extend;
+                if (row1) nI = BADVAL;
+                pj = max4p(nJ, nM + extra, BADVAL, nI + extra, pJ[r]);
+              } else {
+                pm = max4p(nM, dM, dD, dI, dJ);
+                nM += s;
+                pd = max3p(nD, pM[r] + open, pD[r], pI[r]);
+                nD += extend;
+                pi = max4p(nI, vM + open, BADVAL, vI, vJ);
+                nI += extend;
+                nJ = pJ[r];
+                pj = ST_JUMP;
+              }
+            }
+            uint32_t cell = (uint32_t)pm | ((uint32_t)pd << BITS) | ((uint32_t)pi << (2 * BITS));
+            if (NS >= 4) cell |= ((uint32_t)pj << (3 * BITS));
+            if (NS >= 5) cell |= ((uint32_t)pk << (4 * BITS));
+            if (KT::CELLB == 1) {
+              ptrw[r / 4] |= cell << (8 * (r % 4));
+            } else {
+              ptrw[r / 2] |= cell << (16 * (r % 2));
+            }
+
+            // shift the stencil down one row
+            dM = pM[r]; dD = pD[r]; dI = pI[r]; dJ = pJ[r]; dK = pK[r];
+            pM[r] = nM; pD[r] = nD; pI[r] = nI; pJ[r] = nJ; pK[r] = nK;
+            vM = nM; vI = nI; vJ = nJ; vK = nK;
+
+            // ---- back-trace start candidates (updateBacktrace call sites of the three aligners)
+            if (q <= Q) {
+              if (KIND == KIND_JUMP) {
+                if (q == Q) {
+                  const uint32_t seq = phase2 ? (R1 + Q + ((uint32_t)c - R1) - 1) : ((uint32_t)c - 1);
+                  const long long k  = makeKey(nM, seq);
+                  bestKey            = k > bestKey ? k : bestKey;
+                } else {
+                  if (isLastCol1) {
+                    const long long k = makeKey(nM + (int)(Q - q) * offEdge, R1 + q);
+                    bestKey           = k > bestKey ? k : bestKey;
+                  }
+                  if (isLastCol) {
+                    const long long k = makeKey(nM + (int)(Q - q) * offEdge, R1 + Q + R2 + q);
+                    bestKey           = k > bestKey ? k : bestKey;
+                  }
+                }
+              } else {
+                if (q == Q) {
+                  long long k = makeKey(nM, (uint32_t)c - 1);
+                  bestKey     = k > bestKey ? k : bestKey;
+                  if (isLastCol && P.allowEdgeIns) {
+                    k       = makeKey(nI, R1);
+                    bestKey = k > bestKey ? k : bestKey;
+                  }
+                }
+                if (isLastCol && (q < Q || KIND == KIND_INDEL)) {
+                  const long long k = makeKey(nM + (int)(Q - q) * offEdge, R1 + 1 + q);
+                  bestKey           = k > bestKey ? k : bestKey;
+                }
+              }
+            }
+          }
+
+          // row 0 takes part in the off-edge scans as well (queryIndex 0): tM[0] == 0
+          if (q0 == 0) {
+            if (KIND == KIND_JUMP) {
+              if (isLastCol1) { const long long k = makeKey((int)Q * offEdge, R1); bestKey = k > bestKey ? k : bestKey; }
+              if (isLastCol) { const long long k = makeKey((int)Q * offEdge, R1 + Q + R2); bestKey = k > bestKey ? k : bestKey; }
+            } else if (isLastCol) {
+              const long long k = makeKey((int)Q * offEdge, R1 + 1);
+              bestKey           = k > bestKey ? k : bestKey;
+            }
+          }
+
+          // diagonal for the next column = this column's row-above values
+          dgM = upM; dgD = upD; dgI = upI; dgJ = upJ; dgK = upK;
+          lastM = vM; lastD = pD[RT - 1]; lastI = vI; lastJ = vJ; lastK = vK;
+
+          // ---- back-pointers of this (lane, step): contiguous per warp in the skewed layout
+          {
+            uint8_t* stepBase = passPtr + (size_t)t * PL::STEP_BYTES;
+            if (PL::CHUNK_BYTES == 4) {
+              *reinterpret_cast<uint32_t*>(stepBase + lane * 4) = ptrw[0];
+            } else if (PL::CHUNK_BYTES == 8) {
+              *reinterpret_cast<uint2*>(stepBase + lane * 8) = make_uint2(ptrw[0], ptrw[PTRWORDS > 1 ? 1 : 0]);
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < PL::NCHUNK; ++ch) {
+                *reinterpret_cast<uint4*>(stepBase + ((size_t)ch * 32 + lane) * 16) =
+                    make_uint4(ptrw[(ch * 4 + 0) % PTRWORDS], ptrw[(ch * 4 + 1) % PTRWORDS],
+                               ptrw[(ch * 4 + 2) % PTRWORDS], ptrw[(ch * 4 + 3) % PTRWORDS]);
+              }
+            }
+          }
+          // strip boundary row for the next pass
+          if (lane == 31 && pass + 1 < nPass) {
+            int* b = bndBuf + (size_t)c * 5;
+            b[0] = lastM; b[1] = lastD; b[2] = lastI; b[3] = lastJ; b[4] = lastK;
+          }
+        }
+      }  // steps
+      // drain outstanding tile loads of this pass (all issued tiles were waited for above: nextIssue == waitTile
+      // unless the reference is shorter than the issued prefetch)
+      while (waitTile < nextIssue) {
+#if MB200_USE_TMA
+        const uint32_t barAddr = smemAddr(&st.bar[waitTile & 1]);
+        const uint32_t parity  = tilesUsed[waitTile & 1] & 1;
+        uint32_t       ok      = 0;
+        for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+          asm volatile(
+              "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+              : "=r"(ok)
+              : "r"(barAddr), "r"(parity)
+              : "memory");
+          if (ok) break;
+        }
+        if (!ok) stageOk = false;
+        tilesUsed[waitTile & 1]++;
+#endif
+        waitTile++;
+      }
+      __syncwarp();
+    }  // passes
+
+    // ---- best back-trace start over the warp
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const long long o = __shfl_xor_sync(0xffffffffu, bestKey, off);
+      bestKey           = o > bestKey ? o : bestKey;
+    }
+    __threadfence_block();
+    __syncwarp();
+
+    if (lane == 0) {
+      if (!stageOk) atomicExch(P.errFlag, MB200_ERR_CUDA);
+      const int      bestVal = (int)(bestKey >> 32);
+      const uint32_t seq     = 0x7fffffffu - (uint32_t)(bestKey & 0xffffffffLL);
+
+      if (KIND == KIND_JUMP) {
+        // ---------------- JumpAlignerBase::backTraceAlignment  (JumpAlignerBaseImpl.hpp:101-242)
+        uint32_t refBegin, queryBegin;
+        if (seq < R1) { refBegin = seq + 1; queryBegin = Q; }
+        else if (seq < R1 + Q) { refBegin = R1; queryBegin = seq - R1; }
+        else if (seq < R1 + Q + R2) { refBegin = R1 + (seq - R1 - Q) + 1; queryBegin = Q; }
+        else { refBegin = R1 + R2; queryBegin = seq - (R1 + Q + R2); }
+        uint32_t state = ST_MATCH;
+
+        // raw paths in back-trace order: apath1 in segBuf[0..), apath2 in segBuf[half..)
+        const uint32_t half = (uint32_t)(P.segStride / 2);
+        uint32_t       n1 = 0, n2 = 0;
+        uint32_t       psType = MB200_SEG_NONE, psLen = 0;
+        uint32_t       jumpInsertSize = 0;
+        int            beginPos1 = 0, beginPos2 = 0;
+        if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
+        bool isRef2End = false;
+#define PUSH_TO(isRef1, T, L) do { if (isRef1) segBuf[n1++] = MB200_SEG_MAKE(L, T); else segBuf[half + n2++] = MB200_SEG_MAKE(L, T); } while (0)
+#define UPDATE_PATH(isRef1, AT) do { if (psType != (AT)) { if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen); psType = (AT); psLen = 0; } } while (0)
+        while (queryBegin > 0 && refBegin > 0) {
+          if (isRef2End) break;
+          const bool     isRef1    = (refBegin <= R1);
+          const uint32_t refXBegin = refBegin - (isRef1 ? 0 : R1);
+          const uint32_t cell      = ptrBuf[PL::cellOffset(queryBegin, refBegin, RTOT)];
+          const uint32_t next      = (cell >> (BITS * state)) & ((1u << BITS) - 1);
+          if (state == ST_MATCH) {
+            if (!isRef1 && refXBegin == 1 && next == ST_MATCH) isRef2End = true;
+            UPDATE_PATH(isRef1, MB200_SEG_MATCH);
+            queryBegin--;
+            refBegin--;
+          } else if (state == ST_DELETE) {
+            UPDATE_PATH(isRef1, MB200_SEG_DELETE);
+            refBegin--;
+          } else if (state == ST_INSERT) {
+            UPDATE_PATH(isRef1, MB200_SEG_INSERT);
+            queryBegin--;
+          } else {  // ST_JUMP
+            if (psType != MB200_SEG_NONE) {
+              beginPos2 = (int)(refBegin - R1);
+              if (psType == MB200_SEG_INSERT) {
+                jumpInsertSize += psLen;
+                psType = MB200_SEG_NONE;
+                psLen  = 0;
+              } else {
+                UPDATE_PATH(false, MB200_SEG_NONE);
+              }
+            } else {
+              if (next == ST_JUMP) refBegin--;
+            }
+          }
+          state = next;
+          psLen++;
+        }
+        {
+          const bool isRef1 = (refBegin < R1);
+          if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen);
+          if (queryBegin != 0) PUSH_TO(isRef1, MB200_SEG_SOFT_CLIP, queryBegin);
+          if (isRef1) beginPos1 = (int)refBegin; else beginPos2 = (int)(refBegin - R1);
+        }
+#undef PUSH_TO
+#undef UPDATE_PATH
+        uint32_t read1, refl1, read2, refl2;
+        rawLengths(segBuf, n1, read1, refl1);
+        rawLengths(segBuf + half, n2, read2, refl2);
+        (void)read2; (void)refl2;
+
+        uint32_t jumpRange = 0;
+        if (n1 && n2) {
+          uint32_t r1i = (uint32_t)beginPos1 + refl1, r2i = (uint32_t)beginPos2, qi = read1;
+          uint32_t jic = jumpInsertSize;
+          for (;;) {
+            if (r1i == R1) break;
+            if (jic > 0) {
+              if (qi == Q) break;
+              if (ref1[r1i] != qSeq[qi]) break;
+            } else {
+              if (r2i == R2) break;
+              if (ref1[r1i] != ref2[r2i]) break;
+            }
+            jumpRange++;
+            r1i++;
+            if (jic > 0) { jic--; qi++; } else { r2i++; }
+          }
+        }
+        const uint8_t* q2 = qSeq + read1 + jumpInsertSize;
+        const uint32_t c1 = expandPath(segBuf, n1, qSeq, ref1 + beginPos1, nullptr);
+        const uint32_t c2 = expandPath(segBuf + half, n2, q2, ref2 + beginPos2, nullptr);
+        const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)(c1 + c2));
+        if (off + c1 + c2 <= P.cigarCap) {
+          expandPath(segBuf, n1, qSeq, ref1 + beginPos1, P.cigarPool + off);
+          expandPath(segBuf + half, n2, q2, ref2 + beginPos2, P.cigarPool + off + c1);
+        }
+        mb200_jump_result* o = reinterpret_cast<mb200_jump_result*>(P.results) + task.outIndex;
+        o->score = bestVal; o->jumpInsertSize = jumpInsertSize; o->jumpRange = jumpRange;
+        o->beginPos1 = beginPos1; o->beginPos2 = beginPos2;
+        o->cigarLen1 = c1; o->cigarLen2 = c2; o->reserved = 0;
+        o->cigarOff1 = off; o->cigarOff2 = off + c1;
+      } else {
+        // ---------------- SingleRefAlignerBase::backTraceAlignment (SingleRefAlignerSharedImpl.hpp:75-168)
+        const uint32_t R = R1;
+        uint32_t       refBegin, queryBegin, state = ST_MATCH;
+        if (seq < R) { refBegin = seq + 1; queryBegin = Q; }
+        else if (seq == R) { refBegin = R; queryBegin = Q; state = ST_INSERT; }
+        else { refBegin = R; queryBegin = seq - R - 1; }
+        uint32_t n = 0, psType = MB200_SEG_NONE, psLen = 0, isJumped = 0;
+        if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
+        for (;;) {
+          uint32_t next;
+          if (queryBegin >= 1 && refBegin >= 1) {
+            uint32_t cell;
+            if (KT::CELLB == 1) cell = ptrBuf[PL::cellOffset(queryBegin, refBegin, RTOT)];
+            else cell = *reinterpret_cast<const uint16_t*>(ptrBuf + PL::cellOffset(queryBegin, refBegin, RTOT));
+            next = (cell >> (BITS * state)) & ((1u << BITS) - 1);
+          } else {
+            // row 0 / column 0 pointers: all MATCH, except column-0 insert state with edge insertions allowed
+            next = (refBegin == 0 && state == ST_INSERT && P.allowEdgeIns) ? ST_INSERT : ST_MATCH;
+          }
+          uint32_t atype;
+          if (state == ST_MATCH) {
+            if (queryBegin < 1 || refBegin < 1) break;
+            atype = MB200_SEG_MATCH;
+          } else if (state == ST_DELETE || state == ST_JUMP) {
+            if (refBegin < 1) break;
+            atype = MB200_SEG_DELETE;
+          } else {
+            if (queryBegin < 1) break;
+            atype = MB200_SEG_INSERT;
+          }
+          if (psType != atype) {
+            if (psType != MB200_SEG_NONE) segBuf[n++] = MB200_SEG_MAKE(psLen, psType);
+            psType = atype;
+            psLen  = 0;
+          }
+          if (state == ST_MATCH) { queryBegin--; refBegin--; }
+          else if (state == ST_DELETE || state == ST_JUMP) { refBegin--; }
+          else { queryBegin--; }
+          if (state == ST_JUMP || state == ST_JUMPINS) isJumped = 1;
+          state = next;
+          psLen++;
+        }
+        if (psType != MB200_SEG_NONE) segBuf[n++] = MB200_SEG_MAKE(psLen, psType);
+        if (queryBegin != 0) segBuf[n++] = MB200_SEG_MAKE(queryBegin, MB200_SEG_SOFT_CLIP);
+        const int      beginPos = (int)refBegin;
+        const uint32_t cnt      = expandPath(segBuf, n, qSeq, ref1 + beginPos, nullptr);
+        const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)cnt);
+        if (off + cnt <= P.cigarCap) expandPath(segBuf, n, qSeq, ref1 + beginPos, P.cigarPool + off);
+        mb200_aln_result* o = reinterpret_cast<mb200_aln_result*>(P.results) + task.outIndex;
+        o->score = bestVal; o->beginPos = beginPos; o->isJumped = isJumped; o->cigarLen = cnt; o->cigarOff = off;
+      }
+    }
+    __syncwarp();
+  }  // tasks
+}
+
+// ======================================================================================================
+// host side
+template <int KIND, int RT> size_t ptrBytesFor(uint32_t Q, uint32_t rtot)
+{
+  using PL = PtrLayout<RT, KindTraits<KIND>::CELLB>;
+  const size_t nPass = (Q + 32 * RT - 1) / (32 * RT);
+  return nPass * ((size_t)(rtot + 31) * PL::STEP_BYTES);
+}
+
+struct ClassPlan {
+  std::vector<DpTask> tasks;
+  size_t              maxPtr = 0, maxSeg = 0, maxBnd = 0;
+};
+
+template <int KIND, int RT>
+int launchClass(mb200_ctx* ctx, const DpParams& base, const ClassPlan& plan, size_t taskOffset, uint32_t* dCounter)
+{
+  if (plan.tasks.empty()) return MB200_OK;
+  int ctasPerSm = 0;
+  MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, dpAlignKernel<KIND, RT>,
+                                                                      WARPS_PER_CTA * 32, 0));
+  if (ctasPerSm < 1) ctasPerSm = 1;
+  if (ctx->cfg.ctasPerSm && (int)ctx->cfg.ctasPerSm < ctasPerSm) ctasPerSm = (int)ctx->cfg.ctasPerSm;
+  size_t   nSlotsWanted = (size_t)ctx->smCount * ctasPerSm * WARPS_PER_CTA;
+  uint32_t grid         = (uint32_t)(ctx->smCount * ctasPerSm);
+  // no more warps than tasks
+  if (nSlotsWanted > plan.tasks.size()) {
+    grid = (uint32_t)((plan.tasks.size() + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+  }
+  // scratch budget: shrink the grid if the back-pointer scratch would exceed the configured budget
+  const size_t budget   = ctx->cfg.scratchBytes ? (size_t)ctx->cfg.scratchBytes : ((size_t)48 << 30);
+  const size_t ptrSlot  = (plan.maxPtr + 255) & ~(size_t)255;
+  while (grid > 1 && (size_t)grid * WARPS_PER_CTA * ptrSlot > budget) grid = (grid + 1) / 2;
+  const size_t nSlots = (size_t)grid * WARPS_PER_CTA;
+
+  int rc;
+  if ((rc = mb200_reserve(ctx, ctx->dPtrScratch, nSlots * ptrSlot)) != MB200_OK) return rc;
+  const size_t segSlot = (plan.maxSeg + 63) & ~(size_t)63;
+  if ((rc = mb200_reserve(ctx, ctx->dSegScratch, nSlots * segSlot * sizeof(uint32_t))) != MB200_OK) return rc;
+  const size_t bndSlot = (plan.maxBnd + 63) & ~(size_t)63;
+  if ((rc = mb200_reserve(ctx, ctx->dBndScratch, nSlots * bndSlot * sizeof(int) + 256)) != MB200_OK) return rc;
+
+  DpParams P    = base;
+  P.tasks       = reinterpret_cast<const DpTask*>(ctx->dTasks.ptr) + taskOffset;
+  P.nTasks      = (uint32_t)plan.tasks.size();
+  P.workCounter = dCounter;
+  P.ptrScratch  = reinterpret_cast<uint8_t*>(ctx->dPtrScratch.ptr);
+  P.ptrStride   = ptrSlot;
+  P.segScratch  = reinterpret_cast<uint32_t*>(ctx->dSegScratch.ptr);
+  P.segStride   = segSlot;
+  P.bndScratch  = reinterpret_cast<int*>(ctx->dBndScratch.ptr);
+  P.bndStride   = bndSlot;
+  dpAlignKernel<KIND, RT><<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(P);
+  MB200_CUDA_CHECK(ctx, cudaGetLastError());
+  ctx->timing.launches++;
+  return MB200_OK;
+}
+
+template <int KIND>
+int alignBatch(mb200_ctx* ctx, const mb200_scores* scores, int extra, uint32_t n, const uint8_t* pool,
+               uint64_t poolBytes, const mb200_seqview* query, const mb200_seqview* ref1, const mb200_seqview* ref2,
+               void* results, size_t resultBytes, uint32_t* cigarPool, uint64_t cigarCap, uint64_t* cigarUsed)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (!scores || (n && (!pool || !query || !ref1 || !results)) || !cigarUsed) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  if (KIND == KIND_JUMP && scores->isAllowEdgeInsertion)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "GlobalJumpAligner does not support isAllowEdgeInsertion (GlobalJumpAligner.hpp:41)");
+  ctx->timing = mb200_timing();
+  *cigarUsed  = 0;
+  if (n == 0) return MB200_OK;
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+
+  // input checks of the reference (exceptions there, status codes here)
+  for (uint32_t i = 0; i < n; ++i) {
+    if (query[i].len == 0) return mb200_fail(ctx, MB200_ERR_EMPTY_QUERY, "Unexpected empty query sequence");
+    if (KIND == KIND_JUMP) {
+      if (ref1[i].len == 0) return mb200_fail(ctx, MB200_ERR_EMPTY_REF1, "Unexpected empty reference1 sequence");
+      if (ref2[i].len == 0) return mb200_fail(ctx, MB200_ERR_EMPTY_REF2, "Unexpected empty reference2 sequence");
+    } else if (ref1[i].len == 0) {
+      return mb200_fail(ctx, MB200_ERR_EMPTY_REF, "Unexpected empty reference sequence");
+    }
+    if (query[i].off + query[i].len > poolBytes || ref1[i].off + ref1[i].len > poolBytes ||
+        (KIND == KIND_JUMP && ref2[i].off + ref2[i].len > poolBytes))
+      return mb200_fail(ctx, MB200_ERR_BAD_ARG, "sequence view outside the pool");
+  }
+
+  // ---- classes by query length (rows per thread); longest tasks first inside a class
+  ClassPlan plans[3];
+  constexpr uint64_t FRONT = 16;  // device pool is shifted by 16 bytes so aligned-down TMA sources stay inside it
+  for (uint32_t i = 0; i < n; ++i) {
+    DpTask t;
+    t.qOff     = FRONT + query[i].off;
+    t.r1Off    = FRONT + ref1[i].off;
+    t.r2Off    = (KIND == KIND_JUMP) ? FRONT + ref2[i].off : t.r1Off;
+    t.Q        = query[i].len;
+    t.R1       = ref1[i].len;
+    t.R2       = (KIND == KIND_JUMP) ? ref2[i].len : 0;
+    t.outIndex = i;
+    const uint32_t rtot = t.R1 + t.R2;
+    const int      cls  = (t.Q <= 128) ? 0 : (t.Q <= 256 ? 1 : 2);
+    ClassPlan&     p    = plans[cls];
+    p.tasks.push_back(t);
+    size_t pb = cls == 0 ? ptrBytesFor<KIND, 4>(t.Q, rtot) : (cls == 1 ? ptrBytesFor<KIND, 8>(t.Q, rtot) : ptrBytesFor<KIND, 16>(t.Q, rtot));
+    if (pb > p.maxPtr) p.maxPtr = pb;
+    const size_t seg = 2 * ((size_t)t.Q + rtot + 8);
+    if (seg > p.maxSeg) p.maxSeg = seg;
+    const size_t bnd = (t.Q > 512) ? ((size_t)rtot + 2) * 5 : 8;
+    if (bnd > p.maxBnd) p.maxBnd = bnd;
+    ctx->timing.cells += (uint64_t)t.Q * rtot;
+    ctx->timing.algoBytes += (uint64_t)t.Q * rtot * KindTraits<KIND>::CELLB + t.Q + rtot;
+  }
+  std::vector<DpTask> all;
+  all.reserve(n);
+  size_t offsets[3];
+  for (int c = 0; c < 3; ++c) {
+    std::vector<DpTask>& v = plans[c].tasks;
+    std::sort(v.begin(), v.end(), [](const DpTask& a, const DpTask& b) {
+      const uint64_t ca = (uint64_t)a.Q * (a.R1 + a.R2), cb = (uint64_t)b.Q * (b.R1 + b.R2);
+      return ca != cb ? ca > cb : a.outIndex < b.outIndex;
+    });
+    offsets[c] = all.size();
+    all.insert(all.end(), v.begin(), v.end());
+  }
+
+  int rc;
+  if ((rc = mb200_reserve(ctx, ctx->dPool, poolBytes + FRONT + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dTasks, all.size() * sizeof(DpTask))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dResults, (size_t)n * resultBytes)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dCigar, (size_t)(cigarCap ? cigarCap : 1) * sizeof(uint32_t))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dMisc, 256)) != MB200_OK) return rc;
+
+  // dMisc: [0..2] work counters, [4] errFlag, [8..9] cigarUsed (u64)
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dMisc.ptr, 0, 256, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dPool.ptr, 0, FRONT, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->dPool.ptr) + FRONT, pool, poolBytes,
+                                        cudaMemcpyHostToDevice, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->dPool.ptr) + FRONT + poolBytes, 0, 64, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dTasks.ptr, all.data(), all.size() * sizeof(DpTask),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+
+  DpParams P;
+  P.match = scores->match; P.mismatch = scores->mismatch; P.open = scores->open; P.extend = scores->extend;
+  P.offEdge = scores->offEdge; P.allowEdgeIns = scores->isAllowEdgeInsertion ? 1 : 0; P.extra = extra;
+  P.pool      = reinterpret_cast<const uint8_t*>(ctx->dPool.ptr);
+  P.results   = ctx->dResults.ptr;
+  P.cigarPool = reinterpret_cast<uint32_t*>(ctx->dCigar.ptr);
+  P.cigarCap  = cigarCap;
+  uint32_t* misc = reinterpret_cast<uint32_t*>(ctx->dMisc.ptr);
+  P.errFlag   = reinterpret_cast<int*>(misc + 4);
+  P.cigarUsed = reinterpret_cast<unsigned long long*>(misc + 8);
+
+  // the classes run back to back on the ctx stream (they share the scratch buffers)
+  if ((rc = launchClass<KIND, 4>(ctx, P, plans[0], offsets[0], misc + 0)) != MB200_OK) return rc;
+  if ((rc = launchClass<KIND, 8>(ctx, P, plans[1], offsets[1], misc + 1)) != MB200_OK) return rc;
+  if ((rc = launchClass<KIND, 16>(ctx, P, plans[2], offsets[2], misc + 2)) != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+
+  uint32_t hMisc[16];
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(hMisc, ctx->dMisc.ptr, sizeof(hMisc), cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(results, ctx->dResults.ptr, (size_t)n * resultBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned long long used;
+  memcpy(&used, hMisc + 8, sizeof(used));
+  *cigarUsed = used;
+  if (hMisc[4] != 0) return mb200_fail(ctx, (int)hMisc[4], "device-side failure in dpAlignKernel (TMA wait timeout)");
+  if (used > cigarCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "cigar pool too small");
+  if (used) {
+    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(cigarPool, ctx->dCigar.ptr, used * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->timing.h2dMs, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->timing.kernelMs, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->timing.d2hMs, ctx->ev[2], ctx->ev[3]);
+  return MB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb200_jump_align_batch(mb200_ctx* ctx, const mb200_scores* scores, int32_t jumpScore, uint32_t n,
+                           const uint8_t* pool, uint64_t poolBytes, const mb200_seqview* query,
+                           const mb200_seqview* ref1, const mb200_seqview* ref2, mb200_jump_result* results,
+                           uint32_t* cigarPool, uint64_t cigarCap, uint64_t* cigarUsed)
+{
+  if (n && !ref2) return MB200_ERR_BAD_ARG;
+  return alignBatch<KIND_JUMP>(ctx, scores, jumpScore, n, pool, poolBytes, query, ref1, ref2, results,
+                               sizeof(mb200_jump_result), cigarPool, cigarCap, cigarUsed);
+}
+
+int mb200_indel_align_batch(mb200_ctx* ctx, const mb200_scores* scores, int32_t largeIndelScore, uint32_t n,
+                            const uint8_t* pool, uint64_t poolBytes, const mb200_seqview* query,
+                            const mb200_seqview* ref, mb200_aln_result* results, uint32_t* cigarPool,
+                            uint64_t cigarCap, uint64_t* cigarUsed)
+{
+  return alignBatch<KIND_INDEL>(ctx, scores, largeIndelScore, n, pool, poolBytes, query, ref, nullptr, results,
+                                sizeof(mb200_aln_result), cigarPool, cigarCap, cigarUsed);
+}
+
+int mb200_global_align_batch(mb200_ctx* ctx, const mb200_scores* scores, uint32_t n, const uint8_t* pool,
+                             uint64_t poolBytes, const mb200_seqview* query, const mb200_seqview* ref,
+                             mb200_aln_result* results, uint32_t* cigarPool, uint64_t cigarCap, uint64_t* cigarUsed)
+{
+  return alignBatch<KIND_GLOBAL>(ctx, scores, 0, n, pool, poolBytes, query, ref, nullptr, results,
+                                 sizeof(mb200_aln_result), cigarPool, cigarCap, cigarUsed);
+}
+
+}  // extern "C"
