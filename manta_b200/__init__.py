@@ -26,7 +26,8 @@ from ._cabi import (AlignmentResult, AssembledContig, AssemblyReadInfo, Binding,
                     SRAlignmentInfo, Scores, default_asm_opts)
 
 __all__ = ["Context", "AlignmentScores", "GlobalAligner", "GlobalJumpAligner", "GlobalLargeIndelAligner",
-           "IterativeAssemblerOptions", "runIterativeAssembler", "Mb200Error", "library_path"]
+           "IterativeAssemblerOptions", "runIterativeAssembler", "splitReadAligner", "qscore_snp", "Mb200Error",
+           "library_path"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -145,3 +146,45 @@ def runIterativeAssembler(opt: np.ndarray, reads: Sequence[str], ctx: Optional[C
     reference call (lib/assembly/IterativeAssembler.cpp:844-931)"""
     contigs, pseudo, info = (ctx or default_context()).assemble(opt, [list(reads)])[0]
     return contigs, list(reads) + pseudo, info
+
+
+class qscore_snp:
+    """qscore_snp(snp_prob)  lib/blt_util/qscore_snp.cpp:29-41 -- the two per-phred log tables (host libm)"""
+
+    def __init__(self, snp_prob: float):
+        import math
+        self.snp_prob = snp_prob
+        comp_snp3 = 1.0 - (snp_prob / 3.0)
+        self.lnComp, self.lnErr = [], []
+        for i in range(_cabi.MAX_QSCORE + 1):
+            qerr = math.pow(10.0, -float(i) / 10.0)
+            q2p = (qerr * comp_snp3) + ((1 - qerr) * snp_prob)
+            x = -q2p
+            # C semantics: log(0) == -inf (phred 0 with snp_prob 0)
+            self.lnComp.append(math.log1p(x) if abs(x) < 0.01 else (math.log(1 + x) if 1 + x > 0 else -math.inf))
+            self.lnErr.append(math.log(q2p) if q2p > 0 else -math.inf)
+
+
+def qscore_tables(t0: "qscore_snp", t1: "qscore_snp") -> np.ndarray:
+    t = np.zeros(1, dtype=_cabi.QSCORE_TABLES_DT)
+    t["lnComp"][0][0], t["lnComp"][0][1] = t0.lnComp, t1.lnComp
+    t["lnErr"][0][0], t["lnErr"][0][1] = t0.lnErr, t1.lnErr
+    return t
+
+
+def splitReadAligner(flankScoreSize: int, querySeq: str, qualConvert: "qscore_snp", queryQual: Sequence[int],
+                     targetSeq: str, targetBpOffsetRange: Tuple[int, int],
+                     ctx: Optional[Context] = None) -> SRAlignmentInfo:
+    """splitReadAligner  GSC/SplitReadAlignment.hpp:63-70 (batch of one; raises like the reference on bad input)"""
+    sp = _cabi.SeqPool()
+    jobs = np.zeros(1, dtype=_cabi.SR_JOB_DT)
+    jobs["q_off"][0], jobs["q_len"][0] = sp.add(querySeq)
+    jobs["qualOff"][0], _ = sp.add(bytes(queryQual))
+    jobs["t_off"][0], jobs["t_len"][0] = sp.add(targetSeq)
+    jobs["bpBegin"][0], jobs["bpEnd"][0] = targetBpOffsetRange
+    res = (ctx or default_context()).split_align_raw(qscore_tables(qualConvert, qualConvert), (0, 0),
+                                                     flankScoreSize, sp.finish(), jobs)
+    if int(res["status"][0]) != _cabi.MB200_OK:
+        st = int(res["status"][0])
+        raise Mb200Error(st, _cabi.ERROR_MESSAGES.get(st, "status %d" % st))
+    return _cabi.decode_sr(res[0])

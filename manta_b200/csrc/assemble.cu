@@ -1,0 +1,1244 @@
+// assemble.cu -- batched iterative-k de-Bruijn assembler for sm_100a.
+//
+// Replaces (bit-exactly) runIterativeAssembler, lib/assembly/IterativeAssembler.cpp:844-931, with
+//   getKmerCounts :506-550, getRepeatKmers/searchRepeats :555-642, buildContigs :644-720, walk :149-501,
+//   selectContigs :722-842.
+//
+// Mapping (DESIGN.md "assembler kernel"): one CTA per locus (persistent CTAs, global work counter).
+//   * reads are packed once to 2 bits/base (MSB first, so integer order == lexicographic order A<C<G<T) plus
+//     an N-mask bit plane; a k-mer (k <= 96) is three 64-bit words cut out of the packed stream;
+//   * word table: open addressing keyed by the packed k-mer; the word id is the index of the window that
+//     claimed the slot (one atomicCAS, no locks); per word: count, first read, read-support bitset
+//     (<= 32 words of 32 bits == <= 1024 reads incl. pseudo reads), built with atomicOr/atomicAdd so that a
+//     word repeated inside a read counts once (std::set<std::string> readWords, :524-535);
+//   * successor / predecessor word ids are resolved once per word (4 + 4 lookups, all threads) so that the
+//     greedy walk and the cycle search are pure integer graph walks;
+//   * repeat words: homopolymers directly; other cycles are detected by parallel trimming (Kahn).  Only if a
+//     cycle exists is the reference's order-dependent Tarjan replayed exactly: the iteration order of the two
+//     nested std::unordered_map<std::string,...> is reproduced with a parallel formulation of libstdc++'s
+//     hashtable (per rehash level: groups by bucket, ordered by descending first-arrival, members by descending
+//     arrival), then one thread runs the DFS with the same index/low-link/"small circle <= 50" rules;
+//   * seeds: CTA-wide arg-max (count, then lexicographically smallest word);
+//   * walk: warp 0, read sets live one 32-bit word per lane, every std::set operation of the reference is a
+//     lane-wise bit operation + warp vote / __reduce_add;
+//   * contigs of a failed word length are re-packed as pseudo reads for the next one; selectContigs runs on
+//     warp 0; results are bump-allocated into the output pools.
+//
+// Restrictions (documented in DESIGN.md): input bases must be in {A,C,G,T,N} (MB200_ERR_BAD_BASE otherwise),
+// at most 1024 - 2*maxAssemblyCount reads per locus, word lengths 2..96, contigs up to cfg.maxContigLen.
+#include <algorithm>
+#include <cstdint>
+
+#include "mb200_internal.h"
+
+namespace {
+
+constexpr int      ASM_THREADS = 128;
+constexpr uint32_t NONE32      = 0xffffffffu;
+constexpr int      MAX_SETW    = 32;
+
+// libstdc++ std::unordered_map bucket growth (see oracle/orc_assemble.c STL_BUCKETS)
+__constant__ uint32_t STL_BUCKETS_D[22] = {13,     29,     59,      127,     257,     541,      1109,    2357,
+                                           5087,   10273,  20753,   42043,   85229,   172933,   351061,  712697,
+                                           1447153, 2938679, 5967347, 12117689, 24607243, 49969847};
+
+struct WorkLayout {  // byte offsets inside one CTA's workspace
+  size_t readLen, readPackOff, readMaskOff, winStart;
+  size_t packed, nmask;
+  size_t key0, key1, key2;
+  size_t count, firstRead, bits, slot, wordList, succ, pred, indeg, flags, inContig;
+  size_t hashv, seqA, arr, pos, bktHead, bktMin, bktCnt, chainNext, gs, orderA, tmpA;
+  size_t idx, low, wstack, frame;
+  size_t ctgSeq, ctgSets, ctgMeta;
+  size_t total;
+  uint32_t maxReads;   // incl. pseudo reads
+  uint32_t nWinMax, slotsMax, packWords, maskWords, bktMax;
+};
+
+struct AsmParams {
+  mb200_asm_opts       opt;
+  const uint8_t*       pool;
+  const uint64_t*      readOff;
+  const mb200_seqview* views;
+  uint32_t             nLoci;
+  uint32_t*            lociCounter;
+  uint8_t*             work;
+  WorkLayout           L;
+  uint32_t             maxContigLen;
+  mb200_asm_locus*     loci;
+  mb200_contig*        contigs;      // fixed slots: locus*maxAssemblyCount + c
+  mb200_seqview*       pseudo;       // fixed slots: locus*2*maxAssemblyCount + p
+  uint8_t*             contigPool;
+  unsigned long long   contigPoolCap;
+  unsigned long long*  contigPoolUsed;
+  uint32_t*            setPool;
+  unsigned long long   setPoolCap;
+  unsigned long long*  setPoolUsed;
+  int*                 errFlag;
+};
+
+enum { FLAG_UNUSED = 1, FLAG_REPEAT = 2, FLAG_PEELED = 4, FLAG_ONSTACK = 8 };
+
+struct CtgMeta {
+  uint32_t lo, hi;  // contig == ctgSeq[lo, hi)
+  int32_t  consBegin, consEnd;
+};
+
+// ---- packed sequence helpers -----------------------------------------------------------------------
+__device__ __forceinline__ uint64_t getBits(const uint64_t* s, uint32_t bitPos, uint32_t nbits)
+{
+  const uint32_t w = bitPos >> 6, off = bitPos & 63;
+  const uint64_t hi = s[w], lo = s[w + 1];
+  const uint64_t v  = off ? ((hi << off) | (lo >> (64 - off))) : hi;
+  return v >> (64 - nbits);
+}
+
+struct Key {
+  uint64_t k0, k1, k2;
+};
+__device__ __forceinline__ bool keyEq(const Key& a, const Key& b) { return a.k0 == b.k0 && a.k1 == b.k1 && a.k2 == b.k2; }
+__device__ __forceinline__ bool keyLess(const Key& a, const Key& b)
+{
+  if (a.k2 != b.k2) return a.k2 < b.k2;
+  if (a.k1 != b.k1) return a.k1 < b.k1;
+  return a.k0 < b.k0;
+}
+__device__ __forceinline__ uint64_t lowMask(uint32_t nbits) { return nbits >= 64 ? ~0ull : ((1ull << nbits) - 1); }
+
+__device__ __forceinline__ Key extractKey(const uint64_t* s, uint32_t base, uint32_t k)
+{
+  const uint32_t B = 2 * k, bp = 2 * base;
+  Key            r;
+  if (B <= 64) {
+    r.k0 = getBits(s, bp, B);
+    r.k1 = r.k2 = 0;
+  } else if (B <= 128) {
+    r.k1 = getBits(s, bp, B - 64);
+    r.k0 = getBits(s, bp + B - 64, 64);
+    r.k2 = 0;
+  } else {
+    r.k2 = getBits(s, bp, B - 128);
+    r.k1 = getBits(s, bp + B - 128, 64);
+    r.k0 = getBits(s, bp + B - 64, 64);
+  }
+  return r;
+}
+__device__ __forceinline__ Key succKey(const Key& a, uint32_t sym, uint32_t k)
+{
+  const uint32_t B = 2 * k;
+  Key            r;
+  r.k2 = (a.k2 << 2) | (a.k1 >> 62);
+  r.k1 = (a.k1 << 2) | (a.k0 >> 62);
+  r.k0 = (a.k0 << 2) | sym;
+  if (B <= 64) {
+    r.k0 &= lowMask(B);
+    r.k1 = r.k2 = 0;
+  } else if (B <= 128) {
+    r.k1 &= lowMask(B - 64);
+    r.k2 = 0;
+  } else {
+    r.k2 &= lowMask(B - 128);
+  }
+  return r;
+}
+__device__ __forceinline__ Key predKey(const Key& a, uint32_t sym, uint32_t k)
+{
+  const uint32_t B = 2 * k;
+  Key            r;
+  r.k0 = (a.k0 >> 2) | (a.k1 << 62);
+  r.k1 = (a.k1 >> 2) | (a.k2 << 62);
+  r.k2 = a.k2 >> 2;
+  if (B <= 64) r.k0 |= (uint64_t)sym << (B - 2);
+  else if (B <= 128) r.k1 |= (uint64_t)sym << (B - 66);
+  else r.k2 |= (uint64_t)sym << (B - 130);
+  return r;
+}
+__device__ __forceinline__ uint32_t baseAt(const Key& a, uint32_t i, uint32_t k)
+{  // base i (0 = first) of the word
+  const uint32_t pos = 2 * (k - 1 - i);
+  const uint64_t w   = pos < 64 ? a.k0 : (pos < 128 ? a.k1 : a.k2);
+  return (uint32_t)(w >> (pos & 63)) & 3u;
+}
+__device__ __forceinline__ uint32_t hashKey(const Key& a)
+{
+  uint64_t h = a.k0 * 0x9E3779B97F4A7C15ull;
+  h ^= (a.k1 + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+  h ^= (a.k2 + 0x165667B1ull) * 0xD6E8FEB86659FD93ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return (uint32_t)h;
+}
+
+// std::hash<std::string> of the ASCII spelling of a word (libstdc++ _Hash_bytes, see oracle/orc_assemble.c)
+__device__ uint64_t stlHashWord(const Key& a, uint32_t k)
+{
+  const uint64_t mul = (((uint64_t)0xc6a4a793UL) << 32) + (uint64_t)0x5bd1e995UL;
+  uint64_t       h   = 0xc70f6907ull ^ ((uint64_t)k * mul);
+  const uint32_t alen = k & ~7u;
+  for (uint32_t p = 0; p < alen; p += 8) {
+    uint64_t d = 0;
+    for (uint32_t t = 0; t < 8; ++t) d |= (uint64_t)(uint8_t)("ACGT"[baseAt(a, p + t, k)]) << (8 * t);
+    d *= mul;
+    d ^= d >> 47;
+    d *= mul;
+    h ^= d;
+    h *= mul;
+  }
+  if (k & 7) {
+    uint64_t d = 0;
+    for (uint32_t t = 0; t < (k & 7); ++t) d |= (uint64_t)(uint8_t)("ACGT"[baseAt(a, alen + t, k)]) << (8 * t);
+    h ^= d;
+    h *= mul;
+  }
+  h ^= h >> 47;
+  h *= mul;
+  h ^= h >> 47;
+  return h;
+}
+
+// ---- per-CTA view of the workspace -----------------------------------------------------------------
+struct Work {
+  uint32_t *readLen, *readPackOff, *readMaskOff, *winStart;
+  uint64_t *packed, *nmask;
+  uint64_t *key0, *key1, *key2;
+  uint32_t *count, *firstRead, *bits, *slot, *wordList, *succ, *pred, *indeg;
+  uint8_t * flags, *inContig;
+  uint64_t* hashv;
+  uint32_t *seqA, *arr, *pos, *bktHead, *bktMin, *bktCnt, *chainNext, *gs, *orderA, *tmpA;
+  uint32_t *idx, *low, *wstack, *frame;
+  uint8_t*  ctgSeq;
+  uint32_t* ctgSets;
+  CtgMeta*  ctgMeta;
+};
+
+__device__ __forceinline__ Key loadKey(const Work& W, uint32_t id)
+{
+  Key k;
+  k.k0 = W.key0[id];
+  k.k1 = W.key1[id];
+  k.k2 = W.key2[id];
+  return k;
+}
+
+__device__ uint32_t findWord(const Work& W, const Key& key, uint32_t slotMask)
+{
+  uint32_t h = hashKey(key) & slotMask;
+  for (;;) {
+    const uint32_t cur = W.slot[h];
+    if (cur == 0) return NONE32;
+    if (keyEq(loadKey(W, cur - 1), key)) return cur - 1;
+    h = (h + 1) & slotMask;
+  }
+}
+
+// exclusive SUFFIX sum of a[0..m) into out[0..m): out[i] = sum_{j>i} a[j]   (whole CTA, uses sh[ASM_THREADS])
+__device__ void suffixSumExclusive(const uint32_t* a, uint32_t* out, uint32_t m, uint32_t* sh)
+{
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t per = (m + nt - 1) / nt;
+  // thread t owns the chunk [m - (t+1)*per, m - t*per) counted from the END
+  const long long hiL = (long long)m - (long long)tid * per;
+  const long long loL = hiL - per;
+  const uint32_t  hi  = hiL > 0 ? (uint32_t)hiL : 0;
+  const uint32_t  lo  = loL > 0 ? (uint32_t)loL : 0;
+  uint32_t        sum = 0;
+  for (uint32_t i = lo; i < hi; ++i) sum += a[i];
+  sh[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (uint32_t t = 0; t < nt; ++t) {
+      const uint32_t v = sh[t];
+      sh[t]            = run;  // sum of everything after this thread's chunk
+      run += v;
+    }
+  }
+  __syncthreads();
+  uint32_t run = sh[tid];
+  for (uint32_t i = hi; i > lo; --i) {
+    out[i - 1] = run;
+    run += a[i - 1];
+  }
+  __syncthreads();
+}
+
+// Iteration order of a libstdc++ std::unordered_map<std::string,T> filled by operator[] with n keys whose
+// std::hash values are hashIn[0..n) (insertion order).  order[p] = insertion index of the p-th iterated element.
+__device__ void unorderedOrder(const Work& W, const uint64_t* hashIn, uint32_t n, uint32_t* order, uint32_t* sh)
+{
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  uint32_t       prevB = 0;
+  for (int level = 0; level < 22; ++level) {
+    const uint32_t B = STL_BUCKETS_D[level];
+    const uint32_t m = n < B ? n : B;
+    for (uint32_t b = tid; b < B; b += nt) {
+      W.bktHead[b] = NONE32;
+      W.bktMin[b]  = NONE32;
+      W.bktCnt[b]  = 0;
+    }
+    for (uint32_t e = tid; e < m; e += nt) {
+      W.gs[e] = 0;
+      // arrival time: position in the previous level's list for the old elements, own index for the new ones
+      W.arr[e] = (e < prevB) ? W.pos[e] : e;
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < m; e += nt) {
+      const uint32_t b = (uint32_t)(hashIn[e] % B);
+      W.chainNext[e]   = atomicExch(&W.bktHead[b], e);
+      atomicMin(&W.bktMin[b], W.arr[e]);
+      atomicAdd(&W.bktCnt[b], 1u);
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < m; e += nt) {
+      const uint32_t b = (uint32_t)(hashIn[e] % B);
+      if (W.arr[e] == W.bktMin[b]) W.gs[W.arr[e]] = W.bktCnt[b];
+    }
+    __syncthreads();
+    suffixSumExclusive(W.gs, W.tmpA, m, sh);  // tmpA[a] = number of elements in groups created after arrival a
+    for (uint32_t e = tid; e < m; e += nt) {
+      const uint32_t b = (uint32_t)(hashIn[e] % B);
+      const uint32_t a = W.arr[e];
+      uint32_t       rank = 0;
+      for (uint32_t x = W.bktHead[b]; x != NONE32; x = W.chainNext[x])
+        if (W.arr[x] > a) rank++;
+      W.orderA[e] = W.tmpA[W.bktMin[b]] + rank;
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < m; e += nt) W.pos[e] = W.orderA[e];
+    __syncthreads();
+    prevB = B;
+    if (n <= B) break;
+  }
+  for (uint32_t e = tid; e < n; e += nt) order[W.pos[e]] = e;
+  __syncthreads();
+}
+
+// ======================================================================================================
+__global__ void __launch_bounds__(ASM_THREADS) assembleKernel(const AsmParams P)
+{
+  __shared__ uint32_t sh[ASM_THREADS];
+  __shared__ uint32_t shU[16];
+  __shared__ unsigned long long shBest[2];
+
+  const uint32_t tid  = threadIdx.x;
+  const uint32_t nt   = blockDim.x;
+  const uint32_t lane = tid & 31;
+  const uint32_t warp = tid >> 5;
+
+  uint8_t* base = P.work + (size_t)blockIdx.x * P.L.total;
+  Work     W;
+  W.readLen     = reinterpret_cast<uint32_t*>(base + P.L.readLen);
+  W.readPackOff = reinterpret_cast<uint32_t*>(base + P.L.readPackOff);
+  W.readMaskOff = reinterpret_cast<uint32_t*>(base + P.L.readMaskOff);
+  W.winStart    = reinterpret_cast<uint32_t*>(base + P.L.winStart);
+  W.packed      = reinterpret_cast<uint64_t*>(base + P.L.packed);
+  W.nmask       = reinterpret_cast<uint64_t*>(base + P.L.nmask);
+  W.key0        = reinterpret_cast<uint64_t*>(base + P.L.key0);
+  W.key1        = reinterpret_cast<uint64_t*>(base + P.L.key1);
+  W.key2        = reinterpret_cast<uint64_t*>(base + P.L.key2);
+  W.count       = reinterpret_cast<uint32_t*>(base + P.L.count);
+  W.firstRead   = reinterpret_cast<uint32_t*>(base + P.L.firstRead);
+  W.bits        = reinterpret_cast<uint32_t*>(base + P.L.bits);
+  W.slot        = reinterpret_cast<uint32_t*>(base + P.L.slot);
+  W.wordList    = reinterpret_cast<uint32_t*>(base + P.L.wordList);
+  W.succ        = reinterpret_cast<uint32_t*>(base + P.L.succ);
+  W.pred        = reinterpret_cast<uint32_t*>(base + P.L.pred);
+  W.indeg       = reinterpret_cast<uint32_t*>(base + P.L.indeg);
+  W.flags       = reinterpret_cast<uint8_t*>(base + P.L.flags);
+  W.inContig    = reinterpret_cast<uint8_t*>(base + P.L.inContig);
+  W.hashv       = reinterpret_cast<uint64_t*>(base + P.L.hashv);
+  W.seqA        = reinterpret_cast<uint32_t*>(base + P.L.seqA);
+  W.arr         = reinterpret_cast<uint32_t*>(base + P.L.arr);
+  W.pos         = reinterpret_cast<uint32_t*>(base + P.L.pos);
+  W.bktHead     = reinterpret_cast<uint32_t*>(base + P.L.bktHead);
+  W.bktMin      = reinterpret_cast<uint32_t*>(base + P.L.bktMin);
+  W.bktCnt      = reinterpret_cast<uint32_t*>(base + P.L.bktCnt);
+  W.chainNext   = reinterpret_cast<uint32_t*>(base + P.L.chainNext);
+  W.gs          = reinterpret_cast<uint32_t*>(base + P.L.gs);
+  W.orderA      = reinterpret_cast<uint32_t*>(base + P.L.orderA);
+  W.tmpA        = reinterpret_cast<uint32_t*>(base + P.L.tmpA);
+  W.idx         = reinterpret_cast<uint32_t*>(base + P.L.idx);
+  W.low         = reinterpret_cast<uint32_t*>(base + P.L.low);
+  W.wstack      = reinterpret_cast<uint32_t*>(base + P.L.wstack);
+  W.frame       = reinterpret_cast<uint32_t*>(base + P.L.frame);
+  W.ctgSeq      = base + P.L.ctgSeq;
+  W.ctgSets     = reinterpret_cast<uint32_t*>(base + P.L.ctgSets);
+  W.ctgMeta     = reinterpret_cast<CtgMeta*>(base + P.L.ctgMeta);
+
+  const mb200_asm_opts opt     = P.opt;
+  const uint32_t       maxIter = 2 * opt.maxAssemblyCount;  // contigs per word length
+  const uint32_t       ctgBuf  = 2 * P.maxContigLen;        // bytes per contig buffer
+
+  for (;;) {
+    if (tid == 0) shU[0] = atomicAdd(P.lociCounter, 1u);
+    __syncthreads();
+    const uint32_t li = shU[0];
+    __syncthreads();
+    if (li >= P.nLoci) break;
+
+    const uint64_t r0              = P.readOff[li];
+    const uint32_t normalReadCount = (uint32_t)(P.readOff[li + 1] - r0);
+    const uint32_t SW              = (normalReadCount + maxIter + 31) / 32;  // set words of this locus
+    int            status          = MB200_OK;
+
+    // ---------------- pack the normal reads (2 bits/base MSB-first + N mask)
+    if (tid == 0) {
+      uint32_t po = 0, mo = 0;
+      for (uint32_t r = 0; r < normalReadCount; ++r) {
+        const uint32_t len = P.views[r0 + r].len;
+        W.readLen[r]       = len;
+        W.readPackOff[r]   = po;
+        W.readMaskOff[r]   = mo;
+        po += (len + 31) / 32 + 4;
+        mo += (len + 63) / 64 + 3;
+      }
+      shU[1] = po;
+      shU[2] = mo;
+    }
+    __syncthreads();
+    const uint32_t normPackWords = shU[1], normMaskWords = shU[2];
+    bool           badBase       = false;
+    for (uint32_t r = warp; r < normalReadCount; r += nt / 32) {
+      const uint8_t* src = P.pool + P.views[r0 + r].off;
+      const uint32_t len = W.readLen[r];
+      uint64_t*      pk  = W.packed + W.readPackOff[r];
+      uint64_t*      mk  = W.nmask + W.readMaskOff[r];
+      const uint32_t nPk = (len + 31) / 32 + 4, nMk = (len + 63) / 64 + 3;
+      for (uint32_t w = lane; w < nPk; w += 32) {
+        uint64_t v = 0;
+        for (uint32_t b = 0; b < 32; ++b) {
+          const uint32_t i = w * 32 + b;
+          uint32_t       code = 0;
+          if (i < len) {
+            const uint8_t ch = src[i];
+            if (ch == 'A') code = 0;
+            else if (ch == 'C') code = 1;
+            else if (ch == 'G') code = 2;
+            else if (ch == 'T') code = 3;
+            else if (ch != 'N') badBase = true;
+          }
+          v |= (uint64_t)code << (62 - 2 * b);
+        }
+        pk[w] = v;
+      }
+      for (uint32_t w = lane; w < nMk; w += 32) {
+        uint64_t v = 0;
+        for (uint32_t b = 0; b < 64; ++b) {
+          const uint32_t i = w * 64 + b;
+          if (i < len && src[i] != 'A' && src[i] != 'C' && src[i] != 'G' && src[i] != 'T') v |= 1ull << (63 - b);
+        }
+        mk[w] = v;
+      }
+    }
+    if (__syncthreads_or(badBase ? 1 : 0)) status = MB200_ERR_BAD_BASE;
+    if (normalReadCount + maxIter > 32 * MAX_SETW) status = MB200_ERR_UNSUPPORTED;
+
+    uint32_t nReads   = normalReadCount;  // normal + pseudo
+    uint32_t nCtg     = 0;                // contigs of the last buildContigs call
+    uint32_t lastK    = 0;
+
+    if (status == MB200_OK) {
+      for (uint32_t k = opt.minWordLength; k <= opt.maxWordLength; k += opt.wordStepSize) {
+        lastK = k;
+        // ============================ buildContigs(k) ============================
+        // ---- windows
+        if (tid == 0) {
+          uint32_t acc = 0;
+          for (uint32_t r = 0; r < nReads; ++r) {
+            W.winStart[r] = acc;
+            const uint32_t len = W.readLen[r];
+            if (len >= k) acc += len - k + 1;
+          }
+          W.winStart[nReads] = acc;
+          shU[3]             = acc;
+        }
+        __syncthreads();
+        const uint32_t nWin = shU[3];
+        uint32_t       slots = 64;
+        while (slots < 2 * nWin) slots <<= 1;
+        const uint32_t slotMask = slots - 1;
+        for (uint32_t i = tid; i < slots; i += nt) W.slot[i] = 0;
+        for (uint32_t i = tid; i < nWin; i += nt) {
+          W.count[i]     = 0;
+          W.firstRead[i] = NONE32;
+          W.flags[i]     = 0;
+          W.inContig[i]  = 0;
+          W.indeg[i]     = 0;
+          W.key2[i]      = ~0ull;  // invalid window marker (a valid word has key2 < 2^62)
+        }
+        for (uint32_t i = tid; i < nWin * SW; i += nt) W.bits[i] = 0;
+        if (tid == 0) shU[4] = 0;  // nWords
+        __syncthreads();
+
+        // ---- getKmerCounts: keys of all N-free windows, then insertion
+        for (uint32_t r = warp; r < nReads; r += nt / 32) {
+          const uint32_t len = W.readLen[r];
+          if (len < k) continue;
+          const uint64_t* pk = W.packed + W.readPackOff[r];
+          const uint64_t* mk = W.nmask + W.readMaskOff[r];
+          const uint32_t  ws = W.winStart[r];
+          for (uint32_t j = lane; j + k <= len; j += 32) {
+            bool hasN = getBits(mk, j, k < 64 ? k : 64) != 0;
+            if (k > 64) hasN = hasN || (getBits(mk, j + 64, k - 64) != 0);
+            if (hasN) continue;
+            const Key key    = extractKey(pk, j, k);
+            W.key0[ws + j]   = key.k0;
+            W.key1[ws + j]   = key.k1;
+            W.key2[ws + j]   = key.k2;
+          }
+        }
+        __syncthreads();
+        for (uint32_t r = warp; r < nReads; r += nt / 32) {
+          const uint32_t len = W.readLen[r];
+          if (len < k) continue;
+          const uint32_t ws  = W.winStart[r];
+          const uint32_t add = (r >= normalReadCount) ? opt.minCoverage : 1u;  // pseudo reads count minCoverage (:541)
+          for (uint32_t j = lane; j + k <= len; j += 32) {
+            const uint32_t w = ws + j;
+            if (W.key2[w] == ~0ull) continue;
+            const Key key = loadKey(W, w);
+            uint32_t  h   = hashKey(key) & slotMask;
+            uint32_t  owner;
+            for (;;) {
+              uint32_t cur = W.slot[h];
+              if (cur == 0) {
+                cur = atomicCAS(&W.slot[h], 0u, w + 1);
+                if (cur == 0) {
+                  owner = w;
+                  W.wordList[atomicAdd(&shU[4], 1u)] = w;
+                  break;
+                }
+              }
+              if (keyEq(loadKey(W, cur - 1), key)) {
+                owner = cur - 1;
+                break;
+              }
+              h = (h + 1) & slotMask;
+            }
+            const uint32_t bit = 1u << (r & 31);
+            const uint32_t old = atomicOr(&W.bits[(size_t)owner * SW + (r >> 5)], bit);
+            if (!(old & bit)) {
+              atomicAdd(&W.count[owner], add);
+              atomicMin(&W.firstRead[owner], r);
+            }
+          }
+        }
+        __syncthreads();
+        const uint32_t nWords = shU[4];
+
+        // ---- successor / predecessor ids, homopolymer repeats, in-degrees for the trimming pass
+        for (uint32_t i = tid; i < nWords * 4; i += nt) {
+          const uint32_t id  = W.wordList[i >> 2];
+          const uint32_t sym = i & 3;
+          const Key      key = loadKey(W, id);
+          const uint32_t s   = findWord(W, succKey(key, sym, k), slotMask);
+          W.succ[(size_t)id * 4 + sym] = s;
+          W.pred[(size_t)id * 4 + sym] = findWord(W, predKey(key, sym, k), slotMask);
+          if (s == id) {
+            atomicOr(reinterpret_cast<unsigned int*>(W.flags + (id & ~3u)), (unsigned)FLAG_REPEAT << (8 * (id & 3)));
+          } else if (s != NONE32) {
+            atomicAdd(&W.indeg[s], 1u);
+          }
+        }
+        __syncthreads();
+
+        // ---- is there any cycle besides homopolymer self loops?  (Kahn trimming, level synchronous)
+        {
+          uint32_t* queue = W.seqA;  // reuse
+          if (tid == 0) { shU[5] = 0; shU[6] = 0; }
+          __syncthreads();
+          for (uint32_t i = tid; i < nWords; i += nt) {
+            const uint32_t id = W.wordList[i];
+            if (W.indeg[id] == 0) queue[atomicAdd(&shU[5], 1u)] = id;
+          }
+          __syncthreads();
+          uint32_t head = 0;
+          for (;;) {
+            const uint32_t tail = shU[5];
+            if (head == tail) break;
+            __syncthreads();
+            for (uint32_t i = head + tid; i < tail; i += nt) {
+              const uint32_t id = queue[i];
+              const uint4    sc = *reinterpret_cast<const uint4*>(W.succ + (size_t)id * 4);
+              const uint32_t ss[4] = {sc.x, sc.y, sc.z, sc.w};
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                const uint32_t nx = ss[s];
+                if (nx == NONE32 || nx == id) continue;
+                if (atomicSub(&W.indeg[nx], 1u) == 1u) queue[atomicAdd(&shU[5], 1u)] = nx;
+              }
+            }
+            head = tail;
+            __syncthreads();
+          }
+          // shU[5] == number of peeled words
+        }
+        const bool hasCycle = (shU[5] != nWords);
+        __syncthreads();
+
+        if (hasCycle) {
+          // ================= exact replay of getRepeatKmers (hash-order DFS roots) =================
+          // (a) wordCount insertion order: by first read, then lexicographically inside the read
+          uint32_t* bucketStart = W.tmpA;   // [nReads+1]
+          uint32_t* members     = W.orderA; // words grouped by first read (unordered inside the group)
+          for (uint32_t r = tid; r <= nReads; r += nt) W.gs[r] = 0;
+          __syncthreads();
+          for (uint32_t i = tid; i < nWords; i += nt) atomicAdd(&W.gs[W.firstRead[W.wordList[i]]], 1u);
+          __syncthreads();
+          if (tid == 0) {
+            uint32_t acc = 0;
+            for (uint32_t r = 0; r < nReads; ++r) {
+              bucketStart[r] = acc;
+              acc += W.gs[r];
+              W.gs[r] = 0;
+            }
+            bucketStart[nReads] = acc;
+          }
+          __syncthreads();
+          for (uint32_t i = tid; i < nWords; i += nt) {
+            const uint32_t id = W.wordList[i];
+            const uint32_t r  = W.firstRead[id];
+            members[bucketStart[r] + atomicAdd(&W.gs[r], 1u)] = id;
+          }
+          __syncthreads();
+          for (uint32_t i = tid; i < nWords; i += nt) {
+            const uint32_t id  = W.wordList[i];
+            const uint32_t r   = W.firstRead[id];
+            const Key      key = loadKey(W, id);
+            uint32_t       rank = 0;
+            for (uint32_t m = bucketStart[r]; m < bucketStart[r + 1]; ++m)
+              if (keyLess(loadKey(W, members[m]), key)) rank++;
+            const uint32_t p = bucketStart[r] + rank;
+            W.seqA[p]        = id;                 // insertion sequence of wordCount
+            W.hashv[p]       = stlHashWord(key, k);
+          }
+          __syncthreads();
+          // (b) iteration order of wordCount, then of wordIndices (filled while iterating wordCount)
+          uint32_t* order1 = W.idx;  // temporarily
+          unorderedOrder(W, W.hashv, nWords, order1, sh);
+          uint64_t* hash2 = reinterpret_cast<uint64_t*>(W.key0) + 0;  // cannot alias keys: use frame+wstack area
+          hash2           = reinterpret_cast<uint64_t*>(W.wstack);     // wstack+frame are contiguous uint32[nWin] x2
+          for (uint32_t i = tid; i < nWords; i += nt) hash2[i] = W.hashv[order1[i]];
+          __syncthreads();
+          uint32_t* order2 = W.low;
+          unorderedOrder(W, hash2, nWords, order2, sh);
+          // root sequence: word id of the i-th element of wordIndices
+          for (uint32_t i = tid; i < nWords; i += nt) W.chainNext[i] = W.seqA[order1[order2[i]]];
+          __syncthreads();
+          for (uint32_t i = tid; i < nWords; i += nt) {
+            const uint32_t id = W.wordList[i];
+            W.idx[id] = 0;
+            W.low[id] = 0;
+          }
+          __syncthreads();
+          // (c) searchRepeats, recursion unrolled (one thread; the DFS order is inherently sequential)
+          if (tid == 0) {
+            const uint32_t* roots  = W.chainNext;
+            uint32_t        index  = 1;
+            uint32_t        nStack = 0;
+            for (uint32_t ri = 0; ri < nWords; ++ri) {
+              const uint32_t root = roots[ri];
+              if (W.idx[root] != 0) continue;
+              uint32_t depth = 1;
+              W.frame[0]     = root << 3;  // (word << 3) | next symbol
+              W.idx[root] = W.low[root] = index++;
+              W.wstack[nStack++]        = root;
+              W.flags[root] |= FLAG_ONSTACK;
+              while (depth) {
+                const uint32_t fr  = W.frame[depth - 1];
+                const uint32_t w   = fr >> 3;
+                const uint32_t sym = fr & 7;
+                if (sym < 4) {
+                  W.frame[depth - 1] = fr + 1;
+                  const uint32_t nw  = W.succ[(size_t)w * 4 + sym];
+                  if (nw == w) continue;  // homopolymer: already marked
+                  if (nw == NONE32) continue;
+                  if (W.idx[nw] == 0) {
+                    W.frame[depth++] = nw << 3;
+                    W.idx[nw] = W.low[nw] = index++;
+                    W.wstack[nStack++]    = nw;
+                    W.flags[nw] |= FLAG_ONSTACK;
+                  } else if (W.flags[nw] & FLAG_ONSTACK) {
+                    if (W.idx[nw] < W.low[w]) W.low[w] = W.idx[nw];
+                  }
+                } else {
+                  if (W.low[w] == W.idx[w]) {
+                    const uint32_t lastWord = W.wstack[nStack - 1];
+                    if (lastWord == w) {
+                      nStack--;
+                      W.flags[w] &= ~FLAG_ONSTACK;
+                    } else {
+                      const bool isSmallCircle = (W.idx[lastWord] - W.idx[w]) <= 50;
+                      for (;;) {
+                        const uint32_t rw = W.wstack[--nStack];
+                        W.flags[rw] &= ~FLAG_ONSTACK;
+                        if (isSmallCircle) W.flags[rw] |= FLAG_REPEAT;
+                        if (rw == w) break;
+                      }
+                    }
+                  }
+                  depth--;
+                  if (depth) {
+                    const uint32_t parent = W.frame[depth - 1] >> 3;
+                    if (W.low[w] < W.low[parent]) W.low[parent] = W.low[w];
+                  }
+                }
+              }
+            }
+          }
+          __syncthreads();
+        }
+
+        // ---- unusedWords = {count >= minCoverage}
+        for (uint32_t i = tid; i < nWords; i += nt) {
+          const uint32_t id = W.wordList[i];
+          if (W.count[id] >= opt.minCoverage) W.flags[id] |= FLAG_UNUSED;
+        }
+        __syncthreads();
+
+        // ---- contig loop (:685-716)
+        bool isAssemblySuccess = true;
+        nCtg                   = 0;
+        while (nCtg < maxIter) {
+          // seed: max count, ties -> lexicographically smallest word (first in the std::set scan, :686-696)
+          unsigned long long bestCnt = 0;  // (count << 32) | has
+          Key                bestKey = {~0ull, ~0ull, ~0ull};
+          uint32_t           bestId  = NONE32;
+          for (uint32_t i = tid; i < nWords; i += nt) {
+            const uint32_t id = W.wordList[i];
+            if (!(W.flags[id] & FLAG_UNUSED)) continue;
+            const uint32_t c   = W.count[id];
+            const Key      key = loadKey(W, id);
+            if (bestId == NONE32 || c > (uint32_t)bestCnt || (c == (uint32_t)bestCnt && keyLess(key, bestKey))) {
+              bestCnt = c;
+              bestKey = key;
+              bestId  = id;
+            }
+          }
+          // warp reduce then block reduce (4 warps)
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const uint32_t oc  = __shfl_xor_sync(0xffffffffu, (uint32_t)bestCnt, off);
+            const uint32_t oid = __shfl_xor_sync(0xffffffffu, bestId, off);
+            Key            ok;
+            ok.k0 = __shfl_xor_sync(0xffffffffu, bestKey.k0, off);
+            ok.k1 = __shfl_xor_sync(0xffffffffu, bestKey.k1, off);
+            ok.k2 = __shfl_xor_sync(0xffffffffu, bestKey.k2, off);
+            if (oid != NONE32 && (bestId == NONE32 || oc > (uint32_t)bestCnt || (oc == (uint32_t)bestCnt && keyLess(ok, bestKey)))) {
+              bestCnt = oc;
+              bestKey = ok;
+              bestId  = oid;
+            }
+          }
+          if (lane == 0) {
+            sh[warp * 8 + 0] = bestId;
+            sh[warp * 8 + 1] = (uint32_t)bestCnt;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            uint32_t bid = NONE32, bc = 0;
+            Key      bk  = {0, 0, 0};
+            for (uint32_t w = 0; w < nt / 32; ++w) {
+              const uint32_t id = sh[w * 8 + 0];
+              if (id == NONE32) continue;
+              const uint32_t c  = sh[w * 8 + 1];
+              const Key      kk = loadKey(W, id);
+              if (bid == NONE32 || c > bc || (c == bc && keyLess(kk, bk))) {
+                bid = id;
+                bc  = c;
+                bk  = kk;
+              }
+            }
+            shU[7] = bid;
+          }
+          __syncthreads();
+          const uint32_t seed = shU[7];
+          __syncthreads();
+          if (seed == NONE32) break;  // unusedWords.empty()
+
+          // ---------------- walk(seed)  (warp 0; IterativeAssembler.cpp:149-501)
+          if (warp == 0) {
+            uint8_t*       seq     = W.ctgSeq + (size_t)nCtg * ctgBuf;
+            uint32_t*      sets    = W.ctgSets + (size_t)nCtg * 2 * MAX_SETW;
+            const uint32_t serial  = nCtg + 1;
+            const Key      seedKey = loadKey(W, seed);
+            uint32_t       lo = P.maxContigLen - k / 2, hi;
+            hi = lo + k;
+            for (uint32_t i = lane; i < k; i += 32) seq[lo + i] = "ACGT"[baseAt(seedKey, i, k)];
+            uint32_t support = (lane < SW) ? W.bits[(size_t)seed * SW + lane] : 0u;
+            uint32_t reject  = 0;
+            if (lane == 0) W.flags[seed] &= ~FLAG_UNUSED;
+            int  consBegin = 0, consEnd = 0;
+            bool isRepeatFound = false;
+            bool overflow      = false;
+            if (W.flags[seed] & FLAG_REPEAT) {
+              consBegin     = 0;
+              consEnd       = (int)k;
+              isRepeatFound = true;
+            } else {
+              if (lane == 0) W.inContig[seed] = (uint8_t)serial;
+              // rejecting reads from the seed's sibling words (same k-1 prefix)  :185-210
+              {
+                const uint32_t lastSym = (uint32_t)seedKey.k0 & 3u;
+                Key            trunkK  = seedKey;
+                trunkK.k0 &= ~3ull;
+                for (uint32_t s = 0; s < 4; ++s) {
+                  if (s == lastSym) continue;
+                  Key kk = trunkK;
+                  kk.k0 |= s;
+                  const uint32_t id = findWord(W, kk, slotMask);
+                  if (id == NONE32) continue;
+                  if (lane < SW) reject |= W.bits[(size_t)id * SW + lane];
+                }
+              }
+              __syncwarp();
+              uint32_t curWord = seed;
+              for (int mode = 0; mode < 2; ++mode) {
+                const bool isEnd = (mode == 0);
+                uint32_t   conservativeEndOffset = 0;
+                curWord = seed;  // mode 0: last word of the contig == seed; mode 1: first word == seed
+                for (;;) {
+                  const uint4 cand4 = *reinterpret_cast<const uint4*>((isEnd ? W.succ : W.pred) + (size_t)curWord * 4);
+                  const uint32_t cand[4] = {cand4.x, cand4.y, cand4.z, cand4.w};
+                  uint32_t maxBaseCount = 0, maxCnt = 0, maxBase = 0, maxWord = NONE32;
+                  uint32_t maxW = 0, maxCW = 0, sup2Remove = 0, rej2Add = 0;
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) {
+                    const uint32_t id = cand[s];
+                    if (id == NONE32) continue;
+                    const uint32_t cw         = (lane < SW) ? W.bits[(size_t)id * SW + lane] : 0u;
+                    const uint32_t contigWord = support & cw;
+                    const uint32_t shared     = maxCW & cw;
+                    if (!__any_sync(0xffffffffu, contigWord != 0)) continue;
+                    const uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(contigWord));
+                    if (c > maxCnt) {
+                      sup2Remove |= maxCW & ~shared;
+                      rej2Add |= maxW & ~shared;
+                      maxW         = cw;
+                      maxCnt       = c;
+                      maxCW        = contigWord;
+                      maxBaseCount = W.count[id];
+                      maxBase      = (uint32_t)s;
+                      maxWord      = id;
+                    } else {
+                      sup2Remove |= contigWord & ~shared;
+                      rej2Add |= cw & ~shared;
+                    }
+                  }
+                  if (maxBaseCount < opt.minCoverage) break;
+                  if (W.inContig[maxWord] == (uint8_t)serial) {
+                    isRepeatFound = true;
+                    break;
+                  }
+                  // walk backwards one step at the branching point (:375-427); previousWordReads is always empty
+                  if (__any_sync(0xffffffffu, maxW != 0)) {
+                    const Key      curKey = loadKey(W, curWord);
+                    const uint32_t tmpSym = isEnd ? baseAt(curKey, 0, k) : ((uint32_t)curKey.k0 & 3u);
+                    const uint4 alt4 = *reinterpret_cast<const uint4*>((isEnd ? W.pred : W.succ) + (size_t)maxWord * 4);
+                    const uint32_t alt[4] = {alt4.x, alt4.y, alt4.z, alt4.w};
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                      if ((uint32_t)s == tmpSym) continue;
+                      const uint32_t id = alt[s];
+                      if (id == NONE32 || id == maxWord) continue;
+                      const uint32_t back     = (lane < SW) ? W.bits[(size_t)id * SW + lane] : 0u;
+                      const uint32_t toUpdate = back & ~(maxCW & back);
+                      rej2Add |= toUpdate;
+                      sup2Remove |= toUpdate;
+                    }
+                  }
+                  // contig.seq = addBase(contig.seq, maxBase, isEnd)
+                  if (hi - lo + 1 > P.maxContigLen || lo == 0 || hi + 1 >= ctgBuf) {
+                    overflow = true;
+                    break;
+                  }
+                  if (lane == 0) {
+                    if (isEnd) seq[hi] = "ACGT"[maxBase];
+                    else seq[lo - 1] = "ACGT"[maxBase];
+                  }
+                  if (isEnd) hi++; else lo--;
+                  if ((conservativeEndOffset != 0) || (maxBaseCount < opt.minConservativeCoverage)) conservativeEndOffset += 1;
+                  reject |= rej2Add;
+                  support |= maxW & ~reject;
+                  support &= ~sup2Remove;
+                  if (lane == 0) {
+                    W.flags[maxWord] &= ~FLAG_UNUSED;
+                    W.inContig[maxWord] = (uint8_t)serial;
+                  }
+                  __syncwarp();
+                  curWord = maxWord;
+                }
+                if (mode == 0) consEnd = (int)conservativeEndOffset;
+                else consBegin = (int)conservativeEndOffset;
+              }
+              consEnd = (int)(hi - lo) - consEnd;
+            }
+            if (lane < MAX_SETW) {
+              sets[lane]            = support;
+              sets[MAX_SETW + lane] = reject;
+            }
+            if (lane == 0) {
+              CtgMeta m;
+              m.lo = lo; m.hi = hi; m.consBegin = consBegin; m.consEnd = consEnd;
+              W.ctgMeta[nCtg] = m;
+              shU[8]          = isRepeatFound ? 1u : 0u;
+              shU[9]          = overflow ? 1u : 0u;
+            }
+          }
+          __syncthreads();
+          if (shU[8]) isAssemblySuccess = false;
+          if (shU[9]) status = MB200_ERR_ASM_OVERFLOW;
+          nCtg++;
+          __syncthreads();
+          if (status != MB200_OK) break;
+        }
+        if (status != MB200_OK) break;
+        if (isAssemblySuccess) break;
+
+        // ---- pseudo reads for the next word length (:882-910): contigs longer than k + step
+        if (tid == 0) {
+          uint32_t po = normPackWords, mo = normMaskWords, nr = normalReadCount;
+          for (uint32_t c = 0; c < nCtg; ++c) {
+            const uint32_t len = W.ctgMeta[c].hi - W.ctgMeta[c].lo;
+            if (len > k + opt.wordStepSize) {
+              W.readLen[nr]     = len;
+              W.readPackOff[nr] = po;
+              W.readMaskOff[nr] = mo;
+              W.tmpA[nr]        = c;  // source contig
+              po += (len + 31) / 32 + 4;
+              mo += (len + 63) / 64 + 3;
+              nr++;
+            }
+          }
+          shU[10] = nr;
+        }
+        __syncthreads();
+        nReads = shU[10];
+        for (uint32_t r = normalReadCount + warp; r < nReads; r += nt / 32) {
+          const uint32_t c   = W.tmpA[r];
+          const uint8_t* src = W.ctgSeq + (size_t)c * ctgBuf + W.ctgMeta[c].lo;
+          const uint32_t len = W.readLen[r];
+          uint64_t*      pk  = W.packed + W.readPackOff[r];
+          uint64_t*      mk  = W.nmask + W.readMaskOff[r];
+          const uint32_t nPk = (len + 31) / 32 + 4, nMk = (len + 63) / 64 + 3;
+          for (uint32_t w = lane; w < nPk; w += 32) {
+            uint64_t v = 0;
+            for (uint32_t b = 0; b < 32; ++b) {
+              const uint32_t i = w * 32 + b;
+              uint32_t       code = 0;
+              if (i < len) {
+                const uint8_t ch = src[i];
+                code = (ch == 'C') ? 1 : (ch == 'G' ? 2 : (ch == 'T' ? 3 : 0));
+              }
+              v |= (uint64_t)code << (62 - 2 * b);
+            }
+            pk[w] = v;
+          }
+          for (uint32_t w = lane; w < nMk; w += 32) mk[w] = 0;
+        }
+        __syncthreads();
+        // NB: the pseudo reads must be packed from the contig buffers BEFORE the next buildContigs overwrites
+        // them; the copies used for the output (below) are taken from the packed form.
+      }
+    }
+
+    // ================= selectContigs (:722-842) + output (warp 0) =================
+    if (warp == 0) {
+      mb200_asm_locus Lo;
+      memset(&Lo, 0, sizeof(Lo));
+      Lo.firstContig    = li * opt.maxAssemblyCount;
+      Lo.firstPseudo    = li * maxIter;
+      Lo.setWords       = SW;
+      Lo.lastWordLength = lastK;
+      Lo.status         = status;
+      if (status == MB200_OK) {
+        uint32_t usedReads = 0, usedPseudo = 0;  // lane-wise words of the two std::set<unsigned>
+        uint32_t aliveMask = (nCtg >= 32) ? 0xffffffffu : ((1u << nCtg) - 1);  // nCtg <= 2*maxAssemblyCount <= 32
+        uint32_t nSel      = 0;
+        uint32_t selected[1];
+        (void)selected;
+        // pseudo-read membership mask of my word: read index >= normalReadCount
+        uint32_t pseudoMask;
+        {
+          const uint32_t lo = lane * 32;
+          if (normalReadCount <= lo) pseudoMask = 0xffffffffu;
+          else if (normalReadCount >= lo + 32) pseudoMask = 0;
+          else pseudoMask = ~((1u << (normalReadCount - lo)) - 1);
+        }
+        // output bookkeeping gathered in shared memory by lane 0
+        uint32_t outBytes = 0;
+        while (aliveMask && nSel < opt.maxAssemblyCount) {
+          const uint32_t usedNormal   = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(usedReads)) -
+                                      __reduce_add_sync(0xffffffffu, (uint32_t)__popc(usedPseudo));
+          const uint32_t unusedNormal = normalReadCount - usedNormal;
+          if (unusedNormal < opt.minUnusedReads) break;
+          int      sel = -1;
+          uint32_t maxSupport = 0, maxLength = 0, removeMask = 0;
+          for (uint32_t c = 0; c < nCtg; ++c) {
+            if (!((aliveMask >> c) & 1)) continue;
+            const uint32_t sup    = W.ctgSets[(size_t)c * 2 * MAX_SETW + lane];
+            const uint32_t newSup = sup & ~usedReads;
+            const uint32_t newNormal = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(newSup & ~pseudoMask));
+            if (newNormal < opt.minSupportReads) {
+              removeMask |= 1u << c;
+              continue;
+            }
+            const uint32_t curSup = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(newSup));
+            const uint32_t curLen = W.ctgMeta[c].hi - W.ctgMeta[c].lo;
+            if (curSup > maxSupport || (curSup == maxSupport && curLen > maxLength)) {
+              sel        = (int)c;
+              maxSupport = curSup;
+              maxLength  = curLen;
+            }
+          }
+          if (maxSupport == 0) break;
+          // emit the selected contig
+          {
+            const uint32_t c   = (uint32_t)sel;
+            const CtgMeta  m   = W.ctgMeta[c];
+            const uint32_t len = m.hi - m.lo;
+            unsigned long long off = 0, soff = 0;
+            if (lane == 0) {
+              off  = atomicAdd(P.contigPoolUsed, (unsigned long long)len);
+              soff = atomicAdd(P.setPoolUsed, (unsigned long long)(2 * SW));
+            }
+            off  = __shfl_sync(0xffffffffu, off, 0);
+            soff = __shfl_sync(0xffffffffu, soff, 0);
+            const uint8_t* src = W.ctgSeq + (size_t)c * ctgBuf + m.lo;
+            if (off + len <= P.contigPoolCap)
+              for (uint32_t i = lane; i < len; i += 32) P.contigPool[off + i] = src[i];
+            if (soff + 2 * SW <= P.setPoolCap && lane < SW) {
+              P.setPool[soff + lane]      = W.ctgSets[(size_t)c * 2 * MAX_SETW + lane];
+              P.setPool[soff + SW + lane] = W.ctgSets[(size_t)c * 2 * MAX_SETW + MAX_SETW + lane];
+            }
+            if (lane == 0) {
+              mb200_contig o;
+              o.seqOff = off; o.seqLen = len; o.seedReadCount = 0;
+              o.conservativeBegin = m.consBegin; o.conservativeEnd = m.consEnd;
+              o.supportOff = soff; o.rejectOff = soff + SW;
+              P.contigs[(size_t)Lo.firstContig + nSel] = o;
+            }
+            outBytes += len;
+            const uint32_t sup = W.ctgSets[(size_t)c * 2 * MAX_SETW + lane];
+            usedReads |= sup;
+            usedPseudo |= sup & pseudoMask;
+            removeMask |= 1u << c;
+          }
+          aliveMask &= ~removeMask;
+          nSel++;
+        }
+        (void)outBytes;
+        Lo.nContigs = nSel;
+        // pseudo reads appended to the caller's read list (from the packed copies)
+        Lo.nPseudo = nReads - normalReadCount;
+        for (uint32_t r = normalReadCount; r < nReads; ++r) {
+          const uint32_t     len = W.readLen[r];
+          unsigned long long off = 0;
+          if (lane == 0) off = atomicAdd(P.contigPoolUsed, (unsigned long long)len);
+          off = __shfl_sync(0xffffffffu, off, 0);
+          const uint64_t* pk = W.packed + W.readPackOff[r];
+          if (off + len <= P.contigPoolCap)
+            for (uint32_t i = lane; i < len; i += 32)
+              P.contigPool[off + i] = "ACGT"[(pk[i >> 5] >> (62 - 2 * (i & 31))) & 3];
+          if (lane == 0) {
+            mb200_seqview v;
+            v.off = off; v.len = len; v.reserved = 0;
+            P.pseudo[(size_t)Lo.firstPseudo + (r - normalReadCount)] = v;
+          }
+        }
+      } else if (lane == 0) {
+        atomicCAS(P.errFlag, 0, status);
+      }
+      if (lane == 0) P.loci[li] = Lo;
+    }
+    __syncthreads();
+  }
+}
+
+size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci,
+                                    const uint64_t* readOff, const mb200_seqview* readViews, const uint8_t* pool,
+                                    uint64_t poolBytes, mb200_asm_locus* loci, mb200_contig* contigs,
+                                    uint64_t contigCap, mb200_seqview* pseudoReads, uint64_t pseudoCap,
+                                    uint8_t* contigPool, uint64_t contigPoolCap, uint32_t* setPool,
+                                    uint64_t setPoolCap)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (!opts || (nLoci && (!readOff || !loci || !contigs || !pseudoReads || !contigPool || !setPool)))
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  if (opts->minCoverage < 1 || opts->wordStepSize < 1 || opts->minWordLength < 2 || opts->maxWordLength > 96 ||
+      opts->maxAssemblyCount < 1 || opts->maxAssemblyCount > 16)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "assembler options outside the supported range (k in [2,96], maxAssemblyCount in [1,16])");
+  ctx->timing = mb200_timing();
+  if (nLoci == 0) return MB200_OK;
+  if (contigCap < (uint64_t)nLoci * opts->maxAssemblyCount || pseudoCap < (uint64_t)nLoci * 2 * opts->maxAssemblyCount)
+    return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "contig / pseudo-read record arrays too small");
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+
+  const uint64_t nReadsTotal = readOff[nLoci];
+  if (nReadsTotal && (!readViews || !pool)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  const uint32_t A            = opts->maxAssemblyCount;
+  const uint32_t maxContigLen = ctx->cfg.maxContigLen ? ctx->cfg.maxContigLen : 2048;
+  uint32_t       maxReads = 0, maxPackWords = 0, maxMaskWords = 0;
+  uint64_t       maxWin = 0;
+  for (uint32_t li = 0; li < nLoci; ++li) {
+    const uint64_t a = readOff[li], b = readOff[li + 1];
+    if (b < a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "readOff not monotone");
+    uint64_t win = 0, pw = 0, mw = 0;
+    for (uint64_t r = a; r < b; ++r) {
+      const uint32_t len = readViews[r].len;
+      if (readViews[r].off + len > poolBytes) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "read view outside the pool");
+      if (len >= opts->minWordLength) win += len - opts->minWordLength + 1;
+      pw += (len + 31) / 32 + 4;
+      mw += (len + 63) / 64 + 3;
+      ctx->timing.algoBytes += len;
+      ctx->timing.cells += (len >= opts->minWordLength) ? (len - opts->minWordLength + 1) : 0;
+    }
+    if (b - a + 2 * A > 1024) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "more than 1024 reads (incl. pseudo reads) in one locus");
+    maxReads     = std::max<uint32_t>(maxReads, (uint32_t)(b - a));
+    maxWin       = std::max<uint64_t>(maxWin, win);
+    maxPackWords = std::max<uint32_t>(maxPackWords, (uint32_t)pw);
+    maxMaskWords = std::max<uint32_t>(maxMaskWords, (uint32_t)mw);
+  }
+  // ---- workspace layout (per CTA)
+  WorkLayout L;
+  memset(&L, 0, sizeof(L));
+  L.maxReads  = maxReads + 2 * A;
+  const uint64_t nWinMax64 = maxWin + (uint64_t)2 * A * maxContigLen;
+  if (nWinMax64 > 0x3fffffffull) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "locus too large");
+  L.nWinMax   = (uint32_t)nWinMax64 + 64;
+  L.slotsMax  = 64;
+  while (L.slotsMax < 2 * L.nWinMax) L.slotsMax <<= 1;
+  L.packWords = maxPackWords + 2 * A * ((maxContigLen + 31) / 32 + 4) + 8;
+  L.maskWords = maxMaskWords + 2 * A * ((maxContigLen + 63) / 64 + 3) + 8;
+  L.bktMax    = 3 * L.nWinMax + 64;
+  size_t off = 0;
+  auto   put = [&](size_t& field, size_t bytes) {
+    field = off;
+    off   = alignUp(off + bytes, 256);
+  };
+  const size_t NW = L.nWinMax;
+  put(L.readLen, 4 * (size_t)(L.maxReads + 1));
+  put(L.readPackOff, 4 * (size_t)(L.maxReads + 1));
+  put(L.readMaskOff, 4 * (size_t)(L.maxReads + 1));
+  put(L.winStart, 4 * (size_t)(L.maxReads + 2));
+  put(L.packed, 8 * (size_t)L.packWords);
+  put(L.nmask, 8 * (size_t)L.maskWords);
+  put(L.key0, 8 * NW);
+  put(L.key1, 8 * NW);
+  put(L.key2, 8 * NW);
+  put(L.count, 4 * NW);
+  put(L.firstRead, 4 * NW);
+  put(L.bits, 4 * NW * (size_t)((L.maxReads + 31) / 32));
+  put(L.slot, 4 * (size_t)L.slotsMax);
+  put(L.wordList, 4 * NW);
+  put(L.succ, 16 * NW);
+  put(L.pred, 16 * NW);
+  put(L.indeg, 4 * NW);
+  put(L.flags, NW + 8);
+  put(L.inContig, NW + 8);
+  put(L.hashv, 8 * NW);
+  put(L.seqA, 4 * NW);
+  put(L.arr, 4 * NW);
+  put(L.pos, 4 * NW);
+  put(L.bktHead, 4 * (size_t)L.bktMax);
+  put(L.bktMin, 4 * (size_t)L.bktMax);
+  put(L.bktCnt, 4 * (size_t)L.bktMax);
+  put(L.chainNext, 4 * NW);
+  put(L.gs, 4 * (NW + L.maxReads + 2));
+  put(L.orderA, 4 * NW);
+  put(L.tmpA, 4 * (NW + L.maxReads + 2));
+  put(L.idx, 4 * NW);
+  put(L.low, 4 * NW);
+  // wstack and frame are contiguous: together they double as a uint64[nWin] scratch (hash2)
+  L.wstack = off;
+  off += 4 * NW;
+  L.frame = off;
+  off     = alignUp(off + 4 * NW, 256);
+  put(L.ctgSeq, (size_t)2 * A * 2 * maxContigLen);
+  put(L.ctgSets, 4 * (size_t)2 * A * 2 * MAX_SETW);
+  put(L.ctgMeta, sizeof(CtgMeta) * (size_t)2 * A);
+  L.total = alignUp(off, 256);
+
+  int ctasPerSm = 0;
+  MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, assembleKernel, ASM_THREADS, 0));
+  if (ctasPerSm < 1) ctasPerSm = 1;
+  if (ctasPerSm > 8) ctasPerSm = 8;
+  if (ctx->cfg.ctasPerSm && (int)ctx->cfg.ctasPerSm < ctasPerSm) ctasPerSm = (int)ctx->cfg.ctasPerSm;
+  uint32_t grid = (uint32_t)(ctx->smCount * ctasPerSm);
+  if (grid > nLoci) grid = nLoci;
+  const size_t budget = ctx->cfg.scratchBytes ? (size_t)ctx->cfg.scratchBytes : ((size_t)48 << 30);
+  while (grid > 1 && (size_t)grid * L.total > budget) grid = (grid + 1) / 2;
+
+  int rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmWork, (size_t)grid * L.total)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dPool, poolBytes + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dReadOff, 8 * (size_t)(nLoci + 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dViews, sizeof(mb200_seqview) * (size_t)(nReadsTotal + 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut0, sizeof(mb200_asm_locus) * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut1, sizeof(mb200_contig) * (size_t)nLoci * A)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut2, sizeof(mb200_seqview) * (size_t)nLoci * 2 * A)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut3, contigPoolCap + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut4, 4 * (size_t)setPoolCap + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dMisc, 256)) != MB200_OK) return rc;
+
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dMisc.ptr, 0, 256, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dPool.ptr, pool, poolBytes, cudaMemcpyHostToDevice, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dReadOff.ptr, readOff, 8 * (size_t)(nLoci + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (nReadsTotal)
+    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dViews.ptr, readViews, sizeof(mb200_seqview) * (size_t)nReadsTotal, cudaMemcpyHostToDevice, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAsmOut1.ptr, 0, sizeof(mb200_contig) * (size_t)nLoci * A, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAsmOut2.ptr, 0, sizeof(mb200_seqview) * (size_t)nLoci * 2 * A, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+
+  AsmParams P;
+  P.opt          = *opts;
+  P.pool         = reinterpret_cast<const uint8_t*>(ctx->dPool.ptr);
+  P.readOff      = reinterpret_cast<const uint64_t*>(ctx->dReadOff.ptr);
+  P.views        = reinterpret_cast<const mb200_seqview*>(ctx->dViews.ptr);
+  P.nLoci        = nLoci;
+  uint32_t* misc = reinterpret_cast<uint32_t*>(ctx->dMisc.ptr);
+  P.lociCounter  = misc + 0;
+  P.errFlag      = reinterpret_cast<int*>(misc + 4);
+  P.contigPoolUsed = reinterpret_cast<unsigned long long*>(misc + 8);
+  P.setPoolUsed    = reinterpret_cast<unsigned long long*>(misc + 10);
+  P.work         = reinterpret_cast<uint8_t*>(ctx->dAsmWork.ptr);
+  P.L            = L;
+  P.maxContigLen = maxContigLen;
+  P.loci         = reinterpret_cast<mb200_asm_locus*>(ctx->dAsmOut0.ptr);
+  P.contigs      = reinterpret_cast<mb200_contig*>(ctx->dAsmOut1.ptr);
+  P.pseudo       = reinterpret_cast<mb200_seqview*>(ctx->dAsmOut2.ptr);
+  P.contigPool   = reinterpret_cast<uint8_t*>(ctx->dAsmOut3.ptr);
+  P.contigPoolCap = contigPoolCap;
+  P.setPool      = reinterpret_cast<uint32_t*>(ctx->dAsmOut4.ptr);
+  P.setPoolCap   = setPoolCap;
+  assembleKernel<<<grid, ASM_THREADS, 0, ctx->stream>>>(P);
+  MB200_CUDA_CHECK(ctx, cudaGetLastError());
+  ctx->timing.launches = 1;
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+
+  uint32_t hMisc[16];
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(hMisc, ctx->dMisc.ptr, sizeof(hMisc), cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(loci, ctx->dAsmOut0.ptr, sizeof(mb200_asm_locus) * (size_t)nLoci, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(contigs, ctx->dAsmOut1.ptr, sizeof(mb200_contig) * (size_t)nLoci * A, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(pseudoReads, ctx->dAsmOut2.ptr, sizeof(mb200_seqview) * (size_t)nLoci * 2 * A, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned long long usedBytes, usedSets;
+  memcpy(&usedBytes, hMisc + 8, 8);
+  memcpy(&usedSets, hMisc + 10, 8);
+  if (hMisc[4] != 0) return mb200_fail(ctx, (int)hMisc[4], "assembler: a locus failed (bad base / workspace overflow / too many reads)");
+  if (usedBytes > contigPoolCap || usedSets > setPoolCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "assembler output pools too small");
+  if (usedBytes) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(contigPool, ctx->dAsmOut3.ptr, usedBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (usedSets) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(setPool, ctx->dAsmOut4.ptr, 4 * usedSets, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->timing.h2dMs, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->timing.kernelMs, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->timing.d2hMs, ctx->ev[2], ctx->ev[3]);
+  return MB200_OK;
+}
