@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric on BASELINE.json configs[1].
+
+  metric   : SV candidates assembled+aligned per second (one candidate = one SVCandidate junction entering
+             getCandidateAssemblyData, GSC/SVCandidateProcessor.cpp:310: its reads assembled over all word lengths
+             and every resulting contig aligned).
+  workload : synthetic 50 000 candidate loci x 64 reads x 150 bp, assembly k=41..76 + contig-vs-5 kb-window DP
+             (manta_b200.synth.make_candidate_batch), per GPU (weak scaling).
+  step     : one pass of the hot path over one batch.
+  value    : inputs resident in HBM when the timed region starts (mb200_candidates_run), results back on the host.
+  e2e      : the same through the public C-ABI call sequence with HOST (pinned) buffers: upload + run + download.
+  --impl reference : the reference's own CPU implementation of the same path (oracle/_ref = the unmodified
+             reference sources compiled by oracle/build_ref.sh; the C port oracle/_build if that is absent), all
+             host threads, on a bounded sample of the same workload.
+
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from manta_b200 import _cabi as cb  # noqa: E402
+from manta_b200 import synth  # noqa: E402
+
+METRIC = "sv_candidates_assembled_aligned_per_sec"
+UNIT = "candidates/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation of the path, all host threads
+def load_cpu_checker():
+    ref = os.path.join(ROOT, "oracle", "_ref", "libmanta_ref.so")
+    if os.path.exists(ref):
+        return cb.Binding(C.CDLL(ref), "ref_"), "reference"
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    return cb.Binding(C.CDLL(os.path.join(ROOT, "oracle", "_build", "libmanta_oracle.so")), "orc_"), "port"
+
+
+def cpu_candidates(binding, batch, lo, hi, opts):
+    """assemble + align every contig of loci [lo, hi) on one host thread; returns number of candidates done"""
+    asm_opts = np.zeros(1, dtype=cb.ASM_OPTS_DT)
+    asm_opts[0] = opts["asmOpts"][0]
+    rpl = batch.readsPerLocus
+    readOff = (batch.readOff[lo:hi + 1] - batch.readOff[lo]).astype(np.uint64)
+    views = batch.readViews[lo * rpl:hi * rpl]
+    loci, contigs, pseudo, cpool, spool = binding.assemble_raw(asm_opts, readOff, views, batch.pool)
+    # contig sequences are appended to a private pool so that the aligners see (contig, reference) views
+    n = hi - lo
+    qv, r1v, r2v, jq, jr1, jr2 = [], [], [], [], [], []
+    # private pool of this chunk: [reference windows of loci lo..hi) | contigs]
+    r1o, r1l = batch.ref1["off"][lo:hi].astype(np.int64), batch.ref1["len"][lo:hi].astype(np.int64)
+    r2o, r2l = batch.ref2["off"][lo:hi].astype(np.int64), batch.ref2["len"][lo:hi].astype(np.int64)
+    has2 = r2l > 0
+    start = int(min(r1o.min(), r2o[has2].min() if has2.any() else r1o.min()))
+    end = int(max((r1o + r1l).max(), (r2o + r2l)[has2].max() if has2.any() else 0))
+    base = end - start
+    for i in range(n):
+        li = lo + i
+        for k in range(int(loci["nContigs"][i])):
+            cg = contigs[int(loci["firstContig"][i]) + k]
+            v = (base + int(cg["seqOff"]), int(cg["seqLen"]))
+            if batch.isJump[li]:
+                jq.append(v)
+                jr1.append((int(r1o[i]) - start, int(r1l[i])))
+                jr2.append((int(r2o[i]) - start, int(r2l[i])))
+            else:
+                qv.append(v)
+                r1v.append((int(r1o[i]) - start, int(r1l[i])))
+    pool = np.concatenate([batch.pool[start:end], cpool])
+
+    def views_of(lst):
+        a = np.zeros(len(lst), dtype=cb.SEQVIEW_DT)
+        for i, (o, ln) in enumerate(lst):
+            a["off"][i], a["len"][i] = o, ln
+        return a
+    cells = 0
+    if qv:
+        S = cb.Scores(*[int(x) for x in opts["indelScores"][0]])
+        binding.single_align_raw("indel", S, int(opts["largeIndelScore"][0]), pool, views_of(qv), views_of(r1v))
+        cells += sum(q[1] * r[1] for q, r in zip(qv, r1v))
+    if jq:
+        S = cb.Scores(*[int(x) for x in opts["jumpScores"][0]])
+        binding.jump_align_raw(S, int(opts["jumpScore"][0]), pool, views_of(jq), views_of(jr1), views_of(jr2))
+        cells += sum(q[1] * (a[1] + b[1]) for q, a, b in zip(jq, jr1, jr2))
+    return n, cells
+
+
+def run_cpu_sample(binding, batch, opts, n_loci, threads):
+    """static partition of loci [0, n_loci) over `threads` host threads (ctypes releases the GIL)"""
+    chunk = max(1, (n_loci + threads * 4 - 1) // (threads * 4))
+    ranges = [(a, min(n_loci, a + chunk)) for a in range(0, n_loci, chunk)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        done = list(ex.map(lambda r: cpu_candidates(binding, batch, r[0], r[1], opts), ranges))
+    dt = time.perf_counter() - t0
+    return sum(d[0] for d in done), sum(d[1] for d in done), dt
+
+
+def cpu_baseline(batch, opts, target_seconds=12.0):
+    binding, kind = load_cpu_checker()
+    threads = os.cpu_count() or 1
+    probe = min(batch.nLoci, max(threads, 16))
+    n, cells, dt = run_cpu_sample(binding, batch, opts, probe, threads)
+    rate = n / dt
+    want = int(min(batch.nLoci, max(probe, rate * target_seconds)))
+    if want > probe:
+        n, cells, dt = run_cpu_sample(binding, batch, opts, want, threads)
+    return dict(value=n / dt, unit=UNIT, cores=threads, kind=kind,
+                sample="first %d loci of the same batch, %.1f s wall, %d host threads, %.2f GCUPS" %
+                       (n, dt, threads, cells / dt * 1e-9)), n, dt
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, device_index):
+        self.rows = []
+        self.proc = None
+        self.idx = device_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 7:
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def pinned_copy(arr):
+    """a numpy view on pinned host memory holding a copy of arr"""
+    import torch
+    t = torch.empty(arr.nbytes, dtype=torch.uint8, pin_memory=True)
+    v = t.numpy().view(arr.dtype).reshape(arr.shape)
+    v[...] = arr
+    return v, t
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="manta_b200", choices=["manta_b200", "reference"])
+    ap.add_argument("--loci", type=int, default=50000, help="candidate loci per GPU per step (BASELINE configs[1]: 50000)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    opts = cb.default_candidate_opts()
+    config = dict(workload="configs[1]: synthetic %d candidate loci x 64 reads x 150 bp per GPU, k=41..76 assembly + every contig "
+                           "vs 5 kb reference window (60%% large-indel aligner R=5000, 40%% jump aligner R1=R2=2500)" % args.loci,
+                  loci_per_gpu=args.loci, reads_per_locus=64, read_len=150, window=5000, seed=20260923,
+                  l2="inputs (~0.9 GB per batch) and back-pointer stream exceed the 126 MB L2; no flush needed",
+                  parallelism="loci sharded by rank, no data-path collective" + (
+                      "; one NCCL gather of the per-GPU result buffers" if world > 1 else ""))
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample_loci = min(args.loci, 4096)
+        batch = synth.make_candidate_batch(sample_loci, seed=20260923)
+        binding, kind = load_cpu_checker()
+        threads = os.cpu_count() or 1
+        # size one step to ~8 s of CPU work
+        n, cells, dt = run_cpu_sample(binding, batch, opts, min(sample_loci, max(threads, 16)), threads)
+        per_step = int(min(sample_loci, max(threads, n / dt * 8.0)))
+        for _ in range(args.warmup):
+            run_cpu_sample(binding, batch, opts, min(per_step, max(threads, 16)), threads)
+        tot_n, tot_t, tot_cells = 0, 0.0, 0
+        for _ in range(args.steps):
+            n, cells, dt = run_cpu_sample(binding, batch, opts, per_step, threads)
+            tot_n += n
+            tot_t += dt
+            tot_cells += cells
+        value = tot_n / tot_t
+        out = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=1000.0 * tot_t / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None,
+                   dtype="int32", data="synthetic", config=config,
+                   cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind=kind,
+                                     sample="%d loci per step (first loci of the same generator/seed), %d host threads, %.2f GCUPS"
+                                            % (per_step, threads, tot_cells / tot_t * 1e-9)),
+                   e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(out))
+        return 0
+
+    # ---------------------------------------------------------------- manta_b200 arm (GPU)
+    import torch
+    import manta_b200
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = manta_b200.Context(local_rank)
+    batch = synth.make_candidate_batch(args.loci, seed=20260923 + rank)
+    pool_pinned, _keep = pinned_copy(batch.pool)
+    batch.pool = pool_pinned
+
+    def gather_results(out):
+        if dist is None:
+            return
+        # the single collective of the path: per-GPU result buffers to rank 0 over NVLink
+        buf = torch.from_numpy(np.concatenate([out["aln"].view(np.uint8).reshape(-1), out["jump"].view(np.uint8).reshape(-1)])).cuda()
+        lst = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, lst, dst=0)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- resident-input steps (value)
+    ctx.candidates_upload(batch)
+    out = None
+    for _ in range(args.warmup):
+        out = ctx.candidates_run(opts, out)
+        gather_results(out)
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    t0 = time.perf_counter()
+    ev_ms, stage = 0.0, dict(asmMs=0.0, indelMs=0.0, jumpMs=0.0)
+    launches = 0
+    for _ in range(args.steps):
+        out = ctx.candidates_run(opts, out)
+        gather_results(out)
+        t = ctx.candidates_timing()
+        ev_ms += t["totalMs"]
+        launches += t["launches"]
+        for k in stage:
+            stage[k] += t[k]
+    sync_all()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    tim = ctx.candidates_timing()
+
+    # ---- end-to-end steps: host (pinned) buffers in, results out, every step
+    for _ in range(1):
+        ctx.candidates_upload(batch)
+        out = ctx.candidates_run(opts, out)
+    sync_all()
+    t1 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        ctx.candidates_upload(batch)
+        out = ctx.candidates_run(opts, out)
+        gather_results(out)
+        t = ctx.candidates_timing()
+        h2d, d2h = t["h2dBytes"], t["d2hBytes"]
+    sync_all()
+    wall_e2e = time.perf_counter() - t1
+
+    times = torch.tensor([wall, wall_e2e, ev_ms / 1000.0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    wall, wall_e2e, ev_s = [float(x) for x in times.cpu()]
+    total_candidates = args.loci * world * args.steps
+    value = total_candidates / wall
+    e2e_value = total_candidates / wall_e2e
+
+    peak, peak_src = load_peaks()
+    dom_ms = stage["indelMs"] / args.steps
+    dom_bytes = tim["indelBytes"]
+    achieved = dom_bytes / (dom_ms * 1e-3) * 1e-9 if dom_ms > 0 else 0.0
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000.0 * wall / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="int32", data="synthetic", config=config, clocks=clocks,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                gpu_launches=launches,
+                roofline=dict(bound="hbm", kernel="dpAlignKernel<KIND_INDEL> (large-indel aligner, 2 B back-pointer per cell)",
+                              achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None, traffic=None,
+                              peak_source=peak_src, algorithmic_bytes_per_launch_set=dom_bytes, kernel_ms_per_step=dom_ms,
+                              gcups=tim["indelCells"] / (dom_ms * 1e-3) * 1e-9 if dom_ms > 0 else None),
+                stages=dict(device_ms_per_step=ev_s * 1000.0 / args.steps, asm_ms=stage["asmMs"] / args.steps,
+                            indel_ms=dom_ms, jump_ms=stage["jumpMs"] / args.steps, contigs=tim["nContigs"],
+                            indel_cells=tim["indelCells"], jump_cells=tim["jumpCells"],
+                            jump_gcups=(tim["jumpCells"] / (stage["jumpMs"] / args.steps * 1e-3) * 1e-9) if stage["jumpMs"] > 0 else None,
+                            jump_gbs=(tim["jumpBytes"] / (stage["jumpMs"] / args.steps * 1e-3) * 1e-9) if stage["jumpMs"] > 0 else None))
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu, _, _ = cpu_baseline(batch, opts)
+        line["cpu_baseline"] = cpu
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -16,7 +16,7 @@
  *                                called from GSC/SVScorerSplit.cpp:190-226
  *   mb200_assemble_batch     <- runIterativeAssembler                lib/assembly/IterativeAssembler.hpp:43-47
  *                                called from lib/manta/SVCandidateAssembler.cpp:674,697
- *   mb200_candidates_batch   <- the assemble -> align-every-contig composition of
+ *   mb200_candidates_run     <- the assemble -> align-every-contig composition of
  *                                GSC/SVCandidateAssemblyRefiner.cpp:1422-1743 (spanning) and :1925-2039 (complex),
  *                                kept resident on the device (BASELINE.json metric "candidates assembled+aligned").
  *
@@ -260,6 +260,43 @@ MB200_API int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, u
                                    mb200_contig* contigs, uint64_t contigCap, mb200_seqview* pseudoReads,
                                    uint64_t pseudoCap, uint8_t* contigPool, uint64_t contigPoolCap,
                                    uint32_t* setPool, uint64_t setPoolCap);
+
+/* ---- fused candidate path -------------------------------------------------------------------------
+ * "one candidate" = one SVCandidate junction entering getCandidateAssemblyData (GSC/SVCandidateProcessor.cpp:310):
+ * its read set is assembled (all word lengths) and EVERY resulting contig is aligned
+ *   - complex candidates (isJump == 0): GlobalLargeIndelAligner against ref1      (SVCandidateAssemblyRefiner.cpp:2032)
+ *   - spanning candidates (isJump == 1): GlobalJumpAligner against (ref1, ref2)   (SVCandidateAssemblyRefiner.cpp:1668)
+ * with contigs staying resident on the device between the two stages.
+ * Result slot of contig c of locus i is i*maxAssemblyCount + c in alnResults (complex) / jumpResults (spanning). */
+typedef struct mb200_candidate_opts {
+  mb200_asm_opts asmOpts;
+  mb200_scores   indelScores;     /* SVRefinerOptions::smallSVAlignScores (2,-8,-24,-1,-1)  lib/options/SVRefinerOptions.hpp:40 */
+  int32_t        largeIndelScore; /* largeGapOpenScore -100                                 :44 */
+  mb200_scores   jumpScores;      /* spanningAlignScores (2,-8,-12,-1,-1)                   :43 */
+  int32_t        jumpScore;       /* -100                                                   :45 */
+} mb200_candidate_opts;
+
+typedef struct mb200_candidate_timing {
+  float    h2dMs, asmMs, indelMs, jumpMs, d2hMs, totalMs; /* CUDA events on the ctx stream */
+  uint32_t launches, nContigs, nIndelTasks, nJumpTasks;
+  uint64_t asmWindows, indelCells, jumpCells;
+  uint64_t asmBytes, indelBytes, jumpBytes; /* algorithmic HBM bytes per stage */
+  uint64_t h2dBytes, d2hBytes;
+} mb200_candidate_timing;
+
+/* stage one batch of candidate loci in device memory (inputs resident in HBM afterwards) */
+MB200_API int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* readOff,
+                                      const mb200_seqview* readViews, const uint8_t* isJump,
+                                      const mb200_seqview* ref1, const mb200_seqview* ref2, const uint8_t* pool,
+                                      uint64_t poolBytes);
+/* assemble + align every contig of the staged batch; all outputs are host buffers */
+MB200_API int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200_asm_locus* loci,
+                                   mb200_contig* contigs, mb200_seqview* pseudoReads, uint8_t* contigPool,
+                                   uint64_t contigPoolCap, uint64_t* contigPoolUsed, uint32_t* setPool,
+                                   uint64_t setPoolCap, uint64_t* setPoolUsed, mb200_aln_result* alnResults,
+                                   mb200_jump_result* jumpResults, uint32_t* cigarPool, uint64_t cigarCap,
+                                   uint64_t* cigarUsed);
+MB200_API int mb200_candidates_timing(const mb200_ctx* ctx, mb200_candidate_timing* out);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,15 @@ TIMING_DT = np.dtype([("h2dMs", "<f4"), ("kernelMs", "<f4"), ("d2hMs", "<f4"), (
 CONFIG_DT = np.dtype([("ctasPerSm", "<u4"), ("maxContigLen", "<u4"), ("scratchBytes", "<u8"),
                       ("reserved", "<u4", (4,))], align=True)
 
+CAND_OPTS_DT = np.dtype([("asmOpts", ASM_OPTS_DT), ("indelScores", "<i4", (6,)), ("largeIndelScore", "<i4"),
+                         ("jumpScores", "<i4", (6,)), ("jumpScore", "<i4")], align=True)
+CAND_TIMING_DT = np.dtype([("h2dMs", "<f4"), ("asmMs", "<f4"), ("indelMs", "<f4"), ("jumpMs", "<f4"), ("d2hMs", "<f4"),
+                           ("totalMs", "<f4"), ("launches", "<u4"), ("nContigs", "<u4"), ("nIndelTasks", "<u4"),
+                           ("nJumpTasks", "<u4"), ("asmWindows", "<u8"), ("indelCells", "<u8"), ("jumpCells", "<u8"),
+                           ("asmBytes", "<u8"), ("indelBytes", "<u8"), ("jumpBytes", "<u8"), ("h2dBytes", "<u8"),
+                           ("d2hBytes", "<u8")], align=True)
+assert CAND_OPTS_DT.itemsize == 88 and CAND_TIMING_DT.itemsize == 104
+
 assert SEQVIEW_DT.itemsize == 16 and ALN_RESULT_DT.itemsize == 24 and JUMP_RESULT_DT.itemsize == 48
 assert SR_RESULT_DT.itemsize == 56 and SR_JOB_DT.itemsize == 56 and CONTIG_DT.itemsize == 40
 assert ASM_LOCUS_DT.itemsize == 32 and TIMING_DT.itemsize == 32 and CONFIG_DT.itemsize == 32
@@ -337,6 +346,51 @@ class Binding:
             return loci, contigs, pseudo, cpool, spool
         raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "assembler output pool overflow")
 
+    # -- fused candidate path (product library only) -----------------------------------------
+    def candidates_upload(self, batch) -> None:
+        st = self._call("candidates_upload", C.c_uint32(batch.nLoci), _ptr(batch.readOff), _ptr(batch.readViews),
+                        _ptr(batch.isJump), _ptr(batch.ref1), _ptr(batch.ref2), _ptr(batch.pool),
+                        C.c_uint64(batch.pool.size))
+        if st != MB200_OK:
+            self._raise(st)
+        self._cand_shape = (batch.nLoci, int(batch.readViews["len"].sum()), batch.readsPerLocus)
+
+    def candidates_run(self, opts: np.ndarray, out: Optional[dict] = None) -> dict:
+        """run on the staged batch; `out` (from a previous call) is reused to avoid re-allocating host buffers"""
+        nLoci, totalBases, rpl = self._cand_shape
+        A = int(opts["asmOpts"]["maxAssemblyCount"][0])
+        if out is None:
+            out = dict(loci=np.zeros(nLoci, dtype=ASM_LOCUS_DT), contigs=np.zeros(nLoci * A, dtype=CONTIG_DT),
+                       pseudo=np.zeros(nLoci * 2 * A, dtype=SEQVIEW_DT),
+                       contigPool=np.zeros(max(1 << 16, totalBases // 2), dtype=np.uint8),
+                       setPool=np.zeros(max(1024, nLoci * A * 2 * ((rpl + 2 * A + 31) // 32)), dtype=np.uint32),
+                       aln=np.zeros(nLoci * A, dtype=ALN_RESULT_DT), jump=np.zeros(nLoci * A, dtype=JUMP_RESULT_DT),
+                       cigar=np.zeros(max(4096, nLoci * A * 24), dtype=np.uint32))
+        for _ in range(6):
+            used = [C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)]
+            st = self._call("candidates_run", _ptr(opts), _ptr(out["loci"]), _ptr(out["contigs"]), _ptr(out["pseudo"]),
+                            _ptr(out["contigPool"]), C.c_uint64(out["contigPool"].size), C.byref(used[0]),
+                            _ptr(out["setPool"]), C.c_uint64(out["setPool"].size), C.byref(used[1]), _ptr(out["aln"]),
+                            _ptr(out["jump"]), _ptr(out["cigar"]), C.c_uint64(out["cigar"].size), C.byref(used[2]))
+            if st == MB200_ERR_POOL_OVERFLOW:
+                if used[0].value > out["contigPool"].size:
+                    out["contigPool"] = np.zeros(int(used[0].value * 1.25) + 64, dtype=np.uint8)
+                if used[1].value > out["setPool"].size:
+                    out["setPool"] = np.zeros(int(used[1].value * 1.25) + 64, dtype=np.uint32)
+                if used[2].value > out["cigar"].size:
+                    out["cigar"] = np.zeros(int(used[2].value * 1.25) + 64, dtype=np.uint32)
+                continue
+            if st != MB200_OK:
+                self._raise(st)
+            out["used"] = tuple(int(u.value) for u in used)
+            return out
+        raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "candidate output pools overflow")
+
+    def candidates_timing(self) -> dict:
+        t = np.zeros(1, dtype=CAND_TIMING_DT)
+        self._call("candidates_timing", _ptr(t))
+        return {k: (float(t[k][0]) if t[k].dtype.kind == "f" else int(t[k][0])) for k in t.dtype.names}
+
     def assemble(self, opts: np.ndarray, loci_reads: Sequence[Sequence]):
         """returns per locus (contigs, pseudoReads, readInfo) like runIterativeAssembler's outputs"""
         sp = SeqPool()
@@ -351,6 +405,17 @@ class Binding:
         for i, reads in enumerate(loci_reads):
             out.append(decode_locus(loci[i], contigs, pseudo, cpool, spool, len(reads)))
         return out
+
+
+def default_candidate_opts(**asm_kw) -> np.ndarray:
+    """SVRefinerOptions defaults (lib/options/SVRefinerOptions.hpp:40-45) + IterativeAssemblerOptions defaults"""
+    o = np.zeros(1, dtype=CAND_OPTS_DT)
+    o["asmOpts"] = default_asm_opts(**asm_kw)[0]
+    o["indelScores"] = (2, -8, -24, -1, -1, 0)
+    o["largeIndelScore"] = -100
+    o["jumpScores"] = (2, -8, -12, -1, -1, 0)
+    o["jumpScore"] = -100
+    return o
 
 
 def default_asm_opts(**kw) -> np.ndarray:

@@ -1060,43 +1060,34 @@ size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci,
-                                    const uint64_t* readOff, const mb200_seqview* readViews, const uint8_t* pool,
-                                    uint64_t poolBytes, mb200_asm_locus* loci, mb200_contig* contigs,
-                                    uint64_t contigCap, mb200_seqview* pseudoReads, uint64_t pseudoCap,
-                                    uint8_t* contigPool, uint64_t contigPoolCap, uint32_t* setPool,
-                                    uint64_t setPoolCap)
+// Device-level run: inputs (pool, readOff, views) and all outputs live on the device.  hReadOff / hViews are the
+// host copies used only to size the per-CTA workspace.
+int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, const uint64_t* hReadOff,
+                  const mb200_seqview* hViews, uint64_t poolBytes, const uint8_t* dPool, const uint64_t* dReadOff,
+                  const mb200_seqview* dViews, mb200_asm_locus* dLoci, mb200_contig* dContigs, mb200_seqview* dPseudo,
+                  uint8_t* dContigPool, uint64_t contigPoolCap, unsigned long long* dContigPoolUsed, uint32_t* dSetPool,
+                  uint64_t setPoolCap, unsigned long long* dSetPoolUsed, uint32_t* dLociCounter, int* dErrFlag,
+                  uint64_t* cellsOut, uint64_t* algoBytesOut)
 {
-  if (!ctx) return MB200_ERR_BAD_ARG;
-  if (!opts || (nLoci && (!readOff || !loci || !contigs || !pseudoReads || !contigPool || !setPool)))
-    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
   if (opts->minCoverage < 1 || opts->wordStepSize < 1 || opts->minWordLength < 2 || opts->maxWordLength > 96 ||
       opts->maxAssemblyCount < 1 || opts->maxAssemblyCount > 16)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "assembler options outside the supported range (k in [2,96], maxAssemblyCount in [1,16])");
-  ctx->timing = mb200_timing();
-  if (nLoci == 0) return MB200_OK;
-  if (contigCap < (uint64_t)nLoci * opts->maxAssemblyCount || pseudoCap < (uint64_t)nLoci * 2 * opts->maxAssemblyCount)
-    return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "contig / pseudo-read record arrays too small");
-  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
-
-  const uint64_t nReadsTotal = readOff[nLoci];
-  if (nReadsTotal && (!readViews || !pool)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
   const uint32_t A            = opts->maxAssemblyCount;
   const uint32_t maxContigLen = ctx->cfg.maxContigLen ? ctx->cfg.maxContigLen : 2048;
   uint32_t       maxReads = 0, maxPackWords = 0, maxMaskWords = 0;
   uint64_t       maxWin = 0;
   for (uint32_t li = 0; li < nLoci; ++li) {
-    const uint64_t a = readOff[li], b = readOff[li + 1];
+    const uint64_t a = hReadOff[li], b = hReadOff[li + 1];
     if (b < a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "readOff not monotone");
     uint64_t win = 0, pw = 0, mw = 0;
     for (uint64_t r = a; r < b; ++r) {
-      const uint32_t len = readViews[r].len;
-      if (readViews[r].off + len > poolBytes) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "read view outside the pool");
+      const uint32_t len = hViews[r].len;
+      if (hViews[r].off + len > poolBytes) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "read view outside the pool");
       if (len >= opts->minWordLength) win += len - opts->minWordLength + 1;
       pw += (len + 31) / 32 + 4;
       mw += (len + 63) / 64 + 3;
-      ctx->timing.algoBytes += len;
-      ctx->timing.cells += (len >= opts->minWordLength) ? (len - opts->minWordLength + 1) : 0;
+      if (algoBytesOut) *algoBytesOut += len;  // read bytes in (+ contigs/bitsets out, added by the caller)
+      if (cellsOut) *cellsOut += (len >= opts->minWordLength) ? (len - opts->minWordLength + 1) : 0;
     }
     if (b - a + 2 * A > 1024) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "more than 1024 reads (incl. pseudo reads) in one locus");
     maxReads     = std::max<uint32_t>(maxReads, (uint32_t)(b - a));
@@ -1173,9 +1164,56 @@ extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, 
   if (grid > nLoci) grid = nLoci;
   const size_t budget = ctx->cfg.scratchBytes ? (size_t)ctx->cfg.scratchBytes : ((size_t)48 << 30);
   while (grid > 1 && (size_t)grid * L.total > budget) grid = (grid + 1) / 2;
-
   int rc;
   if ((rc = mb200_reserve(ctx, ctx->dAsmWork, (size_t)grid * L.total)) != MB200_OK) return rc;
+
+  AsmParams P;
+  P.opt            = *opts;
+  P.pool           = dPool;
+  P.readOff        = dReadOff;
+  P.views          = dViews;
+  P.nLoci          = nLoci;
+  P.lociCounter    = dLociCounter;
+  P.errFlag        = dErrFlag;
+  P.contigPoolUsed = dContigPoolUsed;
+  P.setPoolUsed    = dSetPoolUsed;
+  P.work           = reinterpret_cast<uint8_t*>(ctx->dAsmWork.ptr);
+  P.L              = L;
+  P.maxContigLen   = maxContigLen;
+  P.loci           = dLoci;
+  P.contigs        = dContigs;
+  P.pseudo         = dPseudo;
+  P.contigPool     = dContigPool;
+  P.contigPoolCap  = contigPoolCap;
+  P.setPool        = dSetPool;
+  P.setPoolCap     = setPoolCap;
+  assembleKernel<<<grid, ASM_THREADS, 0, ctx->stream>>>(P);
+  MB200_CUDA_CHECK(ctx, cudaGetLastError());
+  ctx->timing.launches++;
+  return MB200_OK;
+}
+
+extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci,
+                                    const uint64_t* readOff, const mb200_seqview* readViews, const uint8_t* pool,
+                                    uint64_t poolBytes, mb200_asm_locus* loci, mb200_contig* contigs,
+                                    uint64_t contigCap, mb200_seqview* pseudoReads, uint64_t pseudoCap,
+                                    uint8_t* contigPool, uint64_t contigPoolCap, uint32_t* setPool,
+                                    uint64_t setPoolCap)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (!opts || (nLoci && (!readOff || !loci || !contigs || !pseudoReads || !contigPool || !setPool)))
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  ctx->timing = mb200_timing();
+  if (nLoci == 0) return MB200_OK;
+  const uint32_t A = opts->maxAssemblyCount;
+  if (A < 1 || A > 16) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "maxAssemblyCount outside [1,16]");
+  if (contigCap < (uint64_t)nLoci * A || pseudoCap < (uint64_t)nLoci * 2 * A)
+    return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "contig / pseudo-read record arrays too small");
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const uint64_t nReadsTotal = readOff[nLoci];
+  if (nReadsTotal && (!readViews || !pool)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+
+  int rc;
   if ((rc = mb200_reserve(ctx, ctx->dPool, poolBytes + 64)) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, ctx->dReadOff, 8 * (size_t)(nLoci + 1))) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, ctx->dViews, sizeof(mb200_seqview) * (size_t)(nReadsTotal + 1))) != MB200_OK) return rc;
@@ -1196,30 +1234,15 @@ extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, 
   MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAsmOut2.ptr, 0, sizeof(mb200_seqview) * (size_t)nLoci * 2 * A, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
-  AsmParams P;
-  P.opt          = *opts;
-  P.pool         = reinterpret_cast<const uint8_t*>(ctx->dPool.ptr);
-  P.readOff      = reinterpret_cast<const uint64_t*>(ctx->dReadOff.ptr);
-  P.views        = reinterpret_cast<const mb200_seqview*>(ctx->dViews.ptr);
-  P.nLoci        = nLoci;
   uint32_t* misc = reinterpret_cast<uint32_t*>(ctx->dMisc.ptr);
-  P.lociCounter  = misc + 0;
-  P.errFlag      = reinterpret_cast<int*>(misc + 4);
-  P.contigPoolUsed = reinterpret_cast<unsigned long long*>(misc + 8);
-  P.setPoolUsed    = reinterpret_cast<unsigned long long*>(misc + 10);
-  P.work         = reinterpret_cast<uint8_t*>(ctx->dAsmWork.ptr);
-  P.L            = L;
-  P.maxContigLen = maxContigLen;
-  P.loci         = reinterpret_cast<mb200_asm_locus*>(ctx->dAsmOut0.ptr);
-  P.contigs      = reinterpret_cast<mb200_contig*>(ctx->dAsmOut1.ptr);
-  P.pseudo       = reinterpret_cast<mb200_seqview*>(ctx->dAsmOut2.ptr);
-  P.contigPool   = reinterpret_cast<uint8_t*>(ctx->dAsmOut3.ptr);
-  P.contigPoolCap = contigPoolCap;
-  P.setPool      = reinterpret_cast<uint32_t*>(ctx->dAsmOut4.ptr);
-  P.setPoolCap   = setPoolCap;
-  assembleKernel<<<grid, ASM_THREADS, 0, ctx->stream>>>(P);
-  MB200_CUDA_CHECK(ctx, cudaGetLastError());
-  ctx->timing.launches = 1;
+  rc = mb200_asm_run(ctx, opts, nLoci, readOff, readViews, poolBytes, reinterpret_cast<const uint8_t*>(ctx->dPool.ptr),
+                     reinterpret_cast<const uint64_t*>(ctx->dReadOff.ptr), reinterpret_cast<const mb200_seqview*>(ctx->dViews.ptr),
+                     reinterpret_cast<mb200_asm_locus*>(ctx->dAsmOut0.ptr), reinterpret_cast<mb200_contig*>(ctx->dAsmOut1.ptr),
+                     reinterpret_cast<mb200_seqview*>(ctx->dAsmOut2.ptr), reinterpret_cast<uint8_t*>(ctx->dAsmOut3.ptr),
+                     contigPoolCap, reinterpret_cast<unsigned long long*>(misc + 8), reinterpret_cast<uint32_t*>(ctx->dAsmOut4.ptr),
+                     setPoolCap, reinterpret_cast<unsigned long long*>(misc + 10), misc + 0, reinterpret_cast<int*>(misc + 4),
+                     &ctx->timing.cells, &ctx->timing.algoBytes);
+  if (rc != MB200_OK) return rc;
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 
   uint32_t hMisc[16];
@@ -1235,6 +1258,7 @@ extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, 
   if (usedBytes > contigPoolCap || usedSets > setPoolCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "assembler output pools too small");
   if (usedBytes) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(contigPool, ctx->dAsmOut3.ptr, usedBytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (usedSets) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(setPool, ctx->dAsmOut4.ptr, 4 * usedSets, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->timing.algoBytes += usedBytes + 4 * usedSets;
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   cudaEventElapsedTime(&ctx->timing.h2dMs, ctx->ev[0], ctx->ev[1]);

@@ -1,0 +1,208 @@
+// candidates.cu -- the fused "candidate assembled + aligned" path (BASELINE.json metric).
+//
+// Composition of the reference's per-candidate work in GSC/SVCandidateAssemblyRefiner.cpp: runIterativeAssembler on
+// the candidate's reads (:1925 / lib/manta/SVCandidateAssembler.cpp:674,697), then every contig is aligned with
+// GlobalLargeIndelAligner (complex candidates, :2032) or GlobalJumpAligner (spanning candidates, :1668).
+// The contigs never leave the device between the two stages: the assembler writes them into a device pool and the
+// DP tasks point straight at it; only the 40-byte contig records cross PCIe to let the host bin the DP tasks by
+// query length.
+#include <cstdint>
+#include <vector>
+
+#include "mb200_internal.h"
+
+extern "C" {
+
+int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* readOff, const mb200_seqview* readViews,
+                            const uint8_t* isJump, const mb200_seqview* ref1, const mb200_seqview* ref2,
+                            const uint8_t* pool, uint64_t poolBytes)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (nLoci && (!readOff || !isJump || !ref1 || !ref2 || !pool)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  auto& c      = ctx->cand;
+  c.nLoci      = nLoci;
+  c.poolBytes  = poolBytes;
+  c.readOff.assign(readOff, readOff + nLoci + 1);
+  const uint64_t nReads = nLoci ? readOff[nLoci] : 0;
+  if (nReads && !readViews) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  c.views.assign(readViews, readViews + nReads);
+  c.ref1.assign(ref1, ref1 + nLoci);
+  c.ref2.assign(ref2, ref2 + nLoci);
+  c.isJump.assign(isJump, isJump + nLoci);
+  for (uint32_t i = 0; i < nLoci; ++i) {
+    if (ref1[i].len == 0 || ref1[i].off + ref1[i].len > poolBytes) return mb200_fail(ctx, MB200_ERR_EMPTY_REF, "Unexpected empty reference sequence");
+    if (isJump[i] && (ref2[i].len == 0 || ref2[i].off + ref2[i].len > poolBytes))
+      return mb200_fail(ctx, MB200_ERR_EMPTY_REF2, "Unexpected empty reference2 sequence");
+  }
+  int rc;
+  if ((rc = mb200_reserve(ctx, ctx->dCandPool, poolBytes + MB200_POOL_FRONT + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dCandReadOff, 8 * (size_t)(nLoci + 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dCandViews, sizeof(mb200_seqview) * (size_t)(nReads + 1))) != MB200_OK) return rc;
+  uint8_t* dp = reinterpret_cast<uint8_t*>(ctx->dCandPool.ptr);
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[0], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(dp, 0, MB200_POOL_FRONT, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(dp + MB200_POOL_FRONT, pool, poolBytes, cudaMemcpyHostToDevice, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(dp + MB200_POOL_FRONT + poolBytes, 0, 64, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCandReadOff.ptr, readOff, 8 * (size_t)(nLoci + 1), cudaMemcpyHostToDevice, ctx->stream));
+  if (nReads)
+    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCandViews.ptr, readViews, sizeof(mb200_seqview) * (size_t)nReads, cudaMemcpyHostToDevice, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[1], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->candTiming = mb200_candidate_timing();
+  cudaEventElapsedTime(&ctx->candTiming.h2dMs, ctx->cev[0], ctx->cev[1]);
+  ctx->candTiming.h2dBytes = poolBytes + 8 * (uint64_t)(nLoci + 1) + sizeof(mb200_seqview) * nReads;
+  return MB200_OK;
+}
+
+int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200_asm_locus* loci, mb200_contig* contigs,
+                         mb200_seqview* pseudoReads, uint8_t* contigPool, uint64_t contigPoolCap,
+                         uint64_t* contigPoolUsed, uint32_t* setPool, uint64_t setPoolCap, uint64_t* setPoolUsed,
+                         mb200_aln_result* alnResults, mb200_jump_result* jumpResults, uint32_t* cigarPool,
+                         uint64_t cigarCap, uint64_t* cigarUsed)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (!opts || !loci || !contigs || !pseudoReads || !contigPool || !setPool || !alnResults || !jumpResults ||
+      !cigarPool || !contigPoolUsed || !setPoolUsed || !cigarUsed)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  auto&          c     = ctx->cand;
+  const uint32_t nLoci = c.nLoci;
+  if (nLoci == 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "no staged batch (call mb200_candidates_upload first)");
+  if (opts->jumpScores.isAllowEdgeInsertion) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "jump aligner: isAllowEdgeInsertion unsupported");
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const uint32_t A = opts->asmOpts.maxAssemblyCount;
+  if (A < 1 || A > 16) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "maxAssemblyCount outside [1,16]");
+  mb200_candidate_timing& T = ctx->candTiming;
+  const float             keepH2d = T.h2dMs;
+  const uint64_t          keepH2dBytes = T.h2dBytes;
+  T                       = mb200_candidate_timing();
+  T.h2dMs                 = keepH2d;
+  T.h2dBytes              = keepH2dBytes;
+  ctx->timing             = mb200_timing();
+
+  int rc;
+  const size_t nSlots = (size_t)nLoci * A;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut0, sizeof(mb200_asm_locus) * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut1, sizeof(mb200_contig) * nSlots)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut2, sizeof(mb200_seqview) * nSlots * 2)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut3, contigPoolCap + MB200_POOL_FRONT + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAsmOut4, 4 * (size_t)setPoolCap + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAln, sizeof(mb200_aln_result) * nSlots)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dJump, sizeof(mb200_jump_result) * nSlots)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dCigar, (size_t)(cigarCap ? cigarCap : 1) * sizeof(uint32_t))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dMisc, 256)) != MB200_OK) return rc;
+
+  uint32_t*      misc        = reinterpret_cast<uint32_t*>(ctx->dMisc.ptr);
+  const uint8_t* dPool       = reinterpret_cast<const uint8_t*>(ctx->dCandPool.ptr) + MB200_POOL_FRONT;
+  uint8_t*       dContigPool = reinterpret_cast<uint8_t*>(ctx->dAsmOut3.ptr) + MB200_POOL_FRONT;
+  // dMisc: [0] loci counter, [4] errFlag, [8] contigPoolUsed, [10] setPoolUsed, [12] cigarUsed,
+  //        [16..18] indel class counters, [20..22] jump class counters
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[2], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dMisc.ptr, 0, 256, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAsmOut3.ptr, 0, MB200_POOL_FRONT, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAsmOut1.ptr, 0, sizeof(mb200_contig) * nSlots, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAsmOut2.ptr, 0, sizeof(mb200_seqview) * nSlots * 2, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAln.ptr, 0, sizeof(mb200_aln_result) * nSlots, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJump.ptr, 0, sizeof(mb200_jump_result) * nSlots, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[3], ctx->stream));
+  rc = mb200_asm_run(ctx, &opts->asmOpts, nLoci, c.readOff.data(), c.views.data(), c.poolBytes, dPool,
+                     reinterpret_cast<const uint64_t*>(ctx->dCandReadOff.ptr),
+                     reinterpret_cast<const mb200_seqview*>(ctx->dCandViews.ptr),
+                     reinterpret_cast<mb200_asm_locus*>(ctx->dAsmOut0.ptr), reinterpret_cast<mb200_contig*>(ctx->dAsmOut1.ptr),
+                     reinterpret_cast<mb200_seqview*>(ctx->dAsmOut2.ptr), dContigPool, contigPoolCap,
+                     reinterpret_cast<unsigned long long*>(misc + 8), reinterpret_cast<uint32_t*>(ctx->dAsmOut4.ptr), setPoolCap,
+                     reinterpret_cast<unsigned long long*>(misc + 10), misc + 0, reinterpret_cast<int*>(misc + 4),
+                     &T.asmWindows, &T.asmBytes);
+  if (rc != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[4], ctx->stream));
+
+  // ---- contig records to the host: bin the DP tasks by contig length
+  uint32_t hMisc[32];
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(hMisc, ctx->dMisc.ptr, sizeof(hMisc), cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(loci, ctx->dAsmOut0.ptr, sizeof(mb200_asm_locus) * (size_t)nLoci, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(contigs, ctx->dAsmOut1.ptr, sizeof(mb200_contig) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned long long usedBytes, usedSets;
+  memcpy(&usedBytes, hMisc + 8, 8);
+  memcpy(&usedSets, hMisc + 10, 8);
+  *contigPoolUsed = usedBytes;
+  *setPoolUsed    = usedSets;
+  if (hMisc[4] != 0) return mb200_fail(ctx, (int)hMisc[4], "assembler: a locus failed (bad base / workspace overflow / too many reads)");
+  if (usedBytes > contigPoolCap || usedSets > setPoolCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "assembler output pools too small");
+  T.asmBytes += usedBytes + 4 * usedSets;
+
+  std::vector<DpTask> indelTasks, jumpTasks;
+  for (uint32_t li = 0; li < nLoci; ++li) {
+    for (uint32_t k = 0; k < loci[li].nContigs; ++k) {
+      const mb200_contig& cg = contigs[(size_t)li * A + k];
+      DpTask              t;
+      t.q        = dContigPool + cg.seqOff;
+      t.Q        = cg.seqLen;
+      t.r1       = dPool + c.ref1[li].off;
+      t.R1       = c.ref1[li].len;
+      t.outIndex = li * A + k;
+      if (c.isJump[li]) {
+        t.r2 = dPool + c.ref2[li].off;
+        t.R2 = c.ref2[li].len;
+        jumpTasks.push_back(t);
+      } else {
+        t.r2 = t.r1;
+        t.R2 = 0;
+        indelTasks.push_back(t);
+      }
+      T.nContigs++;
+    }
+  }
+  T.nIndelTasks = (uint32_t)indelTasks.size();
+  T.nJumpTasks  = (uint32_t)jumpTasks.size();
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[5], ctx->stream));
+  if (!indelTasks.empty()) {
+    rc = mb200_dp_run(ctx, MB200_KIND_INDEL, &opts->indelScores, opts->largeIndelScore, indelTasks, ctx->dAln.ptr,
+                      reinterpret_cast<uint32_t*>(ctx->dCigar.ptr), cigarCap, reinterpret_cast<unsigned long long*>(misc + 12),
+                      reinterpret_cast<int*>(misc + 4), misc + 16, &T.indelCells, &T.indelBytes);
+    if (rc != MB200_OK) return rc;
+  }
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[6], ctx->stream));
+  if (!jumpTasks.empty()) {
+    rc = mb200_dp_run(ctx, MB200_KIND_JUMP, &opts->jumpScores, opts->jumpScore, jumpTasks, ctx->dJump.ptr,
+                      reinterpret_cast<uint32_t*>(ctx->dCigar.ptr), cigarCap, reinterpret_cast<unsigned long long*>(misc + 12),
+                      reinterpret_cast<int*>(misc + 4), misc + 20, &T.jumpCells, &T.jumpBytes);
+    if (rc != MB200_OK) return rc;
+  }
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[7], ctx->stream));
+
+  // ---- results to the host
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(hMisc, ctx->dMisc.ptr, sizeof(hMisc), cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(alnResults, ctx->dAln.ptr, sizeof(mb200_aln_result) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(jumpResults, ctx->dJump.ptr, sizeof(mb200_jump_result) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(pseudoReads, ctx->dAsmOut2.ptr, sizeof(mb200_seqview) * nSlots * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  if (usedBytes) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(contigPool, dContigPool, usedBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (usedSets) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(setPool, ctx->dAsmOut4.ptr, 4 * usedSets, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  unsigned long long usedCig;
+  memcpy(&usedCig, hMisc + 12, 8);
+  *cigarUsed = usedCig;
+  if (hMisc[4] != 0) return mb200_fail(ctx, (int)hMisc[4], "device-side failure in dpAlignKernel");
+  if (usedCig > cigarCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "cigar pool too small");
+  if (usedCig) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(cigarPool, ctx->dCigar.ptr, usedCig * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[0], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&T.asmMs, ctx->cev[3], ctx->cev[4]);
+  cudaEventElapsedTime(&T.indelMs, ctx->cev[5], ctx->cev[6]);
+  cudaEventElapsedTime(&T.jumpMs, ctx->cev[6], ctx->cev[7]);
+  cudaEventElapsedTime(&T.d2hMs, ctx->cev[7], ctx->cev[0]);
+  cudaEventElapsedTime(&T.totalMs, ctx->cev[2], ctx->cev[0]);
+  T.launches = ctx->timing.launches;
+  T.d2hBytes = sizeof(mb200_asm_locus) * (uint64_t)nLoci + (sizeof(mb200_contig) + sizeof(mb200_aln_result) + sizeof(mb200_jump_result) + 2 * sizeof(mb200_seqview)) * (uint64_t)nSlots +
+               usedBytes + 4 * usedSets + 4 * usedCig;
+  return MB200_OK;
+}
+
+int mb200_candidates_timing(const mb200_ctx* ctx, mb200_candidate_timing* out)
+{
+  if (!ctx || !out) return MB200_ERR_BAD_ARG;
+  *out = ctx->candTiming;
+  return MB200_OK;
+}
+
+}  // extern "C"

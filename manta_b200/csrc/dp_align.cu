@@ -45,16 +45,9 @@ constexpr int REF_TILE  = 2048;            // bytes per staged reference tile
 constexpr int REF_RING  = 2 * REF_TILE;    // two tiles resident per warp
 constexpr int WARPS_PER_CTA = 4;
 
-struct DpTask {
-  uint64_t qOff, r1Off, r2Off;  // byte offsets into the device pool
-  uint32_t Q, R1, R2;
-  uint32_t outIndex;            // index of the result record
-};
-
 struct DpParams {
   int match, mismatch, open, extend, offEdge, allowEdgeIns;
   int extra;  // jumpScore (KIND_JUMP) or largeIndelScore (KIND_INDEL)
-  const uint8_t* pool;
   const DpTask*  tasks;
   uint32_t       nTasks;
   uint32_t*      workCounter;
@@ -307,9 +300,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpAlignKernel(const DpPara
     const uint32_t Q = task.Q, R1 = task.R1;
     const uint32_t R2   = (KIND == KIND_JUMP) ? task.R2 : 0u;
     const uint32_t RTOT = R1 + R2;
-    const uint8_t* qSeq = P.pool + task.qOff;
-    const uint8_t* ref1 = P.pool + task.r1Off;
-    const uint8_t* ref2 = P.pool + task.r2Off;
+    const uint8_t* qSeq = task.q;
+    const uint8_t* ref1 = task.r1;
+    const uint8_t* ref2 = task.r2;
 
     // ---- reference staging geometry
     RefStage st;
@@ -865,6 +858,60 @@ int launchClass(mb200_ctx* ctx, const DpParams& base, const ClassPlan& plan, siz
 }
 
 template <int KIND>
+int dpRunKind(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vector<DpTask>& tasks, void* dResults,
+              uint32_t* dCigar, uint64_t cigarCap, unsigned long long* dCigarUsed, int* dErrFlag,
+              uint32_t* dWorkCounters, uint64_t* cellsOut, uint64_t* algoBytesOut)
+{
+  // ---- classes by query length (rows per thread); longest tasks first inside a class
+  ClassPlan plans[3];
+  for (const DpTask& t : tasks) {
+    const uint32_t rtot = t.R1 + t.R2;
+    const int      cls  = (t.Q <= 128) ? 0 : (t.Q <= 256 ? 1 : 2);
+    ClassPlan&     p    = plans[cls];
+    p.tasks.push_back(t);
+    size_t pb = cls == 0 ? ptrBytesFor<KIND, 4>(t.Q, rtot) : (cls == 1 ? ptrBytesFor<KIND, 8>(t.Q, rtot) : ptrBytesFor<KIND, 16>(t.Q, rtot));
+    if (pb > p.maxPtr) p.maxPtr = pb;
+    const size_t seg = 2 * ((size_t)t.Q + rtot + 8);
+    if (seg > p.maxSeg) p.maxSeg = seg;
+    const size_t bnd = (t.Q > 512) ? ((size_t)rtot + 2) * 5 : 8;
+    if (bnd > p.maxBnd) p.maxBnd = bnd;
+    if (cellsOut) *cellsOut += (uint64_t)t.Q * rtot;
+    // inputs + one packed back-pointer cell per DP cell (1 B jump/global, 2 B large-indel)
+    if (algoBytesOut) *algoBytesOut += (uint64_t)t.Q * rtot * KindTraits<KIND>::CELLB + t.Q + rtot;
+  }
+  std::vector<DpTask> all;
+  all.reserve(tasks.size());
+  size_t offsets[3];
+  for (int c = 0; c < 3; ++c) {
+    std::vector<DpTask>& v = plans[c].tasks;
+    std::sort(v.begin(), v.end(), [](const DpTask& a, const DpTask& b) {
+      const uint64_t ca = (uint64_t)a.Q * (a.R1 + a.R2), cb = (uint64_t)b.Q * (b.R1 + b.R2);
+      return ca != cb ? ca > cb : a.outIndex < b.outIndex;
+    });
+    offsets[c] = all.size();
+    all.insert(all.end(), v.begin(), v.end());
+  }
+  int rc;
+  if ((rc = mb200_reserve(ctx, ctx->dTasks, all.size() * sizeof(DpTask) + 64)) != MB200_OK) return rc;
+  // pageable source: the runtime stages it before returning, so `all` may go out of scope
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dTasks.ptr, all.data(), all.size() * sizeof(DpTask),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+  DpParams P;
+  P.match = scores->match; P.mismatch = scores->mismatch; P.open = scores->open; P.extend = scores->extend;
+  P.offEdge = scores->offEdge; P.allowEdgeIns = scores->isAllowEdgeInsertion ? 1 : 0; P.extra = extra;
+  P.results   = dResults;
+  P.cigarPool = dCigar;
+  P.cigarCap  = cigarCap;
+  P.errFlag   = dErrFlag;
+  P.cigarUsed = dCigarUsed;
+  // the classes run back to back on the ctx stream (they share the scratch buffers)
+  if ((rc = launchClass<KIND, 4>(ctx, P, plans[0], offsets[0], dWorkCounters + 0)) != MB200_OK) return rc;
+  if ((rc = launchClass<KIND, 8>(ctx, P, plans[1], offsets[1], dWorkCounters + 1)) != MB200_OK) return rc;
+  if ((rc = launchClass<KIND, 16>(ctx, P, plans[2], offsets[2], dWorkCounters + 2)) != MB200_OK) return rc;
+  return MB200_OK;
+}
+
+template <int KIND>
 int alignBatch(mb200_ctx* ctx, const mb200_scores* scores, int extra, uint32_t n, const uint8_t* pool,
                uint64_t poolBytes, const mb200_seqview* query, const mb200_seqview* ref1, const mb200_seqview* ref2,
                void* results, size_t resultBytes, uint32_t* cigarPool, uint64_t cigarCap, uint64_t* cigarUsed)
@@ -891,52 +938,24 @@ int alignBatch(mb200_ctx* ctx, const mb200_scores* scores, int extra, uint32_t n
         (KIND == KIND_JUMP && ref2[i].off + ref2[i].len > poolBytes))
       return mb200_fail(ctx, MB200_ERR_BAD_ARG, "sequence view outside the pool");
   }
-
-  // ---- classes by query length (rows per thread); longest tasks first inside a class
-  ClassPlan plans[3];
-  constexpr uint64_t FRONT = 16;  // device pool is shifted by 16 bytes so aligned-down TMA sources stay inside it
+  int rc;
+  constexpr uint64_t FRONT = MB200_POOL_FRONT;  // aligned-down TMA sources stay inside the allocation
+  if ((rc = mb200_reserve(ctx, ctx->dPool, poolBytes + FRONT + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dResults, (size_t)n * resultBytes)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dCigar, (size_t)(cigarCap ? cigarCap : 1) * sizeof(uint32_t))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dMisc, 256)) != MB200_OK) return rc;
+  const uint8_t* dPool = reinterpret_cast<const uint8_t*>(ctx->dPool.ptr) + FRONT;
+  std::vector<DpTask> tasks(n);
   for (uint32_t i = 0; i < n; ++i) {
-    DpTask t;
-    t.qOff     = FRONT + query[i].off;
-    t.r1Off    = FRONT + ref1[i].off;
-    t.r2Off    = (KIND == KIND_JUMP) ? FRONT + ref2[i].off : t.r1Off;
+    DpTask& t  = tasks[i];
+    t.q        = dPool + query[i].off;
+    t.r1       = dPool + ref1[i].off;
+    t.r2       = (KIND == KIND_JUMP) ? dPool + ref2[i].off : t.r1;
     t.Q        = query[i].len;
     t.R1       = ref1[i].len;
     t.R2       = (KIND == KIND_JUMP) ? ref2[i].len : 0;
     t.outIndex = i;
-    const uint32_t rtot = t.R1 + t.R2;
-    const int      cls  = (t.Q <= 128) ? 0 : (t.Q <= 256 ? 1 : 2);
-    ClassPlan&     p    = plans[cls];
-    p.tasks.push_back(t);
-    size_t pb = cls == 0 ? ptrBytesFor<KIND, 4>(t.Q, rtot) : (cls == 1 ? ptrBytesFor<KIND, 8>(t.Q, rtot) : ptrBytesFor<KIND, 16>(t.Q, rtot));
-    if (pb > p.maxPtr) p.maxPtr = pb;
-    const size_t seg = 2 * ((size_t)t.Q + rtot + 8);
-    if (seg > p.maxSeg) p.maxSeg = seg;
-    const size_t bnd = (t.Q > 512) ? ((size_t)rtot + 2) * 5 : 8;
-    if (bnd > p.maxBnd) p.maxBnd = bnd;
-    ctx->timing.cells += (uint64_t)t.Q * rtot;
-    ctx->timing.algoBytes += (uint64_t)t.Q * rtot * KindTraits<KIND>::CELLB + t.Q + rtot;
   }
-  std::vector<DpTask> all;
-  all.reserve(n);
-  size_t offsets[3];
-  for (int c = 0; c < 3; ++c) {
-    std::vector<DpTask>& v = plans[c].tasks;
-    std::sort(v.begin(), v.end(), [](const DpTask& a, const DpTask& b) {
-      const uint64_t ca = (uint64_t)a.Q * (a.R1 + a.R2), cb = (uint64_t)b.Q * (b.R1 + b.R2);
-      return ca != cb ? ca > cb : a.outIndex < b.outIndex;
-    });
-    offsets[c] = all.size();
-    all.insert(all.end(), v.begin(), v.end());
-  }
-
-  int rc;
-  if ((rc = mb200_reserve(ctx, ctx->dPool, poolBytes + FRONT + 64)) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dTasks, all.size() * sizeof(DpTask))) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dResults, (size_t)n * resultBytes)) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dCigar, (size_t)(cigarCap ? cigarCap : 1) * sizeof(uint32_t))) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dMisc, 256)) != MB200_OK) return rc;
-
   // dMisc: [0..2] work counters, [4] errFlag, [8..9] cigarUsed (u64)
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dMisc.ptr, 0, 256, ctx->stream));
@@ -944,25 +963,12 @@ int alignBatch(mb200_ctx* ctx, const mb200_scores* scores, int extra, uint32_t n
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(ctx->dPool.ptr) + FRONT, pool, poolBytes,
                                         cudaMemcpyHostToDevice, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->dPool.ptr) + FRONT + poolBytes, 0, 64, ctx->stream));
-  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dTasks.ptr, all.data(), all.size() * sizeof(DpTask),
-                                        cudaMemcpyHostToDevice, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-
-  DpParams P;
-  P.match = scores->match; P.mismatch = scores->mismatch; P.open = scores->open; P.extend = scores->extend;
-  P.offEdge = scores->offEdge; P.allowEdgeIns = scores->isAllowEdgeInsertion ? 1 : 0; P.extra = extra;
-  P.pool      = reinterpret_cast<const uint8_t*>(ctx->dPool.ptr);
-  P.results   = ctx->dResults.ptr;
-  P.cigarPool = reinterpret_cast<uint32_t*>(ctx->dCigar.ptr);
-  P.cigarCap  = cigarCap;
   uint32_t* misc = reinterpret_cast<uint32_t*>(ctx->dMisc.ptr);
-  P.errFlag   = reinterpret_cast<int*>(misc + 4);
-  P.cigarUsed = reinterpret_cast<unsigned long long*>(misc + 8);
-
-  // the classes run back to back on the ctx stream (they share the scratch buffers)
-  if ((rc = launchClass<KIND, 4>(ctx, P, plans[0], offsets[0], misc + 0)) != MB200_OK) return rc;
-  if ((rc = launchClass<KIND, 8>(ctx, P, plans[1], offsets[1], misc + 1)) != MB200_OK) return rc;
-  if ((rc = launchClass<KIND, 16>(ctx, P, plans[2], offsets[2], misc + 2)) != MB200_OK) return rc;
+  rc = dpRunKind<KIND>(ctx, scores, extra, tasks, ctx->dResults.ptr, reinterpret_cast<uint32_t*>(ctx->dCigar.ptr), cigarCap,
+                       reinterpret_cast<unsigned long long*>(misc + 8), reinterpret_cast<int*>(misc + 4), misc + 0,
+                       &ctx->timing.cells, &ctx->timing.algoBytes);
+  if (rc != MB200_OK) return rc;
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 
   uint32_t hMisc[16];
@@ -986,6 +992,21 @@ int alignBatch(mb200_ctx* ctx, const mb200_scores* scores, int extra, uint32_t n
 }
 
 }  // namespace
+
+// device-level entry used by the fused candidates path (candidates.cu): results stay on the device
+int mb200_dp_run(mb200_ctx* ctx, int kind, const mb200_scores* scores, int extra, std::vector<DpTask>& tasks,
+                 void* dResults, uint32_t* dCigar, uint64_t cigarCap, unsigned long long* dCigarUsed, int* dErrFlag,
+                 uint32_t* dWorkCounters, uint64_t* cellsOut, uint64_t* algoBytesOut)
+{
+  switch (kind) {
+  case KIND_GLOBAL:
+    return dpRunKind<KIND_GLOBAL>(ctx, scores, extra, tasks, dResults, dCigar, cigarCap, dCigarUsed, dErrFlag, dWorkCounters, cellsOut, algoBytesOut);
+  case KIND_JUMP:
+    return dpRunKind<KIND_JUMP>(ctx, scores, extra, tasks, dResults, dCigar, cigarCap, dCigarUsed, dErrFlag, dWorkCounters, cellsOut, algoBytesOut);
+  default:
+    return dpRunKind<KIND_INDEL>(ctx, scores, extra, tasks, dResults, dCigar, cigarCap, dCigarUsed, dErrFlag, dWorkCounters, cellsOut, algoBytesOut);
+  }
+}
 
 extern "C" {
 

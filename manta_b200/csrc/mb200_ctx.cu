@@ -70,6 +70,12 @@ int mb200_create(int device, const mb200_config* cfg, mb200_ctx** out)
       return MB200_ERR_CUDA;
     }
   }
+  for (int i = 0; i < 8; ++i) {
+    if (cudaEventCreate(&ctx->cev[i]) != cudaSuccess) {
+      delete ctx;
+      return MB200_ERR_CUDA;
+    }
+  }
   *out = ctx;
   return MB200_OK;
 }
@@ -82,12 +88,15 @@ void mb200_destroy(mb200_ctx* ctx)
   DeviceBuffer* bufs[] = {&ctx->dPool,    &ctx->dTasks,   &ctx->dResults, &ctx->dCigar,   &ctx->dPtrScratch,
                           &ctx->dSegScratch, &ctx->dBndScratch, &ctx->dMisc, &ctx->dJobs, &ctx->dTables,
                           &ctx->dAsmWork, &ctx->dAsmOut0, &ctx->dAsmOut1, &ctx->dAsmOut2, &ctx->dAsmOut3,
-                          &ctx->dAsmOut4, &ctx->dViews,   &ctx->dReadOff};
+                          &ctx->dAsmOut4, &ctx->dViews,   &ctx->dReadOff, &ctx->dCandPool, &ctx->dCandReadOff,
+                          &ctx->dCandViews, &ctx->dAln, &ctx->dJump};
   for (DeviceBuffer* b : bufs)
     if (b->ptr) cudaFree(b->ptr);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 8; ++i)
+    if (ctx->cev[i]) cudaEventDestroy(ctx->cev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -30,6 +30,17 @@ struct mb200_ctx {
   // pinned staging
   void*  hPinned      = nullptr;
   size_t hPinnedBytes = 0;
+  // staged candidate batch (mb200_candidates_upload)
+  struct {
+    uint32_t                   nLoci = 0;
+    uint64_t                   poolBytes = 0;
+    std::vector<uint64_t>      readOff;
+    std::vector<mb200_seqview> views, ref1, ref2;
+    std::vector<uint8_t>       isJump;
+  } cand;
+  DeviceBuffer           dCandPool, dCandReadOff, dCandViews, dAln, dJump;
+  mb200_candidate_timing candTiming = {};
+  cudaEvent_t            cev[8]     = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 #define MB200_CUDA_CHECK(ctx, expr)                                                                   \
@@ -45,3 +56,27 @@ struct mb200_ctx {
 int mb200_reserve(mb200_ctx* ctx, DeviceBuffer& buf, size_t bytes);
 int mb200_reserve_pinned(mb200_ctx* ctx, size_t bytes);
 int mb200_fail(mb200_ctx* ctx, int status, const char* msg);
+
+// ---- device-level pieces shared between translation units ---------------------------------------------
+#define MB200_POOL_FRONT 64  // bytes of padding in front of device sequence pools (aligned-down TMA sources)
+
+enum { MB200_KIND_GLOBAL = 0, MB200_KIND_JUMP = 1, MB200_KIND_INDEL = 2 };
+
+struct DpTask {
+  const uint8_t *q, *r1, *r2;  // device pointers
+  uint32_t       Q, R1, R2;
+  uint32_t       outIndex;  // index of the result record
+};
+
+// dp_align.cu: run one aligner kind over `tasks`; results / cigar segments stay on the device
+int mb200_dp_run(mb200_ctx* ctx, int kind, const mb200_scores* scores, int extra, std::vector<DpTask>& tasks,
+                 void* dResults, uint32_t* dCigar, uint64_t cigarCap, unsigned long long* dCigarUsed, int* dErrFlag,
+                 uint32_t* dWorkCounters, uint64_t* cellsOut, uint64_t* algoBytesOut);
+
+// assemble.cu: run the assembler on device-resident inputs, outputs stay on the device
+int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, const uint64_t* hReadOff,
+                  const mb200_seqview* hViews, uint64_t poolBytes, const uint8_t* dPool, const uint64_t* dReadOff,
+                  const mb200_seqview* dViews, mb200_asm_locus* dLoci, mb200_contig* dContigs, mb200_seqview* dPseudo,
+                  uint8_t* dContigPool, uint64_t contigPoolCap, unsigned long long* dContigPoolUsed, uint32_t* dSetPool,
+                  uint64_t setPoolCap, unsigned long long* dSetPoolUsed, uint32_t* dLociCounter, int* dErrFlag,
+                  uint64_t* cellsOut, uint64_t* algoBytesOut);

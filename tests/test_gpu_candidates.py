@@ -1,0 +1,93 @@
+"""Fused candidate path (assemble -> align every contig, contigs resident on the device) against the oracle
+composition of the same reference calls."""
+import numpy as np
+import pytest
+
+from manta_b200 import _cabi as cb
+from manta_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_candidates(orc, batch, opts):
+    """runIterativeAssembler, then GlobalLargeIndelAligner / GlobalJumpAligner on every contig (oracle, CPU)"""
+    asm_opts = np.zeros(1, dtype=cb.ASM_OPTS_DT)
+    asm_opts[0] = opts["asmOpts"][0]
+    loci, contigs, pseudo, cpool, spool = orc.assemble_raw(asm_opts, batch.readOff, batch.readViews, batch.pool)
+    pool = batch.pool
+    out = []
+    for li in range(batch.nLoci):
+        cs, ps, info = cb.decode_locus(loci[li], contigs, pseudo, cpool, spool, batch.readsPerLocus)
+        r1 = bytes(pool[int(batch.ref1["off"][li]):int(batch.ref1["off"][li]) + int(batch.ref1["len"][li])])
+        alns = []
+        if batch.isJump[li]:
+            r2 = bytes(pool[int(batch.ref2["off"][li]):int(batch.ref2["off"][li]) + int(batch.ref2["len"][li])])
+            if cs:
+                alns = orc.jump_align(cb.Scores(*[int(x) for x in opts["jumpScores"][0]]), int(opts["jumpScore"][0]),
+                                      [(c.seq, r1, r2) for c in cs])
+        elif cs:
+            alns = orc.single_align("indel", cb.Scores(*[int(x) for x in opts["indelScores"][0]]),
+                                    int(opts["largeIndelScore"][0]), [(c.seq, r1) for c in cs])
+        out.append((cs, ps, alns))
+    return out
+
+
+def decode_candidates(batch, opts, out):
+    A = int(opts["asmOpts"]["maxAssemblyCount"][0])
+    res = []
+    for li in range(batch.nLoci):
+        cs, ps, info = cb.decode_locus(out["loci"][li], out["contigs"], out["pseudo"], out["contigPool"], out["setPool"],
+                                       batch.readsPerLocus)
+        alns = []
+        for k in range(len(cs)):
+            slot = li * A + k
+            if batch.isJump[li]:
+                alns.append(cb.decode_jump(out["jump"][slot], out["cigar"]))
+            else:
+                alns.append(cb.decode_aln(out["aln"][slot], out["cigar"]))
+        res.append((cs, ps, alns))
+    return res
+
+
+def test_candidates_vs_oracle(gpu, orc):
+    batch = synth.make_candidate_batch(48, seed=7, window=1500)
+    assert 0 < int(batch.isJump.sum()) < batch.nLoci
+    opts = cb.default_candidate_opts()
+    gpu.candidates_upload(batch)
+    out = gpu.candidates_run(opts)
+    got = decode_candidates(batch, opts, out)
+    want = oracle_candidates(orc, batch, opts)
+    for li in range(batch.nLoci):
+        assert got[li] == want[li], li
+    t = gpu.candidates_timing()
+    assert t["nContigs"] == sum(len(w[0]) for w in want) and t["launches"] >= 2
+    # second run on the resident batch (reusing host buffers) gives identical results
+    out2 = gpu.candidates_run(opts, out)
+    assert decode_candidates(batch, opts, out2) == want
+
+
+def test_candidates_full_window_properties(gpu):
+    """BASELINE config-2 sized windows (5 kb): size-independent properties of every alignment"""
+    batch = synth.make_candidate_batch(64, seed=20260923)
+    opts = cb.default_candidate_opts()
+    gpu.candidates_upload(batch)
+    out = gpu.candidates_run(opts)
+    A = int(opts["asmOpts"]["maxAssemblyCount"][0])
+    n = 0
+    for li in range(batch.nLoci):
+        for k in range(int(out["loci"]["nContigs"][li])):
+            slot = li * A + k
+            qlen = int(out["contigs"]["seqLen"][slot])
+            if batch.isJump[li]:
+                r = cb.decode_jump(out["jump"][slot], out["cigar"])
+                cig = r.align1.cigar + r.align2.cigar
+                extra = r.jumpInsertSize
+            else:
+                r = cb.decode_aln(out["aln"][slot], out["cigar"])
+                cig, extra = r.align.cigar, 0
+            import re
+            read_len = sum(int(a) for a, op in re.findall(r"(\d+)([=XIS])", cig)) + extra
+            assert read_len == qlen, (li, k, cig)       # every query base is accounted for exactly once
+            assert r.score <= 2 * qlen                   # cannot beat a perfect match
+            n += 1
+    assert n > 64
