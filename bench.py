@@ -59,64 +59,20 @@ def load_cpu_checker():
     return cb.Binding(C.CDLL(os.path.join(ROOT, "oracle", "_build", "libmanta_oracle.so")), "orc_"), "port"
 
 
-def cpu_candidates(binding, batch, lo, hi, opts):
-    """assemble + align every contig of loci [lo, hi) on one host thread; returns number of candidates done"""
-    asm_opts = np.zeros(1, dtype=cb.ASM_OPTS_DT)
-    asm_opts[0] = opts["asmOpts"][0]
-    rpl = batch.readsPerLocus
-    readOff = (batch.readOff[lo:hi + 1] - batch.readOff[lo]).astype(np.uint64)
-    views = batch.readViews[lo * rpl:hi * rpl]
-    loci, contigs, pseudo, cpool, spool = binding.assemble_raw(asm_opts, readOff, views, batch.pool)
-    # contig sequences are appended to a private pool so that the aligners see (contig, reference) views
-    n = hi - lo
-    qv, r1v, r2v, jq, jr1, jr2 = [], [], [], [], [], []
-    # private pool of this chunk: [reference windows of loci lo..hi) | contigs]
-    r1o, r1l = batch.ref1["off"][lo:hi].astype(np.int64), batch.ref1["len"][lo:hi].astype(np.int64)
-    r2o, r2l = batch.ref2["off"][lo:hi].astype(np.int64), batch.ref2["len"][lo:hi].astype(np.int64)
-    has2 = r2l > 0
-    start = int(min(r1o.min(), r2o[has2].min() if has2.any() else r1o.min()))
-    end = int(max((r1o + r1l).max(), (r2o + r2l)[has2].max() if has2.any() else 0))
-    base = end - start
-    for i in range(n):
-        li = lo + i
-        for k in range(int(loci["nContigs"][i])):
-            cg = contigs[int(loci["firstContig"][i]) + k]
-            v = (base + int(cg["seqOff"]), int(cg["seqLen"]))
-            if batch.isJump[li]:
-                jq.append(v)
-                jr1.append((int(r1o[i]) - start, int(r1l[i])))
-                jr2.append((int(r2o[i]) - start, int(r2l[i])))
-            else:
-                qv.append(v)
-                r1v.append((int(r1o[i]) - start, int(r1l[i])))
-    pool = np.concatenate([batch.pool[start:end], cpool])
-
-    def views_of(lst):
-        a = np.zeros(len(lst), dtype=cb.SEQVIEW_DT)
-        for i, (o, ln) in enumerate(lst):
-            a["off"][i], a["len"][i] = o, ln
-        return a
-    cells = 0
-    if qv:
-        S = cb.Scores(*[int(x) for x in opts["indelScores"][0]])
-        binding.single_align_raw("indel", S, int(opts["largeIndelScore"][0]), pool, views_of(qv), views_of(r1v))
-        cells += sum(q[1] * r[1] for q, r in zip(qv, r1v))
-    if jq:
-        S = cb.Scores(*[int(x) for x in opts["jumpScores"][0]])
-        binding.jump_align_raw(S, int(opts["jumpScore"][0]), pool, views_of(jq), views_of(jr1), views_of(jr2))
-        cells += sum(q[1] * (a[1] + b[1]) for q, a, b in zip(jq, jr1, jr2))
-    return n, cells
-
-
 def run_cpu_sample(binding, batch, opts, n_loci, threads):
-    """static partition of loci [0, n_loci) over `threads` host threads (ctypes releases the GIL)"""
-    chunk = max(1, (n_loci + threads * 4 - 1) // (threads * 4))
-    ranges = [(a, min(n_loci, a + chunk)) for a in range(0, n_loci, chunk)]
+    """the per-candidate composition (runIterativeAssembler, then every contig through the large-indel / jump
+    aligner) on `threads` host threads inside the checker library (ref_candidates_mt / orc_candidates_mt):
+    dynamic hand-out of loci, one set of aligner objects per thread, like the reference's own thread pool"""
+    f = getattr(binding.lib, binding.prefix + "candidates_mt")
+    f.restype = C.c_int
+    nc, cells, ssum = C.c_uint64(), C.c_uint64(), C.c_int64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        done = list(ex.map(lambda r: cpu_candidates(binding, batch, r[0], r[1], opts), ranges))
+    st = f(p(opts), C.c_uint32(n_loci), p(batch.readOff), p(batch.readViews), p(batch.isJump), p(batch.ref1),
+           p(batch.ref2), p(batch.pool), C.c_int(threads), C.byref(nc), C.byref(cells), C.byref(ssum))
     dt = time.perf_counter() - t0
-    return sum(d[0] for d in done), sum(d[1] for d in done), dt
+    assert st == 0
+    return n_loci, int(cells.value), dt
 
 
 def cpu_baseline(batch, opts, target_seconds=12.0):

@@ -206,16 +206,16 @@ def make_candidate_batch(n_loci: int, seed: int = 20260923, reads_per_locus: int
     for li in range(n_loci):
         w1 = ACGT[rng.integers(0, 4, window)]
         kind = rng.random()
-        bp = int(rng.integers(1000, 2500))
+        bp = int(rng.integers(window // 5, window // 2))
         if kind < 0.4:  # deletion
-            dl = int(rng.integers(50, 2001))
+            dl = int(rng.integers(50, max(51, min(2000, window - bp - 200)) + 1))
             alt = np.concatenate([w1[:bp], w1[bp + dl:]])
         elif kind < 0.6:  # novel insertion
             il = int(rng.integers(50, 301))
             alt = np.concatenate([w1[:bp], ACGT[rng.integers(0, 4, il)], w1[bp:]])
         else:
             w2 = ACGT[rng.integers(0, 4, window)]
-            bp2 = int(rng.integers(1000, 2500))
+            bp2 = int(rng.integers(window // 5, window // 2))
             if kind < 0.8:  # inversion: continue on the reverse complement of a second segment
                 seg = COMP[w2[::-1]]
             else:  # translocation

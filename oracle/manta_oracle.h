@@ -52,6 +52,13 @@ ORC_API int orc_assemble_batch(const mb200_asm_opts* opts, uint32_t nLoci, const
 /* libstdc++ std::unordered_map<std::string,T> iteration-order emulation (exported for its own test) */
 ORC_API void orc_unordered_order(uint32_t n, const uint8_t* keys, uint32_t keyLen, uint32_t* order);
 
+/* per-candidate composition (assemble, then align every contig) on `threads` pthreads; scoreSum = sum of all
+ * alignment scores (checksum) */
+ORC_API int orc_candidates_mt(const mb200_candidate_opts* opts, uint32_t nLoci, const uint64_t* readOff,
+                              const mb200_seqview* readViews, const uint8_t* isJump, const mb200_seqview* ref1,
+                              const mb200_seqview* ref2, const uint8_t* pool, int threads, uint64_t* nContigsOut,
+                              uint64_t* cellsOut, int64_t* scoreSumOut);
+
 ORC_API const char* orc_version(void);
 
 #ifdef __cplusplus
