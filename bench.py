@@ -209,9 +209,9 @@ def main():
         if dist is None:
             return
         # the single collective of the path: per-GPU result buffers to rank 0 over NVLink
-        buf = torch.from_numpy(np.concatenate([out["aln"].view(np.uint8).reshape(-1), out["jump"].view(np.uint8).reshape(-1)])).cuda()
-        lst = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, lst, dst=0)
+        from manta_b200 import shard
+        buf = np.concatenate([out["aln"].view(np.uint8).reshape(-1), out["jump"].view(np.uint8).reshape(-1)])
+        shard.gather_buffers(buf, dst=0, device="cuda:%d" % local_rank)
 
     def sync_all():
         torch.cuda.synchronize()

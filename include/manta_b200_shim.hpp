@@ -1,0 +1,330 @@
+// manta_b200_shim.hpp -- header-only C++ adapter from the reference's in-process call seams
+// to the batched C ABI of manta_b200.h.  Each class/function below has the signature, argument meaning and error
+// behaviour of the reference entity it replaces, so a Manta maintainer can swap the include and keep the call site:
+//
+//   mb200::GlobalJumpAligner<int>::align        <- lib/alignment/GlobalJumpAligner.hpp:45-53
+//   mb200::GlobalLargeIndelAligner<int>::align  <- lib/alignment/GlobalLargeIndelAligner.hpp:48-54
+//   mb200::GlobalAligner<int>::align            <- lib/alignment/GlobalAligner.hpp
+//   mb200::splitReadAligner                     <- GSC/SplitReadAlignment.hpp:63-70
+//   mb200::runIterativeAssembler                <- lib/assembly/IterativeAssembler.hpp:43-47
+//
+// The shim is deliberately free of reference headers: result types are minimal look-alikes (same member names) so
+// that this file compiles on its own; INTEGRATION.md shows the three-line conversions to the reference's own
+// ALIGNPATH::path_t / AssembledContig types.  Errors of the C ABI are thrown as mb200::GeneralException, which
+// the integration maps onto illumina::common::GeneralException (same what() text as the reference).
+//
+// Batch size is 1 per call here (drop-in semantics); the staged driver described in INTEGRATION.md calls the
+// batched C entry points directly.
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "manta_b200.h"
+
+namespace mb200 {
+
+struct GeneralException : public std::runtime_error {
+  GeneralException(int st, const std::string& msg) : std::runtime_error(msg), status(st) {}
+  int status;
+};
+
+/// one device context per host thread (the reference keeps one aligner object per worker thread,
+/// GSC/GenerateSVCandidates.cpp:232-250)
+class Context {
+public:
+  explicit Context(int device = 0)
+  {
+    const int st(mb200_create(device, nullptr, &_ctx));
+    if (st != MB200_OK) throw GeneralException(st, "mb200_create failed: no usable sm_100 CUDA device (no CPU fallback)");
+  }
+  ~Context() { mb200_destroy(_ctx); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  mb200_ctx* get() const { return _ctx; }
+  void check(int st) const
+  {
+    if (st != MB200_OK) throw GeneralException(st, mb200_last_error(_ctx));
+  }
+
+private:
+  mb200_ctx* _ctx = nullptr;
+};
+
+// ---- ALIGNPATH look-alikes (lib/blt_util/align_path.hpp:34-60) ----------------------------------
+struct path_segment {
+  unsigned type;  // ALIGNPATH::align_t value
+  unsigned length;
+};
+typedef std::vector<path_segment> path_t;
+
+inline std::string apath_to_cigar(const path_t& apath)
+{
+  static const char codes[] = "?MIDNSHP=X";
+  std::string       s;
+  for (const path_segment& ps : apath) s += std::to_string(ps.length) + codes[ps.type];
+  return s;
+}
+
+struct Alignment {  // lib/alignment/Alignment.hpp:28-41
+  bool   isAligned() const { return !apath.empty(); }
+  int    beginPos = 0;
+  path_t apath;
+};
+
+template <typename ScoreType>
+struct AlignmentScores {  // lib/alignment/AlignmentScores.hpp:23-57
+  AlignmentScores(ScoreType m, ScoreType mm, ScoreType o, ScoreType e, ScoreType oe, bool edgeIns = false)
+    : match(m), mismatch(mm), open(o), extend(e), offEdge(oe), isAllowEdgeInsertion(edgeIns)
+  {
+  }
+  const ScoreType match, mismatch, open, extend, offEdge;
+  const bool      isAllowEdgeInsertion;
+  mb200_scores    c() const { return mb200_scores{match, mismatch, open, extend, offEdge, isAllowEdgeInsertion ? 1 : 0}; }
+};
+
+template <typename ScoreType>
+struct AlignmentResult {  // lib/alignment/SingleRefAlignerShared.hpp:34-47
+  ScoreType score    = 0;
+  bool      isJumped = false;
+  Alignment align;
+};
+
+template <typename ScoreType>
+struct JumpAlignmentResult {  // lib/alignment/JumpAlignerBase.hpp:37-56
+  ScoreType score          = 0;
+  unsigned  jumpInsertSize = 0;
+  unsigned  jumpRange      = 0;
+  Alignment align1, align2;
+};
+
+namespace detail {
+inline path_t toPath(const uint32_t* segs, uint64_t off, uint32_t n)
+{
+  path_t p(n);
+  for (uint32_t i(0); i < n; ++i) p[i] = path_segment{MB200_SEG_TYPE(segs[off + i]), MB200_SEG_LEN(segs[off + i])};
+  return p;
+}
+template <typename SymIter>
+inline mb200_seqview append(std::vector<uint8_t>& pool, SymIter b, SymIter e)
+{
+  mb200_seqview v{pool.size(), 0, 0};
+  for (; b != e; ++b) pool.push_back(static_cast<uint8_t>(*b));
+  v.len = static_cast<uint32_t>(pool.size() - v.off);
+  while (pool.size() % 16) pool.push_back(0);
+  return v;
+}
+}  // namespace detail
+
+/// GlobalJumpAligner<int>::align  lib/alignment/GlobalJumpAligner.hpp:45-53 (throws on empty inputs, Impl:50-58)
+template <typename ScoreType>
+struct GlobalJumpAligner {
+  GlobalJumpAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores, const ScoreType jumpScore)
+    : _ctx(ctx), _scores(scores), _jumpScore(jumpScore)
+  {
+  }
+  template <typename SymIter>
+  void align(const SymIter queryBegin, const SymIter queryEnd, const SymIter ref1Begin, const SymIter ref1End,
+             const SymIter ref2Begin, const SymIter ref2End, JumpAlignmentResult<ScoreType>& result) const
+  {
+    std::vector<uint8_t> pool;
+    const mb200_seqview  q(detail::append(pool, queryBegin, queryEnd));
+    const mb200_seqview  r1(detail::append(pool, ref1Begin, ref1End));
+    const mb200_seqview  r2(detail::append(pool, ref2Begin, ref2End));
+    std::vector<uint32_t> cigar(q.len + r1.len + r2.len + 16);
+    mb200_jump_result     res;
+    uint64_t              used(0);
+    const mb200_scores    sc(_scores.c());
+    _ctx.check(mb200_jump_align_batch(_ctx.get(), &sc, _jumpScore, 1, pool.data(), pool.size(), &q, &r1, &r2, &res,
+                                      cigar.data(), cigar.size(), &used));
+    result                 = JumpAlignmentResult<ScoreType>();
+    result.score           = static_cast<ScoreType>(res.score);
+    result.jumpInsertSize  = res.jumpInsertSize;
+    result.jumpRange       = res.jumpRange;
+    result.align1.beginPos = res.beginPos1;
+    result.align2.beginPos = res.beginPos2;
+    result.align1.apath    = detail::toPath(cigar.data(), res.cigarOff1, res.cigarLen1);
+    result.align2.apath    = detail::toPath(cigar.data(), res.cigarOff2, res.cigarLen2);
+  }
+  const ScoreType& getJumpScore() const { return _jumpScore; }
+
+private:
+  const Context&                   _ctx;
+  const AlignmentScores<ScoreType> _scores;
+  const ScoreType                  _jumpScore;
+};
+
+/// GlobalLargeIndelAligner<int>::align (lib/alignment/GlobalLargeIndelAligner.hpp:48-54) when constructed with a
+/// largeIndelScore, GlobalAligner<int>::align (lib/alignment/GlobalAligner.hpp) otherwise
+template <typename ScoreType>
+struct SingleRefAligner {
+  SingleRefAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores) : _ctx(ctx), _scores(scores), _isIndel(false), _L(0) {}
+  SingleRefAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores, const ScoreType largeIndelScore)
+    : _ctx(ctx), _scores(scores), _isIndel(true), _L(largeIndelScore)
+  {
+  }
+  template <typename SymIter>
+  void align(const SymIter queryBegin, const SymIter queryEnd, const SymIter refBegin, const SymIter refEnd,
+             AlignmentResult<ScoreType>& result) const
+  {
+    std::vector<uint8_t>  pool;
+    const mb200_seqview   q(detail::append(pool, queryBegin, queryEnd));
+    const mb200_seqview   r(detail::append(pool, refBegin, refEnd));
+    std::vector<uint32_t> cigar(q.len + r.len + 16);
+    mb200_aln_result      res;
+    uint64_t              used(0);
+    const mb200_scores    sc(_scores.c());
+    if (_isIndel)
+      _ctx.check(mb200_indel_align_batch(_ctx.get(), &sc, _L, 1, pool.data(), pool.size(), &q, &r, &res, cigar.data(), cigar.size(), &used));
+    else
+      _ctx.check(mb200_global_align_batch(_ctx.get(), &sc, 1, pool.data(), pool.size(), &q, &r, &res, cigar.data(), cigar.size(), &used));
+    result                = AlignmentResult<ScoreType>();
+    result.score          = static_cast<ScoreType>(res.score);
+    result.isJumped       = (res.isJumped != 0);
+    result.align.beginPos = res.beginPos;
+    result.align.apath    = detail::toPath(cigar.data(), res.cigarOff, res.cigarLen);
+  }
+
+private:
+  const Context&                   _ctx;
+  const AlignmentScores<ScoreType> _scores;
+  const bool                       _isIndel;
+  const ScoreType                  _L;
+};
+template <typename ScoreType>
+struct GlobalLargeIndelAligner : public SingleRefAligner<ScoreType> {
+  GlobalLargeIndelAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores, const ScoreType largeIndelScore)
+    : SingleRefAligner<ScoreType>(ctx, scores, largeIndelScore)
+  {
+  }
+};
+template <typename ScoreType>
+struct GlobalAligner : public SingleRefAligner<ScoreType> {
+  GlobalAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores) : SingleRefAligner<ScoreType>(ctx, scores) {}
+};
+
+// ---- split-read scan --------------------------------------------------------------------------------
+struct SRAlignmentInfo {  // GSC/SplitReadAlignment.hpp:35-49
+  unsigned alignPos = 0, leftSize = 0, homSize = 0, rightSize = 0;
+  unsigned leftMismatches = 0, homMismatches = 0, rightMismatches = 0, alignScore = 0;
+  float    alignLnLhood = 0;
+  bool     isEvidence = false, isTier2Evidence = false;
+  float    evidence = 0;
+};
+
+/// splitReadAligner  GSC/SplitReadAlignment.hpp:63-70.  `lnComp`/`lnErr` are the 71-entry tables of the caller's
+/// qscore_snp (qphred_to_ln_comp_error_prob / qphred_to_ln_error_prob, lib/blt_util/qscore_snp.hpp:43-53);
+/// targetBpBegin/End are targetBpOffsetRange.begin_pos()/end_pos().
+inline void splitReadAligner(const Context& ctx, const unsigned flankScoreSize, const std::string& querySeq,
+                             const double* lnComp, const double* lnErr, const uint8_t* queryQual,
+                             const std::string& targetSeq, const int targetBpBegin, const int targetBpEnd,
+                             SRAlignmentInfo& alignment)
+{
+  std::vector<uint8_t> pool;
+  mb200_sr_job         job;
+  std::memset(&job, 0, sizeof(job));
+  job.query   = detail::append(pool, querySeq.begin(), querySeq.end());
+  job.qualOff = detail::append(pool, queryQual, queryQual + querySeq.size()).off;
+  job.target  = detail::append(pool, targetSeq.begin(), targetSeq.end());
+  job.bpBegin = targetBpBegin;
+  job.bpEnd   = targetBpEnd;
+  mb200_qscore_tables t;
+  for (int k(0); k < 2; ++k) {
+    std::memcpy(t.lnComp[k], lnComp, sizeof(t.lnComp[k]));
+    std::memcpy(t.lnErr[k], lnErr, sizeof(t.lnErr[k]));
+  }
+  mb200_sr_result r;
+  ctx.check(mb200_split_align_batch(ctx.get(), &t, flankScoreSize, 1, pool.data(), pool.size(), &job, &r));
+  if (r.status == MB200_ERR_SPLIT_INPUT) throw GeneralException(r.status, "Unexpected split read alignment input.");
+  if (r.status == MB200_ERR_SPLIT_SCAN) throw GeneralException(r.status, "Unexpected split read alignment input condition: scanEnd < scanStart.");
+  if (r.status == MB200_ERR_SPLIT_OUTCOME) throw GeneralException(r.status, "Unexpected split read alignment outcome. ");
+  if (r.status != MB200_OK) throw GeneralException(r.status, "basecall quality out of range");
+  alignment.alignPos = r.alignPos; alignment.leftSize = r.leftSize; alignment.homSize = r.homSize; alignment.rightSize = r.rightSize;
+  alignment.leftMismatches = r.leftMismatches; alignment.homMismatches = r.homMismatches; alignment.rightMismatches = r.rightMismatches;
+  alignment.alignScore = r.alignScore; alignment.alignLnLhood = r.alignLnLhood;
+  alignment.isEvidence = (r.isEvidence != 0); alignment.isTier2Evidence = (r.isTier2Evidence != 0); alignment.evidence = r.evidence;
+}
+
+// ---- assembler ----------------------------------------------------------------------------------------
+struct IterativeAssemblerOptions {  // lib/options/IterativeAssemblerOptions.hpp:26-59
+  unsigned minWordLength = 41, maxWordLength = 76, wordStepSize = 5, minCoverage = 1, minConservativeCoverage = 2;
+  unsigned minUnusedReads = 3, minSupportReads = 2, maxAssemblyCount = 10;
+};
+struct AssembledContig {  // lib/assembly/AssembledContig.hpp:38-50
+  std::string        seq;
+  unsigned           seedReadCount = 0;
+  std::set<unsigned> supportReads, rejectReads;
+  int                conservativeRangeBegin = 0, conservativeRangeEnd = 0;
+};
+struct AssemblyReadInfo {  // lib/assembly/AssemblyReadInfo.hpp:29-41
+  bool                  isUsed = false, isFiltered = false, isPseudo = false;
+  std::vector<unsigned> contigIds;
+};
+typedef std::vector<std::string>      AssemblyReadInput;
+typedef std::vector<AssemblyReadInfo> AssemblyReadOutput;
+typedef std::vector<AssembledContig>  Assembly;
+
+/// runIterativeAssembler  lib/assembly/IterativeAssembler.hpp:43-47: `reads` is mutated (pseudo reads appended),
+/// `readInfo` and `contigs` are filled exactly as the reference leaves them.
+inline void runIterativeAssembler(const Context& ctx, const IterativeAssemblerOptions& opt, AssemblyReadInput& reads,
+                                  AssemblyReadOutput& readInfo, Assembly& contigs)
+{
+  std::vector<uint8_t>       pool;
+  std::vector<mb200_seqview> views;
+  for (const std::string& r : reads) views.push_back(detail::append(pool, r.begin(), r.end()));
+  pool.resize(pool.size() + 64);
+  const uint64_t       readOff[2] = {0, reads.size()};
+  const mb200_asm_opts o{opt.minWordLength, opt.maxWordLength, opt.wordStepSize, opt.minCoverage, opt.minConservativeCoverage,
+                         opt.maxAssemblyCount, opt.minUnusedReads, opt.minSupportReads};
+  const uint32_t             A(opt.maxAssemblyCount);
+  mb200_asm_locus            L;
+  std::vector<mb200_contig>  cs(A);
+  std::vector<mb200_seqview> ps(2 * A);
+  size_t                     poolCap(1 << 16), setCap(4096);
+  std::vector<uint8_t>       cpool;
+  std::vector<uint32_t>      spool;
+  for (;;) {
+    cpool.resize(poolCap);
+    spool.resize(setCap);
+    const int st(mb200_assemble_batch(ctx.get(), &o, 1, readOff, views.data(), pool.data(), pool.size(), &L, cs.data(), A,
+                                      ps.data(), 2 * A, cpool.data(), poolCap, spool.data(), setCap));
+    if (st == MB200_ERR_POOL_OVERFLOW) {
+      poolCap *= 4;
+      setCap *= 4;
+      continue;
+    }
+    ctx.check(st);
+    break;
+  }
+  const unsigned normalReadCount(reads.size());
+  for (uint32_t p(0); p < L.nPseudo; ++p)
+    reads.emplace_back(reinterpret_cast<const char*>(cpool.data() + ps[L.firstPseudo + p].off), ps[L.firstPseudo + p].len);
+  readInfo.assign(reads.size(), AssemblyReadInfo());
+  for (unsigned r(normalReadCount); r < reads.size(); ++r) readInfo[r].isPseudo = true;
+  contigs.clear();
+  for (uint32_t c(0); c < L.nContigs; ++c) {
+    const mb200_contig& m(cs[L.firstContig + c]);
+    AssembledContig     ac;
+    ac.seq.assign(reinterpret_cast<const char*>(cpool.data() + m.seqOff), m.seqLen);
+    ac.conservativeRangeBegin = m.conservativeBegin;
+    ac.conservativeRangeEnd   = m.conservativeEnd;
+    for (uint32_t w(0); w < L.setWords; ++w) {
+      for (uint32_t b(0); b < 32; ++b) {
+        if (spool[m.supportOff + w] & (1u << b)) ac.supportReads.insert(w * 32 + b);
+        if (spool[m.rejectOff + w] & (1u << b)) ac.rejectReads.insert(w * 32 + b);
+      }
+    }
+    for (const unsigned rd : ac.supportReads) {  // IterativeAssembler.cpp:822-831
+      if (rd >= readInfo.size()) continue;       // stale pseudo index after the last word length failed
+      readInfo[rd].isUsed = true;
+      readInfo[rd].contigIds.push_back(c);
+    }
+    contigs.push_back(ac);
+  }
+}
+
+}  // namespace mb200

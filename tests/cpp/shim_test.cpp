@@ -1,0 +1,90 @@
+// Replays known-answer vectors of the reference's own unit tests through the C++ shim (reference call shapes):
+//   lib/alignment/test/GlobalJumpAlignerTest.cpp:68-129, GlobalLargeIndelAlignerTest.cpp:42-76,
+//   lib/assembly/test/IterativeAssemblerTest.cpp:132-170, GSC/test/SplitReadAlignmentTest.cpp:386-428
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "manta_b200_shim.hpp"
+
+#define REQUIRE(x)                                                     \
+  do {                                                                 \
+    if (!(x)) {                                                        \
+      std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #x); \
+      std::exit(1);                                                    \
+    }                                                                  \
+  } while (0)
+
+int main()
+{
+  mb200::Context ctx(0);
+  {
+    typedef int                       score_t;
+    mb200::AlignmentScores<score_t>   scores(2, -4, -5, -1, -1);
+    mb200::GlobalJumpAligner<score_t> aligner(ctx, scores, -3);
+    mb200::JumpAlignmentResult<score_t> result;
+    const std::string seq("ABABAABABACDCDCDyCDCDC"), ref1("xABABABABABAx"), ref2("xCDCDCDCDCDCDCx");
+    aligner.align(seq.begin(), seq.end(), ref1.begin(), ref1.end(), ref2.begin(), ref2.end(), result);
+    REQUIRE(mb200::apath_to_cigar(result.align1.apath) == "5=1D5=");
+    REQUIRE(result.align1.beginPos == 1);
+    REQUIRE(mb200::apath_to_cigar(result.align2.apath) == "6=1I5=");
+    REQUIRE(result.align2.beginPos == 1);
+    bool threw(false);
+    try {
+      const std::string empty;
+      aligner.align(empty.begin(), empty.end(), ref1.begin(), ref1.end(), ref2.begin(), ref2.end(), result);
+    } catch (const mb200::GeneralException& e) {
+      threw = (std::string(e.what()) == "Unexpected empty query sequence");
+    }
+    REQUIRE(threw);
+  }
+  {
+    mb200::AlignmentScores<int>         scores(2, -4, -5, -1, -4);
+    mb200::GlobalLargeIndelAligner<int> aligner(ctx, scores, -10);
+    mb200::AlignmentResult<int>         result;
+    const std::string seq("BCDEFHIKLM"), ref("ABCDEFGHIKLMN");
+    aligner.align(seq.begin(), seq.end(), ref.begin(), ref.end(), result);
+    REQUIRE(mb200::apath_to_cigar(result.align.apath) == "5=1D5=");
+    REQUIRE(result.align.beginPos == 1);
+  }
+  {
+    mb200::IterativeAssemblerOptions opt;
+    opt.minWordLength = 6; opt.maxWordLength = 6; opt.minCoverage = 1; opt.minSupportReads = 1; opt.minUnusedReads = 1;
+    mb200::AssemblyReadInput reads{"ATATAGACGATG", "ACGATGTCTATCTT", "ACGATGTTGGCCTT"};
+    mb200::AssemblyReadOutput readInfo;
+    mb200::Assembly           contigs;
+    mb200::runIterativeAssembler(ctx, opt, reads, readInfo, contigs);
+    REQUIRE(contigs.size() == 2u);
+    REQUIRE(contigs[0].seq == "ATATAGACGATGTCTATCTT");
+    REQUIRE(contigs[1].seq == "ATATAGACGATGTTGGCCTT");
+    REQUIRE(readInfo[0].isUsed && readInfo[0].contigIds.size() == 2 && readInfo[0].contigIds[1] == 1u);
+    REQUIRE(readInfo[2].contigIds[0] == 1u);
+  }
+  {
+    // qscore_snp(1e-3) tables computed like lib/blt_util/qscore_snp.cpp:29-41
+    double lnComp[71], lnErr[71];
+    for (int i = 0; i <= 70; ++i) {
+      const double qerr = std::pow(10., -static_cast<double>(i) / 10.);
+      const double q2p  = (qerr * (1. - 1e-3 / 3.)) + ((1 - qerr) * 1e-3);
+      lnComp[i]         = (std::fabs(-q2p) < 0.01) ? std::log1p(-q2p) : std::log(1 - q2p);
+      lnErr[i]          = std::log(q2p);
+    }
+    const std::string q("TCTATCACCCATCGTACCACTCACGGGAGCTCTCC");
+    const std::string t("GATCACAGGTCTATCACCCTATTAACCACTCACGGGAGCTCTCCATGCATTTGGTATTTTCGTCTGGGGGGTGTGCACGCGATAGCATTGCGAGACGCTGGA");
+    uint8_t qual[35];
+    for (int i = 0; i < 35; ++i) qual[i] = 30;
+    mb200::SRAlignmentInfo info;
+    mb200::splitReadAligner(ctx, 2, q, lnComp, lnErr, qual, t, 8, 50, info);
+    REQUIRE(info.leftSize == 0 && info.rightSize == 34 && info.rightMismatches == 27 && info.homSize == 1 && info.alignScore == 7);
+    bool threw(false);
+    try {
+      mb200::splitReadAligner(ctx, 2, q, lnComp, lnErr, qual, t, 1000, 1050, info);
+    } catch (const mb200::GeneralException&) {
+      threw = true;
+    }
+    REQUIRE(threw);
+  }
+  std::printf("shim_test ok\n");
+  return 0;
+}

@@ -1,0 +1,63 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes shard the edges by EdgeRetrieverBin-style bins and gather
+variable-length result buffers to rank 0 (the single collective of the path)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from manta_b200 import shard
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, counts, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = shard.assign_edges(counts, bin_count=8, rank=rank, world=world)
+    # a per-rank "result buffer" whose length depends on the shard
+    buf = np.repeat(mine.astype(np.uint32), 3).view(np.uint8)
+    got = shard.gather_buffers(buf, dst=0)
+    if rank == 0:
+        ret.put([g.view(np.uint32)[::3].tolist() for g in got])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bins_partition_edges():
+    rng = np.random.default_rng(1)
+    counts = rng.integers(0, 50, 1000)
+    for world in (1, 2, 4, 8):
+        seen = np.concatenate([shard.assign_edges(counts, 32, r, world) for r in range(world)])
+        assert sorted(seen.tolist()) == np.nonzero(counts > 0)[0].tolist()  # every edge exactly once
+    # bins carry (nearly) equal observation mass
+    total = int(counts.sum())
+    for b in range(32):
+        lo, hi = shard.bin_bounds(total, 32, b)
+        assert abs((hi - lo) - total / 32) <= 1
+
+
+def test_gather_world2_gloo():
+    counts = np.random.default_rng(2).integers(0, 20, 300)
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, counts, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(out[0] + out[1]) == np.nonzero(counts > 0)[0].tolist()
+    assert out[0] == shard.assign_edges(counts, 8, 0, 2).tolist()
+    assert out[1] == shard.assign_edges(counts, 8, 1, 2).tolist()
