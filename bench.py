@@ -39,6 +39,18 @@ METRIC = "sv_candidates_assembled_aligned_per_sec"
 UNIT = "candidates/s"
 
 
+def host_threads():
+    """usable host cores: min(nproc, cgroup CPU quota) -- the GPU boxes report 128 CPUs under a 16-core quota"""
+    n = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(int(q) // int(per))))
+    except Exception:
+        pass
+    return n
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -77,7 +89,7 @@ def run_cpu_sample(binding, batch, opts, n_loci, threads):
 
 def cpu_baseline(batch, opts, target_seconds=12.0):
     binding, kind = load_cpu_checker()
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     probe = min(batch.nLoci, max(threads, 16))
     n, cells, dt = run_cpu_sample(binding, batch, opts, probe, threads)
     rate = n / dt
@@ -169,7 +181,7 @@ def main():
         sample_loci = min(args.loci, 4096)
         batch = synth.make_candidate_batch(sample_loci, seed=20260923)
         binding, kind = load_cpu_checker()
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         # size one step to ~8 s of CPU work
         n, cells, dt = run_cpu_sample(binding, batch, opts, min(sample_loci, max(threads, 16)), threads)
         per_step = int(min(sample_loci, max(threads, n / dt * 8.0)))

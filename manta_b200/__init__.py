@@ -51,11 +51,12 @@ def _load_library() -> C.CDLL:
 class Context(Binding):
     """One device context (mb200_ctx): owns the stream and all device buffers."""
 
-    def __init__(self, device: int = 0, ctas_per_sm: int = 0, scratch_bytes: int = 0):
+    def __init__(self, device: int = 0, ctas_per_sm: int = 0, scratch_bytes: int = 0, force_int32: bool = False):
         lib = _load_library()
         cfg = np.zeros(1, dtype=_cabi.CONFIG_DT)
         cfg["ctasPerSm"] = ctas_per_sm
         cfg["scratchBytes"] = scratch_bytes
+        cfg["reserved"][0][0] = 1 if force_int32 else 0  # always use the int32 one-alignment-per-warp DP kernel
         handle = C.c_void_p()
         st = lib.mb200_create(C.c_int(device), cfg.ctypes.data_as(C.c_void_p), C.byref(handle))
         if st != _cabi.MB200_OK:

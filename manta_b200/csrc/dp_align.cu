@@ -45,11 +45,19 @@ constexpr int REF_TILE  = 2048;            // bytes per staged reference tile
 constexpr int REF_RING  = 2 * REF_TILE;    // two tiles resident per warp
 constexpr int WARPS_PER_CTA = 4;
 
+struct DpPair {
+  DpTask a, b;
+  uint32_t dup;  // 1: b is a copy of a (unpaired task), only a's result is emitted
+  uint32_t pad;
+};
+
 struct DpParams {
   int match, mismatch, open, extend, offEdge, allowEdgeIns;
   int extra;  // jumpScore (KIND_JUMP) or largeIndelScore (KIND_INDEL)
   const DpTask*  tasks;
   uint32_t       nTasks;
+  const DpPair*  pairs;   // pair kernel: two tasks per warp (int16x2 lanes)
+  uint32_t       nPairs;
   uint32_t*      workCounter;
   uint8_t*       ptrScratch;
   size_t         ptrStride;  // bytes per warp slot
@@ -153,12 +161,13 @@ __device__ __forceinline__ void stageIssue(const RefStage& st, uint32_t tile, in
 // ---- back-pointer addressing in the skewed layout --------------------------------------------------
 template <int RT, int CELLB> struct PtrLayout {
   static constexpr int BYTES_PER_THREAD = RT * CELLB;                                // per step
-  static constexpr int CHUNK_BYTES      = BYTES_PER_THREAD < 16 ? BYTES_PER_THREAD : 16;
+  // widest vector store (16, 8 or 4 bytes) that divides the per-thread bytes
+  static constexpr int CHUNK_BYTES      = (BYTES_PER_THREAD % 16 == 0) ? 16 : ((BYTES_PER_THREAD % 8 == 0) ? 8 : 4);
   static constexpr int NCHUNK           = BYTES_PER_THREAD / CHUNK_BYTES;
   static constexpr int STEP_BYTES       = 32 * BYTES_PER_THREAD;
   __device__ static __forceinline__ size_t passBytes(uint32_t rtot) { return (size_t)(rtot + 31) * STEP_BYTES; }
   // cell (q>=1, c>=1) -> byte offset
-  __device__ static __forceinline__ size_t cellOffset(uint32_t q, uint32_t c, uint32_t rtot)
+  __device__ static __forceinline__ size_t cellOffset(uint32_t q, uint32_t c, size_t passStride)
   {
     const uint32_t row    = q - 1;
     const uint32_t pass   = row / (32 * RT);
@@ -169,9 +178,29 @@ template <int RT, int CELLB> struct PtrLayout {
     const uint32_t boff   = rr * CELLB;
     const uint32_t chunk  = boff / CHUNK_BYTES;
     const uint32_t inner  = boff % CHUNK_BYTES;
-    return (size_t)pass * passBytes(rtot) + ((size_t)(t * NCHUNK + chunk) * 32 + lane) * CHUNK_BYTES + inner;
+    return (size_t)pass * passStride + ((size_t)(t * NCHUNK + chunk) * 32 + lane) * CHUNK_BYTES + inner;
   }
 };
+
+// one step's back-pointer words of a lane -> the skewed layout (chunk-major so each store instruction of the warp
+// covers one contiguous line)
+template <typename PL, int PTRWORDS>
+__device__ __forceinline__ void storePtrWords(uint8_t* stepBase, int lane, const uint32_t* pw)
+{
+  constexpr int CW = PL::CHUNK_BYTES / 4;
+#pragma unroll
+  for (int ch = 0; ch < PL::NCHUNK; ++ch) {
+    uint8_t* dst = stepBase + ((size_t)ch * 32 + lane) * PL::CHUNK_BYTES;
+    if (CW == 4) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pw[(ch * 4 + 0) % PTRWORDS], pw[(ch * 4 + 1) % PTRWORDS],
+                                                  pw[(ch * 4 + 2) % PTRWORDS], pw[(ch * 4 + 3) % PTRWORDS]);
+    } else if (CW == 2) {
+      *reinterpret_cast<uint2*>(dst) = make_uint2(pw[(ch * 2 + 0) % PTRWORDS], pw[(ch * 2 + 1) % PTRWORDS]);
+    } else {
+      *reinterpret_cast<uint32_t*>(dst) = pw[ch % PTRWORDS];
+    }
+  }
+}
 
 // ---- path emission helpers (lane 0 only) -------------------------------------------------------------
 struct SegWriter {
@@ -250,6 +279,177 @@ __device__ void rawLengths(const uint32_t* raw, uint32_t n, uint32_t& readLen, u
     const uint32_t len  = MB200_SEG_LEN(raw[k]);
     if (segIsReadLen(type)) readLen += len;
     if (segIsRefLen(type)) refLen += len;
+  }
+}
+
+// ---- trace-back + path emission of one finished alignment (lane 0 of the owning warp) -------------------
+// ptrBuf holds the task's back-pointer cells in the skewed layout with `passStride` bytes per pass.
+template <int KIND, int RT>
+__device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t* ptrBuf, size_t passStride,
+                           uint32_t* segBuf, long long bestKey, bool stageOk)
+{
+  using KT           = KindTraits<KIND>;
+  using PL           = PtrLayout<RT, KT::CELLB>;
+  constexpr int BITS = KT::BITS;
+  const uint32_t Q = task.Q, R1 = task.R1;
+  const uint32_t R2   = (KIND == KIND_JUMP) ? task.R2 : 0u;
+  const uint8_t* qSeq = task.q;
+  const uint8_t* ref1 = task.r1;
+  const uint8_t* ref2 = task.r2;
+  {
+    if (!stageOk) atomicExch(P.errFlag, MB200_ERR_CUDA);
+    const int      bestVal = (int)(bestKey >> 32);
+    const uint32_t seq     = 0x7fffffffu - (uint32_t)(bestKey & 0xffffffffLL);
+
+    if (KIND == KIND_JUMP) {
+      // ---------------- JumpAlignerBase::backTraceAlignment  (JumpAlignerBaseImpl.hpp:101-242)
+      uint32_t refBegin, queryBegin;
+      if (seq < R1) { refBegin = seq + 1; queryBegin = Q; }
+      else if (seq < R1 + Q) { refBegin = R1; queryBegin = seq - R1; }
+      else if (seq < R1 + Q + R2) { refBegin = R1 + (seq - R1 - Q) + 1; queryBegin = Q; }
+      else { refBegin = R1 + R2; queryBegin = seq - (R1 + Q + R2); }
+      uint32_t state = ST_MATCH;
+
+      // raw paths in back-trace order: apath1 in segBuf[0..), apath2 in segBuf[half..)
+      const uint32_t half = (uint32_t)(P.segStride / 2);
+      uint32_t       n1 = 0, n2 = 0;
+      uint32_t       psType = MB200_SEG_NONE, psLen = 0;
+      uint32_t       jumpInsertSize = 0;
+      int            beginPos1 = 0, beginPos2 = 0;
+      if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
+      bool isRef2End = false;
+#define PUSH_TO(isRef1, T, L) do { if (isRef1) segBuf[n1++] = MB200_SEG_MAKE(L, T); else segBuf[half + n2++] = MB200_SEG_MAKE(L, T); } while (0)
+#define UPDATE_PATH(isRef1, AT) do { if (psType != (AT)) { if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen); psType = (AT); psLen = 0; } } while (0)
+      while (queryBegin > 0 && refBegin > 0) {
+        if (isRef2End) break;
+        const bool     isRef1    = (refBegin <= R1);
+        const uint32_t refXBegin = refBegin - (isRef1 ? 0 : R1);
+        const uint32_t cell      = ptrBuf[PL::cellOffset(queryBegin, refBegin, passStride)];
+        const uint32_t next      = (cell >> (BITS * state)) & ((1u << BITS) - 1);
+        if (state == ST_MATCH) {
+          if (!isRef1 && refXBegin == 1 && next == ST_MATCH) isRef2End = true;
+          UPDATE_PATH(isRef1, MB200_SEG_MATCH);
+          queryBegin--;
+          refBegin--;
+        } else if (state == ST_DELETE) {
+          UPDATE_PATH(isRef1, MB200_SEG_DELETE);
+          refBegin--;
+        } else if (state == ST_INSERT) {
+          UPDATE_PATH(isRef1, MB200_SEG_INSERT);
+          queryBegin--;
+        } else {  // ST_JUMP
+          if (psType != MB200_SEG_NONE) {
+            beginPos2 = (int)(refBegin - R1);
+            if (psType == MB200_SEG_INSERT) {
+              jumpInsertSize += psLen;
+              psType = MB200_SEG_NONE;
+              psLen  = 0;
+            } else {
+              UPDATE_PATH(false, MB200_SEG_NONE);
+            }
+          } else {
+            if (next == ST_JUMP) refBegin--;
+          }
+        }
+        state = next;
+        psLen++;
+      }
+      {
+        const bool isRef1 = (refBegin < R1);
+        if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen);
+        if (queryBegin != 0) PUSH_TO(isRef1, MB200_SEG_SOFT_CLIP, queryBegin);
+        if (isRef1) beginPos1 = (int)refBegin; else beginPos2 = (int)(refBegin - R1);
+      }
+#undef PUSH_TO
+#undef UPDATE_PATH
+      uint32_t read1, refl1, read2, refl2;
+      rawLengths(segBuf, n1, read1, refl1);
+      rawLengths(segBuf + half, n2, read2, refl2);
+      (void)read2; (void)refl2;
+
+      uint32_t jumpRange = 0;
+      if (n1 && n2) {
+        uint32_t r1i = (uint32_t)beginPos1 + refl1, r2i = (uint32_t)beginPos2, qi = read1;
+        uint32_t jic = jumpInsertSize;
+        for (;;) {
+          if (r1i == R1) break;
+          if (jic > 0) {
+            if (qi == Q) break;
+            if (ref1[r1i] != qSeq[qi]) break;
+          } else {
+            if (r2i == R2) break;
+            if (ref1[r1i] != ref2[r2i]) break;
+          }
+          jumpRange++;
+          r1i++;
+          if (jic > 0) { jic--; qi++; } else { r2i++; }
+        }
+      }
+      const uint8_t* q2 = qSeq + read1 + jumpInsertSize;
+      const uint32_t c1 = expandPath(segBuf, n1, qSeq, ref1 + beginPos1, nullptr);
+      const uint32_t c2 = expandPath(segBuf + half, n2, q2, ref2 + beginPos2, nullptr);
+      const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)(c1 + c2));
+      if (off + c1 + c2 <= P.cigarCap) {
+        expandPath(segBuf, n1, qSeq, ref1 + beginPos1, P.cigarPool + off);
+        expandPath(segBuf + half, n2, q2, ref2 + beginPos2, P.cigarPool + off + c1);
+      }
+      mb200_jump_result* o = reinterpret_cast<mb200_jump_result*>(P.results) + task.outIndex;
+      o->score = bestVal; o->jumpInsertSize = jumpInsertSize; o->jumpRange = jumpRange;
+      o->beginPos1 = beginPos1; o->beginPos2 = beginPos2;
+      o->cigarLen1 = c1; o->cigarLen2 = c2; o->reserved = 0;
+      o->cigarOff1 = off; o->cigarOff2 = off + c1;
+    } else {
+      // ---------------- SingleRefAlignerBase::backTraceAlignment (SingleRefAlignerSharedImpl.hpp:75-168)
+      const uint32_t R = R1;
+      uint32_t       refBegin, queryBegin, state = ST_MATCH;
+      if (seq < R) { refBegin = seq + 1; queryBegin = Q; }
+      else if (seq == R) { refBegin = R; queryBegin = Q; state = ST_INSERT; }
+      else { refBegin = R; queryBegin = seq - R - 1; }
+      uint32_t n = 0, psType = MB200_SEG_NONE, psLen = 0, isJumped = 0;
+      if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
+      for (;;) {
+        uint32_t next;
+        if (queryBegin >= 1 && refBegin >= 1) {
+          uint32_t cell;
+          if (KT::CELLB == 1) cell = ptrBuf[PL::cellOffset(queryBegin, refBegin, passStride)];
+          else cell = *reinterpret_cast<const uint16_t*>(ptrBuf + PL::cellOffset(queryBegin, refBegin, passStride));
+          next = (cell >> (BITS * state)) & ((1u << BITS) - 1);
+        } else {
+          // row 0 / column 0 pointers: all MATCH, except column-0 insert state with edge insertions allowed
+          next = (refBegin == 0 && state == ST_INSERT && P.allowEdgeIns) ? ST_INSERT : ST_MATCH;
+        }
+        uint32_t atype;
+        if (state == ST_MATCH) {
+          if (queryBegin < 1 || refBegin < 1) break;
+          atype = MB200_SEG_MATCH;
+        } else if (state == ST_DELETE || state == ST_JUMP) {
+          if (refBegin < 1) break;
+          atype = MB200_SEG_DELETE;
+        } else {
+          if (queryBegin < 1) break;
+          atype = MB200_SEG_INSERT;
+        }
+        if (psType != atype) {
+          if (psType != MB200_SEG_NONE) segBuf[n++] = MB200_SEG_MAKE(psLen, psType);
+          psType = atype;
+          psLen  = 0;
+        }
+        if (state == ST_MATCH) { queryBegin--; refBegin--; }
+        else if (state == ST_DELETE || state == ST_JUMP) { refBegin--; }
+        else { queryBegin--; }
+        if (state == ST_JUMP || state == ST_JUMPINS) isJumped = 1;
+        state = next;
+        psLen++;
+      }
+      if (psType != MB200_SEG_NONE) segBuf[n++] = MB200_SEG_MAKE(psLen, psType);
+      if (queryBegin != 0) segBuf[n++] = MB200_SEG_MAKE(queryBegin, MB200_SEG_SOFT_CLIP);
+      const int      beginPos = (int)refBegin;
+      const uint32_t cnt      = expandPath(segBuf, n, qSeq, ref1 + beginPos, nullptr);
+      const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)cnt);
+      if (off + cnt <= P.cigarCap) expandPath(segBuf, n, qSeq, ref1 + beginPos, P.cigarPool + off);
+      mb200_aln_result* o = reinterpret_cast<mb200_aln_result*>(P.results) + task.outIndex;
+      o->score = bestVal; o->beginPos = beginPos; o->isJumped = isJumped; o->cigarLen = cnt; o->cigarOff = off;
+    }
   }
 }
 
@@ -588,18 +788,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpAlignKernel(const DpPara
           // ---- back-pointers of this (lane, step): contiguous per warp in the skewed layout
           {
             uint8_t* stepBase = passPtr + (size_t)t * PL::STEP_BYTES;
-            if (PL::CHUNK_BYTES == 4) {
-              *reinterpret_cast<uint32_t*>(stepBase + lane * 4) = ptrw[0];
-            } else if (PL::CHUNK_BYTES == 8) {
-              *reinterpret_cast<uint2*>(stepBase + lane * 8) = make_uint2(ptrw[0], ptrw[PTRWORDS > 1 ? 1 : 0]);
-            } else {
-#pragma unroll
-              for (int ch = 0; ch < PL::NCHUNK; ++ch) {
-                *reinterpret_cast<uint4*>(stepBase + ((size_t)ch * 32 + lane) * 16) =
-                    make_uint4(ptrw[(ch * 4 + 0) % PTRWORDS], ptrw[(ch * 4 + 1) % PTRWORDS],
-                               ptrw[(ch * 4 + 2) % PTRWORDS], ptrw[(ch * 4 + 3) % PTRWORDS]);
-              }
-            }
+            storePtrWords<PL, PTRWORDS>(stepBase, lane, ptrw);
           }
           // strip boundary row for the next pass
           if (lane == 31 && pass + 1 < nPass) {
@@ -640,163 +829,425 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpAlignKernel(const DpPara
     __threadfence_block();
     __syncwarp();
 
-    if (lane == 0) {
-      if (!stageOk) atomicExch(P.errFlag, MB200_ERR_CUDA);
-      const int      bestVal = (int)(bestKey >> 32);
-      const uint32_t seq     = 0x7fffffffu - (uint32_t)(bestKey & 0xffffffffLL);
-
-      if (KIND == KIND_JUMP) {
-        // ---------------- JumpAlignerBase::backTraceAlignment  (JumpAlignerBaseImpl.hpp:101-242)
-        uint32_t refBegin, queryBegin;
-        if (seq < R1) { refBegin = seq + 1; queryBegin = Q; }
-        else if (seq < R1 + Q) { refBegin = R1; queryBegin = seq - R1; }
-        else if (seq < R1 + Q + R2) { refBegin = R1 + (seq - R1 - Q) + 1; queryBegin = Q; }
-        else { refBegin = R1 + R2; queryBegin = seq - (R1 + Q + R2); }
-        uint32_t state = ST_MATCH;
-
-        // raw paths in back-trace order: apath1 in segBuf[0..), apath2 in segBuf[half..)
-        const uint32_t half = (uint32_t)(P.segStride / 2);
-        uint32_t       n1 = 0, n2 = 0;
-        uint32_t       psType = MB200_SEG_NONE, psLen = 0;
-        uint32_t       jumpInsertSize = 0;
-        int            beginPos1 = 0, beginPos2 = 0;
-        if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
-        bool isRef2End = false;
-#define PUSH_TO(isRef1, T, L) do { if (isRef1) segBuf[n1++] = MB200_SEG_MAKE(L, T); else segBuf[half + n2++] = MB200_SEG_MAKE(L, T); } while (0)
-#define UPDATE_PATH(isRef1, AT) do { if (psType != (AT)) { if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen); psType = (AT); psLen = 0; } } while (0)
-        while (queryBegin > 0 && refBegin > 0) {
-          if (isRef2End) break;
-          const bool     isRef1    = (refBegin <= R1);
-          const uint32_t refXBegin = refBegin - (isRef1 ? 0 : R1);
-          const uint32_t cell      = ptrBuf[PL::cellOffset(queryBegin, refBegin, RTOT)];
-          const uint32_t next      = (cell >> (BITS * state)) & ((1u << BITS) - 1);
-          if (state == ST_MATCH) {
-            if (!isRef1 && refXBegin == 1 && next == ST_MATCH) isRef2End = true;
-            UPDATE_PATH(isRef1, MB200_SEG_MATCH);
-            queryBegin--;
-            refBegin--;
-          } else if (state == ST_DELETE) {
-            UPDATE_PATH(isRef1, MB200_SEG_DELETE);
-            refBegin--;
-          } else if (state == ST_INSERT) {
-            UPDATE_PATH(isRef1, MB200_SEG_INSERT);
-            queryBegin--;
-          } else {  // ST_JUMP
-            if (psType != MB200_SEG_NONE) {
-              beginPos2 = (int)(refBegin - R1);
-              if (psType == MB200_SEG_INSERT) {
-                jumpInsertSize += psLen;
-                psType = MB200_SEG_NONE;
-                psLen  = 0;
-              } else {
-                UPDATE_PATH(false, MB200_SEG_NONE);
-              }
-            } else {
-              if (next == ST_JUMP) refBegin--;
-            }
-          }
-          state = next;
-          psLen++;
-        }
-        {
-          const bool isRef1 = (refBegin < R1);
-          if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen);
-          if (queryBegin != 0) PUSH_TO(isRef1, MB200_SEG_SOFT_CLIP, queryBegin);
-          if (isRef1) beginPos1 = (int)refBegin; else beginPos2 = (int)(refBegin - R1);
-        }
-#undef PUSH_TO
-#undef UPDATE_PATH
-        uint32_t read1, refl1, read2, refl2;
-        rawLengths(segBuf, n1, read1, refl1);
-        rawLengths(segBuf + half, n2, read2, refl2);
-        (void)read2; (void)refl2;
-
-        uint32_t jumpRange = 0;
-        if (n1 && n2) {
-          uint32_t r1i = (uint32_t)beginPos1 + refl1, r2i = (uint32_t)beginPos2, qi = read1;
-          uint32_t jic = jumpInsertSize;
-          for (;;) {
-            if (r1i == R1) break;
-            if (jic > 0) {
-              if (qi == Q) break;
-              if (ref1[r1i] != qSeq[qi]) break;
-            } else {
-              if (r2i == R2) break;
-              if (ref1[r1i] != ref2[r2i]) break;
-            }
-            jumpRange++;
-            r1i++;
-            if (jic > 0) { jic--; qi++; } else { r2i++; }
-          }
-        }
-        const uint8_t* q2 = qSeq + read1 + jumpInsertSize;
-        const uint32_t c1 = expandPath(segBuf, n1, qSeq, ref1 + beginPos1, nullptr);
-        const uint32_t c2 = expandPath(segBuf + half, n2, q2, ref2 + beginPos2, nullptr);
-        const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)(c1 + c2));
-        if (off + c1 + c2 <= P.cigarCap) {
-          expandPath(segBuf, n1, qSeq, ref1 + beginPos1, P.cigarPool + off);
-          expandPath(segBuf + half, n2, q2, ref2 + beginPos2, P.cigarPool + off + c1);
-        }
-        mb200_jump_result* o = reinterpret_cast<mb200_jump_result*>(P.results) + task.outIndex;
-        o->score = bestVal; o->jumpInsertSize = jumpInsertSize; o->jumpRange = jumpRange;
-        o->beginPos1 = beginPos1; o->beginPos2 = beginPos2;
-        o->cigarLen1 = c1; o->cigarLen2 = c2; o->reserved = 0;
-        o->cigarOff1 = off; o->cigarOff2 = off + c1;
-      } else {
-        // ---------------- SingleRefAlignerBase::backTraceAlignment (SingleRefAlignerSharedImpl.hpp:75-168)
-        const uint32_t R = R1;
-        uint32_t       refBegin, queryBegin, state = ST_MATCH;
-        if (seq < R) { refBegin = seq + 1; queryBegin = Q; }
-        else if (seq == R) { refBegin = R; queryBegin = Q; state = ST_INSERT; }
-        else { refBegin = R; queryBegin = seq - R - 1; }
-        uint32_t n = 0, psType = MB200_SEG_NONE, psLen = 0, isJumped = 0;
-        if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
-        for (;;) {
-          uint32_t next;
-          if (queryBegin >= 1 && refBegin >= 1) {
-            uint32_t cell;
-            if (KT::CELLB == 1) cell = ptrBuf[PL::cellOffset(queryBegin, refBegin, RTOT)];
-            else cell = *reinterpret_cast<const uint16_t*>(ptrBuf + PL::cellOffset(queryBegin, refBegin, RTOT));
-            next = (cell >> (BITS * state)) & ((1u << BITS) - 1);
-          } else {
-            // row 0 / column 0 pointers: all MATCH, except column-0 insert state with edge insertions allowed
-            next = (refBegin == 0 && state == ST_INSERT && P.allowEdgeIns) ? ST_INSERT : ST_MATCH;
-          }
-          uint32_t atype;
-          if (state == ST_MATCH) {
-            if (queryBegin < 1 || refBegin < 1) break;
-            atype = MB200_SEG_MATCH;
-          } else if (state == ST_DELETE || state == ST_JUMP) {
-            if (refBegin < 1) break;
-            atype = MB200_SEG_DELETE;
-          } else {
-            if (queryBegin < 1) break;
-            atype = MB200_SEG_INSERT;
-          }
-          if (psType != atype) {
-            if (psType != MB200_SEG_NONE) segBuf[n++] = MB200_SEG_MAKE(psLen, psType);
-            psType = atype;
-            psLen  = 0;
-          }
-          if (state == ST_MATCH) { queryBegin--; refBegin--; }
-          else if (state == ST_DELETE || state == ST_JUMP) { refBegin--; }
-          else { queryBegin--; }
-          if (state == ST_JUMP || state == ST_JUMPINS) isJumped = 1;
-          state = next;
-          psLen++;
-        }
-        if (psType != MB200_SEG_NONE) segBuf[n++] = MB200_SEG_MAKE(psLen, psType);
-        if (queryBegin != 0) segBuf[n++] = MB200_SEG_MAKE(queryBegin, MB200_SEG_SOFT_CLIP);
-        const int      beginPos = (int)refBegin;
-        const uint32_t cnt      = expandPath(segBuf, n, qSeq, ref1 + beginPos, nullptr);
-        const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)cnt);
-        if (off + cnt <= P.cigarCap) expandPath(segBuf, n, qSeq, ref1 + beginPos, P.cigarPool + off);
-        mb200_aln_result* o = reinterpret_cast<mb200_aln_result*>(P.results) + task.outIndex;
-        o->score = bestVal; o->beginPos = beginPos; o->isJumped = isJumped; o->cigarLen = cnt; o->cigarOff = off;
-      }
-    }
+    if (lane == 0) emitResult<KIND, RT>(P, task, ptrBuf, PL::passBytes(RTOT), segBuf, bestKey, stageOk);
     __syncwarp();
   }  // tasks
+}
+
+
+// ======================================================================================================
+// int16x2 pair kernel: one warp fills TWO alignments at once, task A in the low and task B in the high 16-bit half
+// of every register (inter-task SIMD).  sm_100a executes the packed max with per-half predicate outputs
+// (VIMNMX.S16x2 R, P, P, a, b -- __vibmax_s16x2) and the packed add (VIADD.16x2 -- __vadd2) natively, so one
+// instruction advances two cells.  Legal only while every score stays inside int16 (the host checks the bound from
+// the scores and the query length; otherwise the int32 kernel above runs) -- within the bound 16-bit two's
+// complement arithmetic is the reference's int arithmetic, sentinel included.  Jump pairs must share R1.
+__device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) | ((uint32_t)v << 16); }
+__device__ __forceinline__ int lo16(uint32_t x) { return (int)(short)(x & 0xffffu); }
+__device__ __forceinline__ int hi16(uint32_t x) { return ((int)x) >> 16; }
+
+// m = max(m, v) per half; where v wins strictly the half's pointer field becomes `code` (pre-shifted)
+template <uint32_t CODE_SHIFTED>
+__device__ __forceinline__ void vmaxp(uint32_t& m, uint32_t v, uint32_t& fa, uint32_t& fb)
+{
+  bool ph, pl;
+  m  = __vibmax_s16x2(m, v, &ph, &pl);
+  fa = pl ? fa : CODE_SHIFTED;
+  fb = ph ? fb : CODE_SHIFTED;
+}
+
+struct StageCursor {
+  RefStage st;
+  uint32_t nextIssue, waitTile;
+  uint32_t used[2];
+};
+
+__device__ __forceinline__ uint32_t stagedIndex(const RefStage& st, uint32_t cz, uint32_t R1, bool isJump)
+{
+  return (isJump && cz >= R1) ? (st.base2 + st.shift2 + (cz - R1)) : (st.shift1 + cz);
+}
+
+__device__ __forceinline__ bool cursorWait(StageCursor& cur)
+{
+#if MB200_USE_TMA
+  const uint32_t barAddr = smemAddr(&cur.st.bar[cur.waitTile & 1]);
+  const uint32_t parity  = cur.used[cur.waitTile & 1] & 1;
+  uint32_t       ok      = 0;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(barAddr), "r"(parity)
+        : "memory");
+    if (ok) break;
+  }
+  cur.used[cur.waitTile & 1]++;
+  cur.waitTile++;
+  return ok != 0;
+#else
+  __syncwarp();
+  cur.waitTile++;
+  return true;
+#endif
+}
+
+template <int KIND, int RT>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParams P)
+{
+  using KT               = KindTraits<KIND>;
+  using PL               = PtrLayout<RT, KT::CELLB>;
+  constexpr int NS       = KT::NS;
+  constexpr int BITS     = KT::BITS;
+  constexpr int STRIP    = 32 * RT;
+  constexpr int PTRWORDS = RT * KT::CELLB / 4;
+  constexpr int ROWBITS  = 8 * KT::CELLB;  // bits of one cell in the pointer words
+  constexpr int ROWSPW   = 32 / ROWBITS;   // cells per 32-bit pointer word
+  static_assert(RT % 4 == 0, "RT must be a multiple of 4");
+
+  __shared__ __align__(128) uint8_t sRing[WARPS_PER_CTA][2][REF_RING];
+  __shared__ __align__(8) uint64_t sBar[WARPS_PER_CTA][2][2];
+  __shared__ uint32_t sTask[WARPS_PER_CTA];
+
+  const int      lane    = threadIdx.x & 31;
+  const int      warp    = threadIdx.x >> 5;
+  const uint32_t slot    = blockIdx.x * WARPS_PER_CTA + warp;
+  const size_t   halfPtr = P.ptrStride / 2;
+  uint8_t*       ptrBufA = P.ptrScratch + (size_t)slot * P.ptrStride;
+  uint8_t*       ptrBufB = ptrBufA + halfPtr;
+  uint32_t*      segBufA = P.segScratch + (size_t)slot * 2 * P.segStride;
+  uint32_t*      segBufB = segBufA + P.segStride;
+  int*           bndBuf  = P.bndScratch + (size_t)slot * P.bndStride;
+
+  StageCursor curA, curB;
+  curA.used[0] = curA.used[1] = curB.used[0] = curB.used[1] = 0;
+#if MB200_USE_TMA
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&sBar[warp][h][b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+#endif
+
+  const int      offEdge = P.offEdge;
+  const uint32_t open2 = pack2(P.open), ext2 = pack2(P.extend), match2 = pack2(P.match);
+  const uint32_t negDelta = (uint32_t)(P.mismatch - P.match) & 0xffffu;  // per-half (mismatch - match)
+  const uint32_t extra2 = pack2(P.extra), BAD2 = pack2(BADVAL);
+  const uint32_t extraMinusOpen2 = pack2(P.extra - P.open);
+  const bool     allowEdgeIns = (KIND != KIND_JUMP) && P.allowEdgeIns;
+
+  for (;;) {
+    if (lane == 0) sTask[warp] = atomicAdd(P.workCounter, 1u);
+    __syncwarp();
+    const uint32_t pairIdx = sTask[warp];
+    __syncwarp();
+    if (pairIdx >= P.nPairs) break;
+    const DpPair   pr = P.pairs[pairIdx];
+    const DpTask   tA = pr.a, tB = pr.b;
+    const uint32_t QA = tA.Q, QB = tB.Q;
+    const uint32_t Q  = QA > QB ? QA : QB;
+    const uint32_t R1 = tA.R1;  // == tB.R1 for jump pairs; single-ref kinds: R1 is the whole reference
+    const uint32_t R1A = tA.R1, R1B = tB.R1;
+    const uint32_t R2A = (KIND == KIND_JUMP) ? tA.R2 : 0u, R2B = (KIND == KIND_JUMP) ? tB.R2 : 0u;
+    const uint32_t RTA = R1A + R2A, RTB = R1B + R2B;
+    const uint32_t RTOT = RTA > RTB ? RTA : RTB;
+    const size_t   passStride = PL::passBytes(RTOT);
+
+    // ---- staging geometry of both halves
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      StageCursor&   cur  = h ? curB : curA;
+      const DpTask&  tk   = h ? tB : tA;
+      RefStage&      st   = cur.st;
+      st.shift1 = (uint32_t)(reinterpret_cast<uintptr_t>(tk.r1) & 15);
+      st.src1   = tk.r1 - st.shift1;
+      st.base2  = (st.shift1 + tk.R1 + 15) & ~15u;
+      if (KIND == KIND_JUMP) {
+        st.shift2 = (uint32_t)(reinterpret_cast<uintptr_t>(tk.r2) & 15);
+        st.src2   = tk.r2 - st.shift2;
+        st.total  = st.base2 + ((st.shift2 + tk.R2 + 15) & ~15u);
+      } else {
+        st.shift2 = 0;
+        st.src2   = st.src1;
+        st.total  = st.base2;
+      }
+      st.ring   = sRing[warp][h];
+      st.bar    = sBar[warp][h];
+      st.nTiles = (st.total + REF_TILE - 1) / REF_TILE;
+    }
+
+    long long bestA = (long long)0x8000000000000000LL, bestB = bestA;
+    bool      stageOk = true;
+
+    const uint32_t nPass = (Q + STRIP - 1) / STRIP;
+    for (uint32_t pass = 0; pass < nPass; ++pass) {
+      const uint32_t q0 = pass * STRIP + lane * RT;
+      // query characters: low half task A, high half task B (0 beyond the end)
+      uint32_t qpair[RT];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const uint32_t row = q0 + r;
+        const uint32_t ca  = (row < QA) ? (uint32_t)__ldg(tA.q + row) : 0u;
+        const uint32_t cb  = (row < QB) ? (uint32_t)__ldg(tB.q + row) : 0u;
+        qpair[r]           = ca | (cb << 16);
+      }
+      // which of my rows is the last query row of A / of B (RT == none)
+      const int rQA = (QA > q0 && QA <= q0 + RT) ? (int)(QA - q0 - 1) : RT;
+      const int rQB = (QB > q0 && QB <= q0 + RT) ? (int)(QB - q0 - 1) : RT;
+
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        StageCursor& cur = h ? curB : curA;
+        stageIssue(cur.st, 0, lane);
+        cur.nextIssue = 1;
+        if (cur.st.nTiles > 1) {
+          stageIssue(cur.st, 1, lane);
+          cur.nextIssue = 2;
+        }
+        cur.waitTile = 0;
+      }
+
+      uint32_t pM[RT], pD[RT], pI[RT], pJ[RT], pK[RT];
+      uint32_t lastM = 0, lastD = BAD2, lastI = BAD2, lastJ = BAD2, lastK = BAD2;
+      uint32_t dgM = 0, dgD = BAD2, dgI = BAD2, dgJ = BAD2, dgK = BAD2;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) { pM[r] = 0; pD[r] = pI[r] = pJ[r] = pK[r] = BAD2; }
+
+      const uint32_t nSteps = RTOT + 31;
+      uint8_t*       passA  = ptrBufA + (size_t)pass * passStride;
+      uint8_t*       passB  = ptrBufB + (size_t)pass * passStride;
+
+      for (uint32_t t = 0; t < nSteps; ++t) {
+        // ---- reference tiles of both halves
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          StageCursor&   cur = h ? curB : curA;
+          const uint32_t rt  = h ? RTB : RTA;
+          const uint32_t r1  = h ? R1B : R1A;
+          const uint32_t cz0 = t < rt ? t : rt - 1;
+          const uint32_t need = stagedIndex(cur.st, cz0, r1, KIND == KIND_JUMP) / REF_TILE;
+          while (cur.waitTile <= need) stageOk = cursorWait(cur) && stageOk;
+          if (cur.nextIssue < cur.st.nTiles) {
+            uint32_t czT = t >= 31 ? t - 31 : 0;
+            if (czT >= rt) czT = rt - 1;
+            if (stagedIndex(cur.st, czT, r1, KIND == KIND_JUMP) / REF_TILE >= cur.nextIssue - 1) {
+              __syncwarp();
+              stageIssue(cur.st, cur.nextIssue, lane);
+              cur.nextIssue++;
+            }
+          }
+        }
+
+        uint32_t upM = __shfl_up_sync(0xffffffffu, lastM, 1);
+        uint32_t upD = __shfl_up_sync(0xffffffffu, lastD, 1);
+        uint32_t upI = __shfl_up_sync(0xffffffffu, lastI, 1);
+        uint32_t upJ = (NS >= 4) ? __shfl_up_sync(0xffffffffu, lastJ, 1) : BAD2;
+        uint32_t upK = (NS >= 5) ? __shfl_up_sync(0xffffffffu, lastK, 1) : BAD2;
+
+        const int  c      = (int)t - lane + 1;
+        const bool active = (c >= 1) && (c <= (int)RTOT);
+        if (lane == 0) {
+          if (pass == 0) {
+            upM = 0;
+            upD = upI = upJ = upK = BAD2;
+          } else if (active) {
+            const uint32_t* b = reinterpret_cast<const uint32_t*>(bndBuf) + (size_t)c * 5;
+            upM = b[0]; upD = b[1]; upI = b[2]; upJ = b[3]; upK = b[4];
+          }
+        }
+
+        if (active) {
+          const bool     phase2 = (KIND == KIND_JUMP) && ((uint32_t)c > R1);
+          const uint32_t cz  = (uint32_t)c - 1;
+          const uint32_t czA = cz < RTA ? cz : RTA - 1;
+          const uint32_t czB = cz < RTB ? cz : RTB - 1;
+          const uint32_t refA = curA.st.ring[stagedIndex(curA.st, czA, R1A, KIND == KIND_JUMP) & (REF_RING - 1)];
+          const uint32_t refB = curB.st.ring[stagedIndex(curB.st, czB, R1B, KIND == KIND_JUMP) & (REF_RING - 1)];
+          const uint32_t refpair = refA | (refB << 16);
+
+          if (c == 1) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              const int q = (int)q0 + r + 1;
+              pM[r] = pack2(q * offEdge);
+              pD[r] = BAD2;
+              pI[r] = allowEdgeIns ? pack2(P.open + q * P.extend) : BAD2;
+              pJ[r] = BAD2;
+              pK[r] = BAD2;
+            }
+            dgM = pack2((int)q0 * offEdge);
+            dgD = BAD2;
+            dgI = allowEdgeIns ? pack2(P.open + (int)q0 * P.extend) : BAD2;
+            dgJ = dgK = BAD2;
+          }
+          if (KIND == KIND_JUMP && (uint32_t)c == R1 + 1) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              pM[r] = pack2(((int)q0 + r + 1) * offEdge);
+              pD[r] = pI[r] = BAD2;
+            }
+            dgM = pack2((int)q0 * offEdge);
+            dgD = dgI = BAD2;
+            if (q0 == 0) dgJ = BAD2;
+          }
+
+          uint32_t dM = dgM, dD = dgD, dI = dgI, dJ = dgJ, dK = dgK;
+          uint32_t vM = upM, vI = upI, vJ = upJ, vK = upK;
+          uint32_t ptrwA[PTRWORDS], ptrwB[PTRWORDS];
+#pragma unroll
+          for (int w = 0; w < PTRWORDS; ++w) ptrwA[w] = ptrwB[w] = 0;
+          uint32_t capA = 0, capB = 0;
+
+#pragma unroll
+          for (int r = 0; r < RT; ++r) {
+            constexpr uint32_t F0 = 0;  // field shifts inside the 32-bit pointer word are added below
+            const int      sh   = ROWBITS * (r % ROWSPW);
+            (void)F0;
+            // substitution score of both halves: match where the characters are equal, mismatch elsewhere
+            const uint32_t d  = qpair[r] ^ refpair;
+            const uint32_t nz = ((d + 0x7fff7fffu) & 0x80008000u) >> 15;  // 1 per half where the characters differ
+            const uint32_t s2 = __vadd2(match2, nz * negDelta);
+            const bool     row1 = (r == 0) && (q0 == 0);
+            uint32_t nM, nD, nI, nJ = BAD2, nK = BAD2;
+            uint32_t fa = 0, fb = 0;  // pointer fields of this cell, A and B
+            if (KIND == KIND_GLOBAL) {
+              { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+            } else if (KIND == KIND_INDEL) {
+              { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); vmaxp<3u>(nM, dJ, a, b); vmaxp<4u>(nM, dK, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); vmaxp<3u << BITS>(nD, BAD2, a, b); vmaxp<4u << BITS>(nD, pK[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nJ = __vadd2(pM[r], extra2); vmaxp<1u << (3 * BITS)>(nJ, BAD2, a, b); vmaxp<2u << (3 * BITS)>(nJ, __vadd2(pI[r], extraMinusOpen2), a, b); vmaxp<3u << (3 * BITS)>(nJ, pJ[r], a, b); vmaxp<4u << (3 * BITS)>(nJ, __vadd2(pK[r], extra2), a, b); if (row1) nJ = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nK = __vadd2(vM, extra2); vmaxp<1u << (4 * BITS)>(nK, BAD2, a, b); vmaxp<4u << (4 * BITS)>(nK, vK, a, b); if (row1) nK = BAD2; fa |= a; fb |= b; }
+            } else {  // KIND_JUMP
+              if (!phase2) {
+                { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nJ = __vadd2(nM, extra2); vmaxp<1u << (3 * BITS)>(nJ, BAD2, a, b); vmaxp<2u << (3 * BITS)>(nJ, __vadd2(nI, extra2), a, b); vmaxp<3u << (3 * BITS)>(nJ, pJ[r], a, b); fa |= a; fb |= b; }
+              } else {
+                { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); vmaxp<3u>(nM, dJ, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); vmaxp<3u << (2 * BITS)>(nI, vJ, a, b); nI = __vadd2(nI, ext2); fa |= a; fb |= b; }
+                nJ = pJ[r];
+                fa |= (uint32_t)ST_JUMP << (3 * BITS);
+                fb |= (uint32_t)ST_JUMP << (3 * BITS);
+              }
+            }
+            ptrwA[r / ROWSPW] |= fa << sh;
+            ptrwB[r / ROWSPW] |= fb << sh;
+
+            dM = pM[r]; dD = pD[r]; dI = pI[r]; dJ = pJ[r]; dK = pK[r];
+            pM[r] = nM; pD[r] = nD; pI[r] = nI; pJ[r] = nJ; pK[r] = nK;
+            vM = nM; vI = nI; vJ = nJ; vK = nK;
+            if (r == rQA) capA = nM;
+            if (r == rQB) capB = nM;
+          }
+
+          // ---- back-trace start candidates (same enumeration as the int32 kernel)
+          const bool validA = (uint32_t)c <= RTA, validB = (uint32_t)c <= RTB;
+          if (rQA < RT && validA) {
+            const uint32_t seq = (KIND == KIND_JUMP && phase2) ? (R1 + QA + ((uint32_t)c - R1) - 1) : ((uint32_t)c - 1);
+            const long long k  = makeKey(lo16(capA), seq);
+            bestA              = k > bestA ? k : bestA;
+          }
+          if (rQB < RT && validB) {
+            const uint32_t seq = (KIND == KIND_JUMP && phase2) ? (R1 + QB + ((uint32_t)c - R1) - 1) : ((uint32_t)c - 1);
+            const long long k  = makeKey(hi16(capB), seq);
+            bestB              = k > bestB ? k : bestB;
+          }
+          const bool edge1 = (KIND == KIND_JUMP) && ((uint32_t)c == R1);
+          const bool edgeA = ((uint32_t)c == RTA), edgeB = ((uint32_t)c == RTB);
+          if (edge1 || edgeA || edgeB) {
+            // off-edge scans after the last column of a reference (rare: not in the hot path)
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              const uint32_t q = q0 + r + 1;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t Qh = h ? QB : QA;
+                if (q > Qh) continue;
+                const int  m    = h ? hi16(pM[r]) : lo16(pM[r]);
+                const bool edge = h ? edgeB : edgeA;
+                long long& best = h ? bestB : bestA;
+                if (KIND == KIND_JUMP) {
+                  const uint32_t R2h = h ? R2B : R2A;
+                  if (q < Qh) {
+                    if (edge1) { const long long k = makeKey(m + (int)(Qh - q) * offEdge, R1 + q); best = k > best ? k : best; }
+                    if (edge) { const long long k = makeKey(m + (int)(Qh - q) * offEdge, R1 + Qh + R2h + q); best = k > best ? k : best; }
+                  }
+                } else if (edge) {
+                  const uint32_t Rh = h ? R1B : R1A;
+                  if (q == Qh && allowEdgeIns) {
+                    const long long k = makeKey(h ? hi16(pI[r]) : lo16(pI[r]), Rh);
+                    best              = k > best ? k : best;
+                  }
+                  if (q < Qh || KIND == KIND_INDEL) {
+                    const long long k = makeKey(m + (int)(Qh - q) * offEdge, Rh + 1 + q);
+                    best              = k > best ? k : best;
+                  }
+                }
+              }
+            }
+            if (q0 == 0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t Qh = h ? QB : QA;
+                const bool edge = h ? edgeB : edgeA;
+                long long& best = h ? bestB : bestA;
+                if (KIND == KIND_JUMP) {
+                  const uint32_t R2h = h ? R2B : R2A;
+                  if (edge1) { const long long k = makeKey((int)Qh * offEdge, R1); best = k > best ? k : best; }
+                  if (edge) { const long long k = makeKey((int)Qh * offEdge, R1 + Qh + R2h); best = k > best ? k : best; }
+                } else if (edge) {
+                  const long long k = makeKey((int)Qh * offEdge, (h ? R1B : R1A) + 1);
+                  best              = k > best ? k : best;
+                }
+              }
+            }
+          }
+
+          dgM = upM; dgD = upD; dgI = upI; dgJ = upJ; dgK = upK;
+          lastM = vM; lastD = pD[RT - 1]; lastI = vI; lastJ = vJ; lastK = vK;
+
+          // ---- back-pointers: one contiguous line per warp and task
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint8_t*        stepBase = (h ? passB : passA) + (size_t)t * PL::STEP_BYTES;
+            const uint32_t* pw       = h ? ptrwB : ptrwA;
+            storePtrWords<PL, PTRWORDS>(stepBase, lane, pw);
+          }
+          if (lane == 31 && pass + 1 < nPass) {
+            uint32_t* b = reinterpret_cast<uint32_t*>(bndBuf) + (size_t)c * 5;
+            b[0] = lastM; b[1] = lastD; b[2] = lastI; b[3] = lastJ; b[4] = lastK;
+          }
+        }
+      }  // steps
+      while (curA.waitTile < curA.nextIssue) stageOk = cursorWait(curA) && stageOk;
+      while (curB.waitTile < curB.nextIssue) stageOk = cursorWait(curB) && stageOk;
+      __syncwarp();
+    }  // passes
+
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const long long oa = __shfl_xor_sync(0xffffffffu, bestA, off);
+      const long long ob = __shfl_xor_sync(0xffffffffu, bestB, off);
+      bestA              = oa > bestA ? oa : bestA;
+      bestB              = ob > bestB ? ob : bestB;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) {
+      emitResult<KIND, RT>(P, tA, ptrBufA, passStride, segBufA, bestA, stageOk);
+      if (!pr.dup) emitResult<KIND, RT>(P, tB, ptrBufB, passStride, segBufB, bestB, stageOk);
+    }
+    __syncwarp();
+  }
 }
 
 // ======================================================================================================
@@ -857,12 +1308,149 @@ int launchClass(mb200_ctx* ctx, const DpParams& base, const ClassPlan& plan, siz
   return MB200_OK;
 }
 
+struct PairPlan {
+  std::vector<DpPair> pairs;
+  size_t              maxPtr = 0, maxSeg = 0, maxBnd = 0;
+};
+
+template <int KIND, int RT>
+int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, size_t pairOffset, uint32_t* dCounter)
+{
+  if (plan.pairs.empty()) return MB200_OK;
+  int ctasPerSm = 0;
+  MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, dpPairKernel<KIND, RT>,
+                                                                      WARPS_PER_CTA * 32, 0));
+  if (ctasPerSm < 1) ctasPerSm = 1;
+  if (ctx->cfg.ctasPerSm && (int)ctx->cfg.ctasPerSm < ctasPerSm) ctasPerSm = (int)ctx->cfg.ctasPerSm;
+  uint32_t grid = (uint32_t)(ctx->smCount * ctasPerSm);
+  if ((size_t)grid * WARPS_PER_CTA > plan.pairs.size()) grid = (uint32_t)((plan.pairs.size() + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+  const size_t budget  = ctx->cfg.scratchBytes ? (size_t)ctx->cfg.scratchBytes : ((size_t)48 << 30);
+  const size_t ptrSlot = (2 * plan.maxPtr + 511) & ~(size_t)511;  // both tasks of a pair
+  while (grid > 1 && (size_t)grid * WARPS_PER_CTA * ptrSlot > budget) grid = (grid + 1) / 2;
+  const size_t nSlots = (size_t)grid * WARPS_PER_CTA;
+  int rc;
+  if ((rc = mb200_reserve(ctx, ctx->dPtrScratch, nSlots * ptrSlot)) != MB200_OK) return rc;
+  const size_t segSlot = (plan.maxSeg + 63) & ~(size_t)63;
+  if ((rc = mb200_reserve(ctx, ctx->dSegScratch, nSlots * 2 * segSlot * sizeof(uint32_t))) != MB200_OK) return rc;
+  const size_t bndSlot = (plan.maxBnd + 63) & ~(size_t)63;
+  if ((rc = mb200_reserve(ctx, ctx->dBndScratch, nSlots * bndSlot * sizeof(int) + 256)) != MB200_OK) return rc;
+  DpParams P    = base;
+  P.pairs       = reinterpret_cast<const DpPair*>(ctx->dTasks.ptr) + pairOffset;
+  P.nPairs      = (uint32_t)plan.pairs.size();
+  P.tasks       = nullptr;
+  P.nTasks      = 0;
+  P.workCounter = dCounter;
+  P.ptrScratch  = reinterpret_cast<uint8_t*>(ctx->dPtrScratch.ptr);
+  P.ptrStride   = ptrSlot;
+  P.segScratch  = reinterpret_cast<uint32_t*>(ctx->dSegScratch.ptr);
+  P.segStride   = segSlot;
+  P.bndScratch  = reinterpret_cast<int*>(ctx->dBndScratch.ptr);
+  P.bndStride   = bndSlot;
+  dpPairKernel<KIND, RT><<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(P);
+  MB200_CUDA_CHECK(ctx, cudaGetLastError());
+  ctx->timing.launches++;
+  return MB200_OK;
+}
+
+// every intermediate of the recurrences stays inside int16 for this score set and query length?
+inline bool fitsInt16(const mb200_scores* sc, int extra, uint32_t maxQ)
+{
+  auto ab = [](int v) { return (long long)(v < 0 ? -v : v); };
+  const long long perBase = std::max(std::max(ab(sc->match), ab(sc->mismatch)), std::max(ab(sc->offEdge), ab(sc->extend)));
+  const long long bound   = 10000 + perBase * (long long)(maxQ + 2) + 2 * ab(sc->open) + 2 * ab(extra) + 4 * ab(sc->extend) + 64;
+  return bound < 32000;
+}
+
+template <int KIND>
+int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vector<DpTask>& tasks, const DpParams& base,
+               uint32_t* dWorkCounters, uint64_t* cellsOut, uint64_t* algoBytesOut)
+{
+  // classes by query length: RT = 4 / 8 / 12 / 16 rows per lane
+  auto classOf = [](uint32_t Q) { return Q <= 128 ? 0 : (Q <= 256 ? 1 : (Q <= 384 ? 2 : 3)); };
+  static const int RTS[4] = {4, 8, 12, 16};
+  std::vector<DpTask> sorted(tasks);
+  std::sort(sorted.begin(), sorted.end(), [&](const DpTask& a, const DpTask& b) {
+    const int ca = classOf(a.Q), cb = classOf(b.Q);
+    if (ca != cb) return ca < cb;
+    if (KIND == KIND_JUMP && a.R1 != b.R1) return a.R1 > b.R1;
+    const uint64_t xa = (uint64_t)a.Q * (a.R1 + a.R2), xb = (uint64_t)b.Q * (b.R1 + b.R2);
+    return xa != xb ? xa > xb : a.outIndex < b.outIndex;
+  });
+  PairPlan plans[4];
+  for (size_t i = 0; i < sorted.size();) {
+    DpPair pr;
+    memset(&pr, 0, sizeof(pr));
+    pr.a           = sorted[i];
+    const int cls  = classOf(pr.a.Q);
+    const bool can = (i + 1 < sorted.size()) && classOf(sorted[i + 1].Q) == cls &&
+                     (KIND != KIND_JUMP || sorted[i + 1].R1 == pr.a.R1);
+    if (can) {
+      pr.b   = sorted[i + 1];
+      pr.dup = 0;
+      i += 2;
+    } else {
+      pr.b   = pr.a;
+      pr.dup = 1;
+      i += 1;
+    }
+    const uint32_t Q    = std::max(pr.a.Q, pr.b.Q);
+    const uint32_t rtot = std::max(pr.a.R1 + pr.a.R2, pr.b.R1 + pr.b.R2);
+    const int      RT   = RTS[cls];
+    const size_t   nPass = (Q + 32 * RT - 1) / (32 * RT);
+    const size_t   pb    = nPass * ((size_t)(rtot + 31) * 32 * RT * KindTraits<KIND>::CELLB);
+    PairPlan&      p     = plans[cls];
+    p.pairs.push_back(pr);
+    p.maxPtr = std::max(p.maxPtr, pb);
+    p.maxSeg = std::max(p.maxSeg, 2 * ((size_t)Q + rtot + 8));
+    p.maxBnd = std::max(p.maxBnd, (Q > (uint32_t)(32 * RT)) ? ((size_t)rtot + 2) * 5 : (size_t)8);
+    for (int h = 0; h < (pr.dup ? 1 : 2); ++h) {
+      const DpTask& t = h ? pr.b : pr.a;
+      if (cellsOut) *cellsOut += (uint64_t)t.Q * (t.R1 + t.R2);
+      if (algoBytesOut) *algoBytesOut += (uint64_t)t.Q * (t.R1 + t.R2) * KindTraits<KIND>::CELLB + t.Q + t.R1 + t.R2;
+    }
+  }
+  // inside a class: largest pairs first (dynamic hand-out, longest processing time first)
+  std::vector<DpPair> all;
+  size_t              offsets[4];
+  for (int c = 0; c < 4; ++c) {
+    std::stable_sort(plans[c].pairs.begin(), plans[c].pairs.end(), [](const DpPair& x, const DpPair& y) {
+      const uint64_t cx = (uint64_t)std::max(x.a.Q, x.b.Q) * std::max(x.a.R1 + x.a.R2, x.b.R1 + x.b.R2);
+      const uint64_t cy = (uint64_t)std::max(y.a.Q, y.b.Q) * std::max(y.a.R1 + y.a.R2, y.b.R1 + y.b.R2);
+      return cx > cy;
+    });
+    offsets[c] = all.size();
+    all.insert(all.end(), plans[c].pairs.begin(), plans[c].pairs.end());
+  }
+  int rc;
+  if ((rc = mb200_reserve(ctx, ctx->dTasks, all.size() * sizeof(DpPair) + 64)) != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dTasks.ptr, all.data(), all.size() * sizeof(DpPair), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = launchPairClass<KIND, 4>(ctx, base, plans[0], offsets[0], dWorkCounters + 0)) != MB200_OK) return rc;
+  if ((rc = launchPairClass<KIND, 8>(ctx, base, plans[1], offsets[1], dWorkCounters + 1)) != MB200_OK) return rc;
+  if ((rc = launchPairClass<KIND, 12>(ctx, base, plans[2], offsets[2], dWorkCounters + 2)) != MB200_OK) return rc;
+  if ((rc = launchPairClass<KIND, 16>(ctx, base, plans[3], offsets[3], dWorkCounters + 3)) != MB200_OK) return rc;
+  return MB200_OK;
+}
+
 template <int KIND>
 int dpRunKind(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vector<DpTask>& tasks, void* dResults,
               uint32_t* dCigar, uint64_t cigarCap, unsigned long long* dCigarUsed, int* dErrFlag,
               uint32_t* dWorkCounters, uint64_t* cellsOut, uint64_t* algoBytesOut)
 {
-  // ---- classes by query length (rows per thread); longest tasks first inside a class
+  DpParams P;
+  memset(&P, 0, sizeof(P));
+  P.match = scores->match; P.mismatch = scores->mismatch; P.open = scores->open; P.extend = scores->extend;
+  P.offEdge = scores->offEdge; P.allowEdgeIns = scores->isAllowEdgeInsertion ? 1 : 0; P.extra = extra;
+  P.results   = dResults;
+  P.cigarPool = dCigar;
+  P.cigarCap  = cigarCap;
+  P.errFlag   = dErrFlag;
+  P.cigarUsed = dCigarUsed;
+
+  uint32_t maxQ = 0;
+  for (const DpTask& t : tasks) maxQ = std::max(maxQ, t.Q);
+  if (!ctx->forceInt32 && fitsInt16(scores, extra, maxQ)) return dpRunPairs<KIND>(ctx, scores, extra, tasks, P, dWorkCounters, cellsOut, algoBytesOut);
+
+  // ---- general int32 path: one alignment per warp, classes by query length, longest tasks first
   ClassPlan plans[3];
   for (const DpTask& t : tasks) {
     const uint32_t rtot = t.R1 + t.R2;
@@ -896,14 +1484,6 @@ int dpRunKind(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vector
   // pageable source: the runtime stages it before returning, so `all` may go out of scope
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dTasks.ptr, all.data(), all.size() * sizeof(DpTask),
                                         cudaMemcpyHostToDevice, ctx->stream));
-  DpParams P;
-  P.match = scores->match; P.mismatch = scores->mismatch; P.open = scores->open; P.extend = scores->extend;
-  P.offEdge = scores->offEdge; P.allowEdgeIns = scores->isAllowEdgeInsertion ? 1 : 0; P.extra = extra;
-  P.results   = dResults;
-  P.cigarPool = dCigar;
-  P.cigarCap  = cigarCap;
-  P.errFlag   = dErrFlag;
-  P.cigarUsed = dCigarUsed;
   // the classes run back to back on the ctx stream (they share the scratch buffers)
   if ((rc = launchClass<KIND, 4>(ctx, P, plans[0], offsets[0], dWorkCounters + 0)) != MB200_OK) return rc;
   if ((rc = launchClass<KIND, 8>(ctx, P, plans[1], offsets[1], dWorkCounters + 1)) != MB200_OK) return rc;

@@ -47,3 +47,13 @@ def gpu():
     ctx = manta_b200.Context(0)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="session")
+def gpu32():
+    """same library, DP forced onto the general int32 kernel (the default picks the int16x2 pair kernel when the
+    score range allows it)"""
+    import manta_b200
+    ctx = manta_b200.Context(0, force_int32=True)
+    yield ctx
+    ctx.close()

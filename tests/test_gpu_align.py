@@ -15,7 +15,13 @@ SCORE_SETS = [((2, -4, -5, -1, -1, 0), -3), ((2, -8, -12, -1, -1, 0), -100), ((2
               ((2, -8, -18, 0, -1, 1), -50), ((1, -4, -5, -1, -2, 1), -10)]
 
 
-def test_alignment_golden_gpu(gpu):
+@pytest.fixture(params=["pair16", "int32"])
+def dev(request, gpu, gpu32):
+    return gpu if request.param == "pair16" else gpu32
+
+
+def test_alignment_golden_gpu(dev):
+    gpu = dev
     for c in load("alignment.json")["cases"]:
         got = run_alignment(gpu, c)
         for k, v in c["expected"].items():
@@ -24,7 +30,8 @@ def test_alignment_golden_gpu(gpu):
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13])
-def test_aligners_vs_oracle(gpu, orc, seed):
+def test_aligners_vs_oracle(dev, orc, seed):
+    gpu = dev
     for si, (sc, extra) in enumerate(SCORE_SETS):
         S = cb.Scores(*sc)
         if not sc[5]:
@@ -35,7 +42,8 @@ def test_aligners_vs_oracle(gpu, orc, seed):
         assert gpu.single_align("global", S, 0, cases) == orc.single_align("global", S, 0, cases)
 
 
-def test_long_sequences_multi_tile_multi_pass(gpu, orc):
+def test_long_sequences_multi_tile_multi_pass(dev, orc):
+    gpu = dev
     """reference windows spanning several 2 KiB staging tiles, queries spanning several 512-row passes,
     and the q > 1250 regime where the -10000 sentinel takes part in the arithmetic (SURVEY.md A.4)"""
     rng = random.Random(5)
@@ -58,7 +66,8 @@ def test_long_sequences_multi_tile_multi_pass(gpu, orc):
     assert gpu.jump_align(S, -100, triples) == orc.jump_align(S, -100, triples)
 
 
-def test_unaligned_views_and_shared_pool(gpu, orc):
+def test_unaligned_views_and_shared_pool(dev, orc):
+    gpu = dev
     """views at arbitrary byte offsets of one shared pool (no 16-byte alignment of the caller's data)"""
     import numpy as np
     rng = random.Random(9)
@@ -92,3 +101,29 @@ def test_empty_input_errors_gpu(gpu):
     with pytest.raises(cb.Mb200Error) as e:
         gpu.single_align("global", S, 0, [("A", "")])
     assert e.value.status == cb.MB200_ERR_EMPTY_REF
+
+
+def test_pair_kernel_batches(gpu, orc):
+    """many tasks of mixed sizes in one call: exercises pairing (odd counts, jump pairs that must share R1,
+    pairs with different Q / R, all four row classes)"""
+    rng = random.Random(17)
+
+    def rs(n):
+        return "".join(rng.choice("ACGT") for _ in range(n))
+    refs = [rs(rng.choice([700, 1500, 2500, 2500, 3100])) for _ in range(6)]
+    S = cb.Scores(2, -8, -24, -1, -1, 0)
+    pairs = []
+    for i in range(41):
+        r = rng.choice(refs)
+        a = rng.randint(0, len(r) - 400)
+        q = r[a:a + rng.randint(20, 200)] + r[a + 250:a + 250 + rng.randint(10, 230)]
+        pairs.append((q, r))
+    assert gpu.single_align("indel", S, -100, pairs) == orc.single_align("indel", S, -100, pairs)
+    assert gpu.single_align("global", S, 0, pairs) == orc.single_align("global", S, 0, pairs)
+    S = cb.Scores(2, -8, -12, -1, -1, 0)
+    triples = []
+    for i in range(37):
+        r1, r2 = rng.choice(refs), rng.choice(refs)
+        a, b = rng.randint(0, len(r1) - 300), rng.randint(0, len(r2) - 300)
+        triples.append((r1[a:a + rng.randint(30, 250)] + r2[b:b + rng.randint(30, 250)], r1, r2))
+    assert gpu.jump_align(S, -100, triples) == orc.jump_align(S, -100, triples)
