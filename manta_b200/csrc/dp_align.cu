@@ -891,7 +891,10 @@ __device__ __forceinline__ bool cursorWait(StageCursor& cur)
 #endif
 }
 
-template <int KIND, int RT>
+// NOBAD: the host proved that the sentinel can never win a max strictly (every running maximum stays above
+// badVal for this score set and query length), so the comparisons against badVal -- and their pointer codes --
+// are dropped.
+template <int KIND, int RT, bool NOBAD>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParams P)
 {
   using KT               = KindTraits<KIND>;
@@ -1117,23 +1120,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
             if (KIND == KIND_GLOBAL) {
               { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
               { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
             } else if (KIND == KIND_INDEL) {
               { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); vmaxp<3u>(nM, dJ, a, b); vmaxp<4u>(nM, dK, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); vmaxp<3u << BITS>(nD, BAD2, a, b); vmaxp<4u << BITS>(nD, pK[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nJ = __vadd2(pM[r], extra2); vmaxp<1u << (3 * BITS)>(nJ, BAD2, a, b); vmaxp<2u << (3 * BITS)>(nJ, __vadd2(pI[r], extraMinusOpen2), a, b); vmaxp<3u << (3 * BITS)>(nJ, pJ[r], a, b); vmaxp<4u << (3 * BITS)>(nJ, __vadd2(pK[r], extra2), a, b); if (row1) nJ = BAD2; fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nK = __vadd2(vM, extra2); vmaxp<1u << (4 * BITS)>(nK, BAD2, a, b); vmaxp<4u << (4 * BITS)>(nK, vK, a, b); if (row1) nK = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); if (!NOBAD) vmaxp<3u << BITS>(nD, BAD2, a, b); vmaxp<4u << BITS>(nD, pK[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nJ = __vadd2(pM[r], extra2); if (!NOBAD) vmaxp<1u << (3 * BITS)>(nJ, BAD2, a, b); vmaxp<2u << (3 * BITS)>(nJ, __vadd2(pI[r], extraMinusOpen2), a, b); vmaxp<3u << (3 * BITS)>(nJ, pJ[r], a, b); vmaxp<4u << (3 * BITS)>(nJ, __vadd2(pK[r], extra2), a, b); if (row1) nJ = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nK = __vadd2(vM, extra2); if (!NOBAD) vmaxp<1u << (4 * BITS)>(nK, BAD2, a, b); vmaxp<4u << (4 * BITS)>(nK, vK, a, b); if (row1) nK = BAD2; fa |= a; fb |= b; }
             } else {  // KIND_JUMP
               if (!phase2) {
                 { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
                 { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
-                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
-                { uint32_t a = 0, b = 0; nJ = __vadd2(nM, extra2); vmaxp<1u << (3 * BITS)>(nJ, BAD2, a, b); vmaxp<2u << (3 * BITS)>(nJ, __vadd2(nI, extra2), a, b); vmaxp<3u << (3 * BITS)>(nJ, pJ[r], a, b); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nJ = __vadd2(nM, extra2); if (!NOBAD) vmaxp<1u << (3 * BITS)>(nJ, BAD2, a, b); vmaxp<2u << (3 * BITS)>(nJ, __vadd2(nI, extra2), a, b); vmaxp<3u << (3 * BITS)>(nJ, pJ[r], a, b); fa |= a; fb |= b; }
               } else {
                 { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); vmaxp<3u>(nM, dJ, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
                 { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); fa |= a; fb |= b; }
-                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); vmaxp<3u << (2 * BITS)>(nI, vJ, a, b); nI = __vadd2(nI, ext2); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); vmaxp<3u << (2 * BITS)>(nI, vJ, a, b); nI = __vadd2(nI, ext2); fa |= a; fb |= b; }
                 nJ = pJ[r];
                 fa |= (uint32_t)ST_JUMP << (3 * BITS);
                 fb |= (uint32_t)ST_JUMP << (3 * BITS);
@@ -1313,12 +1316,12 @@ struct PairPlan {
   size_t              maxPtr = 0, maxSeg = 0, maxBnd = 0;
 };
 
-template <int KIND, int RT>
+template <int KIND, int RT, bool NOBAD>
 int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, size_t pairOffset, uint32_t* dCounter)
 {
   if (plan.pairs.empty()) return MB200_OK;
   int ctasPerSm = 0;
-  MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, dpPairKernel<KIND, RT>,
+  MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, dpPairKernel<KIND, RT, NOBAD>,
                                                                       WARPS_PER_CTA * 32, 0));
   if (ctasPerSm < 1) ctasPerSm = 1;
   if (ctx->cfg.ctasPerSm && (int)ctx->cfg.ctasPerSm < ctasPerSm) ctasPerSm = (int)ctx->cfg.ctasPerSm;
@@ -1346,7 +1349,7 @@ int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, 
   P.segStride   = segSlot;
   P.bndScratch  = reinterpret_cast<int*>(ctx->dBndScratch.ptr);
   P.bndStride   = bndSlot;
-  dpPairKernel<KIND, RT><<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(P);
+  dpPairKernel<KIND, RT, NOBAD><<<grid, WARPS_PER_CTA * 32, 0, ctx->stream>>>(P);
   MB200_CUDA_CHECK(ctx, cudaGetLastError());
   ctx->timing.launches++;
   return MB200_OK;
@@ -1424,10 +1427,25 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
   int rc;
   if ((rc = mb200_reserve(ctx, ctx->dTasks, all.size() * sizeof(DpPair) + 64)) != MB200_OK) return rc;
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dTasks.ptr, all.data(), all.size() * sizeof(DpPair), cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = launchPairClass<KIND, 4>(ctx, base, plans[0], offsets[0], dWorkCounters + 0)) != MB200_OK) return rc;
-  if ((rc = launchPairClass<KIND, 8>(ctx, base, plans[1], offsets[1], dWorkCounters + 1)) != MB200_OK) return rc;
-  if ((rc = launchPairClass<KIND, 12>(ctx, base, plans[2], offsets[2], dWorkCounters + 2)) != MB200_OK) return rc;
-  if ((rc = launchPairClass<KIND, 16>(ctx, base, plans[3], offsets[3], dWorkCounters + 3)) != MB200_OK) return rc;
+  // can badVal ever win a max?  M[q][c] >= -L*q with L = max(|match|,|mismatch|,|offEdge|) (induction over the
+  // recurrences, column 0 and the ref2 re-initialisation included); every max that has badVal as a candidate starts
+  // from M + open / M + extra / M + jump, so below this bound the sentinel never compares strictly greater.
+  uint32_t maxQ = 0;
+  for (const DpTask& t : tasks) maxQ = std::max(maxQ, t.Q);
+  auto ab = [](int v) { return (long long)(v < 0 ? -v : v); };
+  const long long L     = std::max(std::max(ab(scores->match), ab(scores->mismatch)), ab(scores->offEdge));
+  const bool      noBad = (L * (long long)(maxQ + 1) + std::max(ab(scores->open), ab(extra)) + ab(scores->extend) + 8 < 10000);
+  if (noBad) {
+    if ((rc = launchPairClass<KIND, 4, true>(ctx, base, plans[0], offsets[0], dWorkCounters + 0)) != MB200_OK) return rc;
+    if ((rc = launchPairClass<KIND, 8, true>(ctx, base, plans[1], offsets[1], dWorkCounters + 1)) != MB200_OK) return rc;
+    if ((rc = launchPairClass<KIND, 12, true>(ctx, base, plans[2], offsets[2], dWorkCounters + 2)) != MB200_OK) return rc;
+    if ((rc = launchPairClass<KIND, 16, true>(ctx, base, plans[3], offsets[3], dWorkCounters + 3)) != MB200_OK) return rc;
+  } else {
+    if ((rc = launchPairClass<KIND, 4, false>(ctx, base, plans[0], offsets[0], dWorkCounters + 0)) != MB200_OK) return rc;
+    if ((rc = launchPairClass<KIND, 8, false>(ctx, base, plans[1], offsets[1], dWorkCounters + 1)) != MB200_OK) return rc;
+    if ((rc = launchPairClass<KIND, 12, false>(ctx, base, plans[2], offsets[2], dWorkCounters + 2)) != MB200_OK) return rc;
+    if ((rc = launchPairClass<KIND, 16, false>(ctx, base, plans[3], offsets[3], dWorkCounters + 3)) != MB200_OK) return rc;
+  }
   return MB200_OK;
 }
 
