@@ -282,91 +282,133 @@ __device__ void rawLengths(const uint32_t* raw, uint32_t n, uint32_t& readLen, u
   }
 }
 
-// ---- trace-back + path emission of one finished alignment (lane 0 of the owning warp) -------------------
+// ---- trace-back + path emission of one finished alignment (whole warp) ----------------------------------
 // ptrBuf holds the task's back-pointer cells in the skewed layout with `passStride` bytes per pass.
+// The pointer walk is warp-cooperative: in state S the path keeps moving in S's direction (diagonal for MATCH,
+// along the row for DELETE/JUMP, along the column for INSERT/JUMPINS) for as long as the visited cells point back
+// to S, so lane i speculatively fetches the i-th cell ahead and one ballot finds where the run ends -- one memory
+// round trip per <= 32 path steps instead of one per step.  All lanes keep identical copies of the scalar
+// bookkeeping; only lane 0 writes segments.
+template <int KIND, int RT>
+__device__ __forceinline__ uint32_t loadPtrField(const uint8_t* ptrBuf, size_t passStride, uint32_t q, uint32_t c, uint32_t state)
+{
+  using KT = KindTraits<KIND>;
+  using PL = PtrLayout<RT, KT::CELLB>;
+  uint32_t cell;
+  if (KT::CELLB == 1) cell = ptrBuf[PL::cellOffset(q, c, passStride)];
+  else cell = *reinterpret_cast<const uint16_t*>(ptrBuf + PL::cellOffset(q, c, passStride));
+  return (cell >> (KT::BITS * state)) & ((1u << KT::BITS) - 1);
+}
+
 template <int KIND, int RT>
 __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t* ptrBuf, size_t passStride,
-                           uint32_t* segBuf, long long bestKey, bool stageOk)
+                           uint32_t* segBuf, long long bestKey, bool stageOk, int lane)
 {
-  using KT           = KindTraits<KIND>;
-  using PL           = PtrLayout<RT, KT::CELLB>;
-  constexpr int BITS = KT::BITS;
   const uint32_t Q = task.Q, R1 = task.R1;
   const uint32_t R2   = (KIND == KIND_JUMP) ? task.R2 : 0u;
   const uint8_t* qSeq = task.q;
   const uint8_t* ref1 = task.r1;
   const uint8_t* ref2 = task.r2;
-  {
-    if (!stageOk) atomicExch(P.errFlag, MB200_ERR_CUDA);
-    const int      bestVal = (int)(bestKey >> 32);
-    const uint32_t seq     = 0x7fffffffu - (uint32_t)(bestKey & 0xffffffffLL);
+  const uint32_t FULL = 0xffffffffu;
+  if (!stageOk && lane == 0) atomicExch(P.errFlag, MB200_ERR_CUDA);
+  const int      bestVal = (int)(bestKey >> 32);
+  const uint32_t seq     = 0x7fffffffu - (uint32_t)(bestKey & 0xffffffffLL);
 
-    if (KIND == KIND_JUMP) {
-      // ---------------- JumpAlignerBase::backTraceAlignment  (JumpAlignerBaseImpl.hpp:101-242)
-      uint32_t refBegin, queryBegin;
-      if (seq < R1) { refBegin = seq + 1; queryBegin = Q; }
-      else if (seq < R1 + Q) { refBegin = R1; queryBegin = seq - R1; }
-      else if (seq < R1 + Q + R2) { refBegin = R1 + (seq - R1 - Q) + 1; queryBegin = Q; }
-      else { refBegin = R1 + R2; queryBegin = seq - (R1 + Q + R2); }
-      uint32_t state = ST_MATCH;
+  if (KIND == KIND_JUMP) {
+    // ---------------- JumpAlignerBase::backTraceAlignment  (JumpAlignerBaseImpl.hpp:101-242)
+    uint32_t refBegin, queryBegin;
+    if (seq < R1) { refBegin = seq + 1; queryBegin = Q; }
+    else if (seq < R1 + Q) { refBegin = R1; queryBegin = seq - R1; }
+    else if (seq < R1 + Q + R2) { refBegin = R1 + (seq - R1 - Q) + 1; queryBegin = Q; }
+    else { refBegin = R1 + R2; queryBegin = seq - (R1 + Q + R2); }
+    uint32_t state = ST_MATCH;
 
-      // raw paths in back-trace order: apath1 in segBuf[0..), apath2 in segBuf[half..)
-      const uint32_t half = (uint32_t)(P.segStride / 2);
-      uint32_t       n1 = 0, n2 = 0;
-      uint32_t       psType = MB200_SEG_NONE, psLen = 0;
-      uint32_t       jumpInsertSize = 0;
-      int            beginPos1 = 0, beginPos2 = 0;
-      if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
-      bool isRef2End = false;
-#define PUSH_TO(isRef1, T, L) do { if (isRef1) segBuf[n1++] = MB200_SEG_MAKE(L, T); else segBuf[half + n2++] = MB200_SEG_MAKE(L, T); } while (0)
+    // raw paths in back-trace order: apath1 in segBuf[0..), apath2 in segBuf[half..)
+    const uint32_t half = (uint32_t)(P.segStride / 2);
+    uint32_t       n1 = 0, n2 = 0;
+    uint32_t       psType = MB200_SEG_NONE, psLen = 0;
+    uint32_t       jumpInsertSize = 0;
+    int            beginPos1 = 0, beginPos2 = 0;
+    if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
+    bool isRef2End = false;
+#define PUSH_TO(isRef1, T, L) do { if (isRef1) { if (lane == 0) segBuf[n1] = MB200_SEG_MAKE(L, T); n1++; } else { if (lane == 0) segBuf[half + n2] = MB200_SEG_MAKE(L, T); n2++; } } while (0)
 #define UPDATE_PATH(isRef1, AT) do { if (psType != (AT)) { if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen); psType = (AT); psLen = 0; } } while (0)
-      while (queryBegin > 0 && refBegin > 0) {
-        if (isRef2End) break;
-        const bool     isRef1    = (refBegin <= R1);
-        const uint32_t refXBegin = refBegin - (isRef1 ? 0 : R1);
-        const uint32_t cell      = ptrBuf[PL::cellOffset(queryBegin, refBegin, passStride)];
-        const uint32_t next      = (cell >> (BITS * state)) & ((1u << BITS) - 1);
-        if (state == ST_MATCH) {
-          if (!isRef1 && refXBegin == 1 && next == ST_MATCH) isRef2End = true;
-          UPDATE_PATH(isRef1, MB200_SEG_MATCH);
-          queryBegin--;
-          refBegin--;
-        } else if (state == ST_DELETE) {
-          UPDATE_PATH(isRef1, MB200_SEG_DELETE);
-          refBegin--;
-        } else if (state == ST_INSERT) {
-          UPDATE_PATH(isRef1, MB200_SEG_INSERT);
-          queryBegin--;
-        } else {  // ST_JUMP
-          if (psType != MB200_SEG_NONE) {
-            beginPos2 = (int)(refBegin - R1);
-            if (psType == MB200_SEG_INSERT) {
-              jumpInsertSize += psLen;
-              psType = MB200_SEG_NONE;
-              psLen  = 0;
-            } else {
-              UPDATE_PATH(false, MB200_SEG_NONE);
-            }
+    while (queryBegin > 0 && refBegin > 0) {
+      if (isRef2End) break;
+      const bool isRef1 = (refBegin <= R1);
+      if (state == ST_JUMP) {
+        if (psType != MB200_SEG_NONE) {
+          // first visit of the jump state: close the open segment (no move)
+          const uint32_t next = loadPtrField<KIND, RT>(ptrBuf, passStride, queryBegin, refBegin, ST_JUMP);
+          beginPos2 = (int)(refBegin - R1);
+          if (psType == MB200_SEG_INSERT) {
+            jumpInsertSize += psLen;
+            psType = MB200_SEG_NONE;
+            psLen  = 0;
           } else {
-            if (next == ST_JUMP) refBegin--;
+            UPDATE_PATH(false, MB200_SEG_NONE);
           }
+          state = next;
+          psLen++;
+          continue;
         }
-        state = next;
-        psLen++;
+        // walking left along the row while the cells keep pointing to JUMP
+        const uint32_t avail = refBegin < 32u ? refBegin : 32u;
+        uint32_t       nxt   = ST_JUMP;
+        if ((uint32_t)lane < avail) nxt = loadPtrField<KIND, RT>(ptrBuf, passStride, queryBegin, refBegin - lane, ST_JUMP);
+        const uint32_t diff = __ballot_sync(FULL, ((uint32_t)lane < avail) && nxt != ST_JUMP);
+        if (diff) {
+          const int n = __ffs(diff) - 1;  // cells 0..n-1 moved, cell n leaves the jump state without moving
+          refBegin -= (uint32_t)n;
+          state = __shfl_sync(FULL, nxt, n);
+          psLen += (uint32_t)n + 1;
+        } else {
+          refBegin -= avail;
+          psLen += avail;
+        }
+        continue;
       }
-      {
-        const bool isRef1 = (refBegin < R1);
-        if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen);
-        if (queryBegin != 0) PUSH_TO(isRef1, MB200_SEG_SOFT_CLIP, queryBegin);
-        if (isRef1) beginPos1 = (int)refBegin; else beginPos2 = (int)(refBegin - R1);
+      // MATCH / DELETE / INSERT runs
+      uint32_t dq = 0, dc = 0, atype, avail;
+      if (state == ST_MATCH) { dq = 1; dc = 1; atype = MB200_SEG_MATCH; avail = queryBegin < refBegin ? queryBegin : refBegin; }
+      else if (state == ST_DELETE) { dc = 1; atype = MB200_SEG_DELETE; avail = refBegin; }
+      else { dq = 1; atype = MB200_SEG_INSERT; avail = queryBegin; }
+      if (avail > 32u) avail = 32u;
+      uint32_t nxt = state;
+      const uint32_t cq = queryBegin - lane * dq, cc = refBegin - lane * dc;
+      if ((uint32_t)lane < avail) nxt = loadPtrField<KIND, RT>(ptrBuf, passStride, cq, cc, state);
+      const bool valid = (uint32_t)lane < avail;
+      // a MATCH step at the first ref2 column that points back to MATCH ends the alignment (isRef2End)
+      const bool stop  = valid && (state == ST_MATCH) && (cc == R1 + 1) && (nxt == ST_MATCH);
+      const uint32_t ev = __ballot_sync(FULL, valid && (nxt != state || stop));
+      UPDATE_PATH(isRef1, atype);
+      uint32_t consumed;
+      if (ev) {
+        const int n = __ffs(ev) - 1;
+        consumed    = (uint32_t)n + 1;
+        state       = __shfl_sync(FULL, nxt, n);
+        isRef2End   = (__shfl_sync(FULL, stop ? 1 : 0, n) != 0);
+      } else {
+        consumed = avail;
       }
+      queryBegin -= consumed * dq;
+      refBegin -= consumed * dc;
+      psLen += consumed;
+    }
+    {
+      const bool isRef1 = (refBegin < R1);
+      if (psType != MB200_SEG_NONE) PUSH_TO(isRef1, psType, psLen);
+      if (queryBegin != 0) PUSH_TO(isRef1, MB200_SEG_SOFT_CLIP, queryBegin);
+      if (isRef1) beginPos1 = (int)refBegin; else beginPos2 = (int)(refBegin - R1);
+    }
 #undef PUSH_TO
 #undef UPDATE_PATH
+    __syncwarp();
+    if (lane == 0) {
       uint32_t read1, refl1, read2, refl2;
       rawLengths(segBuf, n1, read1, refl1);
       rawLengths(segBuf + half, n2, read2, refl2);
       (void)read2; (void)refl2;
-
       uint32_t jumpRange = 0;
       if (n1 && n2) {
         uint32_t r1i = (uint32_t)beginPos1 + refl1, r2i = (uint32_t)beginPos2, qi = read1;
@@ -398,51 +440,54 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
       o->beginPos1 = beginPos1; o->beginPos2 = beginPos2;
       o->cigarLen1 = c1; o->cigarLen2 = c2; o->reserved = 0;
       o->cigarOff1 = off; o->cigarOff2 = off + c1;
-    } else {
-      // ---------------- SingleRefAlignerBase::backTraceAlignment (SingleRefAlignerSharedImpl.hpp:75-168)
-      const uint32_t R = R1;
-      uint32_t       refBegin, queryBegin, state = ST_MATCH;
-      if (seq < R) { refBegin = seq + 1; queryBegin = Q; }
-      else if (seq == R) { refBegin = R; queryBegin = Q; state = ST_INSERT; }
-      else { refBegin = R; queryBegin = seq - R - 1; }
-      uint32_t n = 0, psType = MB200_SEG_NONE, psLen = 0, isJumped = 0;
-      if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
-      for (;;) {
-        uint32_t next;
-        if (queryBegin >= 1 && refBegin >= 1) {
-          uint32_t cell;
-          if (KT::CELLB == 1) cell = ptrBuf[PL::cellOffset(queryBegin, refBegin, passStride)];
-          else cell = *reinterpret_cast<const uint16_t*>(ptrBuf + PL::cellOffset(queryBegin, refBegin, passStride));
-          next = (cell >> (BITS * state)) & ((1u << BITS) - 1);
-        } else {
-          // row 0 / column 0 pointers: all MATCH, except column-0 insert state with edge insertions allowed
-          next = (refBegin == 0 && state == ST_INSERT && P.allowEdgeIns) ? ST_INSERT : ST_MATCH;
-        }
-        uint32_t atype;
-        if (state == ST_MATCH) {
-          if (queryBegin < 1 || refBegin < 1) break;
-          atype = MB200_SEG_MATCH;
-        } else if (state == ST_DELETE || state == ST_JUMP) {
-          if (refBegin < 1) break;
-          atype = MB200_SEG_DELETE;
-        } else {
-          if (queryBegin < 1) break;
-          atype = MB200_SEG_INSERT;
-        }
-        if (psType != atype) {
-          if (psType != MB200_SEG_NONE) segBuf[n++] = MB200_SEG_MAKE(psLen, psType);
-          psType = atype;
-          psLen  = 0;
-        }
-        if (state == ST_MATCH) { queryBegin--; refBegin--; }
-        else if (state == ST_DELETE || state == ST_JUMP) { refBegin--; }
-        else { queryBegin--; }
-        if (state == ST_JUMP || state == ST_JUMPINS) isJumped = 1;
-        state = next;
-        psLen++;
+    }
+  } else {
+    // ---------------- SingleRefAlignerBase::backTraceAlignment (SingleRefAlignerSharedImpl.hpp:75-168)
+    const uint32_t R = R1;
+    uint32_t       refBegin, queryBegin, state = ST_MATCH;
+    if (seq < R) { refBegin = seq + 1; queryBegin = Q; }
+    else if (seq == R) { refBegin = R; queryBegin = Q; state = ST_INSERT; }
+    else { refBegin = R; queryBegin = seq - R - 1; }
+    uint32_t n = 0, psType = MB200_SEG_NONE, psLen = 0, isJumped = 0;
+    if (queryBegin < Q) { psType = MB200_SEG_SOFT_CLIP; psLen = Q - queryBegin; }
+    for (;;) {
+      uint32_t dq = 0, dc = 0, atype, avail;
+      if (state == ST_MATCH) { dq = 1; dc = 1; atype = MB200_SEG_MATCH; avail = queryBegin < refBegin ? queryBegin : refBegin; }
+      else if (state == ST_DELETE || state == ST_JUMP) { dc = 1; atype = MB200_SEG_DELETE; avail = refBegin; }
+      else { dq = 1; atype = MB200_SEG_INSERT; avail = queryBegin; }
+      if (avail == 0) break;  // the per-state break conditions of the reference (:114,:119,:124)
+      if (avail > 32u) avail = 32u;
+      const bool     valid = (uint32_t)lane < avail;
+      const uint32_t cq = queryBegin - lane * dq, cc = refBegin - lane * dc;
+      uint32_t       nxt = state;
+      if (valid) {
+        if (cq >= 1 && cc >= 1) nxt = loadPtrField<KIND, RT>(ptrBuf, passStride, cq, cc, state);
+        else  // row 0 / column 0 pointers: all MATCH, except the column-0 insert state with edge insertions allowed
+          nxt = (cc == 0 && state == ST_INSERT && P.allowEdgeIns) ? (uint32_t)ST_INSERT : (uint32_t)ST_MATCH;
       }
-      if (psType != MB200_SEG_NONE) segBuf[n++] = MB200_SEG_MAKE(psLen, psType);
-      if (queryBegin != 0) segBuf[n++] = MB200_SEG_MAKE(queryBegin, MB200_SEG_SOFT_CLIP);
+      const uint32_t ev = __ballot_sync(FULL, valid && nxt != state);
+      if (psType != atype) {
+        if (psType != MB200_SEG_NONE) { if (lane == 0) segBuf[n] = MB200_SEG_MAKE(psLen, psType); n++; }
+        psType = atype;
+        psLen  = 0;
+      }
+      if (state == ST_JUMP || state == ST_JUMPINS) isJumped = 1;
+      uint32_t consumed;
+      if (ev) {
+        const int k = __ffs(ev) - 1;
+        consumed    = (uint32_t)k + 1;
+        state       = __shfl_sync(FULL, nxt, k);
+      } else {
+        consumed = avail;
+      }
+      queryBegin -= consumed * dq;
+      refBegin -= consumed * dc;
+      psLen += consumed;
+    }
+    if (psType != MB200_SEG_NONE) { if (lane == 0) segBuf[n] = MB200_SEG_MAKE(psLen, psType); n++; }
+    if (queryBegin != 0) { if (lane == 0) segBuf[n] = MB200_SEG_MAKE(queryBegin, MB200_SEG_SOFT_CLIP); n++; }
+    __syncwarp();
+    if (lane == 0) {
       const int      beginPos = (int)refBegin;
       const uint32_t cnt      = expandPath(segBuf, n, qSeq, ref1 + beginPos, nullptr);
       const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)cnt);
@@ -451,6 +496,7 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
       o->score = bestVal; o->beginPos = beginPos; o->isJumped = isJumped; o->cigarLen = cnt; o->cigarOff = off;
     }
   }
+  __syncwarp();
 }
 
 // ======================================================================================================
@@ -829,7 +875,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpAlignKernel(const DpPara
     __threadfence_block();
     __syncwarp();
 
-    if (lane == 0) emitResult<KIND, RT>(P, task, ptrBuf, PL::passBytes(RTOT), segBuf, bestKey, stageOk);
+    emitResult<KIND, RT>(P, task, ptrBuf, PL::passBytes(RTOT), segBuf, bestKey, stageOk, lane);
     __syncwarp();
   }  // tasks
 }
@@ -1245,10 +1291,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
     }
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) {
-      emitResult<KIND, RT>(P, tA, ptrBufA, passStride, segBufA, bestA, stageOk);
-      if (!pr.dup) emitResult<KIND, RT>(P, tB, ptrBufB, passStride, segBufB, bestB, stageOk);
-    }
+    emitResult<KIND, RT>(P, tA, ptrBufA, passStride, segBufA, bestA, stageOk, lane);
+    if (!pr.dup) emitResult<KIND, RT>(P, tB, ptrBufB, passStride, segBufB, bestB, stageOk, lane);
     __syncwarp();
   }
 }
