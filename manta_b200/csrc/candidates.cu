@@ -96,7 +96,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   const uint8_t* dPool       = reinterpret_cast<const uint8_t*>(ctx->dCandPool.ptr) + MB200_POOL_FRONT;
   uint8_t*       dContigPool = reinterpret_cast<uint8_t*>(ctx->dAsmOut3.ptr) + MB200_POOL_FRONT;
   // dMisc: [0] loci counter, [4] errFlag, [8] contigPoolUsed, [10] setPoolUsed, [12] cigarUsed,
-  //        [16..18] indel class counters, [20..22] jump class counters
+  //        [32..39] indel class work counters, [48..55] jump class work counters
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[2], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dMisc.ptr, 0, 256, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAsmOut3.ptr, 0, MB200_POOL_FRONT, ctx->stream));
@@ -159,14 +159,14 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if (!indelTasks.empty()) {
     rc = mb200_dp_run(ctx, MB200_KIND_INDEL, &opts->indelScores, opts->largeIndelScore, indelTasks, ctx->dAln.ptr,
                       reinterpret_cast<uint32_t*>(ctx->dCigar.ptr), cigarCap, reinterpret_cast<unsigned long long*>(misc + 12),
-                      reinterpret_cast<int*>(misc + 4), misc + 16, &T.indelCells, &T.indelBytes);
+                      reinterpret_cast<int*>(misc + 4), misc + 32, &T.indelCells, &T.indelBytes);
     if (rc != MB200_OK) return rc;
   }
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[6], ctx->stream));
   if (!jumpTasks.empty()) {
     rc = mb200_dp_run(ctx, MB200_KIND_JUMP, &opts->jumpScores, opts->jumpScore, jumpTasks, ctx->dJump.ptr,
                       reinterpret_cast<uint32_t*>(ctx->dCigar.ptr), cigarCap, reinterpret_cast<unsigned long long*>(misc + 12),
-                      reinterpret_cast<int*>(misc + 4), misc + 20, &T.jumpCells, &T.jumpBytes);
+                      reinterpret_cast<int*>(misc + 4), misc + 48, &T.jumpCells, &T.jumpBytes);
     if (rc != MB200_OK) return rc;
   }
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[7], ctx->stream));

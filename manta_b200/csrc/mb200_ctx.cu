@@ -14,7 +14,7 @@ int mb200_reserve(mb200_ctx* ctx, DeviceBuffer& buf, size_t bytes)
 {
   if (bytes <= buf.bytes) return MB200_OK;
   if (buf.ptr) {
-    MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    MB200_CUDA_CHECK(ctx, cudaDeviceSynchronize());  // kernels on the class streams may still use it
     MB200_CUDA_CHECK(ctx, cudaFree(buf.ptr));
     buf.ptr   = nullptr;
     buf.bytes = 0;
@@ -77,6 +77,17 @@ int mb200_create(int device, const mb200_config* cfg, mb200_ctx** out)
       return MB200_ERR_CUDA;
     }
   }
+  for (int i = 0; i < mb200_ctx::kDpClasses; ++i) {
+    if (cudaStreamCreateWithFlags(&ctx->dpStream[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->dpDone[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete ctx;
+      return MB200_ERR_CUDA;
+    }
+  }
+  if (cudaEventCreateWithFlags(&ctx->dpFork, cudaEventDisableTiming) != cudaSuccess) {
+    delete ctx;
+    return MB200_ERR_CUDA;
+  }
   *out = ctx;
   return MB200_OK;
 }
@@ -85,7 +96,17 @@ void mb200_destroy(mb200_ctx* ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < mb200_ctx::kDpClasses; ++i) {
+    if (ctx->dPtrC[i].ptr) cudaFree(ctx->dPtrC[i].ptr);
+    if (ctx->dSegC[i].ptr) cudaFree(ctx->dSegC[i].ptr);
+    if (ctx->dBndC[i].ptr) cudaFree(ctx->dBndC[i].ptr);
+    if (ctx->dpStream[i]) cudaStreamDestroy(ctx->dpStream[i]);
+    if (ctx->dpDone[i]) cudaEventDestroy(ctx->dpDone[i]);
+  }
+  for (int i = 0; i < 3; ++i)
+    if (ctx->dTasksK[i].ptr) cudaFree(ctx->dTasksK[i].ptr);
+  if (ctx->dpFork) cudaEventDestroy(ctx->dpFork);
   DeviceBuffer* bufs[] = {&ctx->dPool,    &ctx->dTasks,   &ctx->dResults, &ctx->dCigar,   &ctx->dPtrScratch,
                           &ctx->dSegScratch, &ctx->dBndScratch, &ctx->dMisc, &ctx->dJobs, &ctx->dTables,
                           &ctx->dAsmWork, &ctx->dAsmOut0, &ctx->dAsmOut1, &ctx->dAsmOut2, &ctx->dAsmOut3,

@@ -40,6 +40,13 @@ struct mb200_ctx {
     std::vector<uint8_t>       isJump;
   } cand;
   DeviceBuffer           dCandPool, dCandReadOff, dCandViews, dAln, dJump;
+  // DP row classes run concurrently on their own streams with their own scratch (hides the per-launch tail)
+  static constexpr int   kDpClasses = 8;
+  cudaStream_t           dpStream[kDpClasses] = {};
+  cudaEvent_t            dpDone[kDpClasses]   = {};
+  cudaEvent_t            dpFork               = nullptr;
+  DeviceBuffer           dPtrC[kDpClasses], dSegC[kDpClasses], dBndC[kDpClasses];
+  DeviceBuffer           dTasksK[3];
   mb200_candidate_timing candTiming = {};
   cudaEvent_t            cev[8]     = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
