@@ -252,3 +252,63 @@ def make_candidate_batch(n_loci: int, seed: int = 20260923, reads_per_locus: int
             pool[rb:rb + window] = w1
             ref1["off"][li], ref1["len"][li] = rb, window
     return CandidateBatch(n_loci, reads_per_locus, read_len, pool, readOff, readViews, isJump, ref1, ref2)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: split-read realign microbench
+def make_split_batch(n_reads: int, seed: int = 5, n_contigs: int = 1000, contig_len: int = 1200, read_len: int = 150):
+    """1000 alt contigs of 1200 bp with a breakpoint at 600+-100 and 0-10 bp of homology, plus two 1200-bp reference
+    windows per contig; `n_reads` reads of 150 bp, each assigned to one contig (70 % spanning the breakpoint at a
+    uniform offset, 30 % flank only), 1 % substitutions, qualities uniform 20-40 except 2 % at Q2; every read is
+    aligned to 4 targets (alt contig with the bp1 / bp2 breakpoint views, ref window 1, ref window 2) like
+    getReadSplitScore (GSC/SVScorerSplit.cpp:190-226).  Returns (pool, jobs[4*n_reads])."""
+    from ._cabi import SR_JOB_DT
+    rng = np.random.default_rng(seed)
+    stride = (contig_len + 15) // 16 * 16
+    tgt_bytes = n_contigs * 3 * stride
+    rstride = read_len
+    pool = np.zeros(tgt_bytes + 2 * n_reads * rstride + 64, dtype=np.uint8)
+    alt = ACGT[rng.integers(0, 4, (n_contigs, contig_len))]
+    ref1 = ACGT[rng.integers(0, 4, (n_contigs, contig_len))]
+    ref2 = ACGT[rng.integers(0, 4, (n_contigs, contig_len))]
+    bp = rng.integers(500, 701, n_contigs)
+    hom = rng.integers(0, 11, n_contigs)
+    # the references share the alt sequence on "their" side of the breakpoint
+    col = np.arange(contig_len)
+    ref1 = np.where(col[None, :] < (bp + hom)[:, None], alt, ref1)
+    ref2 = np.where(col[None, :] >= bp[:, None], alt, ref2)
+    tv = pool[:tgt_bytes].reshape(n_contigs, 3, stride)
+    tv[:, 0, :contig_len] = alt
+    tv[:, 1, :contig_len] = ref1
+    tv[:, 2, :contig_len] = ref2
+    cid = rng.integers(0, n_contigs, n_reads)
+    span = rng.random(n_reads) < 0.7
+    start = np.where(span, bp[cid] - rng.integers(10, read_len - 10, n_reads),
+                     np.where(rng.random(n_reads) < 0.5, bp[cid] - read_len - rng.integers(0, 200, n_reads),
+                              bp[cid] + hom[cid] + rng.integers(0, 200, n_reads)))
+    start = np.clip(start, 0, contig_len - read_len - 1)
+    rd = alt[cid[:, None], start[:, None] + np.arange(read_len)[None, :]]
+    u = rng.random((n_reads, read_len))
+    sub = u < 0.01
+    rd[sub] = ACGT[rng.integers(0, 4, int(sub.sum()))]
+    qual = rng.integers(20, 41, (n_reads, read_len)).astype(np.uint8)
+    qual[rng.random((n_reads, read_len)) < 0.02] = 2
+    rbase = tgt_bytes
+    pool[rbase:rbase + n_reads * rstride] = rd.reshape(-1)
+    qbase = rbase + n_reads * rstride
+    pool[qbase:qbase + n_reads * rstride] = qual.reshape(-1)
+    jobs = np.zeros(4 * n_reads, dtype=SR_JOB_DT)
+    r = np.repeat(np.arange(n_reads, dtype=np.uint64), 4)
+    which = np.tile(np.arange(4), n_reads)
+    jobs["q_off"] = rbase + r * rstride
+    jobs["q_len"] = read_len
+    jobs["qualOff"] = qbase + r * rstride
+    c4 = np.repeat(cid, 4).astype(np.uint64)
+    tsel = np.array([0, 0, 1, 2], dtype=np.uint64)[which]
+    jobs["t_off"] = (c4 * 3 + tsel) * stride
+    jobs["t_len"] = contig_len
+    b4, h4 = np.repeat(bp[cid], 4), np.repeat(hom[cid], 4)
+    jobs["bpBegin"] = b4 - 1
+    jobs["bpEnd"] = b4 - 1 + h4
+    jobs["table"] = np.array([1, 1, 0, 0], dtype=np.uint32)[which]  # alt alleles: snpPrior 0, ref alleles: 1e-3
+    return pool, jobs

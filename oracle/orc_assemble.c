@@ -266,8 +266,9 @@ static void wt_free(wordtab_t* t)
 }
 
 /* getKmerCounts  IterativeAssembler.cpp:506-550 */
-static uint32_t         g_sortK;
-static const uint8_t*   g_sortSeq;
+/* comparator context: thread-local, orc_candidates_mt runs the assembler on many threads */
+static __thread uint32_t       g_sortK;
+static __thread const uint8_t* g_sortSeq;
 static int cmp_offsets(const void* a, const void* b)
 {
   return memcmp(g_sortSeq + *(const uint32_t*)a, g_sortSeq + *(const uint32_t*)b, g_sortK);

@@ -49,3 +49,13 @@ def test_split_reference_api(gpu):
     r = manta_b200.splitReadAligner(2, q, qs, [30] * 35, target, (8, 50), ctx=gpu)
     assert (r.leftSize, r.leftMismatches, r.rightSize, r.rightMismatches, r.homSize, r.homMismatches, r.alignScore) == \
         (0, 0, 34, 27, 1, 1, 7)
+
+
+def test_split_microbench_shape(gpu, orc):
+    """BASELINE configs[4] shape (reads x 4 targets of 1200 bp) from the bench generator"""
+    pool, jobs = synth.make_split_batch(5000)
+    t = manta_b200.qscore_tables(manta_b200.qscore_snp(1e-3), manta_b200.qscore_snp(0.0))
+    a = gpu.split_align_raw(t, (1e-3, 0.0), 50, pool, jobs)
+    b = orc.split_align_raw(t, (1e-3, 0.0), 50, pool, jobs)
+    assert a.tobytes() == b.tobytes()
+    assert int((a["status"] == 0).sum()) == len(jobs) and a["isEvidence"].mean() > 0.1
