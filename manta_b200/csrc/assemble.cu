@@ -318,7 +318,7 @@ __device__ void unorderedOrder(const Work& W, const uint64_t* hashIn, uint32_t n
 }
 
 // ======================================================================================================
-__global__ void __launch_bounds__(ASM_THREADS) assembleKernel(const AsmParams P)
+__global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParams P)
 {
   __shared__ uint32_t sh[ASM_THREADS < 64 ? 64 : ASM_THREADS];
   __shared__ uint32_t shU[16];
@@ -1161,7 +1161,7 @@ int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, co
   int ctasPerSm = 0;
   MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, assembleKernel, ASM_THREADS, 0));
   if (ctasPerSm < 1) ctasPerSm = 1;
-  if (ctasPerSm > 16) ctasPerSm = 16;
+  if (ctasPerSm > 32) ctasPerSm = 32;
   if (ctx->cfg.ctasPerSm && (int)ctx->cfg.ctasPerSm < ctasPerSm) ctasPerSm = (int)ctx->cfg.ctasPerSm;
   uint32_t grid = (uint32_t)(ctx->smCount * ctasPerSm);
   if (grid > nLoci) grid = nLoci;
