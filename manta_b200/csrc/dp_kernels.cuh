@@ -893,13 +893,14 @@ __device__ __forceinline__ int lo16(uint32_t x) { return (int)(short)(x & 0xffff
 __device__ __forceinline__ int hi16(uint32_t x) { return ((int)x) >> 16; }
 
 // m = max(m, v) per half; where v wins strictly the half's pointer field becomes `code` (pre-shifted)
-template <uint32_t CODE_SHIFTED>
-__device__ __forceinline__ void vmaxp(uint32_t& m, uint32_t v, uint32_t& fa, uint32_t& fb)
+// (`code` is a compile-time constant after unrolling: field position inside the cell + the cell's position inside
+// its 32-bit pointer word are folded into it, so the SEL result needs no further shifting)
+__device__ __forceinline__ void vmaxp(uint32_t code, uint32_t& m, uint32_t v, uint32_t& fa, uint32_t& fb)
 {
   bool ph, pl;
   m  = __vibmax_s16x2(m, v, &ph, &pl);
-  fa = pl ? fa : CODE_SHIFTED;
-  fb = ph ? fb : CODE_SHIFTED;
+  fa = pl ? fa : code;
+  fb = ph ? fb : code;
 }
 
 struct StageCursor {
@@ -955,6 +956,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
   __shared__ __align__(128) uint8_t sRing[WARPS_PER_CTA][2][REF_RING];
   __shared__ __align__(8) uint64_t sBar[WARPS_PER_CTA][2][2];
   __shared__ uint32_t sTask[WARPS_PER_CTA];
+  // M of every row of a lane that owns the last query row of A or B (read back with a run-time row index: registers
+  // cannot be indexed dynamically, and a SEL chain in the row loop would sit on the saturated ALU pipe)
+  // ALU-trimming variants (row-Q capture through shared memory, pointer codes pre-shifted to the row's position,
+  // staging checks once per 32 steps).  The 5-state kernel sits on the register cliff and ptxas spills inside the
+  // row loop with them (measured: 112 ms -> 128..207 ms per 20k loci), so it keeps the plain forms.
+  constexpr bool TRIM     = (KIND != KIND_INDEL);
+  constexpr bool SMEM_CAP = TRIM;
+  __shared__ uint32_t sCap[SMEM_CAP ? WARPS_PER_CTA : 1][SMEM_CAP ? 32 : 1][RT];
 
   const int      lane    = threadIdx.x & 31;
   const int      warp    = threadIdx.x >> 5;
@@ -1070,22 +1079,26 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
       uint8_t*       passB  = ptrBufB + (size_t)pass * passStride;
 
       for (uint32_t t = 0; t < nSteps; ++t) {
-        // ---- reference tiles of both halves
+        // ---- reference tiles of both halves: checked once per 32 steps with a 32-column look-ahead for the head
+        // (tiles are 2 KiB, so a tile the head enters inside this block is waited for at the block start)
+        if (!TRIM || (t & 31u) == 0) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          StageCursor&   cur = h ? curB : curA;
-          const uint32_t rt  = h ? RTB : RTA;
-          const uint32_t r1  = h ? R1B : R1A;
-          const uint32_t cz0 = t < rt ? t : rt - 1;
-          const uint32_t need = stagedIndex(cur.st, cz0, r1, KIND == KIND_JUMP) / REF_TILE;
-          while (cur.waitTile <= need) stageOk = cursorWait(cur) && stageOk;
-          if (cur.nextIssue < cur.st.nTiles) {
-            uint32_t czT = t >= 31 ? t - 31 : 0;
-            if (czT >= rt) czT = rt - 1;
-            if (stagedIndex(cur.st, czT, r1, KIND == KIND_JUMP) / REF_TILE >= cur.nextIssue - 1) {
-              __syncwarp();
-              stageIssue(cur.st, cur.nextIssue, lane);
-              cur.nextIssue++;
+          for (int h = 0; h < 2; ++h) {
+            StageCursor&   cur = h ? curB : curA;
+            const uint32_t rt  = h ? RTB : RTA;
+            const uint32_t r1  = h ? R1B : R1A;
+            const uint32_t ahead = TRIM ? 31u : 0u;
+            const uint32_t cz0 = (t + ahead < rt) ? t + ahead : rt - 1;
+            const uint32_t need = stagedIndex(cur.st, cz0, r1, KIND == KIND_JUMP) / REF_TILE;
+            while (cur.waitTile <= need) stageOk = cursorWait(cur) && stageOk;
+            if (cur.nextIssue < cur.st.nTiles) {
+              uint32_t czT = t >= 31 ? t - 31 : 0;
+              if (czT >= rt) czT = rt - 1;
+              if (stagedIndex(cur.st, czT, r1, KIND == KIND_JUMP) / REF_TILE >= cur.nextIssue - 1) {
+                __syncwarp();
+                stageIssue(cur.st, cur.nextIssue, lane);
+                cur.nextIssue++;
+              }
             }
           }
         }
@@ -1153,7 +1166,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
 #pragma unroll
           for (int r = 0; r < RT; ++r) {
             constexpr uint32_t F0 = 0;  // field shifts inside the 32-bit pointer word are added below
-            const int      sh   = ROWBITS * (r % ROWSPW);
+            const int      shRow = ROWBITS * (r % ROWSPW);
+            const int      sh    = TRIM ? shRow : 0;  // folded into the SEL constants, or applied once below
             (void)F0;
             // substitution score of both halves: match where the characters are equal, mismatch elsewhere
             const uint32_t d  = qpair[r] ^ refpair;
@@ -1163,42 +1177,51 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
             uint32_t nM, nD, nI, nJ = BAD2, nK = BAD2;
             uint32_t fa = 0, fb = 0;  // pointer fields of this cell, A and B
             if (KIND == KIND_GLOBAL) {
-              { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nM = dM; vmaxp((1u) << sh, nM, dD, a, b); vmaxp((2u) << sh, nM, dI, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp((1u << BITS) << sh, nD, pD[r], a, b); vmaxp((2u << BITS) << sh, nD, pI[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp((1u << (2 * BITS)) << sh, nI, BAD2, a, b); vmaxp((2u << (2 * BITS)) << sh, nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
             } else if (KIND == KIND_INDEL) {
-              { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); vmaxp<3u>(nM, dJ, a, b); vmaxp<4u>(nM, dK, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); if (!NOBAD) vmaxp<3u << BITS>(nD, BAD2, a, b); vmaxp<4u << BITS>(nD, pK[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nJ = __vadd2(pM[r], extra2); if (!NOBAD) vmaxp<1u << (3 * BITS)>(nJ, BAD2, a, b); vmaxp<2u << (3 * BITS)>(nJ, __vadd2(pI[r], extraMinusOpen2), a, b); vmaxp<3u << (3 * BITS)>(nJ, pJ[r], a, b); vmaxp<4u << (3 * BITS)>(nJ, __vadd2(pK[r], extra2), a, b); if (row1) nJ = BAD2; fa |= a; fb |= b; }
-              { uint32_t a = 0, b = 0; nK = __vadd2(vM, extra2); if (!NOBAD) vmaxp<1u << (4 * BITS)>(nK, BAD2, a, b); vmaxp<4u << (4 * BITS)>(nK, vK, a, b); if (row1) nK = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nM = dM; vmaxp((1u) << sh, nM, dD, a, b); vmaxp((2u) << sh, nM, dI, a, b); vmaxp((3u) << sh, nM, dJ, a, b); vmaxp((4u) << sh, nM, dK, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp((1u << BITS) << sh, nD, pD[r], a, b); vmaxp((2u << BITS) << sh, nD, pI[r], a, b); if (!NOBAD) vmaxp((3u << BITS) << sh, nD, BAD2, a, b); vmaxp((4u << BITS) << sh, nD, pK[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp((1u << (2 * BITS)) << sh, nI, BAD2, a, b); vmaxp((2u << (2 * BITS)) << sh, nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nJ = __vadd2(pM[r], extra2); if (!NOBAD) vmaxp((1u << (3 * BITS)) << sh, nJ, BAD2, a, b); vmaxp((2u << (3 * BITS)) << sh, nJ, __vadd2(pI[r], extraMinusOpen2), a, b); vmaxp((3u << (3 * BITS)) << sh, nJ, pJ[r], a, b); vmaxp((4u << (3 * BITS)) << sh, nJ, __vadd2(pK[r], extra2), a, b); if (row1) nJ = BAD2; fa |= a; fb |= b; }
+              { uint32_t a = 0, b = 0; nK = __vadd2(vM, extra2); if (!NOBAD) vmaxp((1u << (4 * BITS)) << sh, nK, BAD2, a, b); vmaxp((4u << (4 * BITS)) << sh, nK, vK, a, b); if (row1) nK = BAD2; fa |= a; fb |= b; }
             } else {  // KIND_JUMP
               if (!phase2) {
-                { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
-                { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
-                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
-                { uint32_t a = 0, b = 0; nJ = __vadd2(nM, extra2); if (!NOBAD) vmaxp<1u << (3 * BITS)>(nJ, BAD2, a, b); vmaxp<2u << (3 * BITS)>(nJ, __vadd2(nI, extra2), a, b); vmaxp<3u << (3 * BITS)>(nJ, pJ[r], a, b); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nM = dM; vmaxp((1u) << sh, nM, dD, a, b); vmaxp((2u) << sh, nM, dI, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp((1u << BITS) << sh, nD, pD[r], a, b); vmaxp((2u << BITS) << sh, nD, pI[r], a, b); nD = __vadd2(nD, ext2); if (row1) nD = BAD2; fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp((1u << (2 * BITS)) << sh, nI, BAD2, a, b); vmaxp((2u << (2 * BITS)) << sh, nI, vI, a, b); nI = __vadd2(nI, ext2); if (row1) nI = BAD2; fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nJ = __vadd2(nM, extra2); if (!NOBAD) vmaxp((1u << (3 * BITS)) << sh, nJ, BAD2, a, b); vmaxp((2u << (3 * BITS)) << sh, nJ, __vadd2(nI, extra2), a, b); vmaxp((3u << (3 * BITS)) << sh, nJ, pJ[r], a, b); fa |= a; fb |= b; }
               } else {
-                { uint32_t a = 0, b = 0; nM = dM; vmaxp<1u>(nM, dD, a, b); vmaxp<2u>(nM, dI, a, b); vmaxp<3u>(nM, dJ, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
-                { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp<1u << BITS>(nD, pD[r], a, b); vmaxp<2u << BITS>(nD, pI[r], a, b); nD = __vadd2(nD, ext2); fa |= a; fb |= b; }
-                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp<1u << (2 * BITS)>(nI, BAD2, a, b); vmaxp<2u << (2 * BITS)>(nI, vI, a, b); vmaxp<3u << (2 * BITS)>(nI, vJ, a, b); nI = __vadd2(nI, ext2); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nM = dM; vmaxp((1u) << sh, nM, dD, a, b); vmaxp((2u) << sh, nM, dI, a, b); vmaxp((3u) << sh, nM, dJ, a, b); nM = __vadd2(nM, s2); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nD = __vadd2(pM[r], open2); vmaxp((1u << BITS) << sh, nD, pD[r], a, b); vmaxp((2u << BITS) << sh, nD, pI[r], a, b); nD = __vadd2(nD, ext2); fa |= a; fb |= b; }
+                { uint32_t a = 0, b = 0; nI = __vadd2(vM, open2); if (!NOBAD) vmaxp((1u << (2 * BITS)) << sh, nI, BAD2, a, b); vmaxp((2u << (2 * BITS)) << sh, nI, vI, a, b); vmaxp((3u << (2 * BITS)) << sh, nI, vJ, a, b); nI = __vadd2(nI, ext2); fa |= a; fb |= b; }
                 nJ = pJ[r];
-                fa |= (uint32_t)ST_JUMP << (3 * BITS);
-                fb |= (uint32_t)ST_JUMP << (3 * BITS);
+                fa |= ((uint32_t)ST_JUMP << (3 * BITS)) << sh;
+                fb |= ((uint32_t)ST_JUMP << (3 * BITS)) << sh;
               }
             }
-            ptrwA[r / ROWSPW] |= fa << sh;
-            ptrwB[r / ROWSPW] |= fb << sh;
+            ptrwA[r / ROWSPW] |= fa << (shRow - sh);
+            ptrwB[r / ROWSPW] |= fb << (shRow - sh);
 
             dM = pM[r]; dD = pD[r]; dI = pI[r]; dJ = pJ[r]; dK = pK[r];
             pM[r] = nM; pD[r] = nD; pI[r] = nI; pJ[r] = nJ; pK[r] = nK;
             vM = nM; vI = nI; vJ = nJ; vK = nK;
-            if (r == rQA) capA = nM;
-            if (r == rQB) capB = nM;
+            if (!SMEM_CAP) {
+              if (r == rQA) capA = nM;
+              if (r == rQB) capB = nM;
+            }
           }
 
           // ---- back-trace start candidates (same enumeration as the int32 kernel)
           const bool validA = (uint32_t)c <= RTA, validB = (uint32_t)c <= RTB;
+          if (SMEM_CAP && (rQA < RT || rQB < RT)) {
+            uint32_t* cp = sCap[warp][lane];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) cp[r] = pM[r];
+            capA = cp[rQA < RT ? rQA : 0];
+            capB = cp[rQB < RT ? rQB : 0];
+          }
           if (rQA < RT && validA) {
             const uint32_t seq = (KIND == KIND_JUMP && phase2) ? (R1 + QA + ((uint32_t)c - R1) - 1) : ((uint32_t)c - 1);
             const long long k  = makeKey(lo16(capA), seq);
