@@ -71,31 +71,25 @@ def load_cpu_checker():
     return cb.Binding(C.CDLL(os.path.join(ROOT, "oracle", "_build", "libmanta_oracle.so")), "orc_"), "port"
 
 
-def run_cpu_sample(binding, batch, opts, n_loci, threads):
+def run_cpu_sample(binding, batch, opts, n_loci, threads, cuts=None, select=True):
     """the per-candidate composition (runIterativeAssembler, then every contig through the large-indel / jump
     aligner) on `threads` host threads inside the checker library (ref_candidates_mt / orc_candidates_mt):
     dynamic hand-out of loci, one set of aligner objects per thread, like the reference's own thread pool"""
-    f = getattr(binding.lib, binding.prefix + "candidates_mt")
-    f.restype = C.c_int
-    nc, cells, ssum = C.c_uint64(), C.c_uint64(), C.c_int64()
-    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
     t0 = time.perf_counter()
-    st = f(p(opts), C.c_uint32(n_loci), p(batch.readOff), p(batch.readViews), p(batch.isJump), p(batch.ref1),
-           p(batch.ref2), p(batch.pool), C.c_int(threads), C.byref(nc), C.byref(cells), C.byref(ssum))
+    _, cells, _, _ = binding.candidates_mt(opts, batch, n_loci, threads, cuts=cuts, select=select)
     dt = time.perf_counter() - t0
-    assert st == 0
-    return n_loci, int(cells.value), dt
+    return n_loci, cells, dt
 
 
-def cpu_baseline(batch, opts, target_seconds=20.0):
+def cpu_baseline(batch, opts, cuts, select, target_seconds=20.0):
     binding, kind = load_cpu_checker()
     threads = host_threads()
     probe = min(batch.nLoci, max(threads, 16))
-    n, cells, dt = run_cpu_sample(binding, batch, opts, probe, threads)
+    n, cells, dt = run_cpu_sample(binding, batch, opts, probe, threads, cuts, select)
     rate = n / dt
     want = int(min(batch.nLoci, max(probe, rate * target_seconds)))
     if want > probe:
-        n, cells, dt = run_cpu_sample(binding, batch, opts, want, threads)
+        n, cells, dt = run_cpu_sample(binding, batch, opts, want, threads, cuts, select)
     return dict(value=n / dt, unit=UNIT, cores=threads, kind=kind,
                 sample="first %d loci of the same batch, %.1f s wall, %d host threads, %.2f GCUPS" %
                        (n, dt, threads, cells / dt * 1e-9)), n, dt
@@ -200,6 +194,8 @@ def main():
     ap.add_argument("--impl", default="manta_b200", choices=["manta_b200", "reference"])
     ap.add_argument("--loci", type=int, default=50000, help="candidate loci per GPU per step (BASELINE configs[1]: 50000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-refine", action="store_true",
+                    help="leave out the refiner's 10-mer window trim and contig QC / selection (assemble + align only)")
     ap.add_argument("--workload", default="candidates", choices=["candidates", "split"],
                     help="'split' = BASELINE configs[4] split-read realign microbench (not the headline metric)")
     ap.add_argument("--reads", type=int, default=2000000, help="reads of the split-read microbench (x4 targets)")
@@ -212,12 +208,16 @@ def main():
     config = dict(workload="configs[1]: synthetic %d candidate loci x 64 reads x 150 bp per GPU, k=41..76 assembly + every contig "
                            "vs 5 kb reference window (60%% large-indel aligner R=5000, 40%% jump aligner R1=R2=2500)" % args.loci,
                   loci_per_gpu=args.loci, reads_per_locus=64, read_len=150, window=5000, seed=20260923,
+                  refine=("off" if args.no_refine else
+                          "on: complex contigs aligned against the 10-mer-trimmed window (cuts 100/100/800/800, "
+                          "SVCandidateAssemblyRefiner.cpp:1984-2011), contig QC + bestAlignmentIndex selection (:1364, :2119)"),
                   l2="inputs (~0.9 GB per batch) and back-pointer stream exceed the 126 MB L2; no flush needed",
                   parallelism="loci sharded by rank, no data-path collective" + (
                       "; one NCCL gather of the per-GPU result buffers" if world > 1 else ""))
 
     if args.workload == "split":
         return split_microbench(args)
+    refine = not args.no_refine
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -227,14 +227,15 @@ def main():
         batch = synth.make_candidate_batch(sample_loci, seed=20260923)
         binding, kind = load_cpu_checker()
         threads = host_threads()
+        cuts = cb.default_ref_cuts(batch.nLoci) if refine else None
         # size one step to ~8 s of CPU work
-        n, cells, dt = run_cpu_sample(binding, batch, opts, min(sample_loci, max(threads, 16)), threads)
+        n, cells, dt = run_cpu_sample(binding, batch, opts, min(sample_loci, max(threads, 16)), threads, cuts, refine)
         per_step = int(min(sample_loci, max(threads, n / dt * 8.0)))
         for _ in range(args.warmup):
-            run_cpu_sample(binding, batch, opts, min(per_step, max(threads, 16)), threads)
+            run_cpu_sample(binding, batch, opts, min(per_step, max(threads, 16)), threads, cuts, refine)
         tot_n, tot_t, tot_cells = 0, 0.0, 0
         for _ in range(args.steps):
-            n, cells, dt = run_cpu_sample(binding, batch, opts, per_step, threads)
+            n, cells, dt = run_cpu_sample(binding, batch, opts, per_step, threads, cuts, refine)
             tot_n += n
             tot_t += dt
             tot_cells += cells
@@ -261,13 +262,17 @@ def main():
     batch = synth.make_candidate_batch(args.loci, seed=20260923 + rank)
     pool_pinned, _keep = pinned_copy(batch.pool)
     batch.pool = pool_pinned
+    cuts = cb.default_ref_cuts(batch.nLoci) if refine else None
 
     def gather_results(out):
         if dist is None:
             return
         # the single collective of the path: per-GPU result buffers to rank 0 over NVLink
         from manta_b200 import shard
-        buf = np.concatenate([out["aln"].view(np.uint8).reshape(-1), out["jump"].view(np.uint8).reshape(-1)])
+        parts = [out["aln"].view(np.uint8).reshape(-1), out["jump"].view(np.uint8).reshape(-1)]
+        if refine:
+            parts += [out["qc"].view(np.uint8).reshape(-1), out["best"].view(np.uint8).reshape(-1)]
+        buf = np.concatenate(parts)
         shard.gather_buffers(buf, dst=0, device="cuda:%d" % local_rank)
 
     def sync_all():
@@ -277,19 +282,19 @@ def main():
             torch.cuda.synchronize()
 
     # ---- resident-input steps (value)
-    ctx.candidates_upload(batch)
+    ctx.candidates_upload(batch, cuts)
     out = None
     for _ in range(args.warmup):
-        out = ctx.candidates_run(opts, out)
+        out = ctx.candidates_run(opts, out, select=refine)
         gather_results(out)
     sampler = ClockSampler(local_rank)
     sync_all()
     sampler.start()
     t0 = time.perf_counter()
-    ev_ms, stage = 0.0, dict(asmMs=0.0, indelMs=0.0, jumpMs=0.0)
+    ev_ms, stage = 0.0, dict(asmMs=0.0, indelMs=0.0, jumpMs=0.0, trimMs=0.0, qcMs=0.0)
     launches = 0
     for _ in range(args.steps):
-        out = ctx.candidates_run(opts, out)
+        out = ctx.candidates_run(opts, out, select=refine)
         gather_results(out)
         t = ctx.candidates_timing()
         ev_ms += t["totalMs"]
@@ -303,14 +308,14 @@ def main():
 
     # ---- end-to-end steps: host (pinned) buffers in, results out, every step
     for _ in range(1):
-        ctx.candidates_upload(batch)
-        out = ctx.candidates_run(opts, out)
+        ctx.candidates_upload(batch, cuts)
+        out = ctx.candidates_run(opts, out, select=refine)
     sync_all()
     t1 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(args.steps):
-        ctx.candidates_upload(batch)
-        out = ctx.candidates_run(opts, out)
+        ctx.candidates_upload(batch, cuts)
+        out = ctx.candidates_run(opts, out, select=refine)
         gather_results(out)
         t = ctx.candidates_timing()
         h2d, d2h = t["h2dBytes"], t["d2hBytes"]
@@ -351,12 +356,14 @@ def main():
                               peak_source=peak_src, algorithmic_bytes_per_launch_set=dom_bytes, kernel_ms_per_step=dom_ms,
                               gcups=tim["indelCells"] / (dom_ms * 1e-3) * 1e-9 if dom_ms > 0 else None),
                 stages=dict(device_ms_per_step=ev_s * 1000.0 / args.steps, asm_ms=stage["asmMs"] / args.steps,
-                            indel_ms=dom_ms, jump_ms=stage["jumpMs"] / args.steps, contigs=tim["nContigs"],
+                            indel_ms=dom_ms, jump_ms=stage["jumpMs"] / args.steps, trim_ms=stage["trimMs"] / args.steps,
+                            qc_ms=stage["qcMs"] / args.steps, contigs=tim["nContigs"],
+                            selected=(int((out["best"] >= 0).sum()) if refine else None),
                             indel_cells=tim["indelCells"], jump_cells=tim["jumpCells"],
                             jump_gcups=(tim["jumpCells"] / (stage["jumpMs"] / args.steps * 1e-3) * 1e-9) if stage["jumpMs"] > 0 else None,
                             jump_gbs=(tim["jumpBytes"] / (stage["jumpMs"] / args.steps * 1e-3) * 1e-9) if stage["jumpMs"] > 0 else None))
     if rank == 0 and not args.no_cpu_baseline:
-        cpu, _, _ = cpu_baseline(batch, opts)
+        cpu, _, _ = cpu_baseline(batch, opts, cuts, refine)
         line["cpu_baseline"] = cpu
     if dist is not None:
         dist.barrier()

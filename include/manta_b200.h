@@ -261,19 +261,82 @@ MB200_API int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, u
                                    uint64_t pseudoCap, uint8_t* contigPool, uint64_t contigPoolCap,
                                    uint32_t* setPool, uint64_t setPoolCap);
 
+/* ---- reference-window trim + contig QC / selection ------------------------------
+ * The per-contig steps that surround the large-indel / jump DP in the refiner. */
+
+/* edge cuts of a complex candidate's reference window  GSC/SVCandidateAssemblyRefiner.cpp:1915-1918 */
+typedef struct mb200_ref_cuts {
+  int32_t leadingCut;     /* 100 in the normal case (extraRefSplitSize) */
+  int32_t trailingCut;
+  int32_t maxLeadingCut;  /* 800 in the normal case (extraRefSize)      */
+  int32_t maxTrailingCut;
+} mb200_ref_cuts;
+
+/* adjustedLeadingCut / adjustedTrailingCut of one contig  :1984-2011 */
+typedef struct mb200_trim_result {
+  int32_t adjLeadingCut;
+  int32_t adjTrailingCut;
+} mb200_trim_result;
+
+typedef struct mb200_qc_opts {
+  mb200_scores filterScores;            /* SVRefinerOptions::contigFilterScores (2,-8,-18,0,-1)  lib/options/SVRefinerOptions.hpp:50 */
+  uint32_t     minCandidateVariantSize; /* ReadScannerOptions::minCandidateVariantSize = 10      lib/options/ReadScannerOptions.hpp:68 */
+  uint32_t     reserved;
+} mb200_qc_opts;
+
+/* per-contig QC outcome.
+ * complex candidates (:2046-2066): isCandidate = isSmallSVCandidate; the kept candidateSegments are always a
+ *   contiguous run of getLargeIndelSegments(apath, minCandidateVariantSize) (:173): nSegments of them starting at
+ *   ordinal segOrdinal, covering apath[pathFirst .. pathLast]; variantSize = getLargestIndelSize (:210).
+ * spanning candidates: isCandidate = !isJumpAlignmentQCFail (:1266); isLowQuality = isLowQualityJumpAlignment (:1287,
+ *   evaluated for every contig; the reference only looks at it for the top-scoring one). */
+typedef struct mb200_contig_qc {
+  uint32_t isCandidate;
+  uint32_t isLowQuality;
+  uint32_t segOrdinal;
+  uint32_t nSegments;
+  uint32_t pathFirst;
+  uint32_t pathLast;
+  uint32_t variantSize;
+  uint32_t reserved;
+} mb200_contig_qc;
+
+/* 10-mer anchored trim of the reference window of n (contig, window) items  :1984-2011.
+ * MB200_ERR_BAD_ARG if a contig is shorter than 10 bases (the reference's unsigned loop bound underflows there). */
+MB200_API int mb200_ref_trim_batch(mb200_ctx* ctx, uint32_t n, const uint8_t* pool, uint64_t poolBytes,
+                                   const mb200_seqview* contig, const mb200_seqview* ref, const mb200_ref_cuts* cuts,
+                                   mb200_trim_result* out);
+
+/* contig QC and bestAlignmentIndex selection for nLoci candidates.  Contig c of locus i owns slot slotFirst[i] + c
+ * (c < nContigs[i]) of aln (complex, beginPos relative to ref1[i]) / jump (spanning), contigSeq, supportCount
+ * (= AssembledContig::supportReads.size()) and qc.  best[i] = SVCandidateAssemblyData::bestAlignmentIndex or -1 when
+ * the reference selects nothing (complex: rank1/rank2 rule :2119-2227; spanning: selectJumpContigDNA :1364-1398). */
+MB200_API int mb200_select_contigs_batch(mb200_ctx* ctx, const mb200_qc_opts* opts, uint32_t nLoci,
+                                         const uint8_t* isJump, const uint32_t* slotFirst, const uint32_t* nContigs,
+                                         uint32_t nSlots, const mb200_aln_result* aln, const mb200_jump_result* jump,
+                                         const uint32_t* cigarPool, uint64_t cigarLen, const uint8_t* pool,
+                                         uint64_t poolBytes, const mb200_seqview* contigSeq, const mb200_seqview* ref1,
+                                         const uint32_t* supportCount, mb200_contig_qc* qc, int32_t* best);
+
 /* ---- fused candidate path -------------------------------------------------------------------------
  * "one candidate" = one SVCandidate junction entering getCandidateAssemblyData (GSC/SVCandidateProcessor.cpp:310):
  * its read set is assembled (all word lengths) and EVERY resulting contig is aligned
  *   - complex candidates (isJump == 0): GlobalLargeIndelAligner against ref1      (SVCandidateAssemblyRefiner.cpp:2032)
  *   - spanning candidates (isJump == 1): GlobalJumpAligner against (ref1, ref2)   (SVCandidateAssemblyRefiner.cpp:1668)
  * with contigs staying resident on the device between the two stages.
- * Result slot of contig c of locus i is i*maxAssemblyCount + c in alnResults (complex) / jumpResults (spanning). */
+ * Result slot of contig c of locus i is i*maxAssemblyCount + c in alnResults (complex) / jumpResults (spanning).
+ * Optional stages, each to the reference's semantics:
+ *   - cuts != NULL at upload: every complex contig's ref1 window is first trimmed to its outermost shared 10-mers
+ *     (:1984-2011) and beginPos is reported relative to the untrimmed ref1 (:2038); trim[slot] returns the cuts used
+ *   - qc / best != NULL at run: contig QC and bestAlignmentIndex selection (mb200_select_contigs_batch) run on the
+ *     device right after the DP, on the still-resident alignments. */
 typedef struct mb200_candidate_opts {
   mb200_asm_opts asmOpts;
   mb200_scores   indelScores;     /* SVRefinerOptions::smallSVAlignScores (2,-8,-24,-1,-1)  lib/options/SVRefinerOptions.hpp:40 */
   int32_t        largeIndelScore; /* largeGapOpenScore -100                                 :44 */
   mb200_scores   jumpScores;      /* spanningAlignScores (2,-8,-12,-1,-1)                   :43 */
   int32_t        jumpScore;       /* -100                                                   :45 */
+  mb200_qc_opts  qcOpts;          /* contig QC / selection (used when qc/best outputs are requested) */
 } mb200_candidate_opts;
 
 typedef struct mb200_candidate_timing {
@@ -282,20 +345,21 @@ typedef struct mb200_candidate_timing {
   uint64_t asmWindows, indelCells, jumpCells;
   uint64_t asmBytes, indelBytes, jumpBytes; /* algorithmic HBM bytes per stage */
   uint64_t h2dBytes, d2hBytes;
+  float    trimMs, qcMs;                   /* reference-window trim / contig QC + selection kernels */
 } mb200_candidate_timing;
 
 /* stage one batch of candidate loci in device memory (inputs resident in HBM afterwards) */
 MB200_API int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* readOff,
                                       const mb200_seqview* readViews, const uint8_t* isJump,
                                       const mb200_seqview* ref1, const mb200_seqview* ref2, const uint8_t* pool,
-                                      uint64_t poolBytes);
+                                      uint64_t poolBytes, const mb200_ref_cuts* cuts);
 /* assemble + align every contig of the staged batch; all outputs are host buffers */
 MB200_API int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200_asm_locus* loci,
                                    mb200_contig* contigs, mb200_seqview* pseudoReads, uint8_t* contigPool,
                                    uint64_t contigPoolCap, uint64_t* contigPoolUsed, uint32_t* setPool,
                                    uint64_t setPoolCap, uint64_t* setPoolUsed, mb200_aln_result* alnResults,
                                    mb200_jump_result* jumpResults, uint32_t* cigarPool, uint64_t cigarCap,
-                                   uint64_t* cigarUsed);
+                                   uint64_t* cigarUsed, mb200_trim_result* trim, mb200_contig_qc* qc, int32_t* best);
 MB200_API int mb200_candidates_timing(const mb200_ctx* ctx, mb200_candidate_timing* out);
 
 #ifdef __cplusplus

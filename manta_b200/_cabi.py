@@ -85,14 +85,24 @@ TIMING_DT = np.dtype([("h2dMs", "<f4"), ("kernelMs", "<f4"), ("d2hMs", "<f4"), (
 CONFIG_DT = np.dtype([("ctasPerSm", "<u4"), ("maxContigLen", "<u4"), ("scratchBytes", "<u8"),
                       ("reserved", "<u4", (4,))], align=True)
 
+REF_CUTS_DT = np.dtype([("leadingCut", "<i4"), ("trailingCut", "<i4"), ("maxLeadingCut", "<i4"),
+                        ("maxTrailingCut", "<i4")], align=True)
+TRIM_RESULT_DT = np.dtype([("adjLeadingCut", "<i4"), ("adjTrailingCut", "<i4")], align=True)
+QC_OPTS_DT = np.dtype([("filterScores", "<i4", (6,)), ("minCandidateVariantSize", "<u4"), ("reserved", "<u4")],
+                      align=True)
+CONTIG_QC_DT = np.dtype([("isCandidate", "<u4"), ("isLowQuality", "<u4"), ("segOrdinal", "<u4"), ("nSegments", "<u4"),
+                         ("pathFirst", "<u4"), ("pathLast", "<u4"), ("variantSize", "<u4"), ("reserved", "<u4")],
+                        align=True)
 CAND_OPTS_DT = np.dtype([("asmOpts", ASM_OPTS_DT), ("indelScores", "<i4", (6,)), ("largeIndelScore", "<i4"),
-                         ("jumpScores", "<i4", (6,)), ("jumpScore", "<i4")], align=True)
+                         ("jumpScores", "<i4", (6,)), ("jumpScore", "<i4"), ("qcOpts", QC_OPTS_DT)], align=True)
 CAND_TIMING_DT = np.dtype([("h2dMs", "<f4"), ("asmMs", "<f4"), ("indelMs", "<f4"), ("jumpMs", "<f4"), ("d2hMs", "<f4"),
                            ("totalMs", "<f4"), ("launches", "<u4"), ("nContigs", "<u4"), ("nIndelTasks", "<u4"),
                            ("nJumpTasks", "<u4"), ("asmWindows", "<u8"), ("indelCells", "<u8"), ("jumpCells", "<u8"),
                            ("asmBytes", "<u8"), ("indelBytes", "<u8"), ("jumpBytes", "<u8"), ("h2dBytes", "<u8"),
-                           ("d2hBytes", "<u8")], align=True)
-assert CAND_OPTS_DT.itemsize == 88 and CAND_TIMING_DT.itemsize == 104
+                           ("d2hBytes", "<u8"), ("trimMs", "<f4"), ("qcMs", "<f4")], align=True)
+assert CAND_OPTS_DT.itemsize == 120 and CAND_TIMING_DT.itemsize == 112
+assert REF_CUTS_DT.itemsize == 16 and TRIM_RESULT_DT.itemsize == 8 and QC_OPTS_DT.itemsize == 32
+assert CONTIG_QC_DT.itemsize == 32
 
 assert SEQVIEW_DT.itemsize == 16 and ALN_RESULT_DT.itemsize == 24 and JUMP_RESULT_DT.itemsize == 48
 assert SR_RESULT_DT.itemsize == 56 and SR_JOB_DT.itemsize == 56 and CONTIG_DT.itemsize == 40
@@ -346,17 +356,48 @@ class Binding:
             return loci, contigs, pseudo, cpool, spool
         raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "assembler output pool overflow")
 
+    # -- reference-window trim / contig QC + selection ----------------------------------------
+    def ref_trim_raw(self, pool: np.ndarray, contig: np.ndarray, ref: np.ndarray, cuts: np.ndarray) -> np.ndarray:
+        n = len(contig)
+        out = np.zeros(n, dtype=TRIM_RESULT_DT)
+        args = [C.c_uint32(n), _ptr(pool)]
+        if self.ctx is not None:
+            args.append(C.c_uint64(pool.size))
+        st = self._call("ref_trim_batch", *args, _ptr(contig), _ptr(ref), _ptr(cuts), _ptr(out))
+        if st != MB200_OK:
+            self._raise(st)
+        return out
+
+    def select_contigs_raw(self, opts: np.ndarray, isJump: np.ndarray, slotFirst: np.ndarray, nContigs: np.ndarray,
+                           aln: np.ndarray, jump: np.ndarray, cigar: np.ndarray, pool: np.ndarray,
+                           contigSeq: np.ndarray, ref1: np.ndarray, support: np.ndarray):
+        nLoci, nSlots = len(isJump), len(contigSeq)
+        qc = np.zeros(nSlots, dtype=CONTIG_QC_DT)
+        best = np.zeros(nLoci, dtype=np.int32)
+        args = [_ptr(opts), C.c_uint32(nLoci), _ptr(isJump), _ptr(slotFirst), _ptr(nContigs), C.c_uint32(nSlots),
+                _ptr(aln), _ptr(jump), _ptr(cigar)]
+        if self.ctx is not None:
+            args.append(C.c_uint64(cigar.size))
+        args.append(_ptr(pool))
+        if self.ctx is not None:
+            args.append(C.c_uint64(pool.size))
+        st = self._call("select_contigs_batch", *args, _ptr(contigSeq), _ptr(ref1), _ptr(support), _ptr(qc), _ptr(best))
+        if st != MB200_OK:
+            self._raise(st)
+        return qc, best
+
     # -- fused candidate path (product library only) -----------------------------------------
-    def candidates_upload(self, batch) -> None:
+    def candidates_upload(self, batch, cuts: Optional[np.ndarray] = None) -> None:
         st = self._call("candidates_upload", C.c_uint32(batch.nLoci), _ptr(batch.readOff), _ptr(batch.readViews),
                         _ptr(batch.isJump), _ptr(batch.ref1), _ptr(batch.ref2), _ptr(batch.pool),
-                        C.c_uint64(batch.pool.size))
+                        C.c_uint64(batch.pool.size), _ptr(cuts) if cuts is not None else None)
         if st != MB200_OK:
             self._raise(st)
         self._cand_shape = (batch.nLoci, int(batch.readViews["len"].sum()), batch.readsPerLocus)
 
-    def candidates_run(self, opts: np.ndarray, out: Optional[dict] = None) -> dict:
-        """run on the staged batch; `out` (from a previous call) is reused to avoid re-allocating host buffers"""
+    def candidates_run(self, opts: np.ndarray, out: Optional[dict] = None, select: bool = False) -> dict:
+        """run on the staged batch; `out` (from a previous call) is reused to avoid re-allocating host buffers.
+        select=True also returns the per-contig trim / QC records and the per-locus bestAlignmentIndex."""
         nLoci, totalBases, rpl = self._cand_shape
         A = int(opts["asmOpts"]["maxAssemblyCount"][0])
         if out is None:
@@ -366,12 +407,16 @@ class Binding:
                        setPool=np.zeros(max(1024, nLoci * A * 2 * ((rpl + 2 * A + 31) // 32)), dtype=np.uint32),
                        aln=np.zeros(nLoci * A, dtype=ALN_RESULT_DT), jump=np.zeros(nLoci * A, dtype=JUMP_RESULT_DT),
                        cigar=np.zeros(max(4096, nLoci * A * 24), dtype=np.uint32))
+        if select and "qc" not in out:
+            out.update(trim=np.zeros(nLoci * A, dtype=TRIM_RESULT_DT), qc=np.zeros(nLoci * A, dtype=CONTIG_QC_DT),
+                       best=np.zeros(nLoci, dtype=np.int32))
+        sel = [_ptr(out["trim"]), _ptr(out["qc"]), _ptr(out["best"])] if select else [None, None, None]
         for _ in range(6):
             used = [C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)]
             st = self._call("candidates_run", _ptr(opts), _ptr(out["loci"]), _ptr(out["contigs"]), _ptr(out["pseudo"]),
                             _ptr(out["contigPool"]), C.c_uint64(out["contigPool"].size), C.byref(used[0]),
                             _ptr(out["setPool"]), C.c_uint64(out["setPool"].size), C.byref(used[1]), _ptr(out["aln"]),
-                            _ptr(out["jump"]), _ptr(out["cigar"]), C.c_uint64(out["cigar"].size), C.byref(used[2]))
+                            _ptr(out["jump"]), _ptr(out["cigar"]), C.c_uint64(out["cigar"].size), C.byref(used[2]), *sel)
             if st == MB200_ERR_POOL_OVERFLOW:
                 if used[0].value > out["contigPool"].size:
                     out["contigPool"] = np.zeros(int(used[0].value * 1.25) + 64, dtype=np.uint8)
@@ -385,6 +430,19 @@ class Binding:
             out["used"] = tuple(int(u.value) for u in used)
             return out
         raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "candidate output pools overflow")
+
+    def candidates_mt(self, opts: np.ndarray, batch, n_loci: int, threads: int, cuts: Optional[np.ndarray] = None,
+                      select: bool = False):
+        """checker libraries only (ref_/orc_): the multi-threaded CPU composition; returns
+        (nContigs, cells, scoreSum, qcSum)"""
+        nc, cells, ssum, qsum = C.c_uint64(), C.c_uint64(), C.c_int64(), C.c_int64()
+        st = self._call("candidates_mt", _ptr(opts), C.c_uint32(n_loci), _ptr(batch.readOff), _ptr(batch.readViews),
+                        _ptr(batch.isJump), _ptr(batch.ref1), _ptr(batch.ref2), _ptr(batch.pool),
+                        _ptr(cuts) if cuts is not None else None, C.c_int(1 if select else 0), C.c_int(threads),
+                        C.byref(nc), C.byref(cells), C.byref(ssum), C.byref(qsum))
+        if st != MB200_OK:
+            self._raise(st)
+        return int(nc.value), int(cells.value), int(ssum.value), int(qsum.value)
 
     def candidates_timing(self) -> dict:
         t = np.zeros(1, dtype=CAND_TIMING_DT)
@@ -415,7 +473,46 @@ def default_candidate_opts(**asm_kw) -> np.ndarray:
     o["largeIndelScore"] = -100
     o["jumpScores"] = (2, -8, -12, -1, -1, 0)
     o["jumpScore"] = -100
+    o["qcOpts"] = default_qc_opts()[0]
     return o
+
+
+def default_qc_opts() -> np.ndarray:
+    """contigFilterScores (lib/options/SVRefinerOptions.hpp:50) + minCandidateVariantSize (ReadScannerOptions.hpp:68)"""
+    o = np.zeros(1, dtype=QC_OPTS_DT)
+    o["filterScores"] = (2, -8, -18, 0, -1, 0)
+    o["minCandidateVariantSize"] = 10
+    return o
+
+
+def default_ref_cuts(n: int) -> np.ndarray:
+    """the normal-case cuts of a complex candidate's window (GSC/SVCandidateAssemblyRefiner.cpp:1884-1918)"""
+    c = np.zeros(n, dtype=REF_CUTS_DT)
+    c["leadingCut"] = 100
+    c["trailingCut"] = 100
+    c["maxLeadingCut"] = 800
+    c["maxTrailingCut"] = 800
+    return c
+
+
+def qc_checksum(isJump, nContigs, A, trim, qc, best, with_trim: bool) -> int:
+    """the QC checksum the CPU checker libraries report from candidates_mt, rebuilt from flat outputs
+    (slot = locus*A + contig)"""
+    total = 0
+    nLoci = len(isJump)
+    slot = (np.arange(nLoci, dtype=np.int64)[:, None] * A + np.arange(A, dtype=np.int64)[None, :])
+    live = np.arange(A)[None, :] < np.asarray(nContigs, dtype=np.int64)[:, None]
+    s = slot[live]
+    q = qc[s]
+    total += int((q["isCandidate"].astype(np.int64) + 2 * q["isLowQuality"].astype(np.int64) +
+                  4 * q["variantSize"].astype(np.int64) + 8 * q["nSegments"].astype(np.int64) +
+                  64 * q["pathFirst"].astype(np.int64) + 128 * q["pathLast"].astype(np.int64)).sum())
+    if with_trim:
+        cplx = (np.asarray(isJump) == 0)[:, None] & live
+        t = trim[slot[cplx]]
+        total += int((t["adjLeadingCut"].astype(np.int64) * 16 + t["adjTrailingCut"].astype(np.int64) * 32).sum())
+    total += int(((np.asarray(best, dtype=np.int64) + 1) * 1000003).sum())
+    return total
 
 
 def default_asm_opts(**kw) -> np.ndarray:

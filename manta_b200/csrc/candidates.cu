@@ -15,7 +15,7 @@ extern "C" {
 
 int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* readOff, const mb200_seqview* readViews,
                             const uint8_t* isJump, const mb200_seqview* ref1, const mb200_seqview* ref2,
-                            const uint8_t* pool, uint64_t poolBytes)
+                            const uint8_t* pool, uint64_t poolBytes, const mb200_ref_cuts* cuts)
 {
   if (!ctx) return MB200_ERR_BAD_ARG;
   if (nLoci && (!readOff || !isJump || !ref1 || !ref2 || !pool)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
@@ -30,7 +30,11 @@ int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* read
   c.ref1.assign(ref1, ref1 + nLoci);
   c.ref2.assign(ref2, ref2 + nLoci);
   c.isJump.assign(isJump, isJump + nLoci);
+  c.cuts.clear();
+  if (cuts) c.cuts.assign(cuts, cuts + nLoci);
   for (uint32_t i = 0; i < nLoci; ++i) {
+    if (cuts && (cuts[i].leadingCut < 0 || cuts[i].trailingCut < 0 || cuts[i].maxLeadingCut < 0 || cuts[i].maxTrailingCut < 0))
+      return mb200_fail(ctx, MB200_ERR_BAD_ARG, "negative cut");
     if (ref1[i].len == 0 || ref1[i].off + ref1[i].len > poolBytes) return mb200_fail(ctx, MB200_ERR_EMPTY_REF, "Unexpected empty reference sequence");
     if (isJump[i] && (ref2[i].len == 0 || ref2[i].off + ref2[i].len > poolBytes))
       return mb200_fail(ctx, MB200_ERR_EMPTY_REF2, "Unexpected empty reference2 sequence");
@@ -39,6 +43,9 @@ int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* read
   if ((rc = mb200_reserve(ctx, ctx->dCandPool, poolBytes + MB200_POOL_FRONT + 64)) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, ctx->dCandReadOff, 8 * (size_t)(nLoci + 1))) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, ctx->dCandViews, sizeof(mb200_seqview) * (size_t)(nReads + 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcIsJump, (size_t)nLoci + 4)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcRef, sizeof(mb200_seqview) * (size_t)nLoci + 16)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcCuts, sizeof(mb200_ref_cuts) * (size_t)nLoci + 16)) != MB200_OK) return rc;
   uint8_t* dp = reinterpret_cast<uint8_t*>(ctx->dCandPool.ptr);
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[0], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemsetAsync(dp, 0, MB200_POOL_FRONT, ctx->stream));
@@ -47,11 +54,17 @@ int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* read
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCandReadOff.ptr, readOff, 8 * (size_t)(nLoci + 1), cudaMemcpyHostToDevice, ctx->stream));
   if (nReads)
     MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCandViews.ptr, readViews, sizeof(mb200_seqview) * (size_t)nReads, cudaMemcpyHostToDevice, ctx->stream));
+  if (nLoci) {
+    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dQcIsJump.ptr, isJump, (size_t)nLoci, cudaMemcpyHostToDevice, ctx->stream));
+    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dQcRef.ptr, ref1, sizeof(mb200_seqview) * (size_t)nLoci, cudaMemcpyHostToDevice, ctx->stream));
+    if (cuts) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dQcCuts.ptr, cuts, sizeof(mb200_ref_cuts) * (size_t)nLoci, cudaMemcpyHostToDevice, ctx->stream));
+  }
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[1], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->candTiming = mb200_candidate_timing();
   cudaEventElapsedTime(&ctx->candTiming.h2dMs, ctx->cev[0], ctx->cev[1]);
-  ctx->candTiming.h2dBytes = poolBytes + 8 * (uint64_t)(nLoci + 1) + sizeof(mb200_seqview) * nReads;
+  ctx->candTiming.h2dBytes = poolBytes + 8 * (uint64_t)(nLoci + 1) + sizeof(mb200_seqview) * nReads +
+                             (uint64_t)nLoci * (1 + sizeof(mb200_seqview) + (cuts ? sizeof(mb200_ref_cuts) : 0));
   return MB200_OK;
 }
 
@@ -59,7 +72,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
                          mb200_seqview* pseudoReads, uint8_t* contigPool, uint64_t contigPoolCap,
                          uint64_t* contigPoolUsed, uint32_t* setPool, uint64_t setPoolCap, uint64_t* setPoolUsed,
                          mb200_aln_result* alnResults, mb200_jump_result* jumpResults, uint32_t* cigarPool,
-                         uint64_t cigarCap, uint64_t* cigarUsed)
+                         uint64_t cigarCap, uint64_t* cigarUsed, mb200_trim_result* trim, mb200_contig_qc* qc, int32_t* best)
 {
   if (!ctx) return MB200_ERR_BAD_ARG;
   if (!opts || !loci || !contigs || !pseudoReads || !contigPool || !setPool || !alnResults || !jumpResults ||
@@ -68,6 +81,9 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   auto&          c     = ctx->cand;
   const uint32_t nLoci = c.nLoci;
   if (nLoci == 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "no staged batch (call mb200_candidates_upload first)");
+  const bool doTrim   = !c.cuts.empty();
+  const bool doSelect = (qc != nullptr) || (best != nullptr);
+  if (doSelect && (!qc || !best)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "qc and best must be requested together");
   if (opts->jumpScores.isAllowEdgeInsertion) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "jump aligner: isAllowEdgeInsertion unsupported");
   MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   const uint32_t A = opts->asmOpts.maxAssemblyCount;
@@ -91,6 +107,10 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if ((rc = mb200_reserve(ctx, ctx->dJump, sizeof(mb200_jump_result) * nSlots)) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, ctx->dCigar, (size_t)(cigarCap ? cigarCap : 1) * sizeof(uint32_t))) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, ctx->dMisc, 256)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcTrim, sizeof(mb200_trim_result) * nSlots + 16)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQc, sizeof(mb200_contig_qc) * nSlots + 16)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcBest, 4 * (size_t)nLoci + 16)) != MB200_OK) return rc;
+  std::vector<mb200_trim_result> hTrim;
 
   uint32_t*      misc        = reinterpret_cast<uint32_t*>(ctx->dMisc.ptr);
   const uint8_t* dPool       = reinterpret_cast<const uint8_t*>(ctx->dCandPool.ptr) + MB200_POOL_FRONT;
@@ -115,6 +135,24 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
                      &T.asmWindows, &T.asmBytes);
   if (rc != MB200_OK) return rc;
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[4], ctx->stream));
+
+  // ---- slot bookkeeping for the QC, and the 10-mer anchored trim of every complex contig's window (:1984-2011)
+  if (doTrim || doSelect) {
+    rc = mb200_qc_prep_fused(ctx, nLoci, A, reinterpret_cast<const mb200_asm_locus*>(ctx->dAsmOut0.ptr),
+                             reinterpret_cast<const mb200_contig*>(ctx->dAsmOut1.ptr), reinterpret_cast<const uint32_t*>(ctx->dAsmOut4.ptr));
+    if (rc != MB200_OK) return rc;
+  }
+  if (doTrim) {
+    MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dQcTrim.ptr, 0, sizeof(mb200_trim_result) * nSlots, ctx->stream));
+    rc = mb200_trim_run(ctx, (uint32_t)nSlots, A, dContigPool, nullptr, reinterpret_cast<const mb200_contig*>(ctx->dAsmOut1.ptr), dPool,
+                        reinterpret_cast<const mb200_seqview*>(ctx->dQcRef.ptr), reinterpret_cast<const mb200_ref_cuts*>(ctx->dQcCuts.ptr),
+                        reinterpret_cast<const uint8_t*>(ctx->dQcIsJump.ptr), ctx->cfg.maxContigLen ? ctx->cfg.maxContigLen : 2048,
+                        reinterpret_cast<mb200_trim_result*>(ctx->dQcTrim.ptr), reinterpret_cast<int*>(misc + 4));
+    if (rc != MB200_OK) return rc;
+    hTrim.resize(nSlots);
+    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(hTrim.data(), ctx->dQcTrim.ptr, sizeof(mb200_trim_result) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cevX[0], ctx->stream));
 
   // ---- contig records to the host: bin the DP tasks by contig length
   uint32_t hMisc[32];
@@ -146,6 +184,14 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
         t.R2 = c.ref2[li].len;
         jumpTasks.push_back(t);
       } else {
+        if (doTrim) {
+          const mb200_trim_result& tr = hTrim[(size_t)li * A + k];
+          const int64_t            len = (int64_t)t.R1 - tr.adjLeadingCut - tr.adjTrailingCut;
+          if (tr.adjLeadingCut < 0 || tr.adjTrailingCut < 0 || len <= 0)
+            return mb200_fail(ctx, MB200_ERR_EMPTY_REF, "Unexpected empty reference sequence");  // nothing left of the window
+          t.r1 += tr.adjLeadingCut;
+          t.R1 = (uint32_t)len;
+        }
         t.r2 = t.r1;
         t.R2 = 0;
         indelTasks.push_back(t);
@@ -171,6 +217,26 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   }
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[7], ctx->stream));
 
+  // ---- beginPos back to window coordinates (:2038), contig QC and bestAlignmentIndex on the resident alignments
+  if (doTrim) {
+    rc = mb200_apply_trim(ctx, (uint32_t)nSlots, reinterpret_cast<const uint32_t*>(ctx->dQcSlotLocus.ptr),
+                          reinterpret_cast<const uint8_t*>(ctx->dQcIsJump.ptr), reinterpret_cast<const mb200_trim_result*>(ctx->dQcTrim.ptr),
+                          reinterpret_cast<mb200_aln_result*>(ctx->dAln.ptr));
+    if (rc != MB200_OK) return rc;
+  }
+  if (doSelect) {
+    rc = mb200_qc_run(ctx, &opts->qcOpts, nLoci, (uint32_t)nSlots, reinterpret_cast<const uint8_t*>(ctx->dQcIsJump.ptr),
+                      reinterpret_cast<const uint32_t*>(ctx->dQcSlotFirst.ptr), reinterpret_cast<const uint32_t*>(ctx->dQcNContigs.ptr),
+                      reinterpret_cast<const uint32_t*>(ctx->dQcSlotLocus.ptr), reinterpret_cast<const mb200_aln_result*>(ctx->dAln.ptr),
+                      reinterpret_cast<const mb200_jump_result*>(ctx->dJump.ptr), reinterpret_cast<const uint32_t*>(ctx->dCigar.ptr),
+                      dContigPool, reinterpret_cast<const mb200_seqview*>(ctx->dQcViews.ptr), dPool,
+                      reinterpret_cast<const mb200_seqview*>(ctx->dQcRef.ptr), reinterpret_cast<const uint32_t*>(ctx->dQcSupport.ptr),
+                      reinterpret_cast<mb200_contig_qc*>(ctx->dQc.ptr), reinterpret_cast<int32_t*>(ctx->dQcBest.ptr),
+                      reinterpret_cast<const unsigned long long*>(misc + 12), cigarCap, reinterpret_cast<const int*>(misc + 4));
+    if (rc != MB200_OK) return rc;
+  }
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cevX[1], ctx->stream));
+
   // ---- results to the host
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(hMisc, ctx->dMisc.ptr, sizeof(hMisc), cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(alnResults, ctx->dAln.ptr, sizeof(mb200_aln_result) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
@@ -178,6 +244,14 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(pseudoReads, ctx->dAsmOut2.ptr, sizeof(mb200_seqview) * nSlots * 2, cudaMemcpyDeviceToHost, ctx->stream));
   if (usedBytes) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(contigPool, dContigPool, usedBytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (usedSets) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(setPool, ctx->dAsmOut4.ptr, 4 * usedSets, cudaMemcpyDeviceToHost, ctx->stream));
+  if (doSelect) {
+    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(qc, ctx->dQc.ptr, sizeof(mb200_contig_qc) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
+    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(best, ctx->dQcBest.ptr, 4 * (size_t)nLoci, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (trim) {
+    if (doTrim) memcpy(trim, hTrim.data(), sizeof(mb200_trim_result) * nSlots);
+    else memset(trim, 0, sizeof(mb200_trim_result) * nSlots);
+  }
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   unsigned long long usedCig;
   memcpy(&usedCig, hMisc + 12, 8);
@@ -190,11 +264,14 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   cudaEventElapsedTime(&T.asmMs, ctx->cev[3], ctx->cev[4]);
   cudaEventElapsedTime(&T.indelMs, ctx->cev[5], ctx->cev[6]);
   cudaEventElapsedTime(&T.jumpMs, ctx->cev[6], ctx->cev[7]);
-  cudaEventElapsedTime(&T.d2hMs, ctx->cev[7], ctx->cev[0]);
+  cudaEventElapsedTime(&T.trimMs, ctx->cev[4], ctx->cevX[0]);
+  cudaEventElapsedTime(&T.qcMs, ctx->cev[7], ctx->cevX[1]);
+  cudaEventElapsedTime(&T.d2hMs, ctx->cevX[1], ctx->cev[0]);
   cudaEventElapsedTime(&T.totalMs, ctx->cev[2], ctx->cev[0]);
   T.launches = ctx->timing.launches;
   T.d2hBytes = sizeof(mb200_asm_locus) * (uint64_t)nLoci + (sizeof(mb200_contig) + sizeof(mb200_aln_result) + sizeof(mb200_jump_result) + 2 * sizeof(mb200_seqview)) * (uint64_t)nSlots +
-               usedBytes + 4 * usedSets + 4 * usedCig;
+               usedBytes + 4 * usedSets + 4 * usedCig + (doTrim ? sizeof(mb200_trim_result) * (uint64_t)nSlots : 0) +
+               (doSelect ? sizeof(mb200_contig_qc) * (uint64_t)nSlots + 4 * (uint64_t)nLoci : 0);
   return MB200_OK;
 }
 

@@ -77,6 +77,12 @@ int mb200_create(int device, const mb200_config* cfg, mb200_ctx** out)
       return MB200_ERR_CUDA;
     }
   }
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreate(&ctx->cevX[i]) != cudaSuccess) {
+      delete ctx;
+      return MB200_ERR_CUDA;
+    }
+  }
   for (int i = 0; i < mb200_ctx::kDpClasses; ++i) {
     if (cudaStreamCreateWithFlags(&ctx->dpStream[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->dpDone[i], cudaEventDisableTiming) != cudaSuccess) {
@@ -111,7 +117,9 @@ void mb200_destroy(mb200_ctx* ctx)
                           &ctx->dSegScratch, &ctx->dBndScratch, &ctx->dMisc, &ctx->dJobs, &ctx->dTables,
                           &ctx->dAsmWork, &ctx->dAsmOut0, &ctx->dAsmOut1, &ctx->dAsmOut2, &ctx->dAsmOut3,
                           &ctx->dAsmOut4, &ctx->dViews,   &ctx->dReadOff, &ctx->dCandPool, &ctx->dCandReadOff,
-                          &ctx->dCandViews, &ctx->dAln, &ctx->dJump};
+                          &ctx->dCandViews, &ctx->dAln, &ctx->dJump,
+                          &ctx->dQcScratch, &ctx->dQcSupport, &ctx->dQcSlotLocus, &ctx->dQcSlotFirst, &ctx->dQcNContigs,
+                          &ctx->dQcViews, &ctx->dQcRef, &ctx->dQcCuts, &ctx->dQcTrim, &ctx->dQcIsJump, &ctx->dQc, &ctx->dQcBest};
   for (DeviceBuffer* b : bufs)
     if (b->ptr) cudaFree(b->ptr);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
@@ -119,6 +127,8 @@ void mb200_destroy(mb200_ctx* ctx)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 8; ++i)
     if (ctx->cev[i]) cudaEventDestroy(ctx->cev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->cevX[i]) cudaEventDestroy(ctx->cevX[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -38,8 +38,12 @@ struct mb200_ctx {
     std::vector<uint64_t>      readOff;
     std::vector<mb200_seqview> views, ref1, ref2;
     std::vector<uint8_t>       isJump;
+    std::vector<mb200_ref_cuts> cuts;  // empty: no window trim
   } cand;
   DeviceBuffer           dCandPool, dCandReadOff, dCandViews, dAln, dJump;
+  // reference-window trim / contig QC + selection (contig_qc.cu)
+  DeviceBuffer dQcScratch, dQcSupport, dQcSlotLocus, dQcSlotFirst, dQcNContigs, dQcViews, dQcRef, dQcCuts, dQcTrim, dQcIsJump,
+      dQc, dQcBest;
   // DP row classes run concurrently on their own streams with their own scratch (hides the per-launch tail)
   static constexpr int   kDpClasses = 8;
   cudaStream_t           dpStream[kDpClasses] = {};
@@ -49,6 +53,7 @@ struct mb200_ctx {
   DeviceBuffer           dTasksK[3];
   mb200_candidate_timing candTiming = {};
   cudaEvent_t            cev[8]     = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t            cevX[2]    = {nullptr, nullptr};  // end of trim, end of QC
 };
 
 #define MB200_CUDA_CHECK(ctx, expr)                                                                   \
@@ -88,3 +93,19 @@ int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, co
                   uint8_t* dContigPool, uint64_t contigPoolCap, unsigned long long* dContigPoolUsed, uint32_t* dSetPool,
                   uint64_t setPoolCap, unsigned long long* dSetPoolUsed, uint32_t* dLociCounter, int* dErrFlag,
                   uint64_t* cellsOut, uint64_t* algoBytesOut);
+
+// contig_qc.cu: device-level trim / QC / selection (all pointers are device pointers)
+int mb200_trim_run(mb200_ctx* ctx, uint32_t n, uint32_t perLocus, const uint8_t* dContigPool, const mb200_seqview* dContigView,
+                   const mb200_contig* dContigRec, const uint8_t* dRefPool, const mb200_seqview* dRefView,
+                   const mb200_ref_cuts* dCuts, const uint8_t* dIsJump, uint32_t maxContigLen, mb200_trim_result* dOut,
+                   int* dErrFlag);
+// fills ctx->dQcSupport / dQcSlotLocus / dQcSlotFirst / dQcNContigs / dQcViews from the assembler's device outputs
+int mb200_qc_prep_fused(mb200_ctx* ctx, uint32_t nLoci, uint32_t A, const mb200_asm_locus* dLoci, const mb200_contig* dContigs,
+                        const uint32_t* dSetPool);
+int mb200_apply_trim(mb200_ctx* ctx, uint32_t nSlots, const uint32_t* dSlotLocus, const uint8_t* dIsJump,
+                     const mb200_trim_result* dTrim, mb200_aln_result* dAln);
+int mb200_qc_run(mb200_ctx* ctx, const mb200_qc_opts* opts, uint32_t nLoci, uint32_t nSlots, const uint8_t* dIsJump,
+                 const uint32_t* dSlotFirst, const uint32_t* dNContigs, const uint32_t* dSlotLocus, const mb200_aln_result* dAln,
+                 const mb200_jump_result* dJump, const uint32_t* dCigar, const uint8_t* dContigPool,
+                 const mb200_seqview* dContigView, const uint8_t* dRefPool, const mb200_seqview* dRef1, const uint32_t* dSupport,
+                 mb200_contig_qc* dQc, int32_t* dBest, const unsigned long long* dCigarUsed, uint64_t cigarCap, const int* dErrFlag);

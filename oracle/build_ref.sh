@@ -34,7 +34,8 @@ fi
 if [ -x /usr/bin/g++ ]; then CXX=/usr/bin/g++; else CXX=g++; fi
 # Release flags of the reference: -O3 -fomit-frame-pointer, asserts ON (src/cmake/cxxConfigure.cmake:452-454)
 CXXFLAGS="-std=c++11 -O3 -fomit-frame-pointer -fPIC -fvisibility=hidden -ffunction-sections -fdata-sections -w \
-  -I$LIB -I$OUT/boost_1_58_0 -I$OUT/htslib-1.9 -I$HERE/../include"
+  -DBOOST_ERROR_CODE_HEADER_ONLY -DBOOST_SYSTEM_NO_DEPRECATED \
+  -I$LIB -I$OUT/boost_1_58_0 -I$OUT/htslib-1.9 -I$HERE/../include -I$HERE"
 
 SRCS=(
   "$LIB/alignment/Alignment.cpp"
@@ -54,6 +55,7 @@ SRCS=(
   "$GSC/SplitReadAlignment.cpp"
   "$OUT/boost_1_58_0/libs/date_time/src/gregorian/greg_month.cpp"
   "$HERE/ref_shim.cpp"
+  "$HERE/ref_refiner_shim.cpp"
 )
 
 OBJS=()
@@ -61,7 +63,7 @@ pids=()
 for src in "${SRCS[@]}"; do
   obj="$OUT/obj/$(basename "${src%.cpp}").o"
   OBJS+=("$obj")
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/../include/manta_b200.h" -nt "$obj" ]; then
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/../include/manta_b200.h" -nt "$obj" ] || [ "$HERE/manta_oracle.h" -nt "$obj" ]; then
     $CXX $CXXFLAGS -c "$src" -o "$obj" &
     pids+=($!)
   fi

@@ -52,12 +52,30 @@ ORC_API int orc_assemble_batch(const mb200_asm_opts* opts, uint32_t nLoci, const
 /* libstdc++ std::unordered_map<std::string,T> iteration-order emulation (exported for its own test) */
 ORC_API void orc_unordered_order(uint32_t n, const uint8_t* keys, uint32_t keyLen, uint32_t* order);
 
-/* per-candidate composition (assemble, then align every contig) on `threads` pthreads; scoreSum = sum of all
- * alignment scores (checksum) */
+/* 10-mer anchored reference-window trim and contig QC / selection (include/manta_b200.h, rows a5 / a9) */
+ORC_API int orc_ref_trim_batch(uint32_t n, const uint8_t* pool, const mb200_seqview* contig, const mb200_seqview* ref,
+                               const mb200_ref_cuts* cuts, mb200_trim_result* out);
+ORC_API int orc_select_contigs_batch(const mb200_qc_opts* opts, uint32_t nLoci, const uint8_t* isJump,
+                                     const uint32_t* slotFirst, const uint32_t* nContigs, uint32_t nSlots,
+                                     const mb200_aln_result* aln, const mb200_jump_result* jump,
+                                     const uint32_t* cigarPool, const uint8_t* pool, const mb200_seqview* contigSeq,
+                                     const mb200_seqview* ref1, const uint32_t* supportCount, mb200_contig_qc* qc,
+                                     int32_t* best);
+
+/* per-candidate composition (assemble, [trim,] align every contig, [QC + select]) on `threads` pthreads.
+ * cuts == NULL: no trim; doSelect == 0: no QC.  scoreSum = sum of all alignment scores; qcSum = the checksum
+ * MB200_QC_CHECKSUM_* below over trims, QC records and selections (both are reproduced from the GPU outputs). */
 ORC_API int orc_candidates_mt(const mb200_candidate_opts* opts, uint32_t nLoci, const uint64_t* readOff,
                               const mb200_seqview* readViews, const uint8_t* isJump, const mb200_seqview* ref1,
-                              const mb200_seqview* ref2, const uint8_t* pool, int threads, uint64_t* nContigsOut,
-                              uint64_t* cellsOut, int64_t* scoreSumOut);
+                              const mb200_seqview* ref2, const uint8_t* pool, const mb200_ref_cuts* cuts, int doSelect,
+                              int threads, uint64_t* nContigsOut, uint64_t* cellsOut, int64_t* scoreSumOut,
+                              int64_t* qcSumOut);
+
+/* checksum terms: per contig and per locus */
+#define ORC_QC_TERM_TRIM(t) ((int64_t)(t).adjLeadingCut * 16 + (int64_t)(t).adjTrailingCut * 32)
+#define ORC_QC_TERM_CONTIG(q) \
+  ((int64_t)(q).isCandidate + 2 * (int64_t)(q).isLowQuality + 4 * (int64_t)(q).variantSize + 8 * (int64_t)(q).nSegments + 64 * (int64_t)(q).pathFirst + 128 * (int64_t)(q).pathLast)
+#define ORC_QC_TERM_LOCUS(best) (((int64_t)(best) + 1) * 1000003)
 
 ORC_API const char* orc_version(void);
 

@@ -1,0 +1,322 @@
+// ref_refiner_shim.cpp -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Second adapter TU of oracle/_ref/libmanta_ref.so.  The contig QC functions of the refiner are file-static in
+// GSC/SVCandidateAssemblyRefiner.cpp, so this TU #includes that UNMODIFIED source file from where it lies under
+// /root/reference (nothing is copied) and calls the statics directly:
+//   findCandidateVariantsFromComplexSVContigAlignment  GSC/SVCandidateAssemblyRefiner.cpp:430
+//   getLargeIndelSegments / getLargestIndelSize        :173 / :210
+//   isJumpAlignmentQCFail / isLowQualityJumpAlignment  :1266 / :1287
+//   selectJumpContigDNA                                :1364
+// Two pieces of the reference are inline in the member function getSmallSVAssembly (which needs BAM and FASTA files
+// and therefore cannot be driven here): the 10-mer window trim (:1984-2011) and the rank1/rank2 contig selection
+// (:2119-2227).  They are restated below around the reference's own types and marked RESTATED; everything they
+// consume (QC flags, segments, variant sizes) comes from the reference statics.
+// Unused members of the refiner class are dropped at link time (--gc-sections).
+
+#include "applications/GenerateSVCandidates/SVCandidateAssemblyRefiner.cpp"
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <unordered_set>
+
+#include "alignment/GlobalJumpAligner.hpp"
+#include "alignment/GlobalLargeIndelAligner.hpp"
+#include "assembly/IterativeAssembler.hpp"
+
+#include "manta_b200.h"
+#include "manta_oracle.h"  // checksum terms only (macros); no oracle code is linked here
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+AlignmentScores<int> toScores2(const mb200_scores* s)
+{
+  return AlignmentScores<int>(s->match, s->mismatch, s->open, s->extend, s->offEdge, s->isAllowEdgeInsertion != 0);
+}
+
+ALIGNPATH::path_t toPath(const uint32_t* seg, const uint32_t n)
+{
+  ALIGNPATH::path_t p;
+  for (uint32_t i(0); i < n; ++i) {
+    p.emplace_back(static_cast<ALIGNPATH::align_t>(MB200_SEG_TYPE(seg[i])), MB200_SEG_LEN(seg[i]));
+  }
+  return p;
+}
+
+typedef std::vector<std::pair<unsigned, unsigned>> SegSet;
+
+/// QC of one complex-candidate contig: the spanSet loop of getSmallSVAssembly (:2046-2066) over the reference's
+/// findCandidateVariantsFromComplexSVContigAlignment
+void qcComplexContig(const mb200_qc_opts& o, const Alignment& align, const std::string& contigSeq,
+                     const std::string& refSeq, mb200_contig_qc& q)
+{
+  const AlignmentScores<int> scores(toScores2(&o.filterScores));
+  SegSet                     kept;
+  bool                       isSmallSVCandidate(false);
+  for (const unsigned maxQCRefSpan : {100u, 200u}) {
+    SegSet     segments;
+    const bool isCandidate(findCandidateVariantsFromComplexSVContigAlignment(
+        maxQCRefSpan, scores, align, contigSeq, refSeq, o.minCandidateVariantSize, segments));
+    if (!isCandidate) continue;
+    if (segments.size() > kept.size()) kept = segments;
+    isSmallSVCandidate = true;
+  }
+  std::memset(&q, 0, sizeof(q));
+  if (!isSmallSVCandidate) return;
+  SegSet all;
+  getLargeIndelSegments(align.apath, o.minCandidateVariantSize, all);
+  unsigned ordinal(0);
+  while (ordinal < all.size() && all[ordinal] != kept.front()) ordinal++;
+  q.isCandidate = 1;
+  q.segOrdinal  = ordinal;
+  q.nSegments   = static_cast<uint32_t>(kept.size());
+  q.pathFirst   = kept.front().first;
+  q.pathLast    = kept.back().second;
+  q.variantSize = getLargestIndelSize(align.apath, kept);
+}
+
+/// RESTATED from the body of getSmallSVAssembly (:2119-2227): keep the two best QC'd contigs while walking the
+/// contigs in order, then let the runner-up win on score ratio plus read support or variant size
+int32_t selectComplex(const uint32_t nContigs, const mb200_aln_result* aln, const mb200_contig_qc* qc,
+                      const uint32_t* support)
+{
+  ContigScoringInfo rank1, rank2;
+  for (uint32_t c(0); c < nContigs; ++c) {
+    if (!qc[c].isCandidate) continue;
+    ContigScoringInfo cur;
+    cur.isDefined   = true;
+    cur.index       = c;
+    cur.score       = aln[c].score;
+    cur.variantSize = qc[c].variantSize;
+    cur.isJumped    = (aln[c].isJumped != 0);
+    const bool sameJumpState(cur.isJumped == rank1.isJumped);
+    const bool takesRank1(
+        (!rank1.isDefined) || (cur.isJumped && !rank1.isJumped) || (sameJumpState && (cur.score > rank1.score)));
+    if (takesRank1) {
+      if (rank1.isDefined) rank2 = rank1;
+      rank1 = cur;
+    } else if ((!rank2.isDefined) || (cur.score > rank2.score)) {
+      rank2 = cur;
+    }
+  }
+  if (rank2.isDefined && !(rank1.isJumped && !rank2.isJumped)) {
+    const unsigned n1(support[rank1.index]);
+    const unsigned n2(support[rank2.index]);
+    static const float minScoreRatio(0.9f);
+    static const float minSupportReadCountRatio(1.2f);
+    static const float minVariantSizeRatio(1.1f);
+    const bool rank2IsBest(
+        (rank2.score > (rank1.score * minScoreRatio)) &&
+        ((n2 > (n1 * minSupportReadCountRatio)) || (rank2.variantSize > (rank1.variantSize * minVariantSizeRatio))));
+    if (rank2IsBest) rank1 = rank2;
+  }
+  return rank1.isDefined ? static_cast<int32_t>(rank1.index) : -1;
+}
+
+/// spanning candidate: QC flags per contig from the statics, selection by the reference's selectJumpContigDNA
+int32_t selectSpanning(const mb200_qc_opts& o, const uint32_t nContigs, const mb200_jump_result* jump,
+                       const uint32_t* cigarPool, mb200_contig_qc* qc)
+{
+  const AlignmentScores<int> scores(toScores2(&o.filterScores));
+  SVCandidateAssemblyData    ad;
+  ad.contigs.resize(nContigs);
+  ad.spanningAlignments.resize(nContigs);
+  for (uint32_t c(0); c < nContigs; ++c) {
+    JumpAlignmentResult<int>& a(ad.spanningAlignments[c]);
+    a.score           = jump[c].score;
+    a.jumpInsertSize  = jump[c].jumpInsertSize;
+    a.jumpRange       = jump[c].jumpRange;
+    a.align1.beginPos = jump[c].beginPos1;
+    a.align2.beginPos = jump[c].beginPos2;
+    a.align1.apath    = toPath(cigarPool + jump[c].cigarOff1, jump[c].cigarLen1);
+    a.align2.apath    = toPath(cigarPool + jump[c].cigarOff2, jump[c].cigarLen2);
+    std::memset(&qc[c], 0, sizeof(qc[c]));
+    qc[c].isCandidate = isJumpAlignmentQCFail(a) ? 0 : 1;
+    // the reference only evaluates this for the selected contig; it reads nothing but the two paths
+    bool low(true);
+    if (a.align1.isAligned() || a.align2.isAligned()) low = isLowQualityJumpAlignment(a, scores, false);
+    qc[c].isLowQuality = low ? 1 : 0;
+  }
+  const bool isSelected(selectJumpContigDNA(ad, scores));
+  return isSelected ? static_cast<int32_t>(ad.bestAlignmentIndex) : -1;
+}
+
+/// RESTATED from getSmallSVAssembly (:1984-2011): walk inwards from both cut limits to the first reference 10-mer
+/// that also occurs in the contig.  Same container as the reference (a hash set of std::string 10-mers) so that the
+/// CPU baseline pays the reference's cost for this step.
+void trimWindow(const std::string& contig, const std::string& ref, const mb200_ref_cuts& cut, mb200_trim_result& out)
+{
+  static const int                K(10);
+  std::unordered_set<std::string> mers;
+  for (unsigned p(0); p + K <= contig.size(); ++p) mers.insert(contig.substr(p, K));
+  const pos_t refSize(ref.size());
+  const pos_t lowest(cut.leadingCut);
+  const pos_t highest(refSize - (cut.trailingCut + K));
+  const pos_t fwdStop(std::min(static_cast<pos_t>(cut.maxLeadingCut), highest));
+  pos_t       at(lowest);
+  while (at <= fwdStop && mers.count(ref.substr(at, K)) == 0) at++;
+  out.adjLeadingCut = at;
+  const pos_t revStop(std::max(lowest, refSize - cut.maxTrailingCut));
+  at = highest;
+  while (at >= revStop && mers.count(ref.substr(at, K)) == 0) at--;
+  out.adjTrailingCut = refSize - (at + K);
+}
+
+}  // namespace
+
+REF_API int ref_ref_trim_batch(uint32_t n, const uint8_t* pool, const mb200_seqview* contig, const mb200_seqview* ref,
+                               const mb200_ref_cuts* cuts, mb200_trim_result* out)
+{
+  for (uint32_t i(0); i < n; ++i) {
+    if (contig[i].len < 10) return MB200_ERR_BAD_ARG;
+    const std::string c(reinterpret_cast<const char*>(pool + contig[i].off), contig[i].len);
+    const std::string r(reinterpret_cast<const char*>(pool + ref[i].off), ref[i].len);
+    trimWindow(c, r, cuts[i], out[i]);
+  }
+  return MB200_OK;
+}
+
+REF_API int ref_select_contigs_batch(const mb200_qc_opts* opts, uint32_t nLoci, const uint8_t* isJump,
+                                     const uint32_t* slotFirst, const uint32_t* nContigs, uint32_t /*nSlots*/,
+                                     const mb200_aln_result* aln, const mb200_jump_result* jump,
+                                     const uint32_t* cigarPool, const uint8_t* pool, const mb200_seqview* contigSeq,
+                                     const mb200_seqview* ref1, const uint32_t* supportCount, mb200_contig_qc* qc,
+                                     int32_t* best)
+{
+  for (uint32_t li(0); li < nLoci; ++li) {
+    const uint32_t s0(slotFirst[li]);
+    if (isJump[li]) {
+      best[li] = selectSpanning(*opts, nContigs[li], jump + s0, cigarPool, qc + s0);
+      continue;
+    }
+    const std::string refSeq(reinterpret_cast<const char*>(pool + ref1[li].off), ref1[li].len);
+    for (uint32_t c(0); c < nContigs[li]; ++c) {
+      const uint32_t s(s0 + c);
+      Alignment      align;
+      align.beginPos = aln[s].beginPos;
+      align.apath    = toPath(cigarPool + aln[s].cigarOff, aln[s].cigarLen);
+      const std::string contig(reinterpret_cast<const char*>(pool + contigSeq[s].off), contigSeq[s].len);
+      qcComplexContig(*opts, align, contig, refSeq, qc[s]);
+    }
+    best[li] = selectComplex(nContigs[li], aln + s0, qc + s0, supportCount + s0);
+  }
+  return MB200_OK;
+}
+
+/// The reference's per-candidate work on `threads` host threads: runIterativeAssembler on the locus' reads, then
+/// every contig through [the window trim and] GlobalLargeIndelAligner (isJump == 0) or GlobalJumpAligner
+/// (isJump == 1), then [contig QC + selection].  Loci are handed out dynamically (like the reference's ctpl pool
+/// hands out edges, GSC/GenerateSVCandidates.cpp:252-266); each worker owns its aligner objects (they carry mutable
+/// scratch, GlobalJumpAligner.hpp:117-124).  scoreSum / qcSum are checksums the GPU path must reproduce.
+REF_API int ref_candidates_mt(const mb200_candidate_opts* copts, uint32_t nLoci, const uint64_t* readOff,
+                              const mb200_seqview* readViews, const uint8_t* isJump, const mb200_seqview* ref1,
+                              const mb200_seqview* ref2, const uint8_t* pool, const mb200_ref_cuts* cuts, int doSelect,
+                              int threads, uint64_t* nContigsOut, uint64_t* cellsOut, int64_t* scoreSumOut,
+                              int64_t* qcSumOut)
+{
+  IterativeAssemblerOptions opt;
+  opt.minWordLength           = copts->asmOpts.minWordLength;
+  opt.maxWordLength           = copts->asmOpts.maxWordLength;
+  opt.wordStepSize            = copts->asmOpts.wordStepSize;
+  opt.minCoverage             = copts->asmOpts.minCoverage;
+  opt.minConservativeCoverage = copts->asmOpts.minConservativeCoverage;
+  opt.maxAssemblyCount        = copts->asmOpts.maxAssemblyCount;
+  opt.minUnusedReads          = copts->asmOpts.minUnusedReads;
+  opt.minSupportReads         = copts->asmOpts.minSupportReads;
+  if (threads < 1) threads = 1;
+  std::atomic<uint32_t> next(0);
+  std::atomic<uint64_t> nContigs(0), cells(0);
+  std::atomic<int64_t>  scoreSum(0), qcSum(0);
+  auto worker = [&]() {
+    const GlobalLargeIndelAligner<int> indelAligner(toScores2(&copts->indelScores), copts->largeIndelScore);
+    const GlobalJumpAligner<int>       jumpAligner(toScores2(&copts->jumpScores), copts->jumpScore);
+    const AlignmentScores<int>         filterScores(toScores2(&copts->qcOpts.filterScores));
+    uint64_t                           myContigs(0), myCells(0);
+    int64_t                            mySum(0), myQc(0);
+    for (;;) {
+      const uint32_t li(next.fetch_add(1));
+      if (li >= nLoci) break;
+      AssemblyReadInput reads;
+      for (uint64_t r(readOff[li]); r < readOff[li + 1]; ++r) {
+        reads.emplace_back(reinterpret_cast<const char*>(pool + readViews[r].off), readViews[r].len);
+      }
+      AssemblyReadOutput      readInfo;
+      SVCandidateAssemblyData ad;
+      runIterativeAssembler(opt, reads, readInfo, ad.contigs);
+      const unsigned    contigCount(ad.contigs.size());
+      const std::string r1(reinterpret_cast<const char*>(pool + ref1[li].off), ref1[li].len);
+      const char*       r2(reinterpret_cast<const char*>(pool + ref2[li].off));
+      ad.smallSVAlignments.resize(contigCount);
+      ad.spanningAlignments.resize(contigCount);
+      for (unsigned c(0); c < contigCount; ++c) {
+        const std::string& seq(ad.contigs[c].seq);
+        const char*        qb(seq.data());
+        const char*        qe(qb + seq.size());
+        if (isJump[li]) {
+          jumpAligner.align(qb, qe, r1.data(), r1.data() + r1.size(), r2, r2 + ref2[li].len, ad.spanningAlignments[c]);
+          mySum += ad.spanningAlignments[c].score;
+          myCells += static_cast<uint64_t>(seq.size()) * (ref1[li].len + ref2[li].len);
+        } else {
+          mb200_trim_result tr = {0, 0};
+          if (cuts) {
+            trimWindow(seq, r1, cuts[li], tr);
+            myQc += ORC_QC_TERM_TRIM(tr);
+          }
+          AlignmentResult<int>& res(ad.smallSVAlignments[c]);
+          indelAligner.align(qb, qe, r1.data() + tr.adjLeadingCut, r1.data() + r1.size() - tr.adjTrailingCut, res);
+          res.align.beginPos += tr.adjLeadingCut;
+          mySum += res.score;
+          myCells += static_cast<uint64_t>(seq.size()) * (r1.size() - tr.adjLeadingCut - tr.adjTrailingCut);
+        }
+        myContigs++;
+      }
+      if (!doSelect) continue;
+      int32_t best(-1);
+      if (isJump[li]) {
+        // the statics, in the order selectJumpContigDNA uses them (:1364-1398); the per-contig flags of the checksum
+        // need the low-quality test on every contig
+        for (unsigned c(0); c < contigCount; ++c) {
+          const JumpAlignmentResult<int>& a(ad.spanningAlignments[c]);
+          mb200_contig_qc                 q;
+          std::memset(&q, 0, sizeof(q));
+          q.isCandidate = isJumpAlignmentQCFail(a) ? 0 : 1;
+          bool low(true);
+          if (a.align1.isAligned() || a.align2.isAligned()) low = isLowQualityJumpAlignment(a, filterScores, false);
+          q.isLowQuality = low ? 1 : 0;
+          myQc += ORC_QC_TERM_CONTIG(q);
+        }
+        if (selectJumpContigDNA(ad, filterScores)) best = static_cast<int32_t>(ad.bestAlignmentIndex);
+      } else {
+        std::vector<mb200_contig_qc>  qc(contigCount);
+        std::vector<mb200_aln_result> flat(contigCount);
+        std::vector<uint32_t>         support(contigCount);
+        for (unsigned c(0); c < contigCount; ++c) {
+          const AlignmentResult<int>& res(ad.smallSVAlignments[c]);
+          qcComplexContig(copts->qcOpts, res.align, ad.contigs[c].seq, r1, qc[c]);
+          std::memset(&flat[c], 0, sizeof(flat[c]));
+          flat[c].score    = res.score;
+          flat[c].isJumped = res.isJumped ? 1 : 0;
+          support[c]       = static_cast<uint32_t>(ad.contigs[c].supportReads.size());
+          myQc += ORC_QC_TERM_CONTIG(qc[c]);
+        }
+        best = selectComplex(contigCount, flat.data(), qc.data(), support.data());
+      }
+      myQc += ORC_QC_TERM_LOCUS(best);
+    }
+    nContigs += myContigs;
+    cells += myCells;
+    scoreSum += mySum;
+    qcSum += myQc;
+  };
+  std::vector<std::thread> pool_;
+  for (int t(0); t < threads; ++t) pool_.emplace_back(worker);
+  for (std::thread& t : pool_) t.join();
+  *nContigsOut = nContigs;
+  *cellsOut    = cells;
+  *scoreSumOut = scoreSum;
+  if (qcSumOut) *qcSumOut = qcSum;
+  return MB200_OK;
+}

@@ -294,76 +294,6 @@ REF_API void ref_unordered_order(uint32_t n, const uint8_t* keys, uint32_t keyLe
   for (const auto& kv : m) order[k++] = kv.second;
 }
 
-/// The reference's per-candidate work on `threads` host threads: runIterativeAssembler on the locus' reads, then
-/// every contig through GlobalLargeIndelAligner (isJump == 0) or GlobalJumpAligner (isJump == 1).  Loci are handed
-/// out dynamically (like the reference's ctpl pool hands out edges, GSC/GenerateSVCandidates.cpp:252-266); each
-/// worker owns its aligner objects (they carry mutable scratch, GlobalJumpAligner.hpp:117-124).
-/// scoreSum = sum of all alignment scores (a checksum the GPU path must reproduce).
-REF_API int ref_candidates_mt(const mb200_candidate_opts* copts, uint32_t nLoci, const uint64_t* readOff,
-                              const mb200_seqview* readViews, const uint8_t* isJump, const mb200_seqview* ref1,
-                              const mb200_seqview* ref2, const uint8_t* pool, int threads, uint64_t* nContigsOut,
-                              uint64_t* cellsOut, int64_t* scoreSumOut)
-{
-  IterativeAssemblerOptions opt;
-  opt.minWordLength           = copts->asmOpts.minWordLength;
-  opt.maxWordLength           = copts->asmOpts.maxWordLength;
-  opt.wordStepSize            = copts->asmOpts.wordStepSize;
-  opt.minCoverage             = copts->asmOpts.minCoverage;
-  opt.minConservativeCoverage = copts->asmOpts.minConservativeCoverage;
-  opt.maxAssemblyCount        = copts->asmOpts.maxAssemblyCount;
-  opt.minUnusedReads          = copts->asmOpts.minUnusedReads;
-  opt.minSupportReads         = copts->asmOpts.minSupportReads;
-  if (threads < 1) threads = 1;
-  std::atomic<uint32_t> next(0);
-  std::atomic<uint64_t> nContigs(0), cells(0);
-  std::atomic<int64_t>  scoreSum(0);
-  auto worker = [&]() {
-    const GlobalLargeIndelAligner<int> indelAligner(toScores(&copts->indelScores), copts->largeIndelScore);
-    const GlobalJumpAligner<int>       jumpAligner(toScores(&copts->jumpScores), copts->jumpScore);
-    AlignmentResult<int>               ares;
-    JumpAlignmentResult<int>           jres;
-    uint64_t                           myContigs(0), myCells(0);
-    int64_t                            mySum(0);
-    for (;;) {
-      const uint32_t li(next.fetch_add(1));
-      if (li >= nLoci) break;
-      AssemblyReadInput reads;
-      for (uint64_t r(readOff[li]); r < readOff[li + 1]; ++r) {
-        reads.emplace_back(reinterpret_cast<const char*>(pool + readViews[r].off), readViews[r].len);
-      }
-      AssemblyReadOutput readInfo;
-      Assembly           contigs;
-      runIterativeAssembler(opt, reads, readInfo, contigs);
-      const char* r1(reinterpret_cast<const char*>(pool + ref1[li].off));
-      const char* r2(reinterpret_cast<const char*>(pool + ref2[li].off));
-      for (const AssembledContig& c : contigs) {
-        const char* qb(c.seq.data());
-        const char* qe(qb + c.seq.size());
-        if (isJump[li]) {
-          jumpAligner.align(qb, qe, r1, r1 + ref1[li].len, r2, r2 + ref2[li].len, jres);
-          mySum += jres.score;
-          myCells += static_cast<uint64_t>(c.seq.size()) * (ref1[li].len + ref2[li].len);
-        } else {
-          indelAligner.align(qb, qe, r1, r1 + ref1[li].len, ares);
-          mySum += ares.score;
-          myCells += static_cast<uint64_t>(c.seq.size()) * ref1[li].len;
-        }
-        myContigs++;
-      }
-    }
-    nContigs += myContigs;
-    cells += myCells;
-    scoreSum += mySum;
-  };
-  std::vector<std::thread> pool_;
-  for (int t(0); t < threads; ++t) pool_.emplace_back(worker);
-  for (std::thread& t : pool_) t.join();
-  *nContigsOut = nContigs;
-  *cellsOut    = cells;
-  *scoreSumOut = scoreSum;
-  return MB200_OK;
-}
-
 REF_API const char* ref_version()
 {
   return "Illumina/manta reference sources (v1.6.0) via oracle/ref_shim.cpp";

@@ -96,7 +96,6 @@ def test_candidates_full_window_properties(gpu):
 def test_candidates_checksum_full_window(gpu, orc):
     """BASELINE config-2 sized loci: the sum of all alignment scores and the contig count must equal the CPU
     composition (oracle, multi-threaded driver) -- a checksum of checksums over the whole batch"""
-    import ctypes as C
     batch = synth.make_candidate_batch(160, seed=99)
     opts = cb.default_candidate_opts()
     gpu.candidates_upload(batch)
@@ -107,12 +106,7 @@ def test_candidates_checksum_full_window(gpu, orc):
         for k in range(int(out["loci"]["nContigs"][li])):
             total += int(out["jump"]["score"][li * A + k]) if batch.isJump[li] else int(out["aln"]["score"][li * A + k])
             ncontig += 1
-    f = orc.lib.orc_candidates_mt
-    f.restype = C.c_int
-    nc, cells, ssum = C.c_uint64(), C.c_uint64(), C.c_int64()
-    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-    assert f(p(opts), C.c_uint32(batch.nLoci), p(batch.readOff), p(batch.readViews), p(batch.isJump), p(batch.ref1),
-             p(batch.ref2), p(batch.pool), C.c_int(8), C.byref(nc), C.byref(cells), C.byref(ssum)) == 0
-    assert (ncontig, total) == (int(nc.value), int(ssum.value))
+    nc, cells, ssum, _ = orc.candidates_mt(opts, batch, batch.nLoci, 8)
+    assert (ncontig, total) == (nc, ssum)
     t = gpu.candidates_timing()
-    assert t["indelCells"] + t["jumpCells"] == int(cells.value)
+    assert t["indelCells"] + t["jumpCells"] == cells

@@ -1,0 +1,151 @@
+"""Reference-window trim (row a5) and contig QC / bestAlignmentIndex selection (row a9) on the GPU against the
+oracle: standalone entry points on fuzzed inputs, and the fused candidate path with both stages switched on."""
+import numpy as np
+import pytest
+
+from manta_b200 import _cabi as cb
+from manta_b200 import synth
+import qc_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_select_contigs_fuzz(gpu, orc, seed):
+    case = qc_cases.fuzz_case(seed, 400)
+    (qg, bg), (qo, bo) = case.run(gpu), case.run(orc)
+    assert bg.tolist() == bo.tolist()
+    assert qg.tobytes() == qo.tobytes()
+
+
+def test_select_contigs_other_options(gpu, orc):
+    """non-default filter scores / minimum variant size"""
+    case = qc_cases.fuzz_case(77, 300)
+    for scores, minSize in [((1, -4, -6, -1, -1, 0), 5), ((2, -8, -18, 0, -1, 0), 30), ((3, -2, -2, -1, -1, 0), 1)]:
+        o = cb.default_qc_opts()
+        o["filterScores"] = scores
+        o["minCandidateVariantSize"] = minSize
+        (qg, bg), (qo, bo) = case.run(gpu, o), case.run(orc, o)
+        assert bg.tolist() == bo.tolist() and qg.tobytes() == qo.tobytes()
+
+
+def test_select_contigs_edge_cases(gpu, orc):
+    """loci without contigs, a batch without slots, long paths (> the shared-memory staging size)"""
+    case = qc_cases.fuzz_case(9, 50)
+    case.nContigs[:] = 0
+    qg, bg = case.run(gpu)
+    assert bg.tolist() == [-1] * 50
+    # one complex contig with > 600 path segments
+    rng = np.random.default_rng(3)
+    path = []
+    for i in range(300):
+        path += [(qc_cases.EQ, 40), (qc_cases.X, 1)]
+        if i % 25 == 7:
+            path += [(qc_cases.D if i % 2 else qc_cases.I, 12)]
+    path += [(qc_cases.EQ, 60)]
+    contig, ref = qc_cases._apply_path(rng, path, 17)
+    pool = np.concatenate([contig, ref])
+    aln = np.zeros(1, dtype=cb.ALN_RESULT_DT)
+    aln[0] = (500, 17, 0, len(path), 0)
+    cig = np.asarray([(ln << 4) | t for t, ln in path], dtype=np.uint32)
+    c = qc_cases.QcCase(np.zeros(1, np.uint8), np.zeros(1, np.uint32), np.ones(1, np.uint32), aln,
+                        np.zeros(1, dtype=cb.JUMP_RESULT_DT), cig, pool,
+                        np.asarray([(0, len(contig), 0)], dtype=cb.SEQVIEW_DT),
+                        np.asarray([(len(contig), len(ref), 0)], dtype=cb.SEQVIEW_DT), np.asarray([5], np.uint32))
+    (qg, bg), (qo, bo) = c.run(gpu), c.run(orc)
+    assert qg.tobytes() == qo.tobytes() and bg.tolist() == bo.tolist() and qo["nSegments"][0] >= 2
+
+
+def test_select_contigs_bad_args(gpu):
+    case = qc_cases.fuzz_case(5, 20)
+    case.aln["cigarOff"][:] = 10 ** 9
+    if (case.isJump == 0).any() and case.nContigs[case.isJump == 0].sum() > 0:
+        with pytest.raises(cb.Mb200Error) as e:
+            case.run(gpu)
+        assert e.value.status == cb.MB200_ERR_BAD_ARG
+
+
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_ref_trim_fuzz(gpu, orc, seed):
+    pool, contig, refv, cuts = qc_cases.trim_fuzz(seed, 600)
+    assert gpu.ref_trim_raw(pool, contig, refv, cuts).tobytes() == orc.ref_trim_raw(pool, contig, refv, cuts).tobytes()
+
+
+def test_ref_trim_long_contig_and_errors(gpu, orc):
+    rng = np.random.default_rng(1)
+    ref = qc_cases.ACGT[rng.integers(0, 4, 9000)]
+    contig = ref[2000:7000].copy()   # longer than the shared-memory table: per-warp global table
+    pool = np.concatenate([contig, ref])
+    cv = np.asarray([(0, len(contig), 0)], dtype=cb.SEQVIEW_DT)
+    rv = np.asarray([(len(contig), len(ref), 0)], dtype=cb.SEQVIEW_DT)
+    cuts = np.zeros(1, dtype=cb.REF_CUTS_DT)
+    cuts[0] = (100, 100, 3000, 3000)
+    got = gpu.ref_trim_raw(pool, cv, rv, cuts)
+    assert got.tobytes() == orc.ref_trim_raw(pool, cv, rv, cuts).tobytes()
+    assert (int(got["adjLeadingCut"][0]), int(got["adjTrailingCut"][0])) == (2000, 2000)
+    cv["len"][0] = 9
+    with pytest.raises(cb.Mb200Error) as e:
+        gpu.ref_trim_raw(pool, cv, rv, cuts)
+    assert e.value.status == cb.MB200_ERR_BAD_ARG
+
+
+def _fused(gpu, batch, opts, cuts, select):
+    gpu.candidates_upload(batch, cuts)
+    return gpu.candidates_run(opts, select=select)
+
+
+def test_fused_trim_select_vs_oracle(gpu, orc):
+    """assemble -> trim -> align -> QC -> select on the device == the same composition of oracle calls"""
+    batch = synth.make_candidate_batch(64, seed=31, window=1500)
+    opts = cb.default_candidate_opts()
+    cuts = cb.default_ref_cuts(batch.nLoci)
+    cuts["leadingCut"], cuts["trailingCut"], cuts["maxLeadingCut"], cuts["maxTrailingCut"] = 20, 20, 250, 250
+    A = int(opts["asmOpts"]["maxAssemblyCount"][0])
+    case, trims = qc_cases.pipeline_case(orc, batch, opts, cuts)
+    qo, bo = case.run(orc)
+    out = _fused(gpu, batch, opts, cuts, True)
+    assert out["loci"]["nContigs"].tolist() == case.nContigs.tolist()
+    slot = np.concatenate([np.arange(n) + li * A for li, n in enumerate(case.nContigs)]).astype(np.int64)
+    assert out["best"].tolist() == bo.tolist()
+    assert out["qc"][slot].tobytes() == qo.tobytes()
+    assert out["trim"][slot].tobytes() == trims.tobytes()
+    locusOf = slot // A
+    cplx = batch.isJump[locusOf] == 0
+    for k in ("score", "beginPos", "isJumped", "cigarLen"):
+        assert out["aln"][k][slot][cplx].tolist() == case.aln[k][cplx].tolist(), k
+    # the same CIGARs
+    for s, a in zip(slot[cplx], case.aln[cplx]):
+        g = out["aln"][s]
+        assert out["cigar"][int(g["cigarOff"]):int(g["cigarOff"]) + int(g["cigarLen"])].tolist() == \
+            case.cigar[int(a["cigarOff"]):int(a["cigarOff"]) + int(a["cigarLen"])].tolist()
+    assert (bo >= 0).sum() > 10
+    t = gpu.candidates_timing()
+    assert t["trimMs"] > 0 and t["qcMs"] > 0
+    # selection without the trim, and the trim without selection, are independent switches
+    out2 = _fused(gpu, batch, opts, None, True)
+    case2, _ = qc_cases.pipeline_case(orc, batch, opts, None)
+    q2, b2 = case2.run(orc)
+    assert out2["best"].tolist() == b2.tolist() and out2["qc"][slot].tobytes() == q2.tobytes()
+    assert not out2["trim"]["adjLeadingCut"].any()
+    out3 = _fused(gpu, batch, opts, cuts, False)
+    assert out3["aln"]["beginPos"][slot][cplx].tolist() == case.aln["beginPos"][cplx].tolist()
+
+
+def test_fused_trim_select_checksum_full_window(gpu, orc):
+    """BASELINE config-2 sized loci with the refiner's default cuts: alignment-score and QC checksums of the whole
+    batch equal the multi-threaded CPU composition"""
+    batch = synth.make_candidate_batch(160, seed=99)
+    opts = cb.default_candidate_opts()
+    cuts = cb.default_ref_cuts(batch.nLoci)
+    out = _fused(gpu, batch, opts, cuts, True)
+    A = int(opts["asmOpts"]["maxAssemblyCount"][0])
+    nC = out["loci"]["nContigs"]
+    live = np.arange(A)[None, :] < nC[:, None]
+    isJ = (batch.isJump != 0)[:, None]
+    score = np.where(isJ, out["jump"]["score"].reshape(-1, A), out["aln"]["score"].reshape(-1, A))
+    nc, cells, ssum, qsum = orc.candidates_mt(opts, batch, batch.nLoci, 8, cuts, True)
+    assert (int(live.sum()), int(score[live].sum())) == (nc, ssum)
+    assert cb.qc_checksum(batch.isJump, nC, A, out["trim"], out["qc"], out["best"], True) == qsum
+    t = gpu.candidates_timing()
+    assert t["indelCells"] + t["jumpCells"] == cells
+    assert (out["best"] >= 0).sum() > 40

@@ -82,3 +82,63 @@ def test_unordered_order_vs_ref(orc, ref):
         ref.lib.ref_unordered_order(C.c_uint32(n), buf.ctypes.data_as(C.c_void_p), C.c_uint32(k), o1.ctypes.data_as(C.c_void_p))
         orc.lib.orc_unordered_order(C.c_uint32(n), buf.ctypes.data_as(C.c_void_p), C.c_uint32(k), o2.ctypes.data_as(C.c_void_p))
         assert (o1 == o2).all(), n
+
+
+# ---- rows a5 / a9: reference-window trim, contig QC and bestAlignmentIndex selection -------------------------------
+def _same_qc(a, b):
+    (qa, ba), (qb, bb) = a, b
+    assert ba.tolist() == bb.tolist()
+    assert qa.tobytes() == qb.tobytes()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_select_contigs_fuzz_vs_ref(orc, ref, seed):
+    import qc_cases
+    case = qc_cases.fuzz_case(seed, 250)
+    got, want = case.run(orc), case.run(ref)
+    _same_qc(got, want)
+    qc, best = want
+    # the fuzz must actually reach the interesting outcomes
+    cplx = np.repeat(case.isJump == 0, case.nContigs)
+    assert qc["isCandidate"][cplx].sum() > 5 and (qc["nSegments"] > 1).sum() > 0
+    assert (best >= 0).sum() > 5 and (best < 0).sum() > 5 and (best > 0).sum() > 0
+
+
+def test_trim_fuzz_vs_ref(orc, ref):
+    import qc_cases
+    for seed in (5, 6):
+        pool, contig, refv, cuts = qc_cases.trim_fuzz(seed, 400)
+        a = orc.ref_trim_raw(pool, contig, refv, cuts)
+        b = ref.ref_trim_raw(pool, contig, refv, cuts)
+        assert a.tobytes() == b.tobytes()
+        assert len(np.unique(b["adjLeadingCut"])) > 20
+
+
+def test_pipeline_trim_select_vs_ref(orc, ref):
+    """assemble -> trim -> align -> QC -> select on a synthetic batch: the restatement and the reference agree on
+    every intermediate product, and the threaded compositions agree on the checksums"""
+    import qc_cases
+    batch = synth.make_candidate_batch(40, seed=31, window=1500)
+    opts = cb.default_candidate_opts()
+    cuts = cb.default_ref_cuts(batch.nLoci)
+    cuts["leadingCut"], cuts["trailingCut"], cuts["maxLeadingCut"], cuts["maxTrailingCut"] = 20, 20, 250, 250
+    co, to = qc_cases.pipeline_case(orc, batch, opts, cuts)
+    cr, tr = qc_cases.pipeline_case(ref, batch, opts, cuts)
+    assert to.tobytes() == tr.tobytes() and co.aln.tobytes() == cr.aln.tobytes() and co.jump.tobytes() == cr.jump.tobytes()
+    assert co.cigar.tobytes() == cr.cigar.tobytes()
+    got, want = co.run(orc), cr.run(ref)
+    _same_qc(got, want)
+    qc, best = want
+    assert (best >= 0).sum() >= 10
+    for with_cuts in (None, cuts):
+        for sel in (False, True):
+            assert orc.candidates_mt(opts, batch, batch.nLoci, 4, with_cuts, sel) == \
+                ref.candidates_mt(opts, batch, batch.nLoci, 4, with_cuts, sel)
+    # the flat checksum helper reproduces the threaded drivers' qcSum
+    A = int(co.nContigs.max()) if len(co.nContigs) else 1
+    slot = np.concatenate([np.arange(n) + li * A for li, n in enumerate(co.nContigs)]).astype(np.int64)
+    qcA = np.zeros(batch.nLoci * A, dtype=cb.CONTIG_QC_DT)
+    trA = np.zeros(batch.nLoci * A, dtype=cb.TRIM_RESULT_DT)
+    qcA[slot], trA[slot] = qc, tr
+    assert cb.qc_checksum(batch.isJump, co.nContigs, A, trA, qcA, best, True) == \
+        ref.candidates_mt(opts, batch, batch.nLoci, 4, cuts, True)[3]
