@@ -327,4 +327,134 @@ inline void runIterativeAssembler(const Context& ctx, const IterativeAssemblerOp
   }
 }
 
+// ---- reference-window trim, contig QC and selection (refiner rows a5 / a9) ------------------------------------------
+
+typedef std::vector<std::pair<unsigned, unsigned>> CandidateSegmentSetType;  // lib/manta/SVCandidateAssemblyData.hpp:136-137
+
+namespace detail {
+inline mb200_qc_opts qcOpts(const AlignmentScores<int>& contigFilterScores, const unsigned minCandidateVariantSize)
+{
+  mb200_qc_opts o;
+  o.filterScores            = contigFilterScores.c();
+  o.minCandidateVariantSize = minCandidateVariantSize;
+  o.reserved                = 0;
+  return o;
+}
+inline void appendPath(std::vector<uint32_t>& cigar, const path_t& apath, uint64_t& off, uint32_t& len)
+{
+  off = cigar.size();
+  len = static_cast<uint32_t>(apath.size());
+  for (const path_segment& ps : apath) cigar.push_back(MB200_SEG_MAKE(ps.length, ps.type));
+}
+/// the candidate indel runs of a path, as getLargeIndelSegments lists them (GSC/SVCandidateAssemblyRefiner.cpp:173)
+inline CandidateSegmentSetType indelRuns(const path_t& apath, const unsigned minSize)
+{
+  CandidateSegmentSetType runs;
+  const unsigned          n(apath.size());
+  for (unsigned i(0); i < n;) {
+    const bool isIndel((apath[i].type == MB200_SEG_INSERT) || (apath[i].type == MB200_SEG_DELETE));
+    if (!isIndel) { ++i; continue; }
+    const unsigned start(i);
+    bool           isLarge(false);
+    for (; i < n && ((apath[i].type == MB200_SEG_INSERT) || (apath[i].type == MB200_SEG_DELETE)); ++i) {
+      if (apath[i].length >= minSize) isLarge = true;
+    }
+    if (isLarge) runs.emplace_back(start, i - 1);
+  }
+  return runs;
+}
+}  // namespace detail
+
+/// The 10-mer anchored trim of a complex candidate's reference window (GSC/SVCandidateAssemblyRefiner.cpp:1984-2011):
+/// returns adjustedLeadingCut / adjustedTrailingCut for align1RefStr
+inline void trimReferenceWindow(const Context& ctx, const std::string& contigSeq, const std::string& align1RefStr,
+                                const int leadingCut, const int trailingCut, const int maxLeadingCut, const int maxTrailingCut,
+                                int& adjustedLeadingCut, int& adjustedTrailingCut)
+{
+  std::vector<uint8_t>  pool;
+  const mb200_seqview   c(detail::append(pool, contigSeq.begin(), contigSeq.end()));
+  const mb200_seqview   r(detail::append(pool, align1RefStr.begin(), align1RefStr.end()));
+  const mb200_ref_cuts  cuts{leadingCut, trailingCut, maxLeadingCut, maxTrailingCut};
+  mb200_trim_result     out{0, 0};
+  ctx.check(mb200_ref_trim_batch(ctx.get(), 1, pool.data(), pool.size(), &c, &r, &cuts, &out));
+  adjustedLeadingCut  = out.adjLeadingCut;
+  adjustedTrailingCut = out.adjTrailingCut;
+}
+
+/// Contig QC and selection of one complex candidate: the spanSet loop and the rank1/rank2 rule of getSmallSVAssembly
+/// (GSC/SVCandidateAssemblyRefiner.cpp:2046-2066, 2119-2227).  smallSVAlignments[i].align.beginPos is relative to
+/// align1RefStr (after the += adjustedLeadingCut of :2038).  Fills smallSVSegments like assemblyData.smallSVSegments and
+/// returns false when no contig qualifies (bestAlignmentIndex is left alone then, like the reference).
+inline bool selectSmallSVContig(const Context& ctx, const AlignmentScores<int>& contigFilterScores,
+                                const unsigned minCandidateVariantSize, const std::vector<std::string>& contigSeqs,
+                                const std::vector<unsigned>& supportReadCounts,
+                                const std::vector<AlignmentResult<int>>& smallSVAlignments, const std::string& align1RefStr,
+                                std::vector<CandidateSegmentSetType>& smallSVSegments, unsigned& bestAlignmentIndex)
+{
+  const uint32_t                n(static_cast<uint32_t>(contigSeqs.size()));
+  std::vector<uint8_t>          pool;
+  std::vector<uint32_t>         cigar;
+  std::vector<mb200_seqview>    views(n);
+  std::vector<mb200_aln_result> aln(n);
+  std::vector<mb200_jump_result> jump(n);
+  std::vector<uint32_t>         support(supportReadCounts.begin(), supportReadCounts.end());
+  for (uint32_t i(0); i < n; ++i) {
+    views[i] = detail::append(pool, contigSeqs[i].begin(), contigSeqs[i].end());
+    aln[i]   = mb200_aln_result{smallSVAlignments[i].score, static_cast<int32_t>(smallSVAlignments[i].align.beginPos),
+                              smallSVAlignments[i].isJumped ? 1u : 0u, 0, 0};
+    detail::appendPath(cigar, smallSVAlignments[i].align.apath, aln[i].cigarOff, aln[i].cigarLen);
+  }
+  const mb200_seqview ref(detail::append(pool, align1RefStr.begin(), align1RefStr.end()));
+  const mb200_qc_opts o(detail::qcOpts(contigFilterScores, minCandidateVariantSize));
+  const uint8_t       isJump(0);
+  const uint32_t      slotFirst(0);
+  std::vector<mb200_contig_qc> qc(n ? n : 1);
+  int32_t                      best(-1);
+  if (cigar.empty()) cigar.push_back(0);
+  ctx.check(mb200_select_contigs_batch(ctx.get(), &o, 1, &isJump, &slotFirst, &n, n, aln.data(), jump.data(), cigar.data(),
+                                       cigar.size(), pool.data(), pool.size(), views.data(), &ref, support.data(), qc.data(), &best));
+  smallSVSegments.assign(n, CandidateSegmentSetType());
+  for (uint32_t i(0); i < n; ++i) {
+    if (!qc[i].isCandidate) continue;
+    const CandidateSegmentSetType runs(detail::indelRuns(smallSVAlignments[i].align.apath, minCandidateVariantSize));
+    smallSVSegments[i].assign(runs.begin() + qc[i].segOrdinal, runs.begin() + qc[i].segOrdinal + qc[i].nSegments);
+  }
+  if (best < 0) return false;
+  bestAlignmentIndex = static_cast<unsigned>(best);
+  return true;
+}
+
+/// selectJumpContigDNA (GSC/SVCandidateAssemblyRefiner.cpp:1364-1398)
+inline bool selectJumpContigDNA(const Context& ctx, const AlignmentScores<int>& contigFilterScores,
+                                const std::vector<JumpAlignmentResult<int>>& spanningAlignments, unsigned& bestAlignmentIndex)
+{
+  const uint32_t                 n(static_cast<uint32_t>(spanningAlignments.size()));
+  std::vector<uint32_t>          cigar;
+  std::vector<mb200_aln_result>  aln(n ? n : 1);
+  std::vector<mb200_jump_result> jump(n ? n : 1);
+  std::vector<mb200_seqview>     views(n ? n : 1, mb200_seqview{0, 0, 0});
+  std::vector<uint32_t>          support(n ? n : 1, 0);
+  for (uint32_t i(0); i < n; ++i) {
+    const JumpAlignmentResult<int>& a(spanningAlignments[i]);
+    jump[i] = mb200_jump_result{a.score, a.jumpInsertSize, a.jumpRange, static_cast<int32_t>(a.align1.beginPos),
+                                static_cast<int32_t>(a.align2.beginPos), 0, 0, 0, 0, 0};
+    detail::appendPath(cigar, a.align1.apath, jump[i].cigarOff1, jump[i].cigarLen1);
+    detail::appendPath(cigar, a.align2.apath, jump[i].cigarOff2, jump[i].cigarLen2);
+  }
+  if (cigar.empty()) cigar.push_back(0);
+  const std::vector<uint8_t> pool(16, 0);
+  const mb200_seqview        ref{0, 1, 0};
+  const mb200_qc_opts        o(detail::qcOpts(contigFilterScores, 10));
+  const uint8_t              isJump(1);
+  const uint32_t             slotFirst(0);
+  std::vector<mb200_contig_qc> qc(n ? n : 1);
+  int32_t                      best(-1);
+  ctx.check(mb200_select_contigs_batch(ctx.get(), &o, 1, &isJump, &slotFirst, &n, n, aln.data(), jump.data(), cigar.data(),
+                                       cigar.size(), pool.data(), pool.size(), views.data(), &ref, support.data(), qc.data(), &best));
+  if (best < 0) return false;
+  bestAlignmentIndex = static_cast<unsigned>(best);
+  return true;
+}
+
 }  // namespace mb200
+

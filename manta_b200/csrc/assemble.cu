@@ -801,16 +801,39 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                 const bool isEnd = (mode == 0);
                 uint32_t   conservativeEndOffset = 0;
                 curWord = seed;  // mode 0: last word of the contig == seed; mode 1: first word == seed
+                // One dependent round trip per step: as soon as the (up to four) candidate words of a step are known,
+                // every lane fetches one piece of what the step and the NEXT step need about them -- lanes 8s..8s+3 the
+                // candidate's neighbours in walk direction (the next step's candidates), lanes 8s+4..8s+7 its neighbours
+                // against walk direction (the branch check), lanes 0..7 count / inContig, lanes < SW the read bitsets --
+                // all independent loads; the chosen candidate's pieces are then broadcast with shuffles.
+                const uint32_t* fwdArr = isEnd ? W.succ : W.pred;
+                const uint32_t* bwdArr = isEnd ? W.pred : W.succ;
+                uint32_t        c0, c1, c2, c3;
+                {
+                  const uint4 first = *reinterpret_cast<const uint4*>(fwdArr + (size_t)curWord * 4);
+                  c0 = first.x; c1 = first.y; c2 = first.z; c3 = first.w;
+                }
                 for (;;) {
-                  const uint4 cand4 = *reinterpret_cast<const uint4*>((isEnd ? W.succ : W.pred) + (size_t)curWord * 4);
-                  const uint32_t cand[4] = {cand4.x, cand4.y, cand4.z, cand4.w};
-                  uint32_t maxBaseCount = 0, maxCnt = 0, maxBase = 0, maxWord = NONE32;
+                  const uint32_t cand[4] = {c0, c1, c2, c3};
+                  const uint32_t myS     = lane >> 3;
+                  const uint32_t myId    = (myS == 0) ? c0 : ((myS == 1) ? c1 : ((myS == 2) ? c2 : c3));
+                  uint32_t       nbr     = NONE32;
+                  if (myId != NONE32) nbr = ((lane & 4) ? bwdArr : fwdArr)[(size_t)myId * 4 + (lane & 3)];
+                  uint32_t meta = 0;  // lanes 0..3: count of candidate `lane`; lanes 4..7: inContig of candidate `lane - 4`
+                  if (lane < 8) {
+                    const uint32_t id = ((lane & 3) == 0) ? c0 : (((lane & 3) == 1) ? c1 : (((lane & 3) == 2) ? c2 : c3));
+                    if (id != NONE32) meta = (lane < 4) ? W.count[id] : (uint32_t)W.inContig[id];
+                  }
+                  uint32_t cwv[4];
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) cwv[s] = (cand[s] != NONE32 && lane < SW) ? W.bits[(size_t)cand[s] * SW + lane] : 0u;
+                  uint32_t maxCnt = 0, maxBase = 0, maxWord = NONE32;
                   uint32_t maxW = 0, maxCW = 0, sup2Remove = 0, rej2Add = 0;
 #pragma unroll
                   for (int s = 0; s < 4; ++s) {
                     const uint32_t id = cand[s];
                     if (id == NONE32) continue;
-                    const uint32_t cw         = (lane < SW) ? W.bits[(size_t)id * SW + lane] : 0u;
+                    const uint32_t cw         = cwv[s];
                     const uint32_t contigWord = support & cw;
                     const uint32_t shared     = maxCW & cw;
                     if (!__any_sync(0xffffffffu, contigWord != 0)) continue;
@@ -818,39 +841,44 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                     if (c > maxCnt) {
                       sup2Remove |= maxCW & ~shared;
                       rej2Add |= maxW & ~shared;
-                      maxW         = cw;
-                      maxCnt       = c;
-                      maxCW        = contigWord;
-                      maxBaseCount = W.count[id];
-                      maxBase      = (uint32_t)s;
-                      maxWord      = id;
+                      maxW    = cw;
+                      maxCnt  = c;
+                      maxCW   = contigWord;
+                      maxBase = (uint32_t)s;
+                      maxWord = id;
                     } else {
                       sup2Remove |= contigWord & ~shared;
                       rej2Add |= cw & ~shared;
                     }
                   }
+                  if (maxWord == NONE32) break;  // maxBaseCount stays 0 < minCoverage
+                  const uint32_t maxBaseCount = __shfl_sync(0xffffffffu, meta, (int)maxBase);
+                  const uint32_t inC          = __shfl_sync(0xffffffffu, meta, (int)(4 + maxBase));
+                  const uint32_t n0 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 0)), n1 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 1));
+                  const uint32_t n2 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 2)), n3 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 3));
+                  const uint32_t a0 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 4)), a1 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 5));
+                  const uint32_t a2 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 6)), a3 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 7));
                   if (maxBaseCount < opt.minCoverage) break;
-                  if (W.inContig[maxWord] == (uint8_t)serial) {
+                  if ((inC & 0xFFu) == (uint32_t)(uint8_t)serial) {
                     isRepeatFound = true;
                     break;
                   }
-                  // walk backwards one step at the branching point (:375-427); previousWordReads is always empty
+                  // walk backwards one step at the branching point (:375-427); previousWordReads is always empty.
+                  // The reference skips the symbol that leads back to the current word; that neighbour IS the current
+                  // word (links are built from the same table), so the test is on the id and no key has to be loaded.
                   if (__any_sync(0xffffffffu, maxW != 0)) {
-                    const Key      curKey = loadKey(W, curWord);
-                    const uint32_t tmpSym = isEnd ? baseAt(curKey, 0, k) : ((uint32_t)curKey.k0 & 3u);
-                    const uint4 alt4 = *reinterpret_cast<const uint4*>((isEnd ? W.pred : W.succ) + (size_t)maxWord * 4);
-                    const uint32_t alt[4] = {alt4.x, alt4.y, alt4.z, alt4.w};
+                    const uint32_t alt[4] = {a0, a1, a2, a3};
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
-                      if ((uint32_t)s == tmpSym) continue;
                       const uint32_t id = alt[s];
-                      if (id == NONE32 || id == maxWord) continue;
+                      if (id == NONE32 || id == maxWord || id == curWord) continue;
                       const uint32_t back     = (lane < SW) ? W.bits[(size_t)id * SW + lane] : 0u;
                       const uint32_t toUpdate = back & ~(maxCW & back);
                       rej2Add |= toUpdate;
                       sup2Remove |= toUpdate;
                     }
                   }
+                  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
                   // contig.seq = addBase(contig.seq, maxBase, isEnd)
                   if (hi - lo + 1 > P.maxContigLen || lo == 0 || hi + 1 >= ctgBuf) {
                     overflow = true;

@@ -85,6 +85,62 @@ int main()
     }
     REQUIRE(threw);
   }
+  {
+    // refiner rows a5 / a9 on a planted 60-base deletion: trim the window, align, QC + select
+    std::string refBuild;
+    unsigned    x(12345);
+    for (int i = 0; i < 1200; ++i) {
+      x = x * 1664525u + 1013904223u;
+      refBuild.push_back("ACGT"[(x >> 24) & 3]);
+    }
+    const std::string ref(refBuild);
+    const std::string contig(ref.substr(400, 150) + ref.substr(610, 150));
+    int               lead(0), trail(0);
+    mb200::trimReferenceWindow(ctx, contig, ref, 100, 100, 800, 800, lead, trail);
+    REQUIRE(lead == 400 && trail == 1200 - 760);
+    mb200::AlignmentScores<int>         scores(2, -8, -24, -1, -1);
+    mb200::GlobalLargeIndelAligner<int> aligner(ctx, scores, -100);
+    std::vector<mb200::AlignmentResult<int>> alignments(2);
+    aligner.align(contig.begin(), contig.end(), ref.begin() + lead, ref.end() - trail, alignments[0]);
+    alignments[0].align.beginPos += lead;
+    REQUIRE(mb200::apath_to_cigar(alignments[0].align.apath) == "150=60D150=");
+    const std::string flat(ref.substr(300, 200));  // second contig: no variant
+    aligner.align(flat.begin(), flat.end(), ref.begin(), ref.end(), alignments[1]);
+    std::vector<mb200::CandidateSegmentSetType> segments;
+    unsigned                                    bestIndex(99);
+    const mb200::AlignmentScores<int>           filterScores(2, -8, -18, 0, -1);
+    REQUIRE(mb200::selectSmallSVContig(ctx, filterScores, 10, {flat, contig}, {7, 9}, {alignments[1], alignments[0]}, ref, segments, bestIndex));
+    REQUIRE(bestIndex == 1u && segments[0].empty() && segments[1].size() == 1 && segments[1][0].first == 1u && segments[1][0].second == 1u);
+    // spanning: two clean 120-base arms pass, a 10-base arm fails the QC
+    mb200::JumpAlignmentResult<int> good, bad;
+    good.score = 400;
+    good.align1.apath = {{MB200_SEG_SEQ_MATCH, 120}};
+    good.align2.apath = {{MB200_SEG_SEQ_MATCH, 120}};
+    bad = good;
+    bad.score = 500;
+    bad.align2.apath = {{MB200_SEG_SEQ_MATCH, 10}};
+    unsigned best(99);
+    REQUIRE(mb200::selectJumpContigDNA(ctx, filterScores, {bad, good}, best) && best == 1u);
+    REQUIRE(!mb200::selectJumpContigDNA(ctx, filterScores, {bad}, best));
+  }
+  {
+    // GSC/test/SVCandidateAssemblyRefinerTest.cpp:272-358 (test_getLargeIndelSegments) through the shim's run finder
+    auto P = [](std::initializer_list<mb200::path_segment> l) { return mb200::path_t(l); };
+    const unsigned M(MB200_SEG_MATCH), I(MB200_SEG_INSERT), D(MB200_SEG_DELETE);
+    const mb200::path_t path1(P({{M, 35}, {I, 5}, {M, 30}, {D, 6}, {M, 10}, {I, 3}}));
+    REQUIRE(mb200::detail::indelRuns(path1, 10).empty());
+    mb200::CandidateSegmentSetType r(mb200::detail::indelRuns(path1, 6));
+    REQUIRE(r.size() == 1 && r[0].first == 3 && r[0].second == 3);
+    r = mb200::detail::indelRuns(path1, 3);
+    REQUIRE(r.size() == 3 && r[0].first == 1 && r[1].first == 3 && r[2].first == 5 && r[2].second == 5);
+    r = mb200::detail::indelRuns(P({{M, 35}, {I, 5}, {D, 6}, {M, 40}, {I, 3}}), 4);
+    REQUIRE(r.size() == 1 && r[0].first == 1 && r[0].second == 2);
+    r = mb200::detail::indelRuns(P({{M, 35}, {I, 5}, {D, 3}, {M, 40}, {I, 3}}), 4);
+    REQUIRE(r.size() == 1 && r[0].first == 1 && r[0].second == 2);
+    r = mb200::detail::indelRuns(P({{M, 35}, {I, 3}, {D, 5}, {M, 40}, {I, 3}}), 4);
+    REQUIRE(r.size() == 1 && r[0].first == 1 && r[0].second == 2);
+    REQUIRE(mb200::detail::indelRuns(P({{M, 35}, {I, 3}, {D, 3}, {M, 40}, {I, 3}}), 4).empty());
+  }
   std::printf("shim_test ok\n");
   return 0;
 }

@@ -209,6 +209,74 @@ def sr_to_json(r):
     return d
 
 
+# GSC/test/SVCandidateAssemblyRefinerTest.cpp, transcribed by hand.  Each entry is one candidate locus in the shape of
+# mb200_select_contigs_batch: contigs with their alignment CIGARs, and what the reference's unit test asserts.
+REFINER_SCORES = (1, -4, -6, -2, -5, 0)  # AlignmentScores<int> scores(1, -4, -6, -2, -5) in every test below
+_CONTIG = ("TCTATCACCCATCGTACCACTCACGGGAGCTCTCC" * 5)
+_REFSEQ = ("GATCACAGGTCTATCACCCTATTAACCACTCACGGGAGCTCTCCATGCATTTGGT"
+           "ATTTTCGTCTGGGGGGTGTGCACGCGATAGCATTGCGAGACGCTGGA") * 3
+REFINER_UNIT_TESTS = [
+    # test_isJumpAlignmentQCFail (:946-1001): isCandidate == !isJumpAlignmentQCFail
+    dict(src="test_isJumpAlignmentQCFail:946", kind="jump", minSize=10,
+         contigs=[dict(cigar1="94=", cigar2="110=75I1D2=", score=0), dict(cigar1="", cigar2="110=75I1D2=", score=0),
+                  dict(cigar1="19=", cigar2="110=75I1D2=", score=0), dict(cigar1="92=", cigar2="", score=0),
+                  dict(cigar1="92=", cigar2="19=", score=0), dict(cigar1="", cigar2="", score=0)],
+         expected=dict(isCandidate=[1, 0, 0, 0, 0, 0])),
+    # test_isLowQualityJumpAlignment (:1170-1207)
+    dict(src="test_isLowQualityJumpAlignment:1170", kind="jump", minSize=10,
+         contigs=[dict(cigar1="35=5I30=6D10=3I", cigar2="35=", score=0), dict(cigar1="35=", cigar2="35=5I30=6D10=3I", score=0),
+                  dict(cigar1="35=5I30=6D10=3I", cigar2="35=5I30=6D10=3I", score=0), dict(cigar1="35=", cigar2="35=", score=0)],
+         expected=dict(isLowQuality=[1, 1, 1, 0])),
+    # test_selectJumpContigDNA (:1212-1253); note the test assigns alignmentResult1.score twice (64 then 60) and leaves
+    # alignmentResult2.score at its default 0
+    dict(src="test_selectJumpContigDNA:1212 case 1", kind="jump", minSize=10,
+         contigs=[dict(cigar1="35=5I30=6D10=3I", cigar2="35=", score=60), dict(cigar1="35=5X30=6D10=3I", cigar2="35=", score=0)],
+         expected=dict(best=-1)),
+    dict(src="test_selectJumpContigDNA:1212 case 2", kind="jump", minSize=10,
+         contigs=[dict(cigar1="35=5I30=6D10=3I", cigar2="35=", score=60), dict(cigar1="35=5X30=6D10=3I", cigar2="35=", score=0),
+                  dict(cigar1="35=", cigar2="35=", score=70)],
+         expected=dict(best=2)),
+    # test_findCandidateVariantsFromComplexSVContigAlignment (:1022-1072); the batch entry point evaluates the two
+    # maxQCRefSpan values of the caller (:2046), the unit test only 100 -- same outcome for these inputs
+    dict(src="test_findCandidateVariants...:1022 case 1", kind="complex", minSize=10, contig=_CONTIG, ref=_REFSEQ,
+         contigs=[dict(cigar="35=5I30=6D10=3I", beginPos=0, score=10, isJumped=0, support=3)], expected=dict(isCandidate=[0], best=-1)),
+    dict(src="test_findCandidateVariants...:1022 case 2", kind="complex", minSize=6, contig=_CONTIG, ref=_REFSEQ,
+         contigs=[dict(cigar="35=5I30=6D10=3I", beginPos=0, score=10, isJumped=0, support=3)], expected=dict(isCandidate=[0], best=-1)),
+    dict(src="test_findCandidateVariants...:1022 case 3", kind="complex", minSize=3, contig=_CONTIG, ref=_REFSEQ,
+         contigs=[dict(cigar="3I100=5I30=6D100=3I", beginPos=50, score=10, isJumped=0, support=3)],
+         expected=dict(isCandidate=[1], best=0)),
+]
+
+
+def refiner_golden(ref, qc_cases):
+    units = []
+    for t in REFINER_UNIT_TESTS:
+        case, o = qc_cases.unit_case(t, REFINER_SCORES)
+        qc, best = case.run(ref, o)
+        exp = t["expected"]
+        for k in ("isCandidate", "isLowQuality"):
+            if k in exp:
+                assert qc[k].tolist() == exp[k], (t["src"], k, qc[k].tolist())
+        if "best" in exp:
+            assert int(best[0]) == exp["best"], (t["src"], int(best[0]))
+        u = dict(t)
+        u["reference"] = dict(qc=[[int(x) for x in row] for row in qc.tolist()], best=int(best[0]))
+        units.append(u)
+    fuzz = []
+    for seed in (101, 102):
+        case = qc_cases.fuzz_case(seed, 60)
+        qc, best = case.run(ref)
+        fuzz.append(dict(seed=seed, n_loci=60, qc=[[int(x) for x in row] for row in qc.tolist()],
+                         best=[int(x) for x in best]))
+    trims = []
+    for seed in (201,):
+        pool, contig, refv, cuts = qc_cases.trim_fuzz(seed, 200)
+        tr = ref.ref_trim_raw(pool, contig, refv, cuts)
+        trims.append(dict(seed=seed, n=200, trim=[[int(a), int(b)] for a, b in tr.tolist()]))
+    return dict(source="GSC/test/SVCandidateAssemblyRefinerTest.cpp (transcribed) + oracle/_ref on tests/qc_cases.py inputs",
+                scores=list(REFINER_SCORES), unit=units, fuzz=fuzz, trim=trims)
+
+
 def main():
     ref = load_ref()
     out = {}
@@ -290,6 +358,11 @@ def main():
     json.dump(dict(source="std::unordered_map<std::string,unsigned> of this image's libstdc++ via oracle/_ref",
                    cases=uo), open(os.path.join(HERE, "unordered_order.json"), "w"))
     out["unordered_order"] = len(uo)
+    # ---- refiner contig QC / selection (rows a5 / a9)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import qc_cases
+    json.dump(refiner_golden(ref, qc_cases), open(os.path.join(HERE, "refiner_qc.json"), "w"), indent=1)
+    out["refiner_qc"] = "ok"
     print("golden vectors written:", out)
 
 

@@ -82,6 +82,44 @@ def pipeline_case(binding, batch, opts, cuts=None):
     return case, trims
 
 
+def unit_case(t, scores):
+    """one transcribed reference unit test (tests/golden/refiner_qc.json "unit") -> QcCase + options"""
+    import re
+    code = {c: i for i, c in enumerate(cb.SEG_CODES)}
+
+    def segs(cigar):
+        return [(int(n) << 4) | code[c] for n, c in re.findall(r"(\d+)([MIDNSHP=X])", cigar)]
+
+    n = len(t["contigs"])
+    aln = np.zeros(n, dtype=cb.ALN_RESULT_DT)
+    jump = np.zeros(n, dtype=cb.JUMP_RESULT_DT)
+    cig = []
+    contig = np.frombuffer(t.get("contig", "ACGTACGTACGT").encode(), dtype=np.uint8)
+    refseq = np.frombuffer(t.get("ref", "ACGT").encode(), dtype=np.uint8)
+    pool = np.concatenate([contig, refseq]).copy()
+    views = np.zeros(n, dtype=cb.SEQVIEW_DT)
+    views["len"] = len(contig)
+    support = np.zeros(n, dtype=np.uint32)
+    for i, c in enumerate(t["contigs"]):
+        if t["kind"] == "jump":
+            s1, s2 = segs(c["cigar1"]), segs(c["cigar2"])
+            jump[i] = (c["score"], 0, 0, 0, 0, len(s1), len(s2), 0, len(cig), len(cig) + len(s1))
+            cig += s1 + s2
+        else:
+            s1 = segs(c["cigar"])
+            aln[i] = (c["score"], c["beginPos"], c["isJumped"], len(s1), len(cig))
+            cig += s1
+            support[i] = c["support"]
+    case = QcCase(np.asarray([1 if t["kind"] == "jump" else 0], np.uint8), np.zeros(1, np.uint32),
+                           np.asarray([n], np.uint32), aln, jump, np.asarray(cig + [0], dtype=np.uint32), pool, views,
+                           np.asarray([(len(contig), len(refseq), 0)], dtype=cb.SEQVIEW_DT), support)
+    o = cb.default_qc_opts()
+    o["filterScores"] = tuple(scores)
+    o["minCandidateVariantSize"] = t["minSize"]
+    return case, o
+
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def _rand_path(rng, flavour):
     """list of (type, len); flavour steers the corner being exercised"""

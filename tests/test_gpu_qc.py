@@ -79,7 +79,7 @@ def test_ref_trim_long_contig_and_errors(gpu, orc):
     cv = np.asarray([(0, len(contig), 0)], dtype=cb.SEQVIEW_DT)
     rv = np.asarray([(len(contig), len(ref), 0)], dtype=cb.SEQVIEW_DT)
     cuts = np.zeros(1, dtype=cb.REF_CUTS_DT)
-    cuts[0] = (100, 100, 3000, 3000)
+    cuts[0] = (1990, 1990, 3000, 3000)   # start close to the contig: no chance 10-mer hit before it
     got = gpu.ref_trim_raw(pool, cv, rv, cuts)
     assert got.tobytes() == orc.ref_trim_raw(pool, cv, rv, cuts).tobytes()
     assert (int(got["adjLeadingCut"][0]), int(got["adjTrailingCut"][0])) == (2000, 2000)
@@ -149,3 +149,9 @@ def test_fused_trim_select_checksum_full_window(gpu, orc):
     t = gpu.candidates_timing()
     assert t["indelCells"] + t["jumpCells"] == cells
     assert (out["best"] >= 0).sum() > 40
+
+
+def test_refiner_qc_golden(gpu):
+    """the reference's own unit-test answers and the committed reference outputs, through the CUDA path"""
+    from test_oracle_golden import check_refiner_golden
+    check_refiner_golden(gpu)

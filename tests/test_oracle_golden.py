@@ -112,3 +112,30 @@ def test_unordered_order_golden(orc):
         orc.lib.orc_unordered_order(C.c_uint32(n), buf.ctypes.data_as(C.c_void_p), C.c_uint32(c["k"]),
                                     order.ctypes.data_as(C.c_void_p))
         assert [int(x) for x in order[:n]] == c["order"]
+
+
+def check_refiner_golden(binding):
+    import qc_cases
+    g = load("refiner_qc.json")
+    for t in g["unit"]:
+        case, o = qc_cases.unit_case(t, g["scores"])
+        qc, best = case.run(binding, o)
+        for k in ("isCandidate", "isLowQuality"):
+            if k in t["expected"]:
+                assert qc[k].tolist() == t["expected"][k], (t["src"], k)
+        if "best" in t["expected"]:
+            assert int(best[0]) == t["expected"]["best"], t["src"]
+        assert [[int(x) for x in row] for row in qc.tolist()] == t["reference"]["qc"], t["src"]
+        assert int(best[0]) == t["reference"]["best"], t["src"]
+    for f in g["fuzz"]:
+        qc, best = qc_cases.fuzz_case(f["seed"], f["n_loci"]).run(binding)
+        assert [[int(x) for x in row] for row in qc.tolist()] == f["qc"] and best.tolist() == f["best"]
+    for f in g["trim"]:
+        pool, contig, refv, cuts = qc_cases.trim_fuzz(f["seed"], f["n"])
+        tr = binding.ref_trim_raw(pool, contig, refv, cuts)
+        assert [[int(a), int(b)] for a, b in tr.tolist()] == f["trim"]
+
+
+def test_refiner_qc_golden(orc):
+    """GSC/test/SVCandidateAssemblyRefinerTest.cpp known answers + reference outputs on seeded inputs"""
+    check_refiner_golden(orc)
