@@ -801,39 +801,16 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                 const bool isEnd = (mode == 0);
                 uint32_t   conservativeEndOffset = 0;
                 curWord = seed;  // mode 0: last word of the contig == seed; mode 1: first word == seed
-                // One dependent round trip per step: as soon as the (up to four) candidate words of a step are known,
-                // every lane fetches one piece of what the step and the NEXT step need about them -- lanes 8s..8s+3 the
-                // candidate's neighbours in walk direction (the next step's candidates), lanes 8s+4..8s+7 its neighbours
-                // against walk direction (the branch check), lanes 0..7 count / inContig, lanes < SW the read bitsets --
-                // all independent loads; the chosen candidate's pieces are then broadcast with shuffles.
-                const uint32_t* fwdArr = isEnd ? W.succ : W.pred;
-                const uint32_t* bwdArr = isEnd ? W.pred : W.succ;
-                uint32_t        c0, c1, c2, c3;
-                {
-                  const uint4 first = *reinterpret_cast<const uint4*>(fwdArr + (size_t)curWord * 4);
-                  c0 = first.x; c1 = first.y; c2 = first.z; c3 = first.w;
-                }
                 for (;;) {
-                  const uint32_t cand[4] = {c0, c1, c2, c3};
-                  const uint32_t myS     = lane >> 3;
-                  const uint32_t myId    = (myS == 0) ? c0 : ((myS == 1) ? c1 : ((myS == 2) ? c2 : c3));
-                  uint32_t       nbr     = NONE32;
-                  if (myId != NONE32) nbr = ((lane & 4) ? bwdArr : fwdArr)[(size_t)myId * 4 + (lane & 3)];
-                  uint32_t meta = 0;  // lanes 0..3: count of candidate `lane`; lanes 4..7: inContig of candidate `lane - 4`
-                  if (lane < 8) {
-                    const uint32_t id = ((lane & 3) == 0) ? c0 : (((lane & 3) == 1) ? c1 : (((lane & 3) == 2) ? c2 : c3));
-                    if (id != NONE32) meta = (lane < 4) ? W.count[id] : (uint32_t)W.inContig[id];
-                  }
-                  uint32_t cwv[4];
-#pragma unroll
-                  for (int s = 0; s < 4; ++s) cwv[s] = (cand[s] != NONE32 && lane < SW) ? W.bits[(size_t)cand[s] * SW + lane] : 0u;
-                  uint32_t maxCnt = 0, maxBase = 0, maxWord = NONE32;
+                  const uint4 cand4 = *reinterpret_cast<const uint4*>((isEnd ? W.succ : W.pred) + (size_t)curWord * 4);
+                  const uint32_t cand[4] = {cand4.x, cand4.y, cand4.z, cand4.w};
+                  uint32_t maxBaseCount = 0, maxCnt = 0, maxBase = 0, maxWord = NONE32;
                   uint32_t maxW = 0, maxCW = 0, sup2Remove = 0, rej2Add = 0;
 #pragma unroll
                   for (int s = 0; s < 4; ++s) {
                     const uint32_t id = cand[s];
                     if (id == NONE32) continue;
-                    const uint32_t cw         = cwv[s];
+                    const uint32_t cw         = (lane < SW) ? W.bits[(size_t)id * SW + lane] : 0u;
                     const uint32_t contigWord = support & cw;
                     const uint32_t shared     = maxCW & cw;
                     if (!__any_sync(0xffffffffu, contigWord != 0)) continue;
@@ -841,33 +818,28 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                     if (c > maxCnt) {
                       sup2Remove |= maxCW & ~shared;
                       rej2Add |= maxW & ~shared;
-                      maxW    = cw;
-                      maxCnt  = c;
-                      maxCW   = contigWord;
-                      maxBase = (uint32_t)s;
-                      maxWord = id;
+                      maxW         = cw;
+                      maxCnt       = c;
+                      maxCW        = contigWord;
+                      maxBaseCount = W.count[id];
+                      maxBase      = (uint32_t)s;
+                      maxWord      = id;
                     } else {
                       sup2Remove |= contigWord & ~shared;
                       rej2Add |= cw & ~shared;
                     }
                   }
-                  if (maxWord == NONE32) break;  // maxBaseCount stays 0 < minCoverage
-                  const uint32_t maxBaseCount = __shfl_sync(0xffffffffu, meta, (int)maxBase);
-                  const uint32_t inC          = __shfl_sync(0xffffffffu, meta, (int)(4 + maxBase));
-                  const uint32_t n0 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 0)), n1 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 1));
-                  const uint32_t n2 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 2)), n3 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 3));
-                  const uint32_t a0 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 4)), a1 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 5));
-                  const uint32_t a2 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 6)), a3 = __shfl_sync(0xffffffffu, nbr, (int)(maxBase * 8 + 7));
                   if (maxBaseCount < opt.minCoverage) break;
-                  if ((inC & 0xFFu) == (uint32_t)(uint8_t)serial) {
+                  if (W.inContig[maxWord] == (uint8_t)serial) {
                     isRepeatFound = true;
                     break;
                   }
-                  // walk backwards one step at the branching point (:375-427); previousWordReads is always empty.
-                  // The reference skips the symbol that leads back to the current word; that neighbour IS the current
-                  // word (links are built from the same table), so the test is on the id and no key has to be loaded.
+                  // walk backwards one step at the branching point (:375-427); previousWordReads is always empty
+                  // (the symbol the reference skips is the one that leads back to the current word; links are built from
+                  // the same table, so that neighbour IS the current word and the test is on the id -- no key load)
                   if (__any_sync(0xffffffffu, maxW != 0)) {
-                    const uint32_t alt[4] = {a0, a1, a2, a3};
+                    const uint4 alt4 = *reinterpret_cast<const uint4*>((isEnd ? W.pred : W.succ) + (size_t)maxWord * 4);
+                    const uint32_t alt[4] = {alt4.x, alt4.y, alt4.z, alt4.w};
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
                       const uint32_t id = alt[s];
@@ -878,7 +850,6 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                       sup2Remove |= toUpdate;
                     }
                   }
-                  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
                   // contig.seq = addBase(contig.seq, maxBase, isEnd)
                   if (hi - lo + 1 > P.maxContigLen || lo == 0 || hi + 1 >= ctgBuf) {
                     overflow = true;
@@ -1091,10 +1062,41 @@ size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
-// Device-level run: inputs (pool, readOff, views) and all outputs live on the device.  hReadOff / hViews are the
-// host copies used only to size the per-CTA workspace.
-int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, const uint64_t* hReadOff,
-                  const mb200_seqview* hViews, uint64_t poolBytes, const uint8_t* dPool, const uint64_t* dReadOff,
+// Host pass over the read views of a batch: validates them and collects what sizes the per-CTA workspace.  It depends
+// on the first word length only through the window counts, so a staged batch is scanned once and re-used.
+int mb200_asm_scan(mb200_ctx* ctx, uint32_t minWordLength, uint32_t nLoci, const uint64_t* hReadOff, const mb200_seqview* hViews,
+                   uint64_t poolBytes, mb200_asm_input_stats* st)
+{
+  mb200_asm_input_stats s;
+  memset(&s, 0, sizeof(s));
+  s.minWordLength = minWordLength;
+  for (uint32_t li = 0; li < nLoci; ++li) {
+    const uint64_t a = hReadOff[li], b = hReadOff[li + 1];
+    if (b < a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "readOff not monotone");
+    uint64_t win = 0, pw = 0, mw = 0;
+    for (uint64_t r = a; r < b; ++r) {
+      const uint32_t len = hViews[r].len;
+      if (hViews[r].off + len > poolBytes) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "read view outside the pool");
+      if (len >= minWordLength) win += len - minWordLength + 1;
+      pw += (len + 31) / 32 + 4;
+      mw += (len + 63) / 64 + 3;
+      s.totalBases += len;  // read bytes in (+ contigs/bitsets out, added by the caller)
+    }
+    s.totalWindows += win;
+    s.maxReads     = std::max<uint64_t>(s.maxReads, b - a);
+    s.maxWin       = std::max<uint64_t>(s.maxWin, win);
+    s.maxPackWords = std::max<uint64_t>(s.maxPackWords, pw);
+    s.maxMaskWords = std::max<uint64_t>(s.maxMaskWords, mw);
+  }
+  s.valid = 1;
+  *st     = s;
+  return MB200_OK;
+}
+
+// Device-level run: inputs (pool, readOff, views) and all outputs live on the device; `st` is the host scan of the
+// same batch (mb200_asm_scan with opts->minWordLength).
+int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, const mb200_asm_input_stats* st,
+                  const uint8_t* dPool, const uint64_t* dReadOff,
                   const mb200_seqview* dViews, mb200_asm_locus* dLoci, mb200_contig* dContigs, mb200_seqview* dPseudo,
                   uint8_t* dContigPool, uint64_t contigPoolCap, unsigned long long* dContigPoolUsed, uint32_t* dSetPool,
                   uint64_t setPoolCap, unsigned long long* dSetPoolUsed, uint32_t* dLociCounter, int* dErrFlag,
@@ -1103,29 +1105,14 @@ int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, co
   if (opts->minCoverage < 1 || opts->wordStepSize < 1 || opts->minWordLength < 2 || opts->maxWordLength > 96 ||
       opts->maxAssemblyCount < 1 || opts->maxAssemblyCount > 16)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "assembler options outside the supported range (k in [2,96], maxAssemblyCount in [1,16])");
+  if (!st || !st->valid || st->minWordLength != opts->minWordLength) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "stale input scan");
   const uint32_t A            = opts->maxAssemblyCount;
   const uint32_t maxContigLen = ctx->cfg.maxContigLen ? ctx->cfg.maxContigLen : 2048;
-  uint32_t       maxReads = 0, maxPackWords = 0, maxMaskWords = 0;
-  uint64_t       maxWin = 0;
-  for (uint32_t li = 0; li < nLoci; ++li) {
-    const uint64_t a = hReadOff[li], b = hReadOff[li + 1];
-    if (b < a) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "readOff not monotone");
-    uint64_t win = 0, pw = 0, mw = 0;
-    for (uint64_t r = a; r < b; ++r) {
-      const uint32_t len = hViews[r].len;
-      if (hViews[r].off + len > poolBytes) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "read view outside the pool");
-      if (len >= opts->minWordLength) win += len - opts->minWordLength + 1;
-      pw += (len + 31) / 32 + 4;
-      mw += (len + 63) / 64 + 3;
-      if (algoBytesOut) *algoBytesOut += len;  // read bytes in (+ contigs/bitsets out, added by the caller)
-      if (cellsOut) *cellsOut += (len >= opts->minWordLength) ? (len - opts->minWordLength + 1) : 0;
-    }
-    if (b - a + 2 * A > 1024) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "more than 1024 reads (incl. pseudo reads) in one locus");
-    maxReads     = std::max<uint32_t>(maxReads, (uint32_t)(b - a));
-    maxWin       = std::max<uint64_t>(maxWin, win);
-    maxPackWords = std::max<uint32_t>(maxPackWords, (uint32_t)pw);
-    maxMaskWords = std::max<uint32_t>(maxMaskWords, (uint32_t)mw);
-  }
+  if (st->maxReads + 2 * A > 1024) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "more than 1024 reads (incl. pseudo reads) in one locus");
+  const uint32_t maxReads = (uint32_t)st->maxReads, maxPackWords = (uint32_t)st->maxPackWords, maxMaskWords = (uint32_t)st->maxMaskWords;
+  const uint64_t maxWin = st->maxWin;
+  if (algoBytesOut) *algoBytesOut += st->totalBases;
+  if (cellsOut) *cellsOut += st->totalWindows;
   // ---- workspace layout (per CTA)
   WorkLayout L;
   memset(&L, 0, sizeof(L));
@@ -1266,7 +1253,9 @@ extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, 
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
   uint32_t* misc = reinterpret_cast<uint32_t*>(ctx->dMisc.ptr);
-  rc = mb200_asm_run(ctx, opts, nLoci, readOff, readViews, poolBytes, reinterpret_cast<const uint8_t*>(ctx->dPool.ptr),
+  mb200_asm_input_stats st;
+  if ((rc = mb200_asm_scan(ctx, opts->minWordLength, nLoci, readOff, readViews, poolBytes, &st)) != MB200_OK) return rc;
+  rc = mb200_asm_run(ctx, opts, nLoci, &st, reinterpret_cast<const uint8_t*>(ctx->dPool.ptr),
                      reinterpret_cast<const uint64_t*>(ctx->dReadOff.ptr), reinterpret_cast<const mb200_seqview*>(ctx->dViews.ptr),
                      reinterpret_cast<mb200_asm_locus*>(ctx->dAsmOut0.ptr), reinterpret_cast<mb200_contig*>(ctx->dAsmOut1.ptr),
                      reinterpret_cast<mb200_seqview*>(ctx->dAsmOut2.ptr), reinterpret_cast<uint8_t*>(ctx->dAsmOut3.ptr),

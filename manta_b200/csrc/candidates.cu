@@ -6,7 +6,9 @@
 // The contigs never leave the device between the two stages: the assembler writes them into a device pool and the
 // DP tasks point straight at it; only the 40-byte contig records cross PCIe to let the host bin the DP tasks by
 // query length.
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 #include "mb200_internal.h"
@@ -26,7 +28,11 @@ int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* read
   c.readOff.assign(readOff, readOff + nLoci + 1);
   const uint64_t nReads = nLoci ? readOff[nLoci] : 0;
   if (nReads && !readViews) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
-  c.views.assign(readViews, readViews + nReads);
+  c.nReads = nReads;
+  // validate the read views and size the assembler workspace now (for the word length the last run used), so that a
+  // run on the resident batch starts on the device at once; the views themselves are not kept on the host
+  int rcScan;
+  if ((rcScan = mb200_asm_scan(ctx, c.scanWordLength, nLoci, readOff, readViews, poolBytes, &c.scan)) != MB200_OK) return rcScan;
   c.ref1.assign(ref1, ref1 + nLoci);
   c.ref2.assign(ref2, ref2 + nLoci);
   c.isJump.assign(isJump, isJump + nLoci);
@@ -125,7 +131,14 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dAln.ptr, 0, sizeof(mb200_aln_result) * nSlots, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dJump.ptr, 0, sizeof(mb200_jump_result) * nSlots, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[3], ctx->stream));
-  rc = mb200_asm_run(ctx, &opts->asmOpts, nLoci, c.readOff.data(), c.views.data(), c.poolBytes, dPool,
+  if (!c.scan.valid || c.scan.minWordLength != opts->asmOpts.minWordLength) {
+    // first word length differs from the one the batch was scanned for: fetch the views back and scan again
+    std::vector<mb200_seqview> hv(c.nReads ? c.nReads : 1);
+    MB200_CUDA_CHECK(ctx, cudaMemcpy(hv.data(), ctx->dCandViews.ptr, sizeof(mb200_seqview) * (size_t)c.nReads, cudaMemcpyDeviceToHost));
+    if ((rc = mb200_asm_scan(ctx, opts->asmOpts.minWordLength, nLoci, c.readOff.data(), hv.data(), c.poolBytes, &c.scan)) != MB200_OK) return rc;
+    c.scanWordLength = opts->asmOpts.minWordLength;
+  }
+  rc = mb200_asm_run(ctx, &opts->asmOpts, nLoci, &c.scan, dPool,
                      reinterpret_cast<const uint64_t*>(ctx->dCandReadOff.ptr),
                      reinterpret_cast<const mb200_seqview*>(ctx->dCandViews.ptr),
                      reinterpret_cast<mb200_asm_locus*>(ctx->dAsmOut0.ptr), reinterpret_cast<mb200_contig*>(ctx->dAsmOut1.ptr),
@@ -169,7 +182,11 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if (usedBytes > contigPoolCap || usedSets > setPoolCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "assembler output pools too small");
   T.asmBytes += usedBytes + 4 * usedSets;
 
+  const bool trace = std::getenv("MB200_TRACE") != nullptr;  // host-side critical-path times to stderr
+  const auto tHost0 = std::chrono::steady_clock::now();
   std::vector<DpTask> indelTasks, jumpTasks;
+  indelTasks.reserve((size_t)nLoci * 4);
+  jumpTasks.reserve((size_t)nLoci * 4);
   for (uint32_t li = 0; li < nLoci; ++li) {
     for (uint32_t k = 0; k < loci[li].nContigs; ++k) {
       const mb200_contig& cg = contigs[(size_t)li * A + k];
@@ -199,6 +216,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
       T.nContigs++;
     }
   }
+  const auto tHost1 = std::chrono::steady_clock::now();
   T.nIndelTasks = (uint32_t)indelTasks.size();
   T.nJumpTasks  = (uint32_t)jumpTasks.size();
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[5], ctx->stream));
@@ -209,6 +227,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
     if (rc != MB200_OK) return rc;
   }
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[6], ctx->stream));
+  const auto tHost2 = std::chrono::steady_clock::now();
   if (!jumpTasks.empty()) {
     rc = mb200_dp_run(ctx, MB200_KIND_JUMP, &opts->jumpScores, opts->jumpScore, jumpTasks, ctx->dJump.ptr,
                       reinterpret_cast<uint32_t*>(ctx->dCigar.ptr), cigarCap, reinterpret_cast<unsigned long long*>(misc + 12),
@@ -216,6 +235,14 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
     if (rc != MB200_OK) return rc;
   }
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[7], ctx->stream));
+  if (trace) {
+    const auto tHost3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    fprintf(stderr, "[mb200 trace] host critical path: build tasks %.2f ms, plan+launch large-indel DP %.2f ms, plan+launch jump DP %.2f ms\n",
+            ms(tHost0, tHost1), ms(tHost1, tHost2), ms(tHost2, tHost3));
+  }
 
   // ---- beginPos back to window coordinates (:2038), contig QC and bestAlignmentIndex on the resident alignments
   if (doTrim) {

@@ -1378,15 +1378,15 @@ int launchClass(mb200_ctx* ctx, const DpParams& base, const ClassPlan& plan, siz
 }
 
 struct PairPlan {
-  std::vector<DpPair> pairs;
-  size_t              maxPtr = 0, maxSeg = 0, maxBnd = 0;
+  size_t nPairs = 0;
+  size_t maxPtr = 0, maxSeg = 0, maxBnd = 0;
 };
 
 template <int KIND, int RT, bool NOBAD>
 int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, size_t pairOffset, uint32_t* dCounter,
                     int cls, int nActive)
 {
-  if (plan.pairs.empty()) return MB200_OK;
+  if (plan.nPairs == 0) return MB200_OK;
   DeviceBuffer& dPtr = ctx->dPtrC[cls];
   DeviceBuffer& dSeg = ctx->dSegC[cls];
   DeviceBuffer& dBnd = ctx->dBndC[cls];
@@ -1397,7 +1397,7 @@ int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, 
   if (ctasPerSm < 1) ctasPerSm = 1;
   if (ctx->cfg.ctasPerSm && (int)ctx->cfg.ctasPerSm < ctasPerSm) ctasPerSm = (int)ctx->cfg.ctasPerSm;
   uint32_t grid = (uint32_t)(ctx->smCount * ctasPerSm);
-  if ((size_t)grid * WARPS_PER_CTA > plan.pairs.size()) grid = (uint32_t)((plan.pairs.size() + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+  if ((size_t)grid * WARPS_PER_CTA > plan.nPairs) grid = (uint32_t)((plan.nPairs + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
   const size_t budget  = (ctx->cfg.scratchBytes ? (size_t)ctx->cfg.scratchBytes : ((size_t)96 << 30)) / (size_t)(nActive > 0 ? nActive : 1);
   const size_t ptrSlot = (2 * plan.maxPtr + 511) & ~(size_t)511;  // both tasks of a pair
   while (grid > 1 && (size_t)grid * WARPS_PER_CTA * ptrSlot > budget) grid = (grid + 1) / 2;
@@ -1410,7 +1410,7 @@ int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, 
   if ((rc = mb200_reserve(ctx, dBnd, nSlots * bndSlot * sizeof(int) + 256)) != MB200_OK) return rc;
   DpParams P    = base;
   P.pairs       = reinterpret_cast<const DpPair*>(ctx->dTasksK[KIND].ptr) + pairOffset;
-  P.nPairs      = (uint32_t)plan.pairs.size();
+  P.nPairs      = (uint32_t)plan.nPairs;
   P.tasks       = nullptr;
   P.nTasks      = 0;
   P.workCounter = dCounter;
@@ -1421,6 +1421,7 @@ int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, 
   P.bndScratch  = reinterpret_cast<int*>(dBnd.ptr);
   P.bndStride   = bndSlot;
   MB200_CUDA_CHECK(ctx, cudaStreamWaitEvent(strm, ctx->dpFork, 0));
+  MB200_CUDA_CHECK(ctx, cudaStreamWaitEvent(strm, ctx->copyDone[KIND], 0));
   dpPairKernel<KIND, RT, NOBAD><<<grid, WARPS_PER_CTA * 32, 0, strm>>>(P);
   MB200_CUDA_CHECK(ctx, cudaGetLastError());
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->dpDone[cls], strm));
@@ -1454,24 +1455,55 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
       if ((KindTraits<KIND>::CELLB == 1 || USE2[c]) && Q <= (uint32_t)(32 * RTS[c])) return c;
     return NCLS - 1;
   };
-  std::vector<DpTask> sorted(tasks);
-  std::sort(sorted.begin(), sorted.end(), [&](const DpTask& a, const DpTask& b) {
-    const int ca = classOf(a.Q), cb = classOf(b.Q);
-    if (ca != cb) return ca < cb;
-    if (KIND == KIND_JUMP && a.R1 != b.R1) return a.R1 > b.R1;
-    const uint64_t xa = (uint64_t)a.Q * (a.R1 + a.R2), xb = (uint64_t)b.Q * (b.R1 + b.R2);
-    return xa != xb ? xa > xb : a.outIndex < b.outIndex;
-  });
+  // Order of work: class, then (jump) R1 descending so that pair members share it, then cost descending.  This runs on
+  // the critical path between the assembler and the DP kernels, so it is one LSD radix sort over a 64-bit key
+  // (class:3 | ~R1:32 (jump only) | quantised cost, inverted:29) instead of a comparison sort; equal keys keep task order.
+  uint64_t maxCost = 1;
+  for (const DpTask& t : tasks) maxCost = std::max(maxCost, (uint64_t)t.Q * ((uint64_t)t.R1 + t.R2));
+  int costShift = 0;
+  while ((maxCost >> costShift) >= (1ull << 29)) ++costShift;
+  const size_t          n = tasks.size();
+  std::vector<uint64_t> key(n), key2(n);
+  std::vector<uint32_t> idx(n), idx2(n);
+  for (size_t i = 0; i < n; ++i) {
+    const DpTask&  t = tasks[i];
+    const uint64_t cost = ((uint64_t)t.Q * ((uint64_t)t.R1 + t.R2)) >> costShift;
+    key[i] = ((uint64_t)classOf(t.Q) << 61) | (KIND == KIND_JUMP ? ((uint64_t)(uint32_t)(~t.R1) << 29) : 0u) | ((1ull << 29) - 1 - cost);
+    idx[i] = (uint32_t)i;
+  }
+  for (int shift = 0; shift < 64; shift += 11) {
+    size_t hist[2049];
+    memset(hist, 0, sizeof(hist));
+    for (size_t i = 0; i < n; ++i) hist[((key[i] >> shift) & 2047) + 1]++;
+    bool single = false;
+    for (int d = 0; d < 2048; ++d)
+      if (hist[d + 1] == n) single = true;
+    if (single) continue;  // every key has the same digit here
+    for (int d = 0; d < 2048; ++d) hist[d + 1] += hist[d];
+    for (size_t i = 0; i < n; ++i) {
+      const size_t o = hist[(key[i] >> shift) & 2047]++;
+      key2[o] = key[i];
+      idx2[o] = idx[i];
+    }
+    key.swap(key2);
+    idx.swap(idx2);
+  }
+  // pair neighbours; pairs come out class by class, most expensive first (dynamic hand-out, longest processing time first)
   PairPlan plans[NCLS];
-  for (size_t i = 0; i < sorted.size();) {
+  size_t   offsets[NCLS];
+  int      rc;
+  if ((rc = mb200_reserve_pinned_buf(ctx, ctx->hTasksK[KIND], (n + 1) * sizeof(DpPair))) != MB200_OK) return rc;
+  DpPair* all     = reinterpret_cast<DpPair*>(ctx->hTasksK[KIND].ptr);
+  size_t  nAll    = 0;
+  int     lastCls = -1;
+  for (size_t i = 0; i < n;) {
     DpPair pr;
     memset(&pr, 0, sizeof(pr));
-    pr.a           = sorted[i];
-    const int cls  = classOf(pr.a.Q);
-    const bool can = (i + 1 < sorted.size()) && classOf(sorted[i + 1].Q) == cls &&
-                     (KIND != KIND_JUMP || sorted[i + 1].R1 == pr.a.R1);
+    pr.a           = tasks[idx[i]];
+    const int cls  = (int)(key[i] >> 61);
+    const bool can = (i + 1 < n) && (int)(key[i + 1] >> 61) == cls && (KIND != KIND_JUMP || tasks[idx[i + 1]].R1 == pr.a.R1);
     if (can) {
-      pr.b   = sorted[i + 1];
+      pr.b   = tasks[idx[i + 1]];
       pr.dup = 0;
       i += 2;
     } else {
@@ -1479,13 +1511,17 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
       pr.dup = 1;
       i += 1;
     }
+    if (cls != lastCls) {
+      offsets[cls] = nAll;
+      lastCls      = cls;
+    }
     const uint32_t Q    = std::max(pr.a.Q, pr.b.Q);
     const uint32_t rtot = std::max(pr.a.R1 + pr.a.R2, pr.b.R1 + pr.b.R2);
     const int      RT   = RTS[cls];
     const size_t   nPass = (Q + 32 * RT - 1) / (32 * RT);
     const size_t   pb    = nPass * ((size_t)(rtot + 31) * 32 * (size_t)(((RT * KindTraits<KIND>::CELLB + 3) / 4) * 4));  // PtrLayout::STEP_BYTES
     PairPlan&      p     = plans[cls];
-    p.pairs.push_back(pr);
+    p.nPairs++;
     p.maxPtr = std::max(p.maxPtr, pb);
     p.maxSeg = std::max(p.maxSeg, 2 * ((size_t)Q + rtot + 8));
     p.maxBnd = std::max(p.maxBnd, (Q > (uint32_t)(32 * RT)) ? ((size_t)rtot + 2) * 5 : (size_t)8);
@@ -1494,24 +1530,15 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
       if (cellsOut) *cellsOut += (uint64_t)t.Q * (t.R1 + t.R2);
       if (algoBytesOut) *algoBytesOut += (uint64_t)t.Q * (t.R1 + t.R2) * KindTraits<KIND>::CELLB + t.Q + t.R1 + t.R2;
     }
+    all[nAll++] = pr;
   }
-  // inside a class: largest pairs first (dynamic hand-out, longest processing time first)
-  std::vector<DpPair> all;
-  size_t              offsets[NCLS];
-  for (int c = 0; c < NCLS; ++c) {
-    std::stable_sort(plans[c].pairs.begin(), plans[c].pairs.end(), [](const DpPair& x, const DpPair& y) {
-      const uint64_t cx = (uint64_t)std::max(x.a.Q, x.b.Q) * std::max(x.a.R1 + x.a.R2, x.b.R1 + x.b.R2);
-      const uint64_t cy = (uint64_t)std::max(y.a.Q, y.b.Q) * std::max(y.a.R1 + y.a.R2, y.b.R1 + y.b.R2);
-      return cx > cy;
-    });
-    offsets[c] = all.size();
-    all.insert(all.end(), plans[c].pairs.begin(), plans[c].pairs.end());
-  }
-  int rc;
-  if ((rc = mb200_reserve(ctx, ctx->dTasksK[KIND], all.size() * sizeof(DpPair) + 64)) != MB200_OK) return rc;
-  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dTasksK[KIND].ptr, all.data(), all.size() * sizeof(DpPair), cudaMemcpyHostToDevice, ctx->stream));
+  for (int c = 0; c < NCLS; ++c)
+    if (plans[c].nPairs == 0) offsets[c] = 0;
+  if ((rc = mb200_reserve(ctx, ctx->dTasksK[KIND], nAll * sizeof(DpPair) + 64)) != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dTasksK[KIND].ptr, all, nAll * sizeof(DpPair), cudaMemcpyHostToDevice, ctx->copyStream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->copyDone[KIND], ctx->copyStream));
   int nActive = 0;
-  for (int c = 0; c < NCLS; ++c) nActive += plans[c].pairs.empty() ? 0 : 1;
+  for (int c = 0; c < NCLS; ++c) nActive += plans[c].nPairs == 0 ? 0 : 1;
   // every class runs on its own stream with its own scratch, forked from / joined to the ctx stream, so that the
   // tail of one class overlaps the body of the next (largest strips first)
   // can badVal ever win a max?  M[q][c] >= -L*q with L = max(|match|,|mismatch|,|offEdge|) (induction over the

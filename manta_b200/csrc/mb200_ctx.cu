@@ -41,6 +41,21 @@ int mb200_reserve_pinned(mb200_ctx* ctx, size_t bytes)
   return MB200_OK;
 }
 
+int mb200_reserve_pinned_buf(mb200_ctx* ctx, PinnedBuffer& buf, size_t bytes)
+{
+  if (bytes <= buf.bytes) return MB200_OK;
+  if (buf.ptr) {
+    MB200_CUDA_CHECK(ctx, cudaDeviceSynchronize());
+    MB200_CUDA_CHECK(ctx, cudaFreeHost(buf.ptr));
+    buf.ptr   = nullptr;
+    buf.bytes = 0;
+  }
+  size_t want = bytes + bytes / 4 + 4096;
+  MB200_CUDA_CHECK(ctx, cudaMallocHost(&buf.ptr, want));
+  buf.bytes = want;
+  return MB200_OK;
+}
+
 extern "C" {
 
 int mb200_create(int device, const mb200_config* cfg, mb200_ctx** out)
@@ -73,6 +88,16 @@ int mb200_create(int device, const mb200_config* cfg, mb200_ctx** out)
   }
   for (int i = 0; i < 8; ++i) {
     if (cudaEventCreate(&ctx->cev[i]) != cudaSuccess) {
+      delete ctx;
+      return MB200_ERR_CUDA;
+    }
+  }
+  if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return MB200_ERR_CUDA;
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (cudaEventCreateWithFlags(&ctx->copyDone[i], cudaEventDisableTiming) != cudaSuccess) {
       delete ctx;
       return MB200_ERR_CUDA;
     }
@@ -110,8 +135,12 @@ void mb200_destroy(mb200_ctx* ctx)
     if (ctx->dpStream[i]) cudaStreamDestroy(ctx->dpStream[i]);
     if (ctx->dpDone[i]) cudaEventDestroy(ctx->dpDone[i]);
   }
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 3; ++i) {
     if (ctx->dTasksK[i].ptr) cudaFree(ctx->dTasksK[i].ptr);
+    if (ctx->hTasksK[i].ptr) cudaFreeHost(ctx->hTasksK[i].ptr);
+    if (ctx->copyDone[i]) cudaEventDestroy(ctx->copyDone[i]);
+  }
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->dpFork) cudaEventDestroy(ctx->dpFork);
   DeviceBuffer* bufs[] = {&ctx->dPool,    &ctx->dTasks,   &ctx->dResults, &ctx->dCigar,   &ctx->dPtrScratch,
                           &ctx->dSegScratch, &ctx->dBndScratch, &ctx->dMisc, &ctx->dJobs, &ctx->dTables,

@@ -16,6 +16,18 @@ struct DeviceBuffer {
   size_t bytes = 0;
 };
 
+// host scan of an assembler input batch (assemble.cu: mb200_asm_scan)
+struct mb200_asm_input_stats {
+  uint32_t minWordLength;
+  uint32_t valid;
+  uint64_t maxReads, maxPackWords, maxMaskWords, maxWin, totalBases, totalWindows;
+};
+
+struct PinnedBuffer {
+  void*  ptr   = nullptr;
+  size_t bytes = 0;
+};
+
 struct mb200_ctx {
   int          device     = 0;
   int          smCount    = 0;
@@ -36,7 +48,10 @@ struct mb200_ctx {
     uint32_t                   nLoci = 0;
     uint64_t                   poolBytes = 0;
     std::vector<uint64_t>      readOff;
-    std::vector<mb200_seqview> views, ref1, ref2;
+    std::vector<mb200_seqview> ref1, ref2;
+    uint64_t                   nReads = 0;
+    mb200_asm_input_stats      scan   = {};  // of the staged reads, for word length scan.minWordLength
+    uint32_t                   scanWordLength = 41;  // word length the next upload scans for (last one used by run)
     std::vector<uint8_t>       isJump;
     std::vector<mb200_ref_cuts> cuts;  // empty: no window trim
   } cand;
@@ -51,6 +66,11 @@ struct mb200_ctx {
   cudaEvent_t            dpFork               = nullptr;
   DeviceBuffer           dPtrC[kDpClasses], dSegC[kDpClasses], dBndC[kDpClasses];
   DeviceBuffer           dTasksK[3];
+  // DP work lists are built in pinned memory and copied on their own stream, so that planning the next aligner kind
+  // (and enqueueing its kernels) is not serialised behind the kernels already queued on the ctx stream
+  PinnedBuffer           hTasksK[3];
+  cudaStream_t           copyStream  = nullptr;
+  cudaEvent_t            copyDone[3] = {nullptr, nullptr, nullptr};
   mb200_candidate_timing candTiming = {};
   cudaEvent_t            cev[8]     = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t            cevX[2]    = {nullptr, nullptr};  // end of trim, end of QC
@@ -68,6 +88,7 @@ struct mb200_ctx {
 // grow-only device allocation
 int mb200_reserve(mb200_ctx* ctx, DeviceBuffer& buf, size_t bytes);
 int mb200_reserve_pinned(mb200_ctx* ctx, size_t bytes);
+int mb200_reserve_pinned_buf(mb200_ctx* ctx, PinnedBuffer& buf, size_t bytes);
 int mb200_fail(mb200_ctx* ctx, int status, const char* msg);
 
 // ---- device-level pieces shared between translation units ---------------------------------------------
@@ -86,9 +107,11 @@ int mb200_dp_run(mb200_ctx* ctx, int kind, const mb200_scores* scores, int extra
                  void* dResults, uint32_t* dCigar, uint64_t cigarCap, unsigned long long* dCigarUsed, int* dErrFlag,
                  uint32_t* dWorkCounters, uint64_t* cellsOut, uint64_t* algoBytesOut);
 
-// assemble.cu: run the assembler on device-resident inputs, outputs stay on the device
-int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, const uint64_t* hReadOff,
-                  const mb200_seqview* hViews, uint64_t poolBytes, const uint8_t* dPool, const uint64_t* dReadOff,
+// assemble.cu: host scan of the read views, and the run on device-resident inputs (outputs stay on the device)
+int mb200_asm_scan(mb200_ctx* ctx, uint32_t minWordLength, uint32_t nLoci, const uint64_t* hReadOff, const mb200_seqview* hViews,
+                   uint64_t poolBytes, mb200_asm_input_stats* st);
+int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, const mb200_asm_input_stats* st,
+                  const uint8_t* dPool, const uint64_t* dReadOff,
                   const mb200_seqview* dViews, mb200_asm_locus* dLoci, mb200_contig* dContigs, mb200_seqview* dPseudo,
                   uint8_t* dContigPool, uint64_t contigPoolCap, unsigned long long* dContigPoolUsed, uint32_t* dSetPool,
                   uint64_t setPoolCap, unsigned long long* dSetPoolUsed, uint32_t* dLociCounter, int* dErrFlag,

@@ -110,3 +110,17 @@ def test_candidates_checksum_full_window(gpu, orc):
     assert (ncontig, total) == (nc, ssum)
     t = gpu.candidates_timing()
     assert t["indelCells"] + t["jumpCells"] == cells
+
+
+def test_candidates_other_word_length(gpu, orc):
+    """a run whose first word length differs from the one the staged batch was scanned for (re-scan path), followed
+    by a second upload that is scanned for the new word length directly"""
+    batch = synth.make_candidate_batch(24, seed=5, window=1500)
+    opts = cb.default_candidate_opts(minWordLength=46, maxWordLength=66)
+    gpu.candidates_upload(batch)
+    want = oracle_candidates(orc, batch, opts)
+    assert decode_candidates(batch, opts, gpu.candidates_run(opts)) == want
+    gpu.candidates_upload(batch)
+    assert decode_candidates(batch, opts, gpu.candidates_run(opts)) == want
+    opts = cb.default_candidate_opts()
+    assert decode_candidates(batch, opts, gpu.candidates_run(opts)) == oracle_candidates(orc, batch, opts)
