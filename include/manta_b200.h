@@ -348,7 +348,11 @@ typedef struct mb200_candidate_timing {
   float    trimMs, qcMs;                   /* reference-window trim / contig QC + selection kernels */
 } mb200_candidate_timing;
 
-/* stage one batch of candidate loci in device memory (inputs resident in HBM afterwards) */
+/* Stage one batch of candidate loci in device memory (inputs resident in HBM afterwards).  The copy is asynchronous
+ * (its own stream): the caller's buffers must stay untouched until the mb200_candidates_run that consumes the batch
+ * has returned.  Up to two batches can be staged; runs consume them first-in first-out, so
+ *     upload(b0); for (i...) { upload(b[i+1]); run(); }      copies batch i+1 while batch i is processed.
+ * With nothing staged, mb200_candidates_run repeats on the batch it consumed last (resident inputs). */
 MB200_API int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* readOff,
                                       const mb200_seqview* readViews, const uint8_t* isJump,
                                       const mb200_seqview* ref1, const mb200_seqview* ref2, const uint8_t* pool,

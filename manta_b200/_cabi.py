@@ -393,6 +393,8 @@ class Binding:
                         C.c_uint64(batch.pool.size), _ptr(cuts) if cuts is not None else None)
         if st != MB200_OK:
             self._raise(st)
+        # the copy is asynchronous: keep the host arrays alive until the consuming run has returned
+        self._cand_keep = getattr(self, "_cand_keep", [])[-2:] + [(batch, cuts)]
         self._cand_shape = (batch.nLoci, int(batch.readViews["len"].sum()), batch.readsPerLocus)
 
     def candidates_run(self, opts: np.ndarray, out: Optional[dict] = None, select: bool = False) -> dict:

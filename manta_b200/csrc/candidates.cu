@@ -20,24 +20,19 @@ int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* read
                             const uint8_t* pool, uint64_t poolBytes, const mb200_ref_cuts* cuts)
 {
   if (!ctx) return MB200_ERR_BAD_ARG;
-  if (nLoci && (!readOff || !isJump || !ref1 || !ref2 || !pool)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  if (nLoci == 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "empty batch");
+  if (!readOff || !isJump || !ref1 || !ref2 || !pool) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
   MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
-  auto& c      = ctx->cand;
-  c.nLoci      = nLoci;
-  c.poolBytes  = poolBytes;
-  c.readOff.assign(readOff, readOff + nLoci + 1);
-  const uint64_t nReads = nLoci ? readOff[nLoci] : 0;
+  auto& C = ctx->cand;
+  if (C.nQueued == 2) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "two batches are already staged (run one first)");
+  // with one batch staged take the other slot; with none, the slot the last consumed batch does not use (it stays
+  // available for repeated runs until a second upload overwrites it)
+  const int tgt = (C.nQueued == 1) ? 1 - C.queue[0] : (C.cur == 0 ? 1 : 0);
+  if (C.cur == tgt) C.cur = -1;
+  auto& S = C.slot[tgt];
+  if (S.everUploaded) MB200_CUDA_CHECK(ctx, cudaEventSynchronize(S.upEnd));  // an earlier copy into this slot
+  const uint64_t nReads = readOff[nLoci];
   if (nReads && !readViews) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
-  c.nReads = nReads;
-  // validate the read views and size the assembler workspace now (for the word length the last run used), so that a
-  // run on the resident batch starts on the device at once; the views themselves are not kept on the host
-  int rcScan;
-  if ((rcScan = mb200_asm_scan(ctx, c.scanWordLength, nLoci, readOff, readViews, poolBytes, &c.scan)) != MB200_OK) return rcScan;
-  c.ref1.assign(ref1, ref1 + nLoci);
-  c.ref2.assign(ref2, ref2 + nLoci);
-  c.isJump.assign(isJump, isJump + nLoci);
-  c.cuts.clear();
-  if (cuts) c.cuts.assign(cuts, cuts + nLoci);
   for (uint32_t i = 0; i < nLoci; ++i) {
     if (cuts && (cuts[i].leadingCut < 0 || cuts[i].trailingCut < 0 || cuts[i].maxLeadingCut < 0 || cuts[i].maxTrailingCut < 0))
       return mb200_fail(ctx, MB200_ERR_BAD_ARG, "negative cut");
@@ -45,32 +40,44 @@ int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* read
     if (isJump[i] && (ref2[i].len == 0 || ref2[i].off + ref2[i].len > poolBytes))
       return mb200_fail(ctx, MB200_ERR_EMPTY_REF2, "Unexpected empty reference2 sequence");
   }
+  // validate the read views and size the assembler workspace now (for the word length the last run used), so that a
+  // run on the resident batch starts on the device at once; the views themselves are not kept on the host
   int rc;
-  if ((rc = mb200_reserve(ctx, ctx->dCandPool, poolBytes + MB200_POOL_FRONT + 64)) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dCandReadOff, 8 * (size_t)(nLoci + 1))) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dCandViews, sizeof(mb200_seqview) * (size_t)(nReads + 1))) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dQcIsJump, (size_t)nLoci + 4)) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dQcRef, sizeof(mb200_seqview) * (size_t)nLoci + 16)) != MB200_OK) return rc;
-  if ((rc = mb200_reserve(ctx, ctx->dQcCuts, sizeof(mb200_ref_cuts) * (size_t)nLoci + 16)) != MB200_OK) return rc;
-  uint8_t* dp = reinterpret_cast<uint8_t*>(ctx->dCandPool.ptr);
-  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[0], ctx->stream));
-  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(dp, 0, MB200_POOL_FRONT, ctx->stream));
-  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(dp + MB200_POOL_FRONT, pool, poolBytes, cudaMemcpyHostToDevice, ctx->stream));
-  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(dp + MB200_POOL_FRONT + poolBytes, 0, 64, ctx->stream));
-  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCandReadOff.ptr, readOff, 8 * (size_t)(nLoci + 1), cudaMemcpyHostToDevice, ctx->stream));
-  if (nReads)
-    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dCandViews.ptr, readViews, sizeof(mb200_seqview) * (size_t)nReads, cudaMemcpyHostToDevice, ctx->stream));
-  if (nLoci) {
-    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dQcIsJump.ptr, isJump, (size_t)nLoci, cudaMemcpyHostToDevice, ctx->stream));
-    MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dQcRef.ptr, ref1, sizeof(mb200_seqview) * (size_t)nLoci, cudaMemcpyHostToDevice, ctx->stream));
-    if (cuts) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dQcCuts.ptr, cuts, sizeof(mb200_ref_cuts) * (size_t)nLoci, cudaMemcpyHostToDevice, ctx->stream));
-  }
-  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[1], ctx->stream));
-  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  ctx->candTiming = mb200_candidate_timing();
-  cudaEventElapsedTime(&ctx->candTiming.h2dMs, ctx->cev[0], ctx->cev[1]);
-  ctx->candTiming.h2dBytes = poolBytes + 8 * (uint64_t)(nLoci + 1) + sizeof(mb200_seqview) * nReads +
-                             (uint64_t)nLoci * (1 + sizeof(mb200_seqview) + (cuts ? sizeof(mb200_ref_cuts) : 0));
+  if ((rc = mb200_asm_scan(ctx, C.scanWordLength, nLoci, readOff, readViews, poolBytes, &S.scan)) != MB200_OK) return rc;
+  S.nLoci     = nLoci;
+  S.poolBytes = poolBytes;
+  S.nReads    = nReads;
+  S.readOff.assign(readOff, readOff + nLoci + 1);
+  S.ref1.assign(ref1, ref1 + nLoci);
+  S.ref2.assign(ref2, ref2 + nLoci);
+  S.isJump.assign(isJump, isJump + nLoci);
+  S.cuts.clear();
+  if (cuts) S.cuts.assign(cuts, cuts + nLoci);
+  if ((rc = mb200_reserve(ctx, S.dPool, poolBytes + MB200_POOL_FRONT + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, S.dReadOff, 8 * (size_t)(nLoci + 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, S.dViews, sizeof(mb200_seqview) * (size_t)(nReads + 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, S.dIsJump, (size_t)nLoci + 4)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, S.dRef1, sizeof(mb200_seqview) * (size_t)nLoci + 16)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, S.dCuts, sizeof(mb200_ref_cuts) * (size_t)nLoci + 16)) != MB200_OK) return rc;
+  // asynchronous from here on (uploadStream): the copy overlaps a run on the other slot.  The caller's buffers must
+  // stay untouched until the mb200_candidates_run that consumes this batch has returned.
+  cudaStream_t up = ctx->uploadStream;
+  uint8_t*     dp = reinterpret_cast<uint8_t*>(S.dPool.ptr);
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(S.upBegin, up));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(dp, 0, MB200_POOL_FRONT, up));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(dp + MB200_POOL_FRONT, pool, poolBytes, cudaMemcpyHostToDevice, up));
+  MB200_CUDA_CHECK(ctx, cudaMemsetAsync(dp + MB200_POOL_FRONT + poolBytes, 0, 64, up));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dReadOff.ptr, readOff, 8 * (size_t)(nLoci + 1), cudaMemcpyHostToDevice, up));
+  if (nReads) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dViews.ptr, readViews, sizeof(mb200_seqview) * (size_t)nReads, cudaMemcpyHostToDevice, up));
+  // the small per-locus arrays are copied from the slot's own host copies (they outlive the caller's arrays)
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dIsJump.ptr, S.isJump.data(), (size_t)nLoci, cudaMemcpyHostToDevice, up));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dRef1.ptr, S.ref1.data(), sizeof(mb200_seqview) * (size_t)nLoci, cudaMemcpyHostToDevice, up));
+  if (cuts) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dCuts.ptr, S.cuts.data(), sizeof(mb200_ref_cuts) * (size_t)nLoci, cudaMemcpyHostToDevice, up));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(S.upEnd, up));
+  S.everUploaded = true;
+  S.h2dBytes     = poolBytes + 8 * (uint64_t)(nLoci + 1) + sizeof(mb200_seqview) * nReads +
+               (uint64_t)nLoci * (1 + sizeof(mb200_seqview) + (cuts ? sizeof(mb200_ref_cuts) : 0));
+  C.queue[C.nQueued++] = tgt;
   return MB200_OK;
 }
 
@@ -84,9 +91,16 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if (!opts || !loci || !contigs || !pseudoReads || !contigPool || !setPool || !alnResults || !jumpResults ||
       !cigarPool || !contigPoolUsed || !setPoolUsed || !cigarUsed)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
-  auto&          c     = ctx->cand;
+  auto& C = ctx->cand;
+  if (C.nQueued > 0) {  // the oldest staged batch becomes the current one
+    C.cur      = C.queue[0];
+    C.queue[0] = C.queue[1];
+    C.queue[1] = -1;
+    C.nQueued--;
+  }
+  if (C.cur < 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "no staged batch (call mb200_candidates_upload first)");
+  auto&          c     = C.slot[C.cur];
   const uint32_t nLoci = c.nLoci;
-  if (nLoci == 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "no staged batch (call mb200_candidates_upload first)");
   const bool doTrim   = !c.cuts.empty();
   const bool doSelect = (qc != nullptr) || (best != nullptr);
   if (doSelect && (!qc || !best)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "qc and best must be requested together");
@@ -95,12 +109,10 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   const uint32_t A = opts->asmOpts.maxAssemblyCount;
   if (A < 1 || A > 16) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "maxAssemblyCount outside [1,16]");
   mb200_candidate_timing& T = ctx->candTiming;
-  const float             keepH2d = T.h2dMs;
-  const uint64_t          keepH2dBytes = T.h2dBytes;
-  T                       = mb200_candidate_timing();
-  T.h2dMs                 = keepH2d;
-  T.h2dBytes              = keepH2dBytes;
-  ctx->timing             = mb200_timing();
+  T                         = mb200_candidate_timing();
+  T.h2dBytes                = c.h2dBytes;
+  ctx->timing               = mb200_timing();
+  MB200_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, c.upEnd, 0));  // the batch's own upload
 
   int rc;
   const size_t nSlots = (size_t)nLoci * A;
@@ -119,7 +131,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   std::vector<mb200_trim_result> hTrim;
 
   uint32_t*      misc        = reinterpret_cast<uint32_t*>(ctx->dMisc.ptr);
-  const uint8_t* dPool       = reinterpret_cast<const uint8_t*>(ctx->dCandPool.ptr) + MB200_POOL_FRONT;
+  const uint8_t* dPool       = reinterpret_cast<const uint8_t*>(c.dPool.ptr) + MB200_POOL_FRONT;
   uint8_t*       dContigPool = reinterpret_cast<uint8_t*>(ctx->dAsmOut3.ptr) + MB200_POOL_FRONT;
   // dMisc: [0] loci counter, [4] errFlag, [8] contigPoolUsed, [10] setPoolUsed, [12] cigarUsed,
   //        [32..39] indel class work counters, [48..55] jump class work counters
@@ -134,13 +146,13 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if (!c.scan.valid || c.scan.minWordLength != opts->asmOpts.minWordLength) {
     // first word length differs from the one the batch was scanned for: fetch the views back and scan again
     std::vector<mb200_seqview> hv(c.nReads ? c.nReads : 1);
-    MB200_CUDA_CHECK(ctx, cudaMemcpy(hv.data(), ctx->dCandViews.ptr, sizeof(mb200_seqview) * (size_t)c.nReads, cudaMemcpyDeviceToHost));
+    MB200_CUDA_CHECK(ctx, cudaMemcpy(hv.data(), c.dViews.ptr, sizeof(mb200_seqview) * (size_t)c.nReads, cudaMemcpyDeviceToHost));
     if ((rc = mb200_asm_scan(ctx, opts->asmOpts.minWordLength, nLoci, c.readOff.data(), hv.data(), c.poolBytes, &c.scan)) != MB200_OK) return rc;
-    c.scanWordLength = opts->asmOpts.minWordLength;
+    C.scanWordLength = opts->asmOpts.minWordLength;
   }
   rc = mb200_asm_run(ctx, &opts->asmOpts, nLoci, &c.scan, dPool,
-                     reinterpret_cast<const uint64_t*>(ctx->dCandReadOff.ptr),
-                     reinterpret_cast<const mb200_seqview*>(ctx->dCandViews.ptr),
+                     reinterpret_cast<const uint64_t*>(c.dReadOff.ptr),
+                     reinterpret_cast<const mb200_seqview*>(c.dViews.ptr),
                      reinterpret_cast<mb200_asm_locus*>(ctx->dAsmOut0.ptr), reinterpret_cast<mb200_contig*>(ctx->dAsmOut1.ptr),
                      reinterpret_cast<mb200_seqview*>(ctx->dAsmOut2.ptr), dContigPool, contigPoolCap,
                      reinterpret_cast<unsigned long long*>(misc + 8), reinterpret_cast<uint32_t*>(ctx->dAsmOut4.ptr), setPoolCap,
@@ -158,8 +170,8 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if (doTrim) {
     MB200_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dQcTrim.ptr, 0, sizeof(mb200_trim_result) * nSlots, ctx->stream));
     rc = mb200_trim_run(ctx, (uint32_t)nSlots, A, dContigPool, nullptr, reinterpret_cast<const mb200_contig*>(ctx->dAsmOut1.ptr), dPool,
-                        reinterpret_cast<const mb200_seqview*>(ctx->dQcRef.ptr), reinterpret_cast<const mb200_ref_cuts*>(ctx->dQcCuts.ptr),
-                        reinterpret_cast<const uint8_t*>(ctx->dQcIsJump.ptr), ctx->cfg.maxContigLen ? ctx->cfg.maxContigLen : 2048,
+                        reinterpret_cast<const mb200_seqview*>(c.dRef1.ptr), reinterpret_cast<const mb200_ref_cuts*>(c.dCuts.ptr),
+                        reinterpret_cast<const uint8_t*>(c.dIsJump.ptr), ctx->cfg.maxContigLen ? ctx->cfg.maxContigLen : 2048,
                         reinterpret_cast<mb200_trim_result*>(ctx->dQcTrim.ptr), reinterpret_cast<int*>(misc + 4));
     if (rc != MB200_OK) return rc;
     hTrim.resize(nSlots);
@@ -247,17 +259,17 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   // ---- beginPos back to window coordinates (:2038), contig QC and bestAlignmentIndex on the resident alignments
   if (doTrim) {
     rc = mb200_apply_trim(ctx, (uint32_t)nSlots, reinterpret_cast<const uint32_t*>(ctx->dQcSlotLocus.ptr),
-                          reinterpret_cast<const uint8_t*>(ctx->dQcIsJump.ptr), reinterpret_cast<const mb200_trim_result*>(ctx->dQcTrim.ptr),
+                          reinterpret_cast<const uint8_t*>(c.dIsJump.ptr), reinterpret_cast<const mb200_trim_result*>(ctx->dQcTrim.ptr),
                           reinterpret_cast<mb200_aln_result*>(ctx->dAln.ptr));
     if (rc != MB200_OK) return rc;
   }
   if (doSelect) {
-    rc = mb200_qc_run(ctx, &opts->qcOpts, nLoci, (uint32_t)nSlots, reinterpret_cast<const uint8_t*>(ctx->dQcIsJump.ptr),
+    rc = mb200_qc_run(ctx, &opts->qcOpts, nLoci, (uint32_t)nSlots, reinterpret_cast<const uint8_t*>(c.dIsJump.ptr),
                       reinterpret_cast<const uint32_t*>(ctx->dQcSlotFirst.ptr), reinterpret_cast<const uint32_t*>(ctx->dQcNContigs.ptr),
                       reinterpret_cast<const uint32_t*>(ctx->dQcSlotLocus.ptr), reinterpret_cast<const mb200_aln_result*>(ctx->dAln.ptr),
                       reinterpret_cast<const mb200_jump_result*>(ctx->dJump.ptr), reinterpret_cast<const uint32_t*>(ctx->dCigar.ptr),
                       dContigPool, reinterpret_cast<const mb200_seqview*>(ctx->dQcViews.ptr), dPool,
-                      reinterpret_cast<const mb200_seqview*>(ctx->dQcRef.ptr), reinterpret_cast<const uint32_t*>(ctx->dQcSupport.ptr),
+                      reinterpret_cast<const mb200_seqview*>(c.dRef1.ptr), reinterpret_cast<const uint32_t*>(ctx->dQcSupport.ptr),
                       reinterpret_cast<mb200_contig_qc*>(ctx->dQc.ptr), reinterpret_cast<int32_t*>(ctx->dQcBest.ptr),
                       reinterpret_cast<const unsigned long long*>(misc + 12), cigarCap, reinterpret_cast<const int*>(misc + 4));
     if (rc != MB200_OK) return rc;
@@ -288,6 +300,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if (usedCig) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(cigarPool, ctx->dCigar.ptr, usedCig * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[0], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&T.h2dMs, c.upBegin, c.upEnd);
   cudaEventElapsedTime(&T.asmMs, ctx->cev[3], ctx->cev[4]);
   cudaEventElapsedTime(&T.indelMs, ctx->cev[5], ctx->cev[6]);
   cudaEventElapsedTime(&T.jumpMs, ctx->cev[6], ctx->cev[7]);

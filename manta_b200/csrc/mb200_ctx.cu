@@ -92,6 +92,16 @@ int mb200_create(int device, const mb200_config* cfg, mb200_ctx** out)
       return MB200_ERR_CUDA;
     }
   }
+  if (cudaStreamCreateWithFlags(&ctx->uploadStream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return MB200_ERR_CUDA;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreate(&ctx->cand.slot[i].upBegin) != cudaSuccess || cudaEventCreate(&ctx->cand.slot[i].upEnd) != cudaSuccess) {
+      delete ctx;
+      return MB200_ERR_CUDA;
+    }
+  }
   if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return MB200_ERR_CUDA;
@@ -141,12 +151,20 @@ void mb200_destroy(mb200_ctx* ctx)
     if (ctx->copyDone[i]) cudaEventDestroy(ctx->copyDone[i]);
   }
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
+  for (int i = 0; i < 2; ++i) {
+    auto& S = ctx->cand.slot[i];
+    DeviceBuffer* sb[] = {&S.dPool, &S.dReadOff, &S.dViews, &S.dIsJump, &S.dRef1, &S.dCuts};
+    for (DeviceBuffer* b : sb)
+      if (b->ptr) cudaFree(b->ptr);
+    if (S.upBegin) cudaEventDestroy(S.upBegin);
+    if (S.upEnd) cudaEventDestroy(S.upEnd);
+  }
+  if (ctx->uploadStream) cudaStreamDestroy(ctx->uploadStream);
   if (ctx->dpFork) cudaEventDestroy(ctx->dpFork);
   DeviceBuffer* bufs[] = {&ctx->dPool,    &ctx->dTasks,   &ctx->dResults, &ctx->dCigar,   &ctx->dPtrScratch,
                           &ctx->dSegScratch, &ctx->dBndScratch, &ctx->dMisc, &ctx->dJobs, &ctx->dTables,
                           &ctx->dAsmWork, &ctx->dAsmOut0, &ctx->dAsmOut1, &ctx->dAsmOut2, &ctx->dAsmOut3,
-                          &ctx->dAsmOut4, &ctx->dViews,   &ctx->dReadOff, &ctx->dCandPool, &ctx->dCandReadOff,
-                          &ctx->dCandViews, &ctx->dAln, &ctx->dJump,
+                          &ctx->dAsmOut4, &ctx->dViews,   &ctx->dReadOff, &ctx->dAln, &ctx->dJump,
                           &ctx->dQcScratch, &ctx->dQcSupport, &ctx->dQcSlotLocus, &ctx->dQcSlotFirst, &ctx->dQcNContigs,
                           &ctx->dQcViews, &ctx->dQcRef, &ctx->dQcCuts, &ctx->dQcTrim, &ctx->dQcIsJump, &ctx->dQc, &ctx->dQcBest};
   for (DeviceBuffer* b : bufs)

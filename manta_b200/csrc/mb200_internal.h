@@ -43,19 +43,30 @@ struct mb200_ctx {
   // pinned staging
   void*  hPinned      = nullptr;
   size_t hPinnedBytes = 0;
-  // staged candidate batch (mb200_candidates_upload)
-  struct {
-    uint32_t                   nLoci = 0;
-    uint64_t                   poolBytes = 0;
-    std::vector<uint64_t>      readOff;
-    std::vector<mb200_seqview> ref1, ref2;
-    uint64_t                   nReads = 0;
-    mb200_asm_input_stats      scan   = {};  // of the staged reads, for word length scan.minWordLength
-    uint32_t                   scanWordLength = 41;  // word length the next upload scans for (last one used by run)
-    std::vector<uint8_t>       isJump;
+  // staged candidate batches (mb200_candidates_upload): two slots, so that the copy of the next batch (on
+  // uploadStream) overlaps the run on the current one.  Staged batches are consumed first-in first-out by
+  // mb200_candidates_run; with nothing staged a run repeats on `cur`, the batch consumed last.
+  struct CandSlot {
+    uint32_t                    nLoci = 0;
+    uint64_t                    poolBytes = 0, nReads = 0, h2dBytes = 0;
+    std::vector<uint64_t>       readOff;
+    std::vector<mb200_seqview>  ref1, ref2;
+    std::vector<uint8_t>        isJump;
     std::vector<mb200_ref_cuts> cuts;  // empty: no window trim
+    mb200_asm_input_stats       scan = {};  // of the staged reads, for word length scan.minWordLength
+    DeviceBuffer                dPool, dReadOff, dViews, dIsJump, dRef1, dCuts;
+    cudaEvent_t                 upBegin = nullptr, upEnd = nullptr;
+    bool                        everUploaded = false;
+  };
+  struct {
+    CandSlot slot[2];
+    int      cur = -1;
+    int      queue[2] = {-1, -1};  // staged, not yet consumed (oldest first)
+    int      nQueued  = 0;
+    uint32_t scanWordLength = 41;  // word length the next upload scans for (the last one a run used)
   } cand;
-  DeviceBuffer           dCandPool, dCandReadOff, dCandViews, dAln, dJump;
+  cudaStream_t uploadStream = nullptr;
+  DeviceBuffer           dAln, dJump;
   // reference-window trim / contig QC + selection (contig_qc.cu)
   DeviceBuffer dQcScratch, dQcSupport, dQcSlotLocus, dQcSlotFirst, dQcNContigs, dQcViews, dQcRef, dQcCuts, dQcTrim, dQcIsJump,
       dQc, dQcBest;

@@ -124,3 +124,24 @@ def test_candidates_other_word_length(gpu, orc):
     assert decode_candidates(batch, opts, gpu.candidates_run(opts)) == want
     opts = cb.default_candidate_opts()
     assert decode_candidates(batch, opts, gpu.candidates_run(opts)) == oracle_candidates(orc, batch, opts)
+
+
+def test_candidates_staging_queue(gpu, orc):
+    """two staged batches are consumed first-in first-out; with nothing staged a run repeats on the last batch; a
+    third upload before any run is refused"""
+    opts = cb.default_candidate_opts()
+    b1 = synth.make_candidate_batch(16, seed=11, window=1500)
+    b2 = synth.make_candidate_batch(20, seed=12, window=1500)
+    w1, w2 = oracle_candidates(orc, b1, opts), oracle_candidates(orc, b2, opts)
+    gpu.candidates_upload(b1)
+    gpu.candidates_upload(b2)
+    with pytest.raises(cb.Mb200Error):
+        gpu.candidates_upload(b1)
+    gpu._cand_shape = (b1.nLoci, int(b1.readViews["len"].sum()), b1.readsPerLocus)
+    assert decode_candidates(b1, opts, gpu.candidates_run(opts)) == w1
+    gpu.candidates_upload(b1)  # overwrites the slot of the batch just consumed while b2 is still staged
+    gpu._cand_shape = (b2.nLoci, int(b2.readViews["len"].sum()), b2.readsPerLocus)
+    assert decode_candidates(b2, opts, gpu.candidates_run(opts)) == w2
+    gpu._cand_shape = (b1.nLoci, int(b1.readViews["len"].sum()), b1.readsPerLocus)
+    assert decode_candidates(b1, opts, gpu.candidates_run(opts)) == w1
+    assert decode_candidates(b1, opts, gpu.candidates_run(opts)) == w1  # nothing staged: repeat on the resident batch
