@@ -961,8 +961,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
   // ALU-trimming variants (row-Q capture through shared memory, pointer codes pre-shifted to the row's position,
   // staging checks once per 32 steps).  The 5-state kernel sits on the register cliff and ptxas spills inside the
   // row loop with them (measured: 112 ms -> 128..207 ms per 20k loci), so it keeps the plain forms.
-  constexpr bool TRIM     = (KIND != KIND_INDEL);
-  constexpr bool SMEM_CAP = TRIM;
+  // instruction trimming per aligner kind.  The 5-state kind sits at the register limit of 3 CTAs/SM (165 of 168):
+  // pre-shifted pointer codes and the shared-memory (or select-tree) row capture spill there and cost more than they
+  // save (measured: +3 %); checking the reference tiles once per 32 steps costs nothing and saves 6 %.
+  constexpr bool PRESHIFT = (KIND != KIND_INDEL);  // pointer codes pre-shifted to their row slot
+  constexpr bool STAGE32  = true;                  // reference-tile checks once per 32 steps
+  constexpr bool SMEM_CAP = (KIND != KIND_INDEL);  // last-query-row capture through shared memory
   __shared__ uint32_t sCap[SMEM_CAP ? WARPS_PER_CTA : 1][SMEM_CAP ? 32 : 1][RT];
 
   const int      lane    = threadIdx.x & 31;
@@ -1081,13 +1085,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
       for (uint32_t t = 0; t < nSteps; ++t) {
         // ---- reference tiles of both halves: checked once per 32 steps with a 32-column look-ahead for the head
         // (tiles are 2 KiB, so a tile the head enters inside this block is waited for at the block start)
-        if (!TRIM || (t & 31u) == 0) {
+        if (!STAGE32 || (t & 31u) == 0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             StageCursor&   cur = h ? curB : curA;
             const uint32_t rt  = h ? RTB : RTA;
             const uint32_t r1  = h ? R1B : R1A;
-            const uint32_t ahead = TRIM ? 31u : 0u;
+            const uint32_t ahead = STAGE32 ? 31u : 0u;
             const uint32_t cz0 = (t + ahead < rt) ? t + ahead : rt - 1;
             const uint32_t need = stagedIndex(cur.st, cz0, r1, KIND == KIND_JUMP) / REF_TILE;
             while (cur.waitTile <= need) stageOk = cursorWait(cur) && stageOk;
@@ -1167,7 +1171,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
           for (int r = 0; r < RT; ++r) {
             constexpr uint32_t F0 = 0;  // field shifts inside the 32-bit pointer word are added below
             const int      shRow = ROWBITS * (r % ROWSPW);
-            const int      sh    = TRIM ? shRow : 0;  // folded into the SEL constants, or applied once below
+            const int      sh    = PRESHIFT ? shRow : 0;  // folded into the SEL constants, or applied once below
             (void)F0;
             // substitution score of both halves: match where the characters are equal, mismatch elsewhere
             const uint32_t d  = qpair[r] ^ refpair;
