@@ -397,21 +397,22 @@ class Binding:
         self._cand_keep = getattr(self, "_cand_keep", [])[-2:] + [(batch, cuts)]
         self._cand_shape = (batch.nLoci, int(batch.readViews["len"].sum()), batch.readsPerLocus)
 
-    def candidates_run(self, opts: np.ndarray, out: Optional[dict] = None, select: bool = False) -> dict:
+    def candidates_run(self, opts: np.ndarray, out: Optional[dict] = None, select: bool = False, zeros=np.zeros) -> dict:
         """run on the staged batch; `out` (from a previous call) is reused to avoid re-allocating host buffers.
-        select=True also returns the per-contig trim / QC records and the per-locus bestAlignmentIndex."""
+        select=True also returns the per-contig trim / QC records and the per-locus bestAlignmentIndex.
+        `zeros(n, dtype=...)` allocates the host result buffers (pass a pinned-memory allocator for faster copies)."""
         nLoci, totalBases, rpl = self._cand_shape
         A = int(opts["asmOpts"]["maxAssemblyCount"][0])
         if out is None:
-            out = dict(loci=np.zeros(nLoci, dtype=ASM_LOCUS_DT), contigs=np.zeros(nLoci * A, dtype=CONTIG_DT),
-                       pseudo=np.zeros(nLoci * 2 * A, dtype=SEQVIEW_DT),
-                       contigPool=np.zeros(max(1 << 16, totalBases // 2), dtype=np.uint8),
-                       setPool=np.zeros(max(1024, nLoci * A * 2 * ((rpl + 2 * A + 31) // 32)), dtype=np.uint32),
-                       aln=np.zeros(nLoci * A, dtype=ALN_RESULT_DT), jump=np.zeros(nLoci * A, dtype=JUMP_RESULT_DT),
-                       cigar=np.zeros(max(4096, nLoci * A * 24), dtype=np.uint32))
+            out = dict(loci=zeros(nLoci, dtype=ASM_LOCUS_DT), contigs=zeros(nLoci * A, dtype=CONTIG_DT),
+                       pseudo=zeros(nLoci * 2 * A, dtype=SEQVIEW_DT),
+                       contigPool=zeros(max(1 << 16, totalBases // 2), dtype=np.uint8),
+                       setPool=zeros(max(1024, nLoci * A * 2 * ((rpl + 2 * A + 31) // 32)), dtype=np.uint32),
+                       aln=zeros(nLoci * A, dtype=ALN_RESULT_DT), jump=zeros(nLoci * A, dtype=JUMP_RESULT_DT),
+                       cigar=zeros(max(4096, nLoci * A * 24), dtype=np.uint32))
         if select and "qc" not in out:
-            out.update(trim=np.zeros(nLoci * A, dtype=TRIM_RESULT_DT), qc=np.zeros(nLoci * A, dtype=CONTIG_QC_DT),
-                       best=np.zeros(nLoci, dtype=np.int32))
+            out.update(trim=zeros(nLoci * A, dtype=TRIM_RESULT_DT), qc=zeros(nLoci * A, dtype=CONTIG_QC_DT),
+                       best=zeros(nLoci, dtype=np.int32))
         sel = [_ptr(out["trim"]), _ptr(out["qc"]), _ptr(out["best"])] if select else [None, None, None]
         for _ in range(6):
             used = [C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)]
@@ -421,11 +422,11 @@ class Binding:
                             _ptr(out["jump"]), _ptr(out["cigar"]), C.c_uint64(out["cigar"].size), C.byref(used[2]), *sel)
             if st == MB200_ERR_POOL_OVERFLOW:
                 if used[0].value > out["contigPool"].size:
-                    out["contigPool"] = np.zeros(int(used[0].value * 1.25) + 64, dtype=np.uint8)
+                    out["contigPool"] = zeros(int(used[0].value * 1.25) + 64, dtype=np.uint8)
                 if used[1].value > out["setPool"].size:
-                    out["setPool"] = np.zeros(int(used[1].value * 1.25) + 64, dtype=np.uint32)
+                    out["setPool"] = zeros(int(used[1].value * 1.25) + 64, dtype=np.uint32)
                 if used[2].value > out["cigar"].size:
-                    out["cigar"] = np.zeros(int(used[2].value * 1.25) + 64, dtype=np.uint32)
+                    out["cigar"] = zeros(int(used[2].value * 1.25) + 64, dtype=np.uint32)
                 continue
             if st != MB200_OK:
                 self._raise(st)

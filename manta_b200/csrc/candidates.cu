@@ -276,13 +276,16 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   }
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cevX[1], ctx->stream));
 
+  // ---- the assembler's outputs are final since the contig-record sync above: they go to the host on the copy stream
+  // while the DP / QC kernels queued above run
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(pseudoReads, ctx->dAsmOut2.ptr, sizeof(mb200_seqview) * nSlots * 2, cudaMemcpyDeviceToHost, ctx->copyStream));
+  if (usedBytes) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(contigPool, dContigPool, usedBytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+  if (usedSets) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(setPool, ctx->dAsmOut4.ptr, 4 * usedSets, cudaMemcpyDeviceToHost, ctx->copyStream));
+
   // ---- results to the host
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(hMisc, ctx->dMisc.ptr, sizeof(hMisc), cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(alnResults, ctx->dAln.ptr, sizeof(mb200_aln_result) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(jumpResults, ctx->dJump.ptr, sizeof(mb200_jump_result) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
-  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(pseudoReads, ctx->dAsmOut2.ptr, sizeof(mb200_seqview) * nSlots * 2, cudaMemcpyDeviceToHost, ctx->stream));
-  if (usedBytes) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(contigPool, dContigPool, usedBytes, cudaMemcpyDeviceToHost, ctx->stream));
-  if (usedSets) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(setPool, ctx->dAsmOut4.ptr, 4 * usedSets, cudaMemcpyDeviceToHost, ctx->stream));
   if (doSelect) {
     MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(qc, ctx->dQc.ptr, sizeof(mb200_contig_qc) * nSlots, cudaMemcpyDeviceToHost, ctx->stream));
     MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(best, ctx->dQcBest.ptr, 4 * (size_t)nLoci, cudaMemcpyDeviceToHost, ctx->stream));
@@ -300,6 +303,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if (usedCig) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(cigarPool, ctx->dCigar.ptr, usedCig * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[0], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->copyStream));
   cudaEventElapsedTime(&T.h2dMs, c.upBegin, c.upEnd);
   cudaEventElapsedTime(&T.asmMs, ctx->cev[3], ctx->cev[4]);
   cudaEventElapsedTime(&T.indelMs, ctx->cev[5], ctx->cev[6]);

@@ -962,11 +962,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParam
   // staging checks once per 32 steps).  The 5-state kernel sits on the register cliff and ptxas spills inside the
   // row loop with them (measured: 112 ms -> 128..207 ms per 20k loci), so it keeps the plain forms.
   // instruction trimming per aligner kind.  The 5-state kind sits at the register limit of 3 CTAs/SM (165 of 168):
-  // pre-shifted pointer codes and the shared-memory (or select-tree) row capture spill there and cost more than they
-  // save (measured: +3 %); checking the reference tiles once per 32 steps costs nothing and saves 6 %.
+  // pre-shifted pointer codes spill there and cost more than they save (measured: +3 %); checking the reference tiles
+  // once per 32 steps saves 6 %, capturing the last query row through shared memory another 4 %.
   constexpr bool PRESHIFT = (KIND != KIND_INDEL);  // pointer codes pre-shifted to their row slot
   constexpr bool STAGE32  = true;                  // reference-tile checks once per 32 steps
-  constexpr bool SMEM_CAP = (KIND != KIND_INDEL);  // last-query-row capture through shared memory
+  constexpr bool SMEM_CAP = true;                  // last-query-row capture through shared memory
   __shared__ uint32_t sCap[SMEM_CAP ? WARPS_PER_CTA : 1][SMEM_CAP ? 32 : 1][RT];
 
   const int      lane    = threadIdx.x & 31;
