@@ -1451,12 +1451,11 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
   // are fine-grained where contigs live: 130..400 bases)
   constexpr int NCLS = 7;
   static const int RTS[NCLS] = {4, 6, 8, 9, 10, 12, 16};
-  // 2-byte cells (large-indel): odd strips cost more in registers and narrow stores than they save in padding
-  // (measured), so only the multiples of 4 are used there
-  static const bool USE2[NCLS] = {true, false, true, false, false, true, true};
+  // (an earlier version kept the 2-byte kind on multiples of 4 only; with the classes running concurrently the finer
+  // strips pay there too: -9 % large-indel time on the config-2 contig lengths, padding waste 1.30 -> 1.12)
   auto classOf = [](uint32_t Q) {
     for (int c = 0; c < NCLS - 1; ++c)
-      if ((KindTraits<KIND>::CELLB == 1 || USE2[c]) && Q <= (uint32_t)(32 * RTS[c])) return c;
+      if (Q <= (uint32_t)(32 * RTS[c])) return c;
     return NCLS - 1;
   };
   // Order of work: class, then (jump) R1 descending so that pair members share it, then cost descending.  This runs on
