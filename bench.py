@@ -280,16 +280,17 @@ def main():
         _keep.append(t)
     cuts = cb.default_ref_cuts(batch.nLoci) if refine else None
 
+    gather_state = {}
+
     def gather_results(out):
         if dist is None:
             return
         # the single collective of the path: per-GPU result buffers to rank 0 over NVLink
         from manta_b200 import shard
-        parts = [out["aln"].view(np.uint8).reshape(-1), out["jump"].view(np.uint8).reshape(-1)]
+        parts = [out["aln"], out["jump"]]
         if refine:
-            parts += [out["qc"].view(np.uint8).reshape(-1), out["best"].view(np.uint8).reshape(-1)]
-        buf = np.concatenate(parts)
-        shard.gather_buffers(buf, dst=0, device="cuda:%d" % local_rank)
+            parts += [out["qc"], out["best"]]
+        shard.gather_buffers(parts, dst=0, device="cuda:%d" % local_rank, state=gather_state)
 
     def sync_all():
         torch.cuda.synchronize()

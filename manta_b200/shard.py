@@ -39,23 +39,50 @@ def assign_edges(observation_counts: Sequence[int], bin_count: int, rank: int, w
     return np.nonzero(mine)[0]
 
 
-def gather_buffers(buf: np.ndarray, dst: int = 0, device: Optional[str] = None) -> Optional[List[np.ndarray]]:
-    """gather one uint8 buffer per rank to `dst` (None elsewhere) with torch.distributed (nccl or gloo)"""
+def gather_buffers(buf, dst: int = 0, device: Optional[str] = None, state: Optional[dict] = None):
+    """Gather one byte buffer per rank to `dst` with torch.distributed (nccl or gloo).
+
+    `buf` is one array or a sequence of arrays (concatenated on the fly, no host-side copy of the whole buffer).
+    Returns on `dst` a list with one uint8 array per rank (views into a receive buffer that the next call with the
+    same `state` overwrites), None elsewhere.  `state` (a dict the caller keeps) caches the staging tensors between
+    calls: device staging on every rank, pinned receive buffer on `dst`."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = torch.device(device) if device else torch.device("cpu")
-    flat = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
-    n = torch.tensor([flat.size], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(sizes) if sizes else 0
-    padded = torch.zeros(max(mx, 1), dtype=torch.uint8, device=dev)
-    if flat.size:
-        padded[:flat.size] = torch.from_numpy(flat.copy()).to(dev)
-    out = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
-    dist.gather(padded, out, dst=dst)
+    on_gpu = dev.type == "cuda"
+    parts = [buf] if isinstance(buf, np.ndarray) else list(buf)
+    flats = [np.ascontiguousarray(p).view(np.uint8).reshape(-1) for p in parts]
+    total = int(sum(f.size for f in flats))
+    st = state if state is not None else {}
+    # lengths first (they may differ per rank and per call), one small collective and one host sync
+    mine = torch.tensor([total], dtype=torch.int64, device=dev)
+    allsz = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allsz, mine)
+    sizes = [int(x) for x in allsz.cpu().tolist()]
+    mx = max(max(sizes), 1)
+    if st.get("cap", 0) < mx:
+        cap = mx + mx // 8
+        st["cap"] = cap
+        st["stage"] = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        if rank == dst:
+            st["recv"] = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+            st["host"] = torch.empty((world, cap), dtype=torch.uint8, pin_memory=on_gpu)
+    stage = st["stage"]
+    o = 0
+    for f in flats:
+        if f.size:
+            stage[o:o + f.size].copy_(torch.from_numpy(f), non_blocking=True)
+            o += f.size
+    send = stage[:mx]
+    out = [r[:mx] for r in st["recv"]] if rank == dst else None
+    dist.gather(send, out, dst=dst)
     if rank != dst:
         return None
-    return [o[:sizes[i]].cpu().numpy() for i, o in enumerate(out)]
+    host = st["host"]
+    for i in range(world):
+        if sizes[i]:
+            host[i, :sizes[i]].copy_(out[i][:sizes[i]], non_blocking=True)
+    if on_gpu:
+        torch.cuda.current_stream(dev).synchronize()
+    return [host[i, :sizes[i]].numpy() for i in range(world)]

@@ -27,8 +27,17 @@ def _worker(rank, world, port, counts, ret):
     # a per-rank "result buffer" whose length depends on the shard
     buf = np.repeat(mine.astype(np.uint32), 3).view(np.uint8)
     got = shard.gather_buffers(buf, dst=0)
+    first = [g.view(np.uint32)[::3].tolist() for g in got] if rank == 0 else None
+    # the same payload as a sequence of arrays with cached staging buffers, twice (second call: a longer buffer)
+    state = {}
+    half = len(buf) // 2
+    got2 = shard.gather_buffers([buf[:half], buf[half:]], dst=0, state=state)
+    again = [g.copy().view(np.uint32)[::3].tolist() for g in got2] if rank == 0 else None
+    got3 = shard.gather_buffers([buf, buf], dst=0, state=state)
     if rank == 0:
-        ret.put([g.view(np.uint32)[::3].tolist() for g in got])
+        assert again == first
+        assert [g.view(np.uint32)[::3].tolist() for g in got3] == [f + f for f in first]
+        ret.put(first)
     dist.barrier()
     dist.destroy_process_group()
 
