@@ -310,10 +310,17 @@ def main():
     t0 = time.perf_counter()
     ev_ms, stage = 0.0, dict(asmMs=0.0, indelMs=0.0, jumpMs=0.0, trimMs=0.0, qcMs=0.0)
     launches = 0
+    trace = os.environ.get("MB200_BENCH_TRACE")
     for _ in range(args.steps):
+        ta = time.perf_counter()
         out = ctx.candidates_run(opts, out, select=refine, zeros=pinned_zeros)
+        tb = time.perf_counter()
         gather_results(out)
+        tc = time.perf_counter()
         t = ctx.candidates_timing()
+        if trace:
+            print("[bench trace] rank %d: run %.1f ms (device %.1f), gather %.1f ms" % (rank, 1e3 * (tb - ta), t["totalMs"], 1e3 * (tc - tb)),
+                  file=sys.stderr, flush=True)
         ev_ms += t["totalMs"]
         launches += t["launches"]
         for k in stage:

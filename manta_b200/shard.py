@@ -78,6 +78,10 @@ def gather_buffers(buf, dst: int = 0, device: Optional[str] = None, state: Optio
     out = [r[:mx] for r in st["recv"]] if rank == dst else None
     dist.gather(send, out, dst=dst)
     if rank != dst:
+        # wait for the send: the next step's persistent kernels would otherwise occupy every SM and keep the
+        # collective's own kernel (and with it the receiving rank) waiting until they finish
+        if on_gpu:
+            torch.cuda.current_stream(dev).synchronize()
         return None
     host = st["host"]
     for i in range(world):
