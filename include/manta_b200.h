@@ -63,7 +63,9 @@ enum {
   MB200_ERR_BAD_ARG       = 12,
   MB200_ERR_BAD_BASE      = 13, /* assembler input byte outside {A,C,G,T,N} (documented restriction) */
   MB200_ERR_ASM_OVERFLOW  = 14, /* assembler workspace cap exceeded for some locus */
-  MB200_ERR_UNSUPPORTED   = 15
+  MB200_ERR_UNSUPPORTED   = 15,
+  MB200_ERR_SV_RANGE      = 16  /* "Attempting to convert alignment to sv candidate": cipos of a precise variant does
+                                   not start at 0                            GSC/SVCandidateAssemblyRefiner.cpp:768 */
 };
 
 /* ---- alignment path segment types == ALIGNPATH::align_t -------------------------------- */
@@ -318,6 +320,36 @@ MB200_API int mb200_select_contigs_batch(mb200_ctx* ctx, const mb200_qc_opts* op
                                          uint64_t poolBytes, const mb200_seqview* contigSeq, const mb200_seqview* ref1,
                                          const uint32_t* supportCount, mb200_contig_qc* qc, int32_t* best);
 
+/* One refined small SV per kept candidate segment of the selected contig of a complex candidate: the arithmetic of
+ * setSmallCandSV (GSC/SVCandidateAssemblyRefiner.cpp:720-800, called per segment at :2243-2251) with getVariantRange
+ * (:677-717).  Coordinates are offsets into the candidate's ref1 window (the reference adds ref.get_offset()).
+ *   sv.bp1.interval.range = [bp1Begin, bp1End), state RIGHT_OPEN ; sv.bp2.interval.range = [bp2Begin, bp2End), LEFT_OPEN
+ *   sv.insertSeq          = contig[readBegin, readEnd)  ; sv.insertAlignment = apath[pathFirst .. pathLast]
+ *   sv.assemblyAlignIndex = contig ; sv.assemblySegmentIndex = segment
+ * status == MB200_ERR_SV_RANGE where the reference throws (cipos.begin_pos() != 0, :768); the record then still holds
+ * the ranges and cipos, the breakend fields are zero. */
+typedef struct mb200_small_sv {
+  uint32_t locus;
+  uint32_t contig;
+  uint32_t segment;
+  int32_t  status;
+  uint32_t pathFirst, pathLast;
+  int32_t  refBegin, refEnd;
+  int32_t  readBegin, readEnd;
+  int32_t  ciposBegin, ciposEnd;
+  int32_t  bp1Begin, bp1End, bp2Begin, bp2End;
+} mb200_small_sv;
+
+/* Inputs as mb200_select_contigs_batch plus its outputs qc / best.  svFirst[nLoci + 1]: records of candidate i are
+ * svs[svFirst[i] .. svFirst[i+1]) in segment order (none for spanning candidates or best[i] < 0).
+ * MB200_ERR_POOL_OVERFLOW if svCap is too small (*svUsed = records needed). */
+MB200_API int mb200_small_sv_batch(mb200_ctx* ctx, uint32_t minCandidateVariantSize, uint32_t nLoci, const uint8_t* isJump,
+                                   const uint32_t* slotFirst, uint32_t nSlots, const int32_t* best,
+                                   const mb200_contig_qc* qc, const mb200_aln_result* aln, const uint32_t* cigarPool,
+                                   uint64_t cigarLen, const uint8_t* pool, uint64_t poolBytes,
+                                   const mb200_seqview* contigSeq, const mb200_seqview* ref1, uint32_t* svFirst,
+                                   mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed);
+
 /* ---- fused candidate path -------------------------------------------------------------------------
  * "one candidate" = one SVCandidate junction entering getCandidateAssemblyData (GSC/SVCandidateProcessor.cpp:310):
  * its read set is assembled (all word lengths) and EVERY resulting contig is aligned
@@ -365,6 +397,10 @@ MB200_API int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* o
                                    mb200_jump_result* jumpResults, uint32_t* cigarPool, uint64_t cigarCap,
                                    uint64_t* cigarUsed, mb200_trim_result* trim, mb200_contig_qc* qc, int32_t* best);
 MB200_API int mb200_candidates_timing(const mb200_ctx* ctx, mb200_candidate_timing* out);
+/* refined small SVs (mb200_small_sv_batch) of the batch the last mb200_candidates_run with qc/best worked on, computed
+ * on the still-resident alignments */
+MB200_API int mb200_candidates_small_svs(mb200_ctx* ctx, uint32_t* svFirst, mb200_small_sv* svs, uint64_t svCap,
+                                         uint64_t* svUsed);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ MB200_ERR_BAD_ARG = 12
 MB200_ERR_BAD_BASE = 13
 MB200_ERR_ASM_OVERFLOW = 14
 MB200_ERR_UNSUPPORTED = 15
+MB200_ERR_SV_RANGE = 16
 
 # messages the reference throws for the same conditions (GlobalJumpAlignerImpl.hpp:50-58 etc.)
 ERROR_MESSAGES = {
@@ -93,6 +94,11 @@ QC_OPTS_DT = np.dtype([("filterScores", "<i4", (6,)), ("minCandidateVariantSize"
 CONTIG_QC_DT = np.dtype([("isCandidate", "<u4"), ("isLowQuality", "<u4"), ("segOrdinal", "<u4"), ("nSegments", "<u4"),
                          ("pathFirst", "<u4"), ("pathLast", "<u4"), ("variantSize", "<u4"), ("reserved", "<u4")],
                         align=True)
+SMALL_SV_DT = np.dtype([("locus", "<u4"), ("contig", "<u4"), ("segment", "<u4"), ("status", "<i4"), ("pathFirst", "<u4"),
+                        ("pathLast", "<u4"), ("refBegin", "<i4"), ("refEnd", "<i4"), ("readBegin", "<i4"), ("readEnd", "<i4"),
+                        ("ciposBegin", "<i4"), ("ciposEnd", "<i4"), ("bp1Begin", "<i4"), ("bp1End", "<i4"), ("bp2Begin", "<i4"),
+                        ("bp2End", "<i4")], align=True)
+assert SMALL_SV_DT.itemsize == 64
 CAND_OPTS_DT = np.dtype([("asmOpts", ASM_OPTS_DT), ("indelScores", "<i4", (6,)), ("largeIndelScore", "<i4"),
                          ("jumpScores", "<i4", (6,)), ("jumpScore", "<i4"), ("qcOpts", QC_OPTS_DT)], align=True)
 CAND_TIMING_DT = np.dtype([("h2dMs", "<f4"), ("asmMs", "<f4"), ("indelMs", "<f4"), ("jumpMs", "<f4"), ("d2hMs", "<f4"),
@@ -385,6 +391,49 @@ class Binding:
         if st != MB200_OK:
             self._raise(st)
         return qc, best
+
+    def small_sv_raw(self, minSize: int, isJump: np.ndarray, slotFirst: np.ndarray, best: np.ndarray, qc: np.ndarray,
+                     aln: np.ndarray, cigar: np.ndarray, pool: np.ndarray, contigSeq: np.ndarray, ref1: np.ndarray):
+        """refined small SVs of the selected contigs; returns (svFirst[nLoci+1], records)"""
+        nLoci, nSlots = len(isJump), len(contigSeq)
+        svFirst = np.zeros(nLoci + 1, dtype=np.uint32)
+        cap = max(16, nLoci)
+        for _ in range(4):
+            svs = np.zeros(cap, dtype=SMALL_SV_DT)
+            used = C.c_uint64(0)
+            args = [C.c_uint32(minSize), C.c_uint32(nLoci), _ptr(isJump), _ptr(slotFirst), C.c_uint32(nSlots), _ptr(best),
+                    _ptr(qc), _ptr(aln), _ptr(cigar)]
+            if self.ctx is not None:
+                args.append(C.c_uint64(cigar.size))
+            args.append(_ptr(pool))
+            if self.ctx is not None:
+                args.append(C.c_uint64(pool.size))
+            st = self._call("small_sv_batch", *args, _ptr(contigSeq), _ptr(ref1), _ptr(svFirst), _ptr(svs), C.c_uint64(cap),
+                            C.byref(used))
+            if st == MB200_ERR_POOL_OVERFLOW:
+                cap = int(used.value) + 16
+                continue
+            if st != MB200_OK:
+                self._raise(st)
+            return svFirst, svs[:int(used.value)]
+        raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "small SV record overflow")
+
+    def candidates_small_svs(self):
+        """refined small SVs of the last fused run (product library only)"""
+        nLoci = self._cand_shape[0]
+        svFirst = np.zeros(nLoci + 1, dtype=np.uint32)
+        cap = max(16, nLoci)
+        for _ in range(4):
+            svs = np.zeros(cap, dtype=SMALL_SV_DT)
+            used = C.c_uint64(0)
+            st = self._call("candidates_small_svs", _ptr(svFirst), _ptr(svs), C.c_uint64(cap), C.byref(used))
+            if st == MB200_ERR_POOL_OVERFLOW:
+                cap = int(used.value) + 16
+                continue
+            if st != MB200_OK:
+                self._raise(st)
+            return svFirst, svs[:int(used.value)]
+        raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "small SV record overflow")
 
     # -- fused candidate path (product library only) -----------------------------------------
     def candidates_upload(self, batch, cuts: Optional[np.ndarray] = None) -> None:

@@ -1251,6 +1251,7 @@ extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, 
   if (!opts || (nLoci && (!readOff || !loci || !contigs || !pseudoReads || !contigPool || !setPool)))
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
   ctx->timing = mb200_timing();
+  ctx->candSv.valid = false;  // shares device buffers with the fused path's resident results
   if (nLoci == 0) return MB200_OK;
   const uint32_t A = opts->maxAssemblyCount;
   if (A < 1 || A > 16) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "maxAssemblyCount outside [1,16]");

@@ -112,6 +112,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   T                         = mb200_candidate_timing();
   T.h2dBytes                = c.h2dBytes;
   ctx->timing               = mb200_timing();
+  ctx->candSv.valid         = false;
   MB200_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, c.upEnd, 0));  // the batch's own upload
 
   int rc;
@@ -313,9 +314,47 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   cudaEventElapsedTime(&T.d2hMs, ctx->cevX[1], ctx->cev[0]);
   cudaEventElapsedTime(&T.totalMs, ctx->cev[2], ctx->cev[0]);
   T.launches = ctx->timing.launches;
+  if (doSelect) {
+    ctx->candSv.valid   = true;
+    ctx->candSv.slot    = C.cur;
+    ctx->candSv.nLoci   = nLoci;
+    ctx->candSv.minSize = opts->qcOpts.minCandidateVariantSize;
+  }
   T.d2hBytes = sizeof(mb200_asm_locus) * (uint64_t)nLoci + (sizeof(mb200_contig) + sizeof(mb200_aln_result) + sizeof(mb200_jump_result) + 2 * sizeof(mb200_seqview)) * (uint64_t)nSlots +
                usedBytes + 4 * usedSets + 4 * usedCig + (doTrim ? sizeof(mb200_trim_result) * (uint64_t)nSlots : 0) +
                (doSelect ? sizeof(mb200_contig_qc) * (uint64_t)nSlots + 4 * (uint64_t)nLoci : 0);
+  return MB200_OK;
+}
+
+int mb200_candidates_small_svs(mb200_ctx* ctx, uint32_t* svFirst, mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (!svFirst || !svUsed || (svCap && !svs)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  *svUsed = 0;
+  if (!ctx->candSv.valid || ctx->candSv.slot != ctx->cand.cur)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "no fused run with contig selection to refine (run mb200_candidates_run with qc/best first)");
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  auto&          c     = ctx->cand.slot[ctx->candSv.slot];
+  const uint32_t nLoci = ctx->candSv.nLoci;
+  int            rc;
+  if ((rc = mb200_reserve(ctx, ctx->dSvFirst, 4 * (size_t)(nLoci + 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dSvs, sizeof(mb200_small_sv) * (size_t)(svCap ? svCap : 1))) != MB200_OK) return rc;
+  const uint8_t* dPool       = reinterpret_cast<const uint8_t*>(c.dPool.ptr) + MB200_POOL_FRONT;
+  const uint8_t* dContigPool = reinterpret_cast<const uint8_t*>(ctx->dAsmOut3.ptr) + MB200_POOL_FRONT;
+  rc = mb200_small_sv_run(ctx, ctx->candSv.minSize, nLoci, reinterpret_cast<const uint8_t*>(c.dIsJump.ptr),
+                          reinterpret_cast<const uint32_t*>(ctx->dQcSlotFirst.ptr), reinterpret_cast<const int32_t*>(ctx->dQcBest.ptr),
+                          reinterpret_cast<const mb200_contig_qc*>(ctx->dQc.ptr), reinterpret_cast<const mb200_aln_result*>(ctx->dAln.ptr),
+                          reinterpret_cast<const uint32_t*>(ctx->dCigar.ptr), dContigPool,
+                          reinterpret_cast<const mb200_seqview*>(ctx->dQcViews.ptr), dPool, reinterpret_cast<const mb200_seqview*>(c.dRef1.ptr),
+                          reinterpret_cast<uint32_t*>(ctx->dSvFirst.ptr), reinterpret_cast<mb200_small_sv*>(ctx->dSvs.ptr), svCap);
+  if (rc != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(svFirst, ctx->dSvFirst.ptr, 4 * (size_t)(nLoci + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint64_t used = svFirst[nLoci];
+  *svUsed             = used;
+  if (used > svCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "small SV record array too small");
+  if (used) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(svs, ctx->dSvs.ptr, sizeof(mb200_small_sv) * (size_t)used, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return MB200_OK;
 }
 

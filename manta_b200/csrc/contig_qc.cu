@@ -521,6 +521,127 @@ __global__ void applyTrimKernel(uint32_t nSlots, const uint32_t* slotLocus, cons
   aln[slot].beginPos += trim[slot].adjLeadingCut;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// refined small SVs: setSmallCandSV (:720-800) over the kept segments of the selected contig (:2243-2251)
+struct SvParams {
+  uint32_t                nLoci, minSize;
+  const uint8_t*          isJump;
+  const uint32_t*         slotFirst;
+  const int32_t*          best;
+  const mb200_contig_qc*  qc;
+  const mb200_aln_result* aln;
+  const uint32_t*         cigar;
+  const uint8_t*          contigPool;
+  const mb200_seqview*    contigView;
+  const uint8_t*          refPool;
+  const mb200_seqview*    ref1;
+  uint32_t*               svFirst;  // [nLoci + 1]
+  mb200_small_sv*         svs;
+  unsigned long long      svCap;
+};
+
+// svFirst = exclusive prefix sum of the per-candidate record counts (one CTA; the counts are tiny)
+__global__ void __launch_bounds__(1024) svOffsetsKernel(const SvParams P)
+{
+  __shared__ uint32_t sSum[1024];
+  const uint32_t      tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t      per = (P.nLoci + nt - 1) / nt;
+  const uint32_t      lo = min(P.nLoci, tid * per), hi = min(P.nLoci, lo + per);
+  auto count = [&](uint32_t li) -> uint32_t {
+    if (P.isJump[li] || P.best[li] < 0) return 0u;
+    return P.qc[P.slotFirst[li] + (uint32_t)P.best[li]].nSegments;
+  };
+  uint32_t mine = 0;
+  for (uint32_t li = lo; li < hi; ++li) mine += count(li);
+  sSum[tid] = mine;
+  __syncthreads();
+  for (uint32_t d = 1; d < nt; d <<= 1) {
+    const uint32_t v = (tid >= d) ? sSum[tid - d] : 0u;
+    __syncthreads();
+    sSum[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = sSum[tid] - mine;
+  for (uint32_t li = lo; li < hi; ++li) {
+    P.svFirst[li] = run;
+    run += count(li);
+  }
+  if (tid == nt - 1) P.svFirst[P.nLoci] = sSum[tid];
+}
+
+__global__ void __launch_bounds__(QC_WARPS * 32) smallSvKernel(const SvParams P)
+{
+  const int      lane  = threadIdx.x & 31;
+  const uint32_t gwarp = blockIdx.x * QC_WARPS + (threadIdx.x >> 5);
+  const uint32_t nwarp = gridDim.x * QC_WARPS;
+  for (uint32_t li = gwarp; li < P.nLoci; li += nwarp) {
+    if (P.isJump[li] || P.best[li] < 0) continue;
+    const uint32_t         s    = P.slotFirst[li] + (uint32_t)P.best[li];
+    const mb200_contig_qc  q    = P.qc[s];
+    const mb200_aln_result r    = P.aln[s];
+    const uint32_t*        path = P.cigar + r.cigarOff;
+    const uint32_t         n    = r.cigarLen;
+    const uint8_t*         read = P.contigPool + P.contigView[s].off;
+    const int64_t          readLen = P.contigView[s].len;
+    const uint8_t*         ref  = P.refPool + P.ref1[li].off;
+    const int64_t          refLen = P.ref1[li].len;
+    // skip to the first kept candidate run
+    uint32_t f = 0, l = 0, from = 0;
+    bool     ok = true;
+    for (uint32_t k = 0; k <= q.segOrdinal && ok; ++k) {
+      ok   = nextRun(path, n, from, P.minSize, f, l);
+      from = l + 1;
+    }
+    for (uint32_t k = 0; k < q.nSegments && ok; ++k) {
+      mb200_small_sv v;
+      memset(&v, 0, sizeof(v));
+      v.locus = li; v.contig = (uint32_t)P.best[li]; v.segment = k; v.pathFirst = f; v.pathLast = l;
+      int32_t readPos = 0, refPos = r.beginPos;
+      for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t t = MB200_SEG_TYPE(path[i]), len = MB200_SEG_LEN(path[i]);
+        if (i == f) { v.refBegin = refPos; v.readBegin = readPos; }
+        if (segIsRef(t)) refPos += (int32_t)len;
+        if (segIsRead(t)) readPos += (int32_t)len;
+        if (i == l) { v.refEnd = refPos; v.readEnd = readPos; }
+      }
+      // getVariantRange (:677-717): lanes compare 32 positions per round
+      const int64_t maxRight = min(refLen - v.refEnd, readLen - v.readEnd);
+      int32_t       right = (int32_t)max((int64_t)0, maxRight);
+      for (int64_t base = 0; base < maxRight; base += 32) {
+        const int64_t  o    = base + lane;
+        const bool     stop = (o >= maxRight) || (ref[v.refBegin + o] != read[v.readBegin + o]);
+        const uint32_t b    = __ballot_sync(0xffffffffu, stop);
+        if (b) { right = (int32_t)(base + (__ffs(b) - 1)); break; }
+      }
+      const int32_t minLeft = max(-v.refBegin, -v.readBegin);
+      int32_t       left    = 0;
+      for (int32_t base = 0;; base += 32) {
+        const int32_t j  = base + lane;  // candidate offset -j
+        const int32_t ri = v.refEnd - j - 1, qi = v.readEnd - j - 1;
+        const bool    stop = (-j < minLeft) || ri < 0 || qi < 0 || (ref[ri] != read[qi]);
+        const uint32_t b   = __ballot_sync(0xffffffffu, stop);
+        if (b) { left = -(base + (__ffs(b) - 1)); break; }
+      }
+      v.ciposBegin = left;
+      v.ciposEnd   = right;
+      if (left != 0) v.status = MB200_ERR_SV_RANGE;
+      else {
+        v.bp1Begin = v.refBegin - 1;
+        v.bp1End   = v.bp1Begin + right + 1;
+        v.bp2Begin = v.refEnd;
+        v.bp2End   = v.bp2Begin + right + 1;
+      }
+      const unsigned long long at = (unsigned long long)P.svFirst[li] + k;
+      if (lane == 0 && at < P.svCap) P.svs[at] = v;
+      if (k + 1 < q.nSegments) {
+        ok   = nextRun(path, n, from, P.minSize, f, l);
+        from = l + 1;
+      }
+    }
+  }
+}
+
 int gridFor(const mb200_ctx* ctx, uint32_t nItems)
 {
   const uint32_t want = (nItems + QC_WARPS - 1) / QC_WARPS;
@@ -609,6 +730,25 @@ int mb200_qc_run(mb200_ctx* ctx, const mb200_qc_opts* opts, uint32_t nLoci, uint
   return MB200_OK;
 }
 
+int mb200_small_sv_run(mb200_ctx* ctx, uint32_t minSize, uint32_t nLoci, const uint8_t* dIsJump, const uint32_t* dSlotFirst,
+                       const int32_t* dBest, const mb200_contig_qc* dQc, const mb200_aln_result* dAln, const uint32_t* dCigar,
+                       const uint8_t* dContigPool, const mb200_seqview* dContigView, const uint8_t* dRefPool,
+                       const mb200_seqview* dRef1, uint32_t* dSvFirst, mb200_small_sv* dSvs, uint64_t svCap)
+{
+  if (nLoci == 0) return MB200_OK;
+  SvParams P;
+  memset(&P, 0, sizeof(P));
+  P.nLoci = nLoci; P.minSize = minSize; P.isJump = dIsJump; P.slotFirst = dSlotFirst; P.best = dBest; P.qc = dQc; P.aln = dAln;
+  P.cigar = dCigar; P.contigPool = dContigPool; P.contigView = dContigView; P.refPool = dRefPool; P.ref1 = dRef1;
+  P.svFirst = dSvFirst; P.svs = dSvs; P.svCap = svCap;
+  svOffsetsKernel<<<1, 1024, 0, ctx->stream>>>(P);
+  MB200_CUDA_CHECK(ctx, cudaGetLastError());
+  smallSvKernel<<<gridFor(ctx, nLoci), QC_WARPS * 32, 0, ctx->stream>>>(P);
+  MB200_CUDA_CHECK(ctx, cudaGetLastError());
+  ctx->timing.launches += 2;
+  return MB200_OK;
+}
+
 // ---- host-pointer C ABI ------------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -629,6 +769,7 @@ int mb200_ref_trim_batch(mb200_ctx* ctx, uint32_t n, const uint8_t* pool, uint64
   if (maxLen >= EMPTY16) return mb200_fail(ctx, MB200_ERR_UNSUPPORTED, "contig longer than 65534 bases");
   MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   ctx->timing = mb200_timing();
+  ctx->candSv.valid = false;  // shares device buffers with the fused path's resident results
   int rc;
   if ((rc = mb200_reserve(ctx, ctx->dPool, poolBytes + 64)) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, ctx->dQcViews, sizeof(mb200_seqview) * (size_t)n)) != MB200_OK) return rc;
@@ -697,6 +838,7 @@ int mb200_select_contigs_batch(mb200_ctx* ctx, const mb200_qc_opts* opts, uint32
   }
   MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   ctx->timing = mb200_timing();
+  ctx->candSv.valid = false;  // shares device buffers with the fused path's resident results
   int          rc;
   const size_t ns = nSlots ? nSlots : 1;
   if ((rc = mb200_reserve(ctx, ctx->dPool, poolBytes + 64)) != MB200_OK) return rc;
@@ -741,6 +883,89 @@ int mb200_select_contigs_batch(mb200_ctx* ctx, const mb200_qc_opts* opts, uint32
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
   if (nSlots) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(qc, ctx->dQc.ptr, sizeof(mb200_contig_qc) * (size_t)nSlots, cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(best, ctx->dQcBest.ptr, 4 * (size_t)nLoci, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->timing.h2dMs, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->timing.kernelMs, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->timing.d2hMs, ctx->ev[2], ctx->ev[3]);
+  return MB200_OK;
+}
+
+int mb200_small_sv_batch(mb200_ctx* ctx, uint32_t minCandidateVariantSize, uint32_t nLoci, const uint8_t* isJump,
+                         const uint32_t* slotFirst, uint32_t nSlots, const int32_t* best, const mb200_contig_qc* qc,
+                         const mb200_aln_result* aln, const uint32_t* cigarPool, uint64_t cigarLen, const uint8_t* pool,
+                         uint64_t poolBytes, const mb200_seqview* contigSeq, const mb200_seqview* ref1, uint32_t* svFirst,
+                         mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (!svFirst || !svUsed) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  *svUsed = 0;
+  if (nLoci == 0) { svFirst[0] = 0; return MB200_OK; }
+  if (!isJump || !slotFirst || !best || !ref1 || !pool || (svCap && !svs)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  if (nSlots && (!qc || !aln || !cigarPool || !contigSeq)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  for (uint32_t li = 0; li < nLoci; ++li) {
+    if (ref1[li].off + ref1[li].len > poolBytes) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "view outside the pool");
+    if (isJump[li] || best[li] < 0) continue;
+    const uint64_t s = (uint64_t)slotFirst[li] + (uint32_t)best[li];
+    if (s >= nSlots) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "best contig outside the result arrays");
+    if (aln[s].cigarOff + aln[s].cigarLen > cigarLen) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "path outside the cigar pool");
+    if (contigSeq[s].off + contigSeq[s].len > poolBytes) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "view outside the pool");
+    if (aln[s].beginPos < 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "negative beginPos");
+    uint64_t span = 0, rd = 0;
+    for (uint32_t i = 0; i < aln[s].cigarLen; ++i) {
+      const uint32_t seg = cigarPool[aln[s].cigarOff + i], t = MB200_SEG_TYPE(seg);
+      if (t == MB200_SEG_MATCH || t == MB200_SEG_DELETE || t == MB200_SEG_SKIP || t == MB200_SEG_SEQ_MATCH || t == MB200_SEG_SEQ_MISMATCH) span += MB200_SEG_LEN(seg);
+      if (t == MB200_SEG_MATCH || t == MB200_SEG_INSERT || t == MB200_SEG_SOFT_CLIP || t == MB200_SEG_SEQ_MATCH || t == MB200_SEG_SEQ_MISMATCH) rd += MB200_SEG_LEN(seg);
+    }
+    if ((uint64_t)aln[s].beginPos + span > ref1[li].len) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "alignment runs past the end of ref1");
+    if (rd > contigSeq[s].len) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "alignment path longer than the contig");
+  }
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  ctx->timing = mb200_timing();
+  ctx->candSv.valid = false;  // shares device buffers with the fused path's resident results
+  int          rc;
+  const size_t ns = nSlots ? nSlots : 1;
+  if ((rc = mb200_reserve(ctx, ctx->dPool, poolBytes + 64)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dCigar, 4 * (size_t)(cigarLen ? cigarLen : 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dAln, sizeof(mb200_aln_result) * ns)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcViews, sizeof(mb200_seqview) * ns)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcRef, sizeof(mb200_seqview) * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcSlotFirst, 4 * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcIsJump, (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQc, sizeof(mb200_contig_qc) * ns)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcBest, 4 * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dSvFirst, 4 * (size_t)(nLoci + 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dSvs, sizeof(mb200_small_sv) * (size_t)(svCap ? svCap : 1))) != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+#define MB200_UP(buf, src, bytes) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync((buf).ptr, (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
+  MB200_UP(ctx->dPool, pool, poolBytes);
+  if (cigarLen) MB200_UP(ctx->dCigar, cigarPool, 4 * (size_t)cigarLen);
+  if (nSlots) {
+    MB200_UP(ctx->dAln, aln, sizeof(mb200_aln_result) * (size_t)nSlots);
+    MB200_UP(ctx->dQcViews, contigSeq, sizeof(mb200_seqview) * (size_t)nSlots);
+    MB200_UP(ctx->dQc, qc, sizeof(mb200_contig_qc) * (size_t)nSlots);
+  }
+  MB200_UP(ctx->dQcRef, ref1, sizeof(mb200_seqview) * (size_t)nLoci);
+  MB200_UP(ctx->dQcSlotFirst, slotFirst, 4 * (size_t)nLoci);
+  MB200_UP(ctx->dQcIsJump, isJump, (size_t)nLoci);
+  MB200_UP(ctx->dQcBest, best, 4 * (size_t)nLoci);
+#undef MB200_UP
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  const uint8_t* dp = reinterpret_cast<const uint8_t*>(ctx->dPool.ptr);
+  rc = mb200_small_sv_run(ctx, minCandidateVariantSize, nLoci, reinterpret_cast<const uint8_t*>(ctx->dQcIsJump.ptr),
+                          reinterpret_cast<const uint32_t*>(ctx->dQcSlotFirst.ptr), reinterpret_cast<const int32_t*>(ctx->dQcBest.ptr),
+                          reinterpret_cast<const mb200_contig_qc*>(ctx->dQc.ptr), reinterpret_cast<const mb200_aln_result*>(ctx->dAln.ptr),
+                          reinterpret_cast<const uint32_t*>(ctx->dCigar.ptr), dp, reinterpret_cast<const mb200_seqview*>(ctx->dQcViews.ptr), dp,
+                          reinterpret_cast<const mb200_seqview*>(ctx->dQcRef.ptr), reinterpret_cast<uint32_t*>(ctx->dSvFirst.ptr),
+                          reinterpret_cast<mb200_small_sv*>(ctx->dSvs.ptr), svCap);
+  if (rc != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(svFirst, ctx->dSvFirst.ptr, 4 * (size_t)(nLoci + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint64_t used = svFirst[nLoci];
+  *svUsed             = used;
+  if (used > svCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "small SV record array too small");
+  if (used) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(svs, ctx->dSvs.ptr, sizeof(mb200_small_sv) * (size_t)used, cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   cudaEventElapsedTime(&ctx->timing.h2dMs, ctx->ev[0], ctx->ev[1]);

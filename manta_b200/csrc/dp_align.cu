@@ -25,6 +25,7 @@ int alignBatch(mb200_ctx* ctx, const mb200_scores* scores, int extra, uint32_t n
   if (KIND == KIND_JUMP && scores->isAllowEdgeInsertion)
     return mb200_fail(ctx, MB200_ERR_BAD_ARG, "GlobalJumpAligner does not support isAllowEdgeInsertion (GlobalJumpAligner.hpp:41)");
   ctx->timing = mb200_timing();
+  ctx->candSv.valid = false;  // shares device buffers with the fused path's resident results
   *cigarUsed  = 0;
   if (n == 0) return MB200_OK;
   MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));

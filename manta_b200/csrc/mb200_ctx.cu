@@ -166,7 +166,7 @@ void mb200_destroy(mb200_ctx* ctx)
                           &ctx->dAsmWork, &ctx->dAsmOut0, &ctx->dAsmOut1, &ctx->dAsmOut2, &ctx->dAsmOut3,
                           &ctx->dAsmOut4, &ctx->dViews,   &ctx->dReadOff, &ctx->dAln, &ctx->dJump,
                           &ctx->dQcScratch, &ctx->dQcSupport, &ctx->dQcSlotLocus, &ctx->dQcSlotFirst, &ctx->dQcNContigs,
-                          &ctx->dQcViews, &ctx->dQcRef, &ctx->dQcCuts, &ctx->dQcTrim, &ctx->dQcIsJump, &ctx->dQc, &ctx->dQcBest};
+                          &ctx->dQcViews, &ctx->dQcRef, &ctx->dQcCuts, &ctx->dQcTrim, &ctx->dQcIsJump, &ctx->dQc, &ctx->dQcBest, &ctx->dSvFirst, &ctx->dSvs};
   for (DeviceBuffer* b : bufs)
     if (b->ptr) cudaFree(b->ptr);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);

@@ -69,7 +69,13 @@ struct mb200_ctx {
   DeviceBuffer           dAln, dJump;
   // reference-window trim / contig QC + selection (contig_qc.cu)
   DeviceBuffer dQcScratch, dQcSupport, dQcSlotLocus, dQcSlotFirst, dQcNContigs, dQcViews, dQcRef, dQcCuts, dQcTrim, dQcIsJump,
-      dQc, dQcBest;
+      dQc, dQcBest, dSvFirst, dSvs;
+  // what mb200_candidates_small_svs needs to know about the last fused run
+  struct {
+    bool     valid = false;
+    int      slot = -1;
+    uint32_t nLoci = 0, minSize = 0;
+  } candSv;
   // DP row classes run concurrently on their own streams with their own scratch (hides the per-launch tail)
   static constexpr int   kDpClasses = 8;
   cudaStream_t           dpStream[kDpClasses] = {};
@@ -136,6 +142,10 @@ int mb200_trim_run(mb200_ctx* ctx, uint32_t n, uint32_t perLocus, const uint8_t*
 // fills ctx->dQcSupport / dQcSlotLocus / dQcSlotFirst / dQcNContigs / dQcViews from the assembler's device outputs
 int mb200_qc_prep_fused(mb200_ctx* ctx, uint32_t nLoci, uint32_t A, const mb200_asm_locus* dLoci, const mb200_contig* dContigs,
                         const uint32_t* dSetPool);
+int mb200_small_sv_run(mb200_ctx* ctx, uint32_t minSize, uint32_t nLoci, const uint8_t* dIsJump, const uint32_t* dSlotFirst,
+                       const int32_t* dBest, const mb200_contig_qc* dQc, const mb200_aln_result* dAln, const uint32_t* dCigar,
+                       const uint8_t* dContigPool, const mb200_seqview* dContigView, const uint8_t* dRefPool,
+                       const mb200_seqview* dRef1, uint32_t* dSvFirst, mb200_small_sv* dSvs, uint64_t svCap);
 int mb200_apply_trim(mb200_ctx* ctx, uint32_t nSlots, const uint32_t* dSlotLocus, const uint8_t* dIsJump,
                      const mb200_trim_result* dTrim, mb200_aln_result* dAln);
 int mb200_qc_run(mb200_ctx* ctx, const mb200_qc_opts* opts, uint32_t nLoci, uint32_t nSlots, const uint8_t* dIsJump,

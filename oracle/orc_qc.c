@@ -335,6 +335,79 @@ int orc_select_contigs_batch(const mb200_qc_opts* opts, uint32_t nLoci, const ui
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * refined small SVs: setSmallCandSV :720-800 over the kept segments of the selected contig (:2243-2251)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* getVariantRange  :677-717 */
+static void variant_range(const uint8_t* ref, int64_t refLen, int32_t refB, int32_t refE, const uint8_t* read, int64_t readLen,
+                          int32_t readB, int32_t readE, int32_t* left, int32_t* right)
+{
+  int64_t maxRight = refLen - refE;
+  if (readLen - readE < maxRight) maxRight = readLen - readE;
+  int32_t r = 0;
+  for (; r < maxRight; ++r)
+    if (ref[refB + r] != read[readB + r]) break;
+  const int32_t minLeft = (-refB > -readB) ? -refB : -readB;
+  int32_t       l       = 0;
+  for (; l >= minLeft; --l) {
+    /* (the reference indexes position -1 here when an empty range slides to the very start: undefined there,
+     *  a stop here) */
+    if (refE + l - 1 < 0 || readE + l - 1 < 0) break;
+    if (ref[refE + l - 1] != read[readE + l - 1]) break;
+  }
+  *left  = l;
+  *right = r;
+}
+
+int orc_small_sv_batch(uint32_t minCandidateVariantSize, uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst,
+                       uint32_t nSlots, const int32_t* best, const mb200_contig_qc* qc, const mb200_aln_result* aln,
+                       const uint32_t* cigarPool, const uint8_t* pool, const mb200_seqview* contigSeq,
+                       const mb200_seqview* ref1, uint32_t* svFirst, mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed)
+{
+  (void)nSlots;
+  uint64_t used = 0;
+  for (uint32_t li = 0; li < nLoci; ++li) {
+    svFirst[li] = (uint32_t)used;
+    if (isJump[li] || best[li] < 0) continue;
+    const uint32_t          s    = slotFirst[li] + (uint32_t)best[li];
+    const mb200_contig_qc*  q    = &qc[s];
+    const mb200_aln_result* r    = &aln[s];
+    const uint32_t*         path = cigarPool + r->cigarOff;
+    const uint32_t          n    = r->cigarLen;
+    seg_t*                  segs = (seg_t*)malloc(sizeof(seg_t) * (n ? n : 1));
+    large_indel_segments(path, n, minCandidateVariantSize, segs, n ? n : 1);
+    for (uint32_t k = 0; k < q->nSegments; ++k, ++used) {
+      if (used >= svCap) continue;
+      const seg_t    sg = segs[q->segOrdinal + k];
+      mb200_small_sv v;
+      memset(&v, 0, sizeof(v));
+      v.locus = li; v.contig = (uint32_t)best[li]; v.segment = k; v.pathFirst = sg.first; v.pathLast = sg.last;
+      int32_t readPos = 0, refPos = r->beginPos;
+      for (uint32_t i = 0; i < n; ++i) {
+        if (i == sg.first) { v.refBegin = refPos; v.readBegin = readPos; }
+        if (seg_is_ref(MB200_SEG_TYPE(path[i]))) refPos += (int32_t)MB200_SEG_LEN(path[i]);
+        if (seg_is_read(MB200_SEG_TYPE(path[i]))) readPos += (int32_t)MB200_SEG_LEN(path[i]);
+        if (i == sg.last) { v.refEnd = refPos; v.readEnd = readPos; }
+      }
+      variant_range(pool + ref1[li].off, ref1[li].len, v.refBegin, v.refEnd, pool + contigSeq[s].off, contigSeq[s].len,
+                    v.readBegin, v.readEnd, &v.ciposBegin, &v.ciposEnd);
+      if (v.ciposBegin != 0) v.status = MB200_ERR_SV_RANGE;
+      else {
+        v.bp1Begin = v.refBegin - 1;
+        v.bp1End   = v.bp1Begin + v.ciposEnd + 1;
+        v.bp2Begin = v.refEnd;
+        v.bp2End   = v.bp2Begin + v.ciposEnd + 1;
+      }
+      svs[used] = v;
+    }
+    free(segs);
+  }
+  svFirst[nLoci] = (uint32_t)used;
+  *svUsed        = used;
+  return used > svCap ? MB200_ERR_POOL_OVERFLOW : MB200_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
  * 10-mer anchored reference trim  :1984-2011
  * ------------------------------------------------------------------------------------------------------------- */
 #define MER 10

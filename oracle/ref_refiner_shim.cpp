@@ -206,6 +206,72 @@ REF_API int ref_select_contigs_batch(const mb200_qc_opts* opts, uint32_t nLoci, 
   return MB200_OK;
 }
 
+/// Refined small SVs through the reference's own setSmallCandSV (:720) for every kept segment of the selected contig
+/// (the loop of getSmallSVAssembly :2243-2251); readRange / refRange / cipos are recomputed here from the SVCandidate
+/// the static returns (bp1 = [refBegin - 1, +cipos.end + 1), bp2 = [refEnd, ...), insertSeq = contig[readRange]).
+REF_API int ref_small_sv_batch(uint32_t minCandidateVariantSize, uint32_t nLoci, const uint8_t* isJump,
+                               const uint32_t* slotFirst, uint32_t /*nSlots*/, const int32_t* best, const mb200_contig_qc* qc,
+                               const mb200_aln_result* aln, const uint32_t* cigarPool, const uint8_t* pool,
+                               const mb200_seqview* contigSeq, const mb200_seqview* ref1, uint32_t* svFirst,
+                               mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed)
+{
+  uint64_t   used(0);
+  GSCOptions opt;
+  for (uint32_t li(0); li < nLoci; ++li) {
+    svFirst[li] = static_cast<uint32_t>(used);
+    if (isJump[li] || best[li] < 0) continue;
+    const uint32_t s(slotFirst[li] + static_cast<uint32_t>(best[li]));
+    Alignment      align;
+    align.beginPos = aln[s].beginPos;
+    align.apath    = toPath(cigarPool + aln[s].cigarOff, aln[s].cigarLen);
+    const std::string        contig(reinterpret_cast<const char*>(pool + contigSeq[s].off), contigSeq[s].len);
+    reference_contig_segment ref;
+    ref.seq() = std::string(reinterpret_cast<const char*>(pool + ref1[li].off), ref1[li].len);
+    ref.set_offset(0);
+    SegSet all;
+    getLargeIndelSegments(align.apath, minCandidateVariantSize, all);
+    for (uint32_t k(0); k < qc[s].nSegments; ++k, ++used) {
+      if (used >= svCap) continue;
+      const std::pair<unsigned, unsigned> segRange(all[qc[s].segOrdinal + k]);
+      mb200_small_sv                      v;
+      std::memset(&v, 0, sizeof(v));
+      v.locus = li; v.contig = static_cast<uint32_t>(best[li]); v.segment = k;
+      v.pathFirst = segRange.first; v.pathLast = segRange.second;
+      // the two ranges, like the head of setSmallCandSV (they are not returned by it)
+      {
+        pos_t readPos(0), refPos(align.beginPos);
+        for (unsigned i(0); i < align.apath.size(); ++i) {
+          const ALIGNPATH::path_segment& ps(align.apath[i]);
+          if (i == segRange.first) { v.refBegin = refPos; v.readBegin = readPos; }
+          if (is_segment_type_ref_length(ps.type)) refPos += ps.length;
+          if (is_segment_type_read_length(ps.type)) readPos += ps.length;
+          if (i == segRange.second) { v.refEnd = refPos; v.readEnd = readPos; }
+        }
+      }
+      const known_pos_range2 cipos(getVariantRange(
+          ref.seq(), known_pos_range2(v.refBegin, v.refEnd), contig, known_pos_range2(v.readBegin, v.readEnd)));
+      v.ciposBegin = cipos.begin_pos();
+      v.ciposEnd   = cipos.end_pos();
+      SVCandidate sv;
+      try {
+        setSmallCandSV(ref, contig, align, segRange, sv, opt);
+        v.bp1Begin = sv.bp1.interval.range.begin_pos();
+        v.bp1End   = sv.bp1.interval.range.end_pos();
+        v.bp2Begin = sv.bp2.interval.range.begin_pos();
+        v.bp2End   = sv.bp2.interval.range.end_pos();
+        if (sv.insertSeq != contig.substr(v.readBegin, v.readEnd - v.readBegin)) v.status = -1;  // would be a shim bug
+        if (sv.insertAlignment.size() != (segRange.second - segRange.first + 1)) v.status = -2;
+      } catch (const illumina::common::GeneralException&) {
+        v.status = MB200_ERR_SV_RANGE;
+      }
+      svs[used] = v;
+    }
+  }
+  svFirst[nLoci] = static_cast<uint32_t>(used);
+  *svUsed        = used;
+  return used > svCap ? MB200_ERR_POOL_OVERFLOW : MB200_OK;
+}
+
 /// The reference's per-candidate work on `threads` host threads: runIterativeAssembler on the locus' reads, then
 /// every contig through [the window trim and] GlobalLargeIndelAligner (isJump == 0) or GlobalJumpAligner
 /// (isJump == 1), then [contig QC + selection].  Loci are handed out dynamically (like the reference's ctpl pool

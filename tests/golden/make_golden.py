@@ -248,6 +248,46 @@ REFINER_UNIT_TESTS = [
 ]
 
 
+# test_GetVariantRange (:103-140) and test_setSmallCandSV (:1074-1118), as single-contig candidates whose alignment
+# path puts the event where the unit test's ranges are
+_SV_REF = ("AATATTACCCTTAGTTCTCATTAGTAAATGGATGTGAAAGTCAGGACATTCCAAAAGAAAGAACTAGAACTCACTCGGCC"
+           "AGAAAACCCCCATTTCAGTTTTTACACAGAAAAATTCTTACAGTCTATGTTTCACTAAGAATGTCTGCTGTGCAAAACCCT"
+           "CAAACTTTTTAGAACGTTTTTTTTGTTCCAAGTTAGAGAACGGCAATCAGTAATCTATTACCCAAAGTGCTTCTCCTTTCCA"
+           "GGTTTCATGTTAGAGTGATTCTAATATGTGTGTGCTATCAACTGCCTACACAGAAAACTGAGAGACAAAGGCTTTCTCCTTTT"
+           "CCACACATTATCCTTCATTCAGACTTAATGCCTGCAGGTCCGGTTTAATGATTTCCCAGAGTTTATGAACGAAAAAGAAAAAC"
+           "AAAGCAATAAAAACAAAAATCAAAGTTAAATTTCCTCAAAAGTTTTCAAGAAGGAAGTAGTCAGGACAAAAACAAAGGGAATG"
+           "AGGGCACTTTGTCTCAGGATACAAATTAAAGATCACTGTGGTGGCCTCTGTGGGGTGGTTATAAAGGGGACCAGGTGTATACT"
+           "AGGAAGTCATTTAGTTTTAGAAATGTAAATATGTGTAAATGTTTTAATTTTACTCAACTTGCCAGAGGTAGAATGTCCCTGGA"
+           "CAACTAACTGATACATTTCTTTAGGGCCAATCGCTGGCTTTAGAAGAGCCTCAGCTAATCACAGTAGAGCTGGACTGTTGTGG"
+           "TTTTCCATTCCTTTGCATCGTATTCCTCAGTCTCTGCGGAAGGCACTGCTCCTTCCTTTCCTTTCTAAATCTCTCTCTGTCTCTC"
+           "TCTCTCTCTCTCTCTCTCTCGCTCTCTCCTCCCCTAGTTTATCCTGGACTCATGCTGAGCTCAGCAACCCTTGAACTCATTTTCT"
+           "ATCTGACATGT")
+_SV_READ = ("ATTCCTTTGCATCGTATTCCTCAGTCTCTGCGGAAGGCACTGCTCCTTCCTTTCCTTTCTAAATCTCTCTCTGTCTCT"
+            "CTCTCTCTCTCTCTCTCTCTCTCTCTCGCTCTCTCCTCCCCTAGTTTATCCTGGACTCATGCTGAGCTCAGCAACCCTT"
+            "GAACTCATTTTCTATCTGAC")
+SMALL_SV_UNIT_TESTS = [
+    dict(src="test_GetVariantRange:103 left shifted, deletion order", ref="ABCDDDABC", contig="ABCDDABC", cigar="3=1D5=",
+         beginPos=0, minSize=1, expected=dict(cipos=[0, 2])),
+    dict(src="test_GetVariantRange:103 left shifted, insertion order", ref="ABCDDABC", contig="ABCDDDABC", cigar="3=1I5=",
+         beginPos=0, minSize=1, expected=dict(cipos=[0, 2])),
+    dict(src="test_GetVariantRange:103 right shifted, deletion order", ref="ABCDDDABC", contig="ABCDDABC", cigar="5=1D3=",
+         beginPos=0, minSize=1, expected=dict(cipos=[-2, 0])),
+    dict(src="test_GetVariantRange:103 right shifted, insertion order", ref="ABCDDABC", contig="ABCDDDABC", cigar="5=1I3=",
+         beginPos=0, minSize=1, expected=dict(cipos=[-2, 0])),
+    dict(src="test_setSmallCandSV:1074", ref=_SV_REF, contig=_SV_READ, cigar="73=6I98=", beginPos=747, minSize=6,
+         expected=dict(bp1=[819, 846], bp2=[820, 847], insertSize=6)),
+]
+
+
+def small_sv_unit_case(t, qc_cases):
+    u = dict(kind="complex", minSize=t["minSize"], contig=t["contig"], ref=t["ref"],
+             contigs=[dict(cigar=t["cigar"], beginPos=t["beginPos"], score=1, isJumped=0, support=1)])
+    case, _ = qc_cases.unit_case(u, REFINER_SCORES)
+    qc = np.zeros(1, dtype=cb.CONTIG_QC_DT)
+    qc[0]["isCandidate"], qc[0]["nSegments"], qc[0]["pathFirst"], qc[0]["pathLast"] = 1, 1, 1, 1
+    return case, qc, np.zeros(1, dtype=np.int32)
+
+
 def refiner_golden(ref, qc_cases):
     units = []
     for t in REFINER_UNIT_TESTS:
@@ -273,8 +313,34 @@ def refiner_golden(ref, qc_cases):
         pool, contig, refv, cuts = qc_cases.trim_fuzz(seed, 200)
         tr = ref.ref_trim_raw(pool, contig, refv, cuts)
         trims.append(dict(seed=seed, n=200, trim=[[int(a), int(b)] for a, b in tr.tolist()]))
+    sv_units = []
+    for t in SMALL_SV_UNIT_TESTS:
+        case, qc, best = small_sv_unit_case(t, qc_cases)
+        first, svs = case.small_svs(ref, qc, best, t["minSize"])
+        assert len(svs) == 1
+        v, exp = svs[0], t["expected"]
+        if "cipos" in exp:
+            assert [int(v["ciposBegin"]), int(v["ciposEnd"])] == exp["cipos"], t["src"]
+        if "bp1" in exp:
+            assert [int(v["bp1Begin"]), int(v["bp1End"])] == exp["bp1"] and [int(v["bp2Begin"]), int(v["bp2End"])] == exp["bp2"]
+            assert int(v["readEnd"]) - int(v["readBegin"]) == exp["insertSize"] and int(v["status"]) == 0
+        u = dict(t)
+        u["reference"] = [int(x) for x in v.tolist()]
+        sv_units.append(u)
+    sv_fuzz = []
+    for seed in (101,):
+        case = qc_cases.fuzz_case(seed, 60)
+        qc, best = case.run(ref)
+        first, svs = case.small_svs(ref, qc, best)
+        ok = svs["status"] == 0
+        rows = [[int(x) for x in row] for row in svs.tolist()]
+        ci = list(svs.dtype.names).index("ciposBegin")
+        for r, o in zip(rows, ok):
+            if not o:
+                r[ci] = None  # undefined in the reference where it throws
+        sv_fuzz.append(dict(seed=seed, n_loci=60, svFirst=[int(x) for x in first], svs=rows))
     return dict(source="GSC/test/SVCandidateAssemblyRefinerTest.cpp (transcribed) + oracle/_ref on tests/qc_cases.py inputs",
-                scores=list(REFINER_SCORES), unit=units, fuzz=fuzz, trim=trims)
+                scores=list(REFINER_SCORES), unit=units, fuzz=fuzz, trim=trims, small_sv_unit=sv_units, small_sv_fuzz=sv_fuzz)
 
 
 def main():

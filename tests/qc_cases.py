@@ -23,6 +23,10 @@ class QcCase:
         self.aln, self.jump, self.cigar, self.pool = aln, jump, cigar, pool
         self.contigSeq, self.ref1, self.support = contigSeq, ref1, support
 
+    def small_svs(self, binding, qc, best, minSize=10):
+        return binding.small_sv_raw(minSize, self.isJump, self.slotFirst, best, qc, self.aln, self.cigar, self.pool,
+                                    self.contigSeq, self.ref1)
+
     def run(self, binding, opts=None):
         opts = cb.default_qc_opts() if opts is None else opts
         return binding.select_contigs_raw(opts, self.isJump, self.slotFirst, self.nContigs, self.aln, self.jump,

@@ -155,3 +155,45 @@ def test_refiner_qc_golden(gpu):
     """the reference's own unit-test answers and the committed reference outputs, through the CUDA path"""
     from test_oracle_golden import check_refiner_golden
     check_refiner_golden(gpu)
+
+
+def _svs_equal(a, b):
+    (fa, sa), (fb, sb) = a, b
+    assert fa.tolist() == fb.tolist()
+    assert sa.tobytes() == sb.tobytes()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_small_sv_fuzz(gpu, orc, seed):
+    case = qc_cases.fuzz_case(seed, 400)
+    qc, best = case.run(orc)
+    _svs_equal(case.small_svs(gpu, qc, best), case.small_svs(orc, qc, best))
+    # another minimum size: different candidate runs, same bookkeeping
+    o = cb.default_qc_opts()
+    o["minCandidateVariantSize"] = 25
+    qc, best = case.run(orc, o)
+    _svs_equal(case.small_svs(gpu, qc, best, 25), case.small_svs(orc, qc, best, 25))
+
+
+def test_small_sv_golden(gpu):
+    from test_oracle_golden import check_small_sv_golden
+    check_small_sv_golden(gpu)
+
+
+def test_fused_small_svs(gpu, orc):
+    """refined small SVs straight from the resident results of a fused run == the oracle on the same pipeline"""
+    batch = synth.make_candidate_batch(64, seed=77, window=1500)
+    opts = cb.default_candidate_opts()
+    cuts = cb.default_ref_cuts(batch.nLoci)
+    cuts["leadingCut"], cuts["trailingCut"], cuts["maxLeadingCut"], cuts["maxTrailingCut"] = 20, 20, 250, 250
+    case, _ = qc_cases.pipeline_case(orc, batch, opts, cuts)
+    qo, bo = case.run(orc)
+    first_o, svs_o = case.small_svs(orc, qo, bo)
+    _fused(gpu, batch, opts, cuts, True)
+    first_g, svs_g = gpu.candidates_small_svs()
+    assert first_g.tolist() == first_o.tolist() and svs_g.tobytes() == svs_o.tobytes()
+    assert (svs_o["status"] == 0).sum() >= 10
+    # a run without selection leaves nothing to refine
+    _fused(gpu, batch, opts, cuts, False)
+    with pytest.raises(cb.Mb200Error):
+        gpu.candidates_small_svs()

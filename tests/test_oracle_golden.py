@@ -136,6 +136,38 @@ def check_refiner_golden(binding):
         assert [[int(a), int(b)] for a, b in tr.tolist()] == f["trim"]
 
 
+def check_small_sv_golden(binding):
+    import qc_cases
+    from manta_b200 import _cabi as cb
+    g = load("refiner_qc.json")
+    for t in g["small_sv_unit"]:
+        u = dict(kind="complex", minSize=t["minSize"], contig=t["contig"], ref=t["ref"],
+                 contigs=[dict(cigar=t["cigar"], beginPos=t["beginPos"], score=1, isJumped=0, support=1)])
+        case, _ = qc_cases.unit_case(u, g["scores"])
+        qc = np.zeros(1, dtype=cb.CONTIG_QC_DT)
+        qc[0]["isCandidate"], qc[0]["nSegments"], qc[0]["pathFirst"], qc[0]["pathLast"] = 1, 1, 1, 1
+        first, svs = case.small_svs(binding, qc, np.zeros(1, dtype=np.int32), t["minSize"])
+        assert first.tolist() == [0, 1] and [int(x) for x in svs[0].tolist()] == t["reference"], t["src"]
+        exp = t["expected"]
+        if "cipos" in exp:
+            assert [int(svs[0]["ciposBegin"]), int(svs[0]["ciposEnd"])] == exp["cipos"], t["src"]
+        if "bp1" in exp:
+            assert [int(svs[0]["bp1Begin"]), int(svs[0]["bp1End"])] == exp["bp1"], t["src"]
+            assert [int(svs[0]["bp2Begin"]), int(svs[0]["bp2End"])] == exp["bp2"], t["src"]
+    for f in g["small_sv_fuzz"]:
+        case = qc_cases.fuzz_case(f["seed"], f["n_loci"])
+        qc, best = case.run(binding)
+        first, svs = case.small_svs(binding, qc, best)
+        assert [int(x) for x in first] == f["svFirst"]
+        for got, want in zip(svs.tolist(), f["svs"]):
+            assert all(w is None or int(a) == w for a, w in zip(got, want))
+
+
+def test_small_sv_golden(orc):
+    """test_GetVariantRange / test_setSmallCandSV known answers + reference outputs on seeded inputs"""
+    check_small_sv_golden(orc)
+
+
 def test_refiner_qc_golden(orc):
     """GSC/test/SVCandidateAssemblyRefinerTest.cpp known answers + reference outputs on seeded inputs"""
     check_refiner_golden(orc)
