@@ -456,5 +456,45 @@ inline bool selectJumpContigDNA(const Context& ctx, const AlignmentScores<int>& 
   return true;
 }
 
+/// setSmallCandSV for every kept segment of the selected contig (GSC/SVCandidateAssemblyRefiner.cpp:2243-2251, 720-800).
+/// Returns one record per segment of smallSVSegments[bestAlignmentIndex]; a record with status MB200_ERR_SV_RANGE is
+/// where the reference throws ("Attempting to convert alignment to sv candidate", :768) -- the shim throws there too.
+/// Coordinates are offsets into align1RefStr: add bp1ref.get_offset() like the reference does.
+inline std::vector<mb200_small_sv> refineSmallSVs(const Context& ctx, const unsigned minCandidateVariantSize,
+                                                  const std::string& bestContigSeq, const AlignmentResult<int>& bestAlign,
+                                                  const CandidateSegmentSetType& candidateSegments,
+                                                  const unsigned bestAlignmentIndex, const std::string& align1RefStr)
+{
+  std::vector<mb200_small_sv> out;
+  if (candidateSegments.empty()) return out;
+  const CandidateSegmentSetType runs(detail::indelRuns(bestAlign.align.apath, minCandidateVariantSize));
+  unsigned                      ordinal(0);
+  while (ordinal < runs.size() && runs[ordinal] != candidateSegments.front()) ordinal++;
+  if (ordinal + candidateSegments.size() > runs.size()) throw GeneralException(MB200_ERR_BAD_ARG, "candidate segments do not belong to this alignment");
+  std::vector<uint8_t>  pool;
+  std::vector<uint32_t> cigar;
+  const mb200_seqview   cv(detail::append(pool, bestContigSeq.begin(), bestContigSeq.end()));
+  const mb200_seqview   rv(detail::append(pool, align1RefStr.begin(), align1RefStr.end()));
+  mb200_aln_result      aln{bestAlign.score, static_cast<int32_t>(bestAlign.align.beginPos), bestAlign.isJumped ? 1u : 0u, 0, 0};
+  detail::appendPath(cigar, bestAlign.align.apath, aln.cigarOff, aln.cigarLen);
+  mb200_contig_qc qc{1, 0, ordinal, static_cast<uint32_t>(candidateSegments.size()), candidateSegments.front().first,
+                     candidateSegments.back().second, 0, 0};
+  const uint8_t  isJump(0);
+  const uint32_t slotFirst(0);
+  const int32_t  best(0);
+  uint32_t       svFirst[2] = {0, 0};
+  uint64_t       used(0);
+  out.resize(candidateSegments.size());
+  ctx.check(mb200_small_sv_batch(ctx.get(), minCandidateVariantSize, 1, &isJump, &slotFirst, 1, &best, &qc, &aln, cigar.data(),
+                                 cigar.size(), pool.data(), pool.size(), &cv, &rv, svFirst, out.data(), out.size(), &used));
+  out.resize(used);
+  for (mb200_small_sv& v : out) {
+    v.contig = bestAlignmentIndex;
+    if (v.status == MB200_ERR_SV_RANGE) throw GeneralException(MB200_ERR_SV_RANGE, "Attempting to convert alignment to sv candidate.");
+  }
+  return out;
+}
+
 }  // namespace mb200
+
 

@@ -111,6 +111,12 @@ int main()
     const mb200::AlignmentScores<int>           filterScores(2, -8, -18, 0, -1);
     REQUIRE(mb200::selectSmallSVContig(ctx, filterScores, 10, {flat, contig}, {7, 9}, {alignments[1], alignments[0]}, ref, segments, bestIndex));
     REQUIRE(bestIndex == 1u && segments[0].empty() && segments[1].size() == 1 && segments[1][0].first == 1u && segments[1][0].second == 1u);
+    // refined SV of the selected contig (setSmallCandSV): the planted deletion, no homology at the breakpoint expected
+    // beyond what the random sequence gives; bp2 - bp1 == deletion length + 1
+    const std::vector<mb200_small_sv> svs(mb200::refineSmallSVs(ctx, 10, contig, alignments[0], segments[1], bestIndex, ref));
+    REQUIRE(svs.size() == 1 && svs[0].status == 0 && svs[0].contig == 1u && svs[0].segment == 0u);
+    REQUIRE(svs[0].refEnd - svs[0].refBegin == 60 && svs[0].readBegin == svs[0].readEnd && svs[0].ciposBegin == 0);
+    REQUIRE(svs[0].bp2Begin - svs[0].bp1Begin == 61 && svs[0].bp1End - svs[0].bp1Begin == svs[0].ciposEnd + 1);
     // spanning: two clean 120-base arms pass, a 10-base arm fails the QC
     mb200::JumpAlignmentResult<int> good, bad;
     good.score = 400;
