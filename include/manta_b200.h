@@ -350,6 +350,34 @@ MB200_API int mb200_small_sv_batch(mb200_ctx* ctx, uint32_t minCandidateVariantS
                                    const mb200_seqview* contigSeq, const mb200_seqview* ref1, uint32_t* svFirst,
                                    mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed);
 
+/* Refined breakends of a spanning candidate from its selected jump alignment: generateRefinedSVCandidateFromJumpAlignment
+ * (GSC/SVCandidateAssemblyRefiner.cpp:1190-1223) = adjustAssembledBreakend (:59-86) on both breakends.  What the
+ * refiner knows about the candidate besides the alignment: */
+typedef struct mb200_jump_orient {
+  uint8_t isBp2AlignedFirst; /* SVCandidateAssemblyData::bporient  lib/manta/SVCandidateAssemblyData.hpp:39-58 */
+  uint8_t isBp1Reversed;
+  uint8_t isBp2Reversed;
+  uint8_t bp1RightOpen;      /* sv.bp1.state == SVBreakendState::RIGHT_OPEN (else the breakend sits at the alignment begin) */
+  uint8_t bp2RightOpen;
+  uint8_t reserved[3];
+} mb200_jump_orient;
+
+typedef struct mb200_jump_sv {
+  int32_t  valid;       /* 1 for a spanning candidate with a selected contig, else 0 (rest zero) */
+  uint32_t contig;      /* sv.assemblyAlignIndex */
+  int32_t  bp1Begin, bp1End; /* sv.bp1.interval.range as offsets into bp1's reference window (add bp1ref.get_offset()) */
+  int32_t  bp2Begin, bp2End;
+  int32_t  insertBegin, insertEnd; /* sv.insertSeq = contig[insertBegin, insertEnd), reverse-complemented if isBp1Reversed
+                                      (getFwdStrandInsertSegment, lib/alignment/AlignmentUtil.cpp) */
+} mb200_jump_sv;
+
+/* ref1 / ref2 are the windows the contigs were aligned to as align1 / align2 (bp1's window is ref2 when
+ * isBp2AlignedFirst).  out[nLoci]. */
+MB200_API int mb200_jump_sv_batch(mb200_ctx* ctx, uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst,
+                                  uint32_t nSlots, const int32_t* best, const mb200_jump_result* jump,
+                                  const uint32_t* cigarPool, uint64_t cigarLen, const mb200_seqview* ref1,
+                                  const mb200_seqview* ref2, const mb200_jump_orient* orient, mb200_jump_sv* out);
+
 /* ---- fused candidate path -------------------------------------------------------------------------
  * "one candidate" = one SVCandidate junction entering getCandidateAssemblyData (GSC/SVCandidateProcessor.cpp:310):
  * its read set is assembled (all word lengths) and EVERY resulting contig is aligned
@@ -401,6 +429,9 @@ MB200_API int mb200_candidates_timing(const mb200_ctx* ctx, mb200_candidate_timi
  * on the still-resident alignments */
 MB200_API int mb200_candidates_small_svs(mb200_ctx* ctx, uint32_t* svFirst, mb200_small_sv* svs, uint64_t svCap,
                                          uint64_t* svUsed);
+/* refined spanning breakends (mb200_jump_sv_batch) of the same run; orient[nLoci] (entries of complex candidates are
+ * ignored), out[nLoci] */
+MB200_API int mb200_candidates_jump_svs(mb200_ctx* ctx, const mb200_jump_orient* orient, mb200_jump_sv* out);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,11 @@ QC_OPTS_DT = np.dtype([("filterScores", "<i4", (6,)), ("minCandidateVariantSize"
 CONTIG_QC_DT = np.dtype([("isCandidate", "<u4"), ("isLowQuality", "<u4"), ("segOrdinal", "<u4"), ("nSegments", "<u4"),
                          ("pathFirst", "<u4"), ("pathLast", "<u4"), ("variantSize", "<u4"), ("reserved", "<u4")],
                         align=True)
+JUMP_ORIENT_DT = np.dtype([("isBp2AlignedFirst", "u1"), ("isBp1Reversed", "u1"), ("isBp2Reversed", "u1"), ("bp1RightOpen", "u1"),
+                           ("bp2RightOpen", "u1"), ("reserved", "u1", (3,))])
+JUMP_SV_DT = np.dtype([("valid", "<i4"), ("contig", "<u4"), ("bp1Begin", "<i4"), ("bp1End", "<i4"), ("bp2Begin", "<i4"),
+                       ("bp2End", "<i4"), ("insertBegin", "<i4"), ("insertEnd", "<i4")], align=True)
+assert JUMP_ORIENT_DT.itemsize == 8 and JUMP_SV_DT.itemsize == 32
 SMALL_SV_DT = np.dtype([("locus", "<u4"), ("contig", "<u4"), ("segment", "<u4"), ("status", "<i4"), ("pathFirst", "<u4"),
                         ("pathLast", "<u4"), ("refBegin", "<i4"), ("refEnd", "<i4"), ("readBegin", "<i4"), ("readEnd", "<i4"),
                         ("ciposBegin", "<i4"), ("ciposEnd", "<i4"), ("bp1Begin", "<i4"), ("bp1End", "<i4"), ("bp2Begin", "<i4"),
@@ -417,6 +422,27 @@ class Binding:
                 self._raise(st)
             return svFirst, svs[:int(used.value)]
         raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "small SV record overflow")
+
+    def jump_sv_raw(self, isJump: np.ndarray, slotFirst: np.ndarray, nSlots: int, best: np.ndarray, jump: np.ndarray,
+                    cigar: np.ndarray, ref1: np.ndarray, ref2: np.ndarray, orient: np.ndarray) -> np.ndarray:
+        """refined breakends of the selected spanning contigs (one record per candidate)"""
+        nLoci = len(isJump)
+        out = np.zeros(nLoci, dtype=JUMP_SV_DT)
+        args = [C.c_uint32(nLoci), _ptr(isJump), _ptr(slotFirst), C.c_uint32(nSlots), _ptr(best), _ptr(jump), _ptr(cigar)]
+        if self.ctx is not None:
+            args.append(C.c_uint64(cigar.size))
+        st = self._call("jump_sv_batch", *args, _ptr(ref1), _ptr(ref2), _ptr(orient), _ptr(out))
+        if st != MB200_OK:
+            self._raise(st)
+        return out
+
+    def candidates_jump_svs(self, orient: np.ndarray) -> np.ndarray:
+        """refined spanning breakends of the last fused run (product library only)"""
+        out = np.zeros(self._cand_shape[0], dtype=JUMP_SV_DT)
+        st = self._call("candidates_jump_svs", _ptr(orient), _ptr(out))
+        if st != MB200_OK:
+            self._raise(st)
+        return out
 
     def candidates_small_svs(self):
         """refined small SVs of the last fused run (product library only)"""

@@ -58,6 +58,7 @@ int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* read
   if ((rc = mb200_reserve(ctx, S.dViews, sizeof(mb200_seqview) * (size_t)(nReads + 1))) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, S.dIsJump, (size_t)nLoci + 4)) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, S.dRef1, sizeof(mb200_seqview) * (size_t)nLoci + 16)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, S.dRef2, sizeof(mb200_seqview) * (size_t)nLoci + 16)) != MB200_OK) return rc;
   if ((rc = mb200_reserve(ctx, S.dCuts, sizeof(mb200_ref_cuts) * (size_t)nLoci + 16)) != MB200_OK) return rc;
   // asynchronous from here on (uploadStream): the copy overlaps a run on the other slot.  The caller's buffers must
   // stay untouched until the mb200_candidates_run that consumes this batch has returned.
@@ -72,11 +73,12 @@ int mb200_candidates_upload(mb200_ctx* ctx, uint32_t nLoci, const uint64_t* read
   // the small per-locus arrays are copied from the slot's own host copies (they outlive the caller's arrays)
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dIsJump.ptr, S.isJump.data(), (size_t)nLoci, cudaMemcpyHostToDevice, up));
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dRef1.ptr, S.ref1.data(), sizeof(mb200_seqview) * (size_t)nLoci, cudaMemcpyHostToDevice, up));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dRef2.ptr, S.ref2.data(), sizeof(mb200_seqview) * (size_t)nLoci, cudaMemcpyHostToDevice, up));
   if (cuts) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(S.dCuts.ptr, S.cuts.data(), sizeof(mb200_ref_cuts) * (size_t)nLoci, cudaMemcpyHostToDevice, up));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(S.upEnd, up));
   S.everUploaded = true;
   S.h2dBytes     = poolBytes + 8 * (uint64_t)(nLoci + 1) + sizeof(mb200_seqview) * nReads +
-               (uint64_t)nLoci * (1 + sizeof(mb200_seqview) + (cuts ? sizeof(mb200_ref_cuts) : 0));
+               (uint64_t)nLoci * (1 + 2 * sizeof(mb200_seqview) + (cuts ? sizeof(mb200_ref_cuts) : 0));
   C.queue[C.nQueued++] = tgt;
   return MB200_OK;
 }
@@ -299,8 +301,11 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   unsigned long long usedCig;
   memcpy(&usedCig, hMisc + 12, 8);
   *cigarUsed = usedCig;
-  if (hMisc[4] != 0) return mb200_fail(ctx, (int)hMisc[4], "device-side failure in dpAlignKernel");
-  if (usedCig > cigarCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "cigar pool too small");
+  if (hMisc[4] != 0 || usedCig > cigarCap) {
+    MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->copyStream));  // copies into the caller's buffers are in flight
+    if (hMisc[4] != 0) return mb200_fail(ctx, (int)hMisc[4], "device-side failure in dpAlignKernel");
+    return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "cigar pool too small");
+  }
   if (usedCig) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(cigarPool, ctx->dCigar.ptr, usedCig * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->cev[0], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -354,6 +359,30 @@ int mb200_candidates_small_svs(mb200_ctx* ctx, uint32_t* svFirst, mb200_small_sv
   *svUsed             = used;
   if (used > svCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "small SV record array too small");
   if (used) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(svs, ctx->dSvs.ptr, sizeof(mb200_small_sv) * (size_t)used, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MB200_OK;
+}
+
+int mb200_candidates_jump_svs(mb200_ctx* ctx, const mb200_jump_orient* orient, mb200_jump_sv* out)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (!orient || !out) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  if (!ctx->candSv.valid || ctx->candSv.slot != ctx->cand.cur)
+    return mb200_fail(ctx, MB200_ERR_BAD_ARG, "no fused run with contig selection to refine (run mb200_candidates_run with qc/best first)");
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  auto&          c     = ctx->cand.slot[ctx->candSv.slot];
+  const uint32_t nLoci = ctx->candSv.nLoci;
+  int            rc;
+  if ((rc = mb200_reserve(ctx, ctx->dSvFirst, sizeof(mb200_jump_orient) * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dSvs, sizeof(mb200_jump_sv) * (size_t)nLoci)) != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dSvFirst.ptr, orient, sizeof(mb200_jump_orient) * (size_t)nLoci, cudaMemcpyHostToDevice, ctx->stream));
+  rc = mb200_jump_sv_run(ctx, nLoci, reinterpret_cast<const uint8_t*>(c.dIsJump.ptr), reinterpret_cast<const uint32_t*>(ctx->dQcSlotFirst.ptr),
+                         reinterpret_cast<const int32_t*>(ctx->dQcBest.ptr), reinterpret_cast<const mb200_jump_result*>(ctx->dJump.ptr),
+                         reinterpret_cast<const uint32_t*>(ctx->dCigar.ptr), reinterpret_cast<const mb200_seqview*>(c.dRef1.ptr),
+                         reinterpret_cast<const mb200_seqview*>(c.dRef2.ptr), reinterpret_cast<const mb200_jump_orient*>(ctx->dSvFirst.ptr),
+                         reinterpret_cast<mb200_jump_sv*>(ctx->dSvs.ptr));
+  if (rc != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->dSvs.ptr, sizeof(mb200_jump_sv) * (size_t)nLoci, cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   return MB200_OK;
 }

@@ -642,6 +642,68 @@ __global__ void __launch_bounds__(QC_WARPS * 32) smallSvKernel(const SvParams P)
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// refined spanning breakends: generateRefinedSVCandidateFromJumpAlignment (:1190-1223), adjustAssembledBreakend (:59-86)
+struct JumpSvParams {
+  uint32_t                 nLoci;
+  const uint8_t*           isJump;
+  const uint32_t*          slotFirst;
+  const int32_t*           best;
+  const mb200_jump_result* jump;
+  const uint32_t*          cigar;
+  const mb200_seqview*     ref1;
+  const mb200_seqview*     ref2;
+  const mb200_jump_orient* orient;
+  mb200_jump_sv*           out;
+};
+
+__device__ __forceinline__ void adjustBreakend(int32_t beginPos, uint32_t refSpan, bool isAlign1, uint32_t jumpRange, uint32_t refSize,
+                                               bool isReversed, bool rightOpen, int32_t& rb, int32_t& re)
+{
+  const int32_t alignEnd = beginPos + (int32_t)refSpan;
+  const int32_t beginOff = isReversed ? ((int32_t)refSize - alignEnd) : beginPos;  // getAlignBeginOffset, AlignmentUtil.hpp:38
+  const int32_t endOff   = isReversed ? ((int32_t)refSize - beginPos) : alignEnd;  // getAlignEndOffset :49
+  const int32_t bpOff    = rightOpen ? (endOff - 1) : beginOff;
+  if (isAlign1 == rightOpen) { rb = bpOff; re = bpOff + (int32_t)jumpRange + 1; }
+  else { rb = bpOff - (int32_t)jumpRange; re = bpOff + 1; }
+}
+
+__global__ void jumpSvKernel(const JumpSvParams P)
+{
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= P.nLoci) return;
+  mb200_jump_sv v;
+  memset(&v, 0, sizeof(v));
+  if (P.isJump[li] && P.best[li] >= 0) {
+    const mb200_jump_result r  = P.jump[P.slotFirst[li] + (uint32_t)P.best[li]];
+    const mb200_jump_orient o  = P.orient[li];
+    const uint32_t*         p1 = P.cigar + r.cigarOff1;
+    const uint32_t*         p2 = P.cigar + r.cigarOff2;
+    uint32_t                span1 = 0, span2 = 0, read1 = 0;
+    for (uint32_t i = 0; i < r.cigarLen1; ++i) {
+      const uint32_t t = MB200_SEG_TYPE(p1[i]), len = MB200_SEG_LEN(p1[i]);
+      if (segIsRef(t)) span1 += len;
+      if (segIsRead(t)) read1 += len;
+    }
+    for (uint32_t i = 0; i < r.cigarLen2; ++i)
+      if (segIsRef(MB200_SEG_TYPE(p2[i]))) span2 += MB200_SEG_LEN(p2[i]);
+    v.valid  = 1;
+    v.contig = (uint32_t)P.best[li];
+    // bp1 takes align2 (and its window) when bp2 was aligned first (:1196-1222, :1544-1547)
+    if (!o.isBp2AlignedFirst) {
+      adjustBreakend(r.beginPos1, span1, true, r.jumpRange, P.ref1[li].len, o.isBp1Reversed != 0, o.bp1RightOpen != 0, v.bp1Begin, v.bp1End);
+      adjustBreakend(r.beginPos2, span2, false, r.jumpRange, P.ref2[li].len, o.isBp2Reversed != 0, o.bp2RightOpen != 0, v.bp2Begin, v.bp2End);
+    } else {
+      adjustBreakend(r.beginPos2, span2, false, r.jumpRange, P.ref2[li].len, o.isBp1Reversed != 0, o.bp1RightOpen != 0, v.bp1Begin, v.bp1End);
+      adjustBreakend(r.beginPos1, span1, true, r.jumpRange, P.ref1[li].len, o.isBp2Reversed != 0, o.bp2RightOpen != 0, v.bp2Begin, v.bp2End);
+    }
+    v.insertBegin = (int32_t)read1;
+    v.insertEnd   = (int32_t)(read1 + r.jumpInsertSize);
+  }
+  P.out[li] = v;
+}
+
 int gridFor(const mb200_ctx* ctx, uint32_t nItems)
 {
   const uint32_t want = (nItems + QC_WARPS - 1) / QC_WARPS;
@@ -746,6 +808,21 @@ int mb200_small_sv_run(mb200_ctx* ctx, uint32_t minSize, uint32_t nLoci, const u
   smallSvKernel<<<gridFor(ctx, nLoci), QC_WARPS * 32, 0, ctx->stream>>>(P);
   MB200_CUDA_CHECK(ctx, cudaGetLastError());
   ctx->timing.launches += 2;
+  return MB200_OK;
+}
+
+int mb200_jump_sv_run(mb200_ctx* ctx, uint32_t nLoci, const uint8_t* dIsJump, const uint32_t* dSlotFirst, const int32_t* dBest,
+                      const mb200_jump_result* dJump, const uint32_t* dCigar, const mb200_seqview* dRef1, const mb200_seqview* dRef2,
+                      const mb200_jump_orient* dOrient, mb200_jump_sv* dOut)
+{
+  if (nLoci == 0) return MB200_OK;
+  JumpSvParams P;
+  memset(&P, 0, sizeof(P));
+  P.nLoci = nLoci; P.isJump = dIsJump; P.slotFirst = dSlotFirst; P.best = dBest; P.jump = dJump; P.cigar = dCigar;
+  P.ref1 = dRef1; P.ref2 = dRef2; P.orient = dOrient; P.out = dOut;
+  jumpSvKernel<<<(nLoci + 127) / 128, 128, 0, ctx->stream>>>(P);
+  MB200_CUDA_CHECK(ctx, cudaGetLastError());
+  ctx->timing.launches++;
   return MB200_OK;
 }
 
@@ -966,6 +1043,62 @@ int mb200_small_sv_batch(mb200_ctx* ctx, uint32_t minCandidateVariantSize, uint3
   *svUsed             = used;
   if (used > svCap) return mb200_fail(ctx, MB200_ERR_POOL_OVERFLOW, "small SV record array too small");
   if (used) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(svs, ctx->dSvs.ptr, sizeof(mb200_small_sv) * (size_t)used, cudaMemcpyDeviceToHost, ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(&ctx->timing.h2dMs, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&ctx->timing.kernelMs, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&ctx->timing.d2hMs, ctx->ev[2], ctx->ev[3]);
+  return MB200_OK;
+}
+
+int mb200_jump_sv_batch(mb200_ctx* ctx, uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst, uint32_t nSlots,
+                        const int32_t* best, const mb200_jump_result* jump, const uint32_t* cigarPool, uint64_t cigarLen,
+                        const mb200_seqview* ref1, const mb200_seqview* ref2, const mb200_jump_orient* orient, mb200_jump_sv* out)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  if (nLoci == 0) return MB200_OK;
+  if (!isJump || !slotFirst || !best || !ref1 || !ref2 || !orient || !out) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  if (nSlots && (!jump || !cigarPool)) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "null argument");
+  for (uint32_t li = 0; li < nLoci; ++li) {
+    if (!isJump[li] || best[li] < 0) continue;
+    const uint64_t s = (uint64_t)slotFirst[li] + (uint32_t)best[li];
+    if (s >= nSlots) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "best contig outside the result arrays");
+    if (jump[s].cigarOff1 + jump[s].cigarLen1 > cigarLen || jump[s].cigarOff2 + jump[s].cigarLen2 > cigarLen)
+      return mb200_fail(ctx, MB200_ERR_BAD_ARG, "path outside the cigar pool");
+  }
+  MB200_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  ctx->timing = mb200_timing();
+  ctx->candSv.valid = false;  // shares device buffers with the fused path's resident results
+  int          rc;
+  const size_t ns = nSlots ? nSlots : 1;
+  if ((rc = mb200_reserve(ctx, ctx->dCigar, 4 * (size_t)(cigarLen ? cigarLen : 1))) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dJump, sizeof(mb200_jump_result) * ns)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcRef, sizeof(mb200_seqview) * (size_t)nLoci * 2)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcSlotFirst, 4 * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcIsJump, (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dQcBest, 4 * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dSvFirst, sizeof(mb200_jump_orient) * (size_t)nLoci)) != MB200_OK) return rc;
+  if ((rc = mb200_reserve(ctx, ctx->dSvs, sizeof(mb200_jump_sv) * (size_t)nLoci)) != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+#define MB200_UP(dst, src, bytes) MB200_CUDA_CHECK(ctx, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, ctx->stream))
+  mb200_seqview* dRef = reinterpret_cast<mb200_seqview*>(ctx->dQcRef.ptr);
+  if (cigarLen) MB200_UP(ctx->dCigar.ptr, cigarPool, 4 * (size_t)cigarLen);
+  if (nSlots) MB200_UP(ctx->dJump.ptr, jump, sizeof(mb200_jump_result) * (size_t)nSlots);
+  MB200_UP(dRef, ref1, sizeof(mb200_seqview) * (size_t)nLoci);
+  MB200_UP(dRef + nLoci, ref2, sizeof(mb200_seqview) * (size_t)nLoci);
+  MB200_UP(ctx->dQcSlotFirst.ptr, slotFirst, 4 * (size_t)nLoci);
+  MB200_UP(ctx->dQcIsJump.ptr, isJump, (size_t)nLoci);
+  MB200_UP(ctx->dQcBest.ptr, best, 4 * (size_t)nLoci);
+  MB200_UP(ctx->dSvFirst.ptr, orient, sizeof(mb200_jump_orient) * (size_t)nLoci);
+#undef MB200_UP
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  rc = mb200_jump_sv_run(ctx, nLoci, reinterpret_cast<const uint8_t*>(ctx->dQcIsJump.ptr), reinterpret_cast<const uint32_t*>(ctx->dQcSlotFirst.ptr),
+                         reinterpret_cast<const int32_t*>(ctx->dQcBest.ptr), reinterpret_cast<const mb200_jump_result*>(ctx->dJump.ptr),
+                         reinterpret_cast<const uint32_t*>(ctx->dCigar.ptr), dRef, dRef + nLoci,
+                         reinterpret_cast<const mb200_jump_orient*>(ctx->dSvFirst.ptr), reinterpret_cast<mb200_jump_sv*>(ctx->dSvs.ptr));
+  if (rc != MB200_OK) return rc;
+  MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->dSvs.ptr, sizeof(mb200_jump_sv) * (size_t)nLoci, cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   cudaEventElapsedTime(&ctx->timing.h2dMs, ctx->ev[0], ctx->ev[1]);

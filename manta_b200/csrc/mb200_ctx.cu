@@ -153,7 +153,7 @@ void mb200_destroy(mb200_ctx* ctx)
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   for (int i = 0; i < 2; ++i) {
     auto& S = ctx->cand.slot[i];
-    DeviceBuffer* sb[] = {&S.dPool, &S.dReadOff, &S.dViews, &S.dIsJump, &S.dRef1, &S.dCuts};
+    DeviceBuffer* sb[] = {&S.dPool, &S.dReadOff, &S.dViews, &S.dIsJump, &S.dRef1, &S.dRef2, &S.dCuts};
     for (DeviceBuffer* b : sb)
       if (b->ptr) cudaFree(b->ptr);
     if (S.upBegin) cudaEventDestroy(S.upBegin);

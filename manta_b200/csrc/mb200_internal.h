@@ -54,7 +54,7 @@ struct mb200_ctx {
     std::vector<uint8_t>        isJump;
     std::vector<mb200_ref_cuts> cuts;  // empty: no window trim
     mb200_asm_input_stats       scan = {};  // of the staged reads, for word length scan.minWordLength
-    DeviceBuffer                dPool, dReadOff, dViews, dIsJump, dRef1, dCuts;
+    DeviceBuffer                dPool, dReadOff, dViews, dIsJump, dRef1, dRef2, dCuts;
     cudaEvent_t                 upBegin = nullptr, upEnd = nullptr;
     bool                        everUploaded = false;
   };
@@ -146,6 +146,9 @@ int mb200_small_sv_run(mb200_ctx* ctx, uint32_t minSize, uint32_t nLoci, const u
                        const int32_t* dBest, const mb200_contig_qc* dQc, const mb200_aln_result* dAln, const uint32_t* dCigar,
                        const uint8_t* dContigPool, const mb200_seqview* dContigView, const uint8_t* dRefPool,
                        const mb200_seqview* dRef1, uint32_t* dSvFirst, mb200_small_sv* dSvs, uint64_t svCap);
+int mb200_jump_sv_run(mb200_ctx* ctx, uint32_t nLoci, const uint8_t* dIsJump, const uint32_t* dSlotFirst, const int32_t* dBest,
+                      const mb200_jump_result* dJump, const uint32_t* dCigar, const mb200_seqview* dRef1, const mb200_seqview* dRef2,
+                      const mb200_jump_orient* dOrient, mb200_jump_sv* dOut);
 int mb200_apply_trim(mb200_ctx* ctx, uint32_t nSlots, const uint32_t* dSlotLocus, const uint8_t* dIsJump,
                      const mb200_trim_result* dTrim, mb200_aln_result* dAln);
 int mb200_qc_run(mb200_ctx* ctx, const mb200_qc_opts* opts, uint32_t nLoci, uint32_t nSlots, const uint8_t* dIsJump,

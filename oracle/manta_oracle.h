@@ -68,6 +68,11 @@ ORC_API int orc_small_sv_batch(uint32_t minCandidateVariantSize, uint32_t nLoci,
                                const mb200_seqview* contigSeq, const mb200_seqview* ref1, uint32_t* svFirst,
                                mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed);
 
+ORC_API int orc_jump_sv_batch(uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst, uint32_t nSlots,
+                              const int32_t* best, const mb200_jump_result* jump, const uint32_t* cigarPool,
+                              const mb200_seqview* ref1, const mb200_seqview* ref2, const mb200_jump_orient* orient,
+                              mb200_jump_sv* out);
+
 /* per-candidate composition (assemble, [trim,] align every contig, [QC + select]) on `threads` pthreads.
  * cuts == NULL: no trim; doSelect == 0: no QC.  scoreSum = sum of all alignment scores; qcSum = the checksum
  * MB200_QC_CHECKSUM_* below over trims, QC records and selections (both are reproduced from the GPU outputs). */

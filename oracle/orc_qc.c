@@ -408,6 +408,53 @@ int orc_small_sv_batch(uint32_t minCandidateVariantSize, uint32_t nLoci, const u
 }
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * refined spanning breakends: generateRefinedSVCandidateFromJumpAlignment :1190-1223, adjustAssembledBreakend :59-86
+ * ------------------------------------------------------------------------------------------------------------- */
+static void adjust_breakend(int32_t beginPos, const uint32_t* path, uint32_t n, int isAlign1, uint32_t jumpRange,
+                            uint32_t refSize, int isReversed, int rightOpen, int32_t* rb, int32_t* re)
+{
+  const int32_t alignEnd = beginPos + (int32_t)path_ref_length(path, n); /* alignEnd()  lib/alignment/Alignment.hpp */
+  /* getAlignBeginOffset / getAlignEndOffset  lib/alignment/AlignmentUtil.hpp:38-56 */
+  const int32_t beginOff = isReversed ? ((int32_t)refSize - alignEnd) : beginPos;
+  const int32_t endOff   = isReversed ? ((int32_t)refSize - beginPos) : alignEnd;
+  const int32_t bpOff    = rightOpen ? (endOff - 1) : beginOff;
+  const int     leftAligned = (isAlign1 != 0) == (rightOpen != 0);
+  if (leftAligned) { *rb = bpOff; *re = bpOff + (int32_t)jumpRange + 1; }
+  else { *rb = bpOff - (int32_t)jumpRange; *re = bpOff + 1; }
+}
+
+int orc_jump_sv_batch(uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst, uint32_t nSlots, const int32_t* best,
+                      const mb200_jump_result* jump, const uint32_t* cigarPool, const mb200_seqview* ref1,
+                      const mb200_seqview* ref2, const mb200_jump_orient* orient, mb200_jump_sv* out)
+{
+  (void)nSlots;
+  for (uint32_t li = 0; li < nLoci; ++li) {
+    mb200_jump_sv v;
+    memset(&v, 0, sizeof(v));
+    if (isJump[li] && best[li] >= 0) {
+      const mb200_jump_result* r = &jump[slotFirst[li] + (uint32_t)best[li]];
+      const mb200_jump_orient* o = &orient[li];
+      const uint32_t*          p1 = cigarPool + r->cigarOff1;
+      const uint32_t*          p2 = cigarPool + r->cigarOff2;
+      v.valid  = 1;
+      v.contig = (uint32_t)best[li];
+      /* bp1 takes align2 (and ref2's window) when bp2 was aligned first */
+      if (!o->isBp2AlignedFirst) {
+        adjust_breakend(r->beginPos1, p1, r->cigarLen1, 1, r->jumpRange, ref1[li].len, o->isBp1Reversed, o->bp1RightOpen, &v.bp1Begin, &v.bp1End);
+        adjust_breakend(r->beginPos2, p2, r->cigarLen2, 0, r->jumpRange, ref2[li].len, o->isBp2Reversed, o->bp2RightOpen, &v.bp2Begin, &v.bp2End);
+      } else {
+        adjust_breakend(r->beginPos2, p2, r->cigarLen2, 0, r->jumpRange, ref2[li].len, o->isBp1Reversed, o->bp1RightOpen, &v.bp1Begin, &v.bp1End);
+        adjust_breakend(r->beginPos1, p1, r->cigarLen1, 1, r->jumpRange, ref1[li].len, o->isBp2Reversed, o->bp2RightOpen, &v.bp2Begin, &v.bp2End);
+      }
+      v.insertBegin = (int32_t)path_read_length(p1, r->cigarLen1);
+      v.insertEnd   = v.insertBegin + (int32_t)r->jumpInsertSize;
+    }
+    out[li] = v;
+  }
+  return MB200_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------------------
  * 10-mer anchored reference trim  :1984-2011
  * ------------------------------------------------------------------------------------------------------------- */
 #define MER 10

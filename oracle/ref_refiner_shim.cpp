@@ -272,6 +272,56 @@ REF_API int ref_small_sv_batch(uint32_t minCandidateVariantSize, uint32_t nLoci,
   return used > svCap ? MB200_ERR_POOL_OVERFLOW : MB200_OK;
 }
 
+/// Refined spanning breakends through the reference's own generateRefinedSVCandidateFromJumpAlignment (:1190), which
+/// applies adjustAssembledBreakend (:59) to both breakends; only the window sizes of bp1ref / bp2ref matter to it.
+REF_API int ref_jump_sv_batch(uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst, uint32_t /*nSlots*/,
+                              const int32_t* best, const mb200_jump_result* jump, const uint32_t* cigarPool,
+                              const mb200_seqview* ref1, const mb200_seqview* ref2, const mb200_jump_orient* orient,
+                              mb200_jump_sv* out)
+{
+  for (uint32_t li(0); li < nLoci; ++li) {
+    mb200_jump_sv v;
+    std::memset(&v, 0, sizeof(v));
+    if (isJump[li] && best[li] >= 0) {
+      const mb200_jump_result& r(jump[slotFirst[li] + static_cast<uint32_t>(best[li])]);
+      const mb200_jump_orient& o(orient[li]);
+      SVCandidateAssemblyData  ad;
+      ad.bestAlignmentIndex = static_cast<unsigned>(best[li]);
+      ad.spanningAlignments.resize(ad.bestAlignmentIndex + 1);
+      JumpAlignmentResult<int>& a(ad.spanningAlignments[ad.bestAlignmentIndex]);
+      a.score           = r.score;
+      a.jumpInsertSize  = r.jumpInsertSize;
+      a.jumpRange       = r.jumpRange;
+      a.align1.beginPos = r.beginPos1;
+      a.align2.beginPos = r.beginPos2;
+      a.align1.apath    = toPath(cigarPool + r.cigarOff1, r.cigarLen1);
+      a.align2.apath    = toPath(cigarPool + r.cigarOff2, r.cigarLen2);
+      ad.bporient.isBp2AlignedFirst = (o.isBp2AlignedFirst != 0);
+      ad.bporient.isBp1Reversed     = (o.isBp1Reversed != 0);
+      ad.bporient.isBp2Reversed     = (o.isBp2Reversed != 0);
+      // align1 was aligned to bp2's window when bp2 is aligned first (:1544-1547)
+      ad.bp1ref.seq() = std::string(o.isBp2AlignedFirst ? ref2[li].len : ref1[li].len, 'N');
+      ad.bp2ref.seq() = std::string(o.isBp2AlignedFirst ? ref1[li].len : ref2[li].len, 'N');
+      ad.bp1ref.set_offset(0);
+      ad.bp2ref.set_offset(0);
+      SVCandidate sv;
+      sv.bp1.state = o.bp1RightOpen ? SVBreakendState::RIGHT_OPEN : SVBreakendState::LEFT_OPEN;
+      sv.bp2.state = o.bp2RightOpen ? SVBreakendState::RIGHT_OPEN : SVBreakendState::LEFT_OPEN;
+      generateRefinedSVCandidateFromJumpAlignment(ad, sv);
+      v.valid       = 1;
+      v.contig      = sv.assemblyAlignIndex;
+      v.bp1Begin    = sv.bp1.interval.range.begin_pos();
+      v.bp1End      = sv.bp1.interval.range.end_pos();
+      v.bp2Begin    = sv.bp2.interval.range.begin_pos();
+      v.bp2End      = sv.bp2.interval.range.end_pos();
+      v.insertBegin = static_cast<int32_t>(apath_read_length(a.align1.apath));  // getFwdStrandQuerySegments, AlignmentUtil.cpp
+      v.insertEnd   = v.insertBegin + static_cast<int32_t>(a.jumpInsertSize);
+    }
+    out[li] = v;
+  }
+  return MB200_OK;
+}
+
 /// The reference's per-candidate work on `threads` host threads: runIterativeAssembler on the locus' reads, then
 /// every contig through [the window trim and] GlobalLargeIndelAligner (isJump == 0) or GlobalJumpAligner
 /// (isJump == 1), then [contig QC + selection].  Loci are handed out dynamically (like the reference's ctpl pool

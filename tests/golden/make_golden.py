@@ -279,6 +279,34 @@ SMALL_SV_UNIT_TESTS = [
 ]
 
 
+# test_generateRefinedSVCandidateFromJumpAlignment (:852-938); the unit test's reference offsets (bp1ref 100, bp2ref 150)
+# are subtracted: the batch entry point reports window offsets
+JUMP_SV_UNIT_TESTS = [
+    dict(src="test_generateRefinedSVCandidateFromJumpAlignment:852 case 1", cigar1="35=", begin1=40, cigar2="10=75I1D2=", begin2=70,
+         jumpRange=2, ref1Len=175, ref2Len=306, orient=dict(isBp2Reversed=1, bp1RightOpen=1, bp2RightOpen=1),
+         expected=dict(bp1=[174 - 100, 177 - 100], bp2=[383 - 150, 386 - 150])),
+    dict(src="test_generateRefinedSVCandidateFromJumpAlignment:852 case 2", cigar1="92=", begin1=397, cigar2="110=75I1D2=", begin2=510,
+         jumpRange=2, ref1Len=175, ref2Len=306, orient=dict(bp1RightOpen=1, bp2RightOpen=0),
+         expected=dict(bp1=[588 - 100, 591 - 100], bp2=[660 - 150, 663 - 150])),
+]
+
+
+def jump_sv_unit_case(t):
+    import re as _re
+    code = {c: i for i, c in enumerate(cb.SEG_CODES)}
+    segs = lambda cg: [(int(n) << 4) | code[c] for n, c in _re.findall(r"(\d+)([MIDNSHP=X])", cg)]  # noqa: E731
+    s1, s2 = segs(t["cigar1"]), segs(t["cigar2"])
+    jump = np.zeros(1, dtype=cb.JUMP_RESULT_DT)
+    jump[0] = (100, 0, t["jumpRange"], t["begin1"], t["begin2"], len(s1), len(s2), 0, 0, len(s1))
+    ref1 = np.asarray([(0, t["ref1Len"], 0)], dtype=cb.SEQVIEW_DT)
+    ref2 = np.asarray([(0, t["ref2Len"], 0)], dtype=cb.SEQVIEW_DT)
+    orient = np.zeros(1, dtype=cb.JUMP_ORIENT_DT)
+    for k, v in t["orient"].items():
+        orient[k] = v
+    return (np.ones(1, np.uint8), np.zeros(1, np.uint32), 1, np.zeros(1, np.int32), jump,
+            np.asarray(s1 + s2, dtype=np.uint32), ref1, ref2, orient)
+
+
 def small_sv_unit_case(t, qc_cases):
     u = dict(kind="complex", minSize=t["minSize"], contig=t["contig"], ref=t["ref"],
              contigs=[dict(cigar=t["cigar"], beginPos=t["beginPos"], score=1, isJumped=0, support=1)])
@@ -339,8 +367,24 @@ def refiner_golden(ref, qc_cases):
             if not o:
                 r[ci] = None  # undefined in the reference where it throws
         sv_fuzz.append(dict(seed=seed, n_loci=60, svFirst=[int(x) for x in first], svs=rows))
+    jump_units = []
+    for t in JUMP_SV_UNIT_TESTS:
+        v = ref.jump_sv_raw(*jump_sv_unit_case(t))[0]
+        assert [int(v["bp1Begin"]), int(v["bp1End"])] == t["expected"]["bp1"], t["src"]
+        assert [int(v["bp2Begin"]), int(v["bp2End"])] == t["expected"]["bp2"], t["src"]
+        u = dict(t)
+        u["reference"] = [int(x) for x in v.tolist()]
+        jump_units.append(u)
+    jump_fuzz = []
+    for seed in (301,):
+        case = qc_cases.fuzz_case(seed, 80)
+        ref1, ref2, orient = qc_cases.jump_sv_inputs(case, seed)
+        qc, best = case.run(ref)
+        got = ref.jump_sv_raw(case.isJump, case.slotFirst, len(case.jump), best, case.jump, case.cigar, ref1, ref2, orient)
+        jump_fuzz.append(dict(seed=seed, n_loci=80, svs=[[int(x) for x in row] for row in got.tolist()]))
     return dict(source="GSC/test/SVCandidateAssemblyRefinerTest.cpp (transcribed) + oracle/_ref on tests/qc_cases.py inputs",
-                scores=list(REFINER_SCORES), unit=units, fuzz=fuzz, trim=trims, small_sv_unit=sv_units, small_sv_fuzz=sv_fuzz)
+                scores=list(REFINER_SCORES), unit=units, fuzz=fuzz, trim=trims, small_sv_unit=sv_units, small_sv_fuzz=sv_fuzz,
+                jump_sv_unit=jump_units, jump_sv_fuzz=jump_fuzz)
 
 
 def main():

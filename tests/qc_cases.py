@@ -290,3 +290,23 @@ def trim_fuzz(seed, n=300):
         chunks.append(r)
         off += rl
     return np.concatenate(chunks), contig, ref, cuts
+
+
+def jump_sv_inputs(case, seed):
+    """orientation flags, window sizes and alignment offsets for the spanning candidates of a QcCase (mutates the
+    jump records: beginPos1/2, jumpRange, jumpInsertSize).  Returns (ref1 views, ref2 views, orient)."""
+    rng = np.random.default_rng(seed)
+    n = len(case.isJump)
+    ref1 = np.zeros(n, dtype=cb.SEQVIEW_DT)
+    ref2 = np.zeros(n, dtype=cb.SEQVIEW_DT)
+    ref1["len"] = rng.integers(1500, 6000, n)
+    ref2["len"] = rng.integers(1500, 6000, n)
+    orient = np.zeros(n, dtype=cb.JUMP_ORIENT_DT)
+    for k in ("isBp2AlignedFirst", "isBp1Reversed", "isBp2Reversed", "bp1RightOpen", "bp2RightOpen"):
+        orient[k] = rng.integers(0, 2, n)
+    m = len(case.jump)
+    case.jump["beginPos1"] = rng.integers(0, 1000, m)
+    case.jump["beginPos2"] = rng.integers(0, 1000, m)
+    case.jump["jumpRange"] = rng.integers(0, 30, m) * (rng.random(m) < 0.5)
+    case.jump["jumpInsertSize"] = rng.integers(0, 40, m) * (rng.random(m) < 0.3)
+    return ref1, ref2, orient

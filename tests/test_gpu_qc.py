@@ -197,3 +197,67 @@ def test_fused_small_svs(gpu, orc):
     _fused(gpu, batch, opts, cuts, False)
     with pytest.raises(cb.Mb200Error):
         gpu.candidates_small_svs()
+
+
+def test_fused_select_cigar_overflow_and_empty_loci(gpu, orc):
+    """a CIGAR pool that is too small: the QC kernels must stand down (the pool is incomplete), the call reports the
+    overflow with the size needed, and the retry is exact; loci without reads produce no contigs and best == -1"""
+    import ctypes as C
+    batch = synth.make_candidate_batch(24, seed=13, window=1500)
+    # empty the reads of two loci (one complex, one spanning if present)
+    ro = batch.readOff.copy()
+    for li in (3, 4):
+        n = int(ro[li + 1] - ro[li])
+        ro[li + 1:] -= n
+    keep = np.ones(len(batch.readViews), dtype=bool)
+    for li in (3, 4):
+        keep[int(batch.readOff[li]):int(batch.readOff[li + 1])] = False
+    batch.readViews = batch.readViews[keep].copy()
+    batch.readOff = ro
+    opts = cb.default_candidate_opts()
+    gpu.candidates_upload(batch)
+    out = gpu.candidates_run(opts, select=True)           # sizes everything
+    assert out["best"][3] == -1 and out["best"][4] == -1 and out["loci"]["nContigs"][3] == 0
+    want_best, want_qc = out["best"].copy(), out["qc"].copy()
+    small = dict(out)
+    small["cigar"] = np.zeros(8, dtype=np.uint32)          # far too small
+    used = [C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    st = gpu._call("candidates_run", p(opts), p(small["loci"]), p(small["contigs"]), p(small["pseudo"]), p(small["contigPool"]),
+                   C.c_uint64(small["contigPool"].size), C.byref(used[0]), p(small["setPool"]), C.c_uint64(small["setPool"].size),
+                   C.byref(used[1]), p(small["aln"]), p(small["jump"]), p(small["cigar"]), C.c_uint64(8), C.byref(used[2]),
+                   p(small["trim"]), p(small["qc"]), p(small["best"]))
+    assert st == cb.MB200_ERR_POOL_OVERFLOW and used[2].value > 8
+    out2 = gpu.candidates_run(opts, select=True)
+    assert out2["best"].tolist() == want_best.tolist() and out2["qc"].tobytes() == want_qc.tobytes()
+    case, _ = qc_cases.pipeline_case(orc, batch, opts, None)
+    assert case.run(orc)[1].tolist() == want_best.tolist()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_jump_sv_fuzz(gpu, orc, seed):
+    case = qc_cases.fuzz_case(seed, 500)
+    ref1, ref2, orient = qc_cases.jump_sv_inputs(case, seed)
+    qc, best = case.run(orc)
+    args = (case.isJump, case.slotFirst, len(case.jump), best, case.jump, case.cigar, ref1, ref2, orient)
+    assert gpu.jump_sv_raw(*args).tobytes() == orc.jump_sv_raw(*args).tobytes()
+
+
+def test_jump_sv_golden(gpu):
+    from test_oracle_golden import check_jump_sv_golden
+    check_jump_sv_golden(gpu)
+
+
+def test_fused_jump_svs(gpu, orc):
+    batch = synth.make_candidate_batch(64, seed=78, window=1500)
+    opts = cb.default_candidate_opts()
+    case, _ = qc_cases.pipeline_case(orc, batch, opts, None)
+    qo, bo = case.run(orc)
+    rng = np.random.default_rng(4)
+    orient = np.zeros(batch.nLoci, dtype=cb.JUMP_ORIENT_DT)
+    for k in ("isBp2AlignedFirst", "isBp1Reversed", "isBp2Reversed", "bp1RightOpen", "bp2RightOpen"):
+        orient[k] = rng.integers(0, 2, batch.nLoci)
+    want = orc.jump_sv_raw(case.isJump, case.slotFirst, len(case.jump), bo, case.jump, case.cigar, batch.ref1, batch.ref2, orient)
+    _fused(gpu, batch, opts, None, True)
+    got = gpu.candidates_jump_svs(orient)
+    assert got.tobytes() == want.tobytes() and int(want["valid"].sum()) >= 5

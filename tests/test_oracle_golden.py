@@ -163,6 +163,39 @@ def check_small_sv_golden(binding):
             assert all(w is None or int(a) == w for a, w in zip(got, want))
 
 
+def check_jump_sv_golden(binding):
+    import re
+    import qc_cases
+    from manta_b200 import _cabi as cb
+    g = load("refiner_qc.json")
+    code = {c: i for i, c in enumerate(cb.SEG_CODES)}
+    segs = lambda cg: [(int(n) << 4) | code[c] for n, c in re.findall(r"(\d+)([MIDNSHP=X])", cg)]  # noqa: E731
+    for t in g["jump_sv_unit"]:
+        s1, s2 = segs(t["cigar1"]), segs(t["cigar2"])
+        jump = np.zeros(1, dtype=cb.JUMP_RESULT_DT)
+        jump[0] = (100, 0, t["jumpRange"], t["begin1"], t["begin2"], len(s1), len(s2), 0, 0, len(s1))
+        orient = np.zeros(1, dtype=cb.JUMP_ORIENT_DT)
+        for k, v in t["orient"].items():
+            orient[k] = v
+        got = binding.jump_sv_raw(np.ones(1, np.uint8), np.zeros(1, np.uint32), 1, np.zeros(1, np.int32), jump,
+                                  np.asarray(s1 + s2, dtype=np.uint32), np.asarray([(0, t["ref1Len"], 0)], dtype=cb.SEQVIEW_DT),
+                                  np.asarray([(0, t["ref2Len"], 0)], dtype=cb.SEQVIEW_DT), orient)[0]
+        assert [int(got["bp1Begin"]), int(got["bp1End"])] == t["expected"]["bp1"], t["src"]
+        assert [int(got["bp2Begin"]), int(got["bp2End"])] == t["expected"]["bp2"], t["src"]
+        assert [int(x) for x in got.tolist()] == t["reference"], t["src"]
+    for f in g["jump_sv_fuzz"]:
+        case = qc_cases.fuzz_case(f["seed"], f["n_loci"])
+        ref1, ref2, orient = qc_cases.jump_sv_inputs(case, f["seed"])
+        qc, best = case.run(binding)
+        got = binding.jump_sv_raw(case.isJump, case.slotFirst, len(case.jump), best, case.jump, case.cigar, ref1, ref2, orient)
+        assert [[int(x) for x in row] for row in got.tolist()] == f["svs"]
+
+
+def test_jump_sv_golden(orc):
+    """test_generateRefinedSVCandidateFromJumpAlignment known answers + reference outputs on seeded inputs"""
+    check_jump_sv_golden(orc)
+
+
 def test_small_sv_golden(orc):
     """test_GetVariantRange / test_setSmallCandSV known answers + reference outputs on seeded inputs"""
     check_small_sv_golden(orc)

@@ -176,3 +176,20 @@ def test_small_sv_pipeline_vs_ref(orc, ref):
     got, want = case.small_svs(orc, qc, best), case.small_svs(ref, qc, best)
     _same_svs(got, want)
     assert (want[1]["status"] == 0).sum() >= 10
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_jump_sv_fuzz_vs_ref(orc, ref, seed):
+    """adjustAssembledBreakend over every combination of breakend state, alignment order and strand"""
+    import qc_cases
+    case = qc_cases.fuzz_case(seed, 400)
+    ref1, ref2, orient = qc_cases.jump_sv_inputs(case, seed)
+    qc, best = case.run(ref)
+    a = orc.jump_sv_raw(case.isJump, case.slotFirst, len(case.jump), best, case.jump, case.cigar, ref1, ref2, orient)
+    b = ref.jump_sv_raw(case.isJump, case.slotFirst, len(case.jump), best, case.jump, case.cigar, ref1, ref2, orient)
+    assert a.tobytes() == b.tobytes()
+    v = b[b["valid"] == 1]
+    assert len(v) > 30
+    combos = {(int(o["isBp2AlignedFirst"]), int(o["isBp1Reversed"]), int(o["isBp2Reversed"]), int(o["bp1RightOpen"]), int(o["bp2RightOpen"]))
+              for o in orient[b["valid"] == 1]}
+    assert len(combos) >= 20
