@@ -942,7 +942,9 @@ __device__ __forceinline__ bool cursorWait(StageCursor& cur)
 // badVal for this score set and query length), so the comparisons against badVal -- and their pointer codes --
 // are dropped.
 template <int KIND, int RT, bool NOBAD>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) dpPairKernel(const DpParams P)
+// strips of up to 8 rows per lane are held to 168 registers (3 CTAs/SM): left alone, ptxas spends 176-238 registers on
+// the 1-byte kinds there and drops the occupancy to 2 CTAs/SM for nothing (measured: -7 % jump time with the cap)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 8) ? 3 : 1) dpPairKernel(const DpParams P)
 {
   using KT               = KindTraits<KIND>;
   using PL               = PtrLayout<RT, KT::CELLB>;
