@@ -2,13 +2,15 @@
 """bench.py -- BASELINE.json metric on BASELINE.json configs[1].
 
   metric   : SV candidates assembled+aligned per second (one candidate = one SVCandidate junction entering
-             getCandidateAssemblyData, GSC/SVCandidateProcessor.cpp:310: its reads assembled over all word lengths
-             and every resulting contig aligned).
+             getCandidateAssemblyData, GSC/SVCandidateProcessor.cpp:310: its reads assembled over all word lengths,
+             every resulting contig aligned -- complex candidates against the 10-mer-trimmed window -- and the
+             refiner's contig QC / bestAlignmentIndex selection; --no-refine leaves the trim and the QC out).
   workload : synthetic 50 000 candidate loci x 64 reads x 150 bp, assembly k=41..76 + contig-vs-5 kb-window DP
              (manta_b200.synth.make_candidate_batch), per GPU (weak scaling).
   step     : one pass of the hot path over one batch.
   value    : inputs resident in HBM when the timed region starts (mb200_candidates_run), results back on the host.
-  e2e      : the same through the public C-ABI call sequence with HOST (pinned) buffers: upload + run + download.
+  e2e      : the same through the public C-ABI call sequence with HOST (pinned) buffers: upload + run + download; the
+             library stages batches in two slots, so the upload of step i+1 is issued before step i runs.
   --impl reference : the reference's own CPU implementation of the same path (oracle/_ref = the unmodified
              reference sources compiled by oracle/build_ref.sh; the C port oracle/_build if that is absent), all
              host threads, on a bounded sample of the same workload.

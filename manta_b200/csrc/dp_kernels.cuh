@@ -944,7 +944,13 @@ __device__ __forceinline__ bool cursorWait(StageCursor& cur)
 template <int KIND, int RT, bool NOBAD>
 // strips of up to 8 rows per lane are held to 168 registers (3 CTAs/SM): left alone, ptxas spends 176-238 registers on
 // the 1-byte kinds there and drops the occupancy to 2 CTAs/SM for nothing (measured: -7 % jump time with the cap)
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 8) ? 3 : 1) dpPairKernel(const DpParams P)
+#ifndef MB200_X_CAPRT
+#define MB200_X_CAPRT 8
+#endif
+#ifndef MB200_X_CAP4
+#define MB200_X_CAP4 0
+#endif
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_X_CAP4) ? 4 : ((RT <= MB200_X_CAPRT) ? 3 : 1)) dpPairKernel(const DpParams P)
 {
   using KT               = KindTraits<KIND>;
   using PL               = PtrLayout<RT, KT::CELLB>;
