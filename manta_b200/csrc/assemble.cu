@@ -202,6 +202,58 @@ __device__ uint64_t stlHashWord(const Key& a, uint32_t k)
   return h;
 }
 
+// bit j of x -> bit 2j (Morton spread), used to interleave the two bit planes of 32 packed bases
+__device__ __forceinline__ uint64_t spread32(uint32_t x)
+{
+  uint64_t v = x;
+  v = (v | (v << 16)) & 0x0000FFFF0000FFFFull;
+  v = (v | (v << 8)) & 0x00FF00FF00FF00FFull;
+  v = (v | (v << 4)) & 0x0F0F0F0F0F0F0F0Full;
+  v = (v | (v << 2)) & 0x3333333333333333ull;
+  v = (v | (v << 1)) & 0x5555555555555555ull;
+  return v;
+}
+
+// Pack one read: 2 bits/base MSB-first (32 bases per word, nPk words incl. 4 zero words of padding) and the N-mask
+// bit plane (64 bases per word, nMk words).  One lane per base: three ballots per 32 bases give the two code bit
+// planes and the mask; lane c of a group of 32 chunks then assembles word c.  Returns true if a byte outside
+// {A,C,G,T,N} was seen (only checked when `checkAlphabet`).
+__device__ bool packRead(const uint8_t* src, uint32_t len, uint64_t* pk, uint64_t* mk, uint32_t nPk, uint32_t nMk, bool checkAlphabet,
+                         int lane)
+{
+  bool           bad     = false;
+  const uint32_t nChunks = (len + 31) / 32;
+  uint32_t       maskDone = 0;
+  for (uint32_t c0 = 0; c0 < nPk; c0 += 32) {
+    uint32_t       myHi = 0, myLo = 0, myN = 0;
+    const uint32_t cEnd = min(nChunks, c0 + 32);
+    for (uint32_t c = c0; c < cEnd; ++c) {
+      const uint32_t i    = c * 32 + lane;
+      uint32_t       code = 0;
+      bool           isN  = false;
+      if (i < len) {
+        const uint8_t ch = src[i];
+        code             = (ch == 'C') ? 1u : ((ch == 'G') ? 2u : ((ch == 'T') ? 3u : 0u));
+        isN              = (ch != 'A') && (code == 0);
+        if (checkAlphabet && isN && ch != 'N') bad = true;
+      }
+      const uint32_t hi = __ballot_sync(0xffffffffu, (code & 2u) != 0);
+      const uint32_t lo = __ballot_sync(0xffffffffu, (code & 1u) != 0);
+      const uint32_t nn = __ballot_sync(0xffffffffu, isN);
+      if ((uint32_t)lane == c - c0) { myHi = hi; myLo = lo; myN = nn; }
+    }
+    const uint32_t w = c0 + lane;
+    if (w < nPk) pk[w] = (spread32(__brev(myHi)) << 1) | spread32(__brev(myLo));
+    const uint32_t nA = __shfl_sync(0xffffffffu, myN, (2 * lane) & 31);
+    const uint32_t nB = __shfl_sync(0xffffffffu, myN, (2 * lane + 1) & 31);
+    const uint32_t wm = c0 / 2 + lane;
+    if (lane < 16 && wm < nMk) mk[wm] = ((uint64_t)__brev(nA) << 32) | (uint64_t)__brev(nB);
+    maskDone = c0 / 2 + 16;
+  }
+  for (uint32_t wm = maskDone + lane; wm < nMk; wm += 32) mk[wm] = 0;
+  return __any_sync(0xffffffffu, bad);
+}
+
 // ---- per-CTA view of the workspace -----------------------------------------------------------------
 struct Work {
   uint32_t *readLen, *readPackOff, *readMaskOff, *winStart;
@@ -410,31 +462,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
       uint64_t*      pk  = W.packed + W.readPackOff[r];
       uint64_t*      mk  = W.nmask + W.readMaskOff[r];
       const uint32_t nPk = (len + 31) / 32 + 4, nMk = (len + 63) / 64 + 3;
-      for (uint32_t w = lane; w < nPk; w += 32) {
-        uint64_t v = 0;
-        for (uint32_t b = 0; b < 32; ++b) {
-          const uint32_t i = w * 32 + b;
-          uint32_t       code = 0;
-          if (i < len) {
-            const uint8_t ch = src[i];
-            if (ch == 'A') code = 0;
-            else if (ch == 'C') code = 1;
-            else if (ch == 'G') code = 2;
-            else if (ch == 'T') code = 3;
-            else if (ch != 'N') badBase = true;
-          }
-          v |= (uint64_t)code << (62 - 2 * b);
-        }
-        pk[w] = v;
-      }
-      for (uint32_t w = lane; w < nMk; w += 32) {
-        uint64_t v = 0;
-        for (uint32_t b = 0; b < 64; ++b) {
-          const uint32_t i = w * 64 + b;
-          if (i < len && src[i] != 'A' && src[i] != 'C' && src[i] != 'G' && src[i] != 'T') v |= 1ull << (63 - b);
-        }
-        mk[w] = v;
-      }
+      if (packRead(src, len, pk, mk, nPk, nMk, true, lane)) badBase = true;
     }
     if (__syncthreads_or(badBase ? 1 : 0)) status = MB200_ERR_BAD_BASE;
     if (normalReadCount + maxIter > 32 * MAX_SETW) status = MB200_ERR_UNSUPPORTED;
@@ -926,20 +954,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           uint64_t*      pk  = W.packed + W.readPackOff[r];
           uint64_t*      mk  = W.nmask + W.readMaskOff[r];
           const uint32_t nPk = (len + 31) / 32 + 4, nMk = (len + 63) / 64 + 3;
-          for (uint32_t w = lane; w < nPk; w += 32) {
-            uint64_t v = 0;
-            for (uint32_t b = 0; b < 32; ++b) {
-              const uint32_t i = w * 32 + b;
-              uint32_t       code = 0;
-              if (i < len) {
-                const uint8_t ch = src[i];
-                code = (ch == 'C') ? 1 : (ch == 'G' ? 2 : (ch == 'T' ? 3 : 0));
-              }
-              v |= (uint64_t)code << (62 - 2 * b);
-            }
-            pk[w] = v;
-          }
-          for (uint32_t w = lane; w < nMk; w += 32) mk[w] = 0;
+          packRead(src, len, pk, mk, nPk, nMk, false, lane);
         }
         __syncthreads();
         // NB: the pseudo reads must be packed from the contig buffers BEFORE the next buildContigs overwrites

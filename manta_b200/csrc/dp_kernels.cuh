@@ -941,16 +941,12 @@ __device__ __forceinline__ bool cursorWait(StageCursor& cur)
 // NOBAD: the host proved that the sentinel can never win a max strictly (every running maximum stays above
 // badVal for this score set and query length), so the comparisons against badVal -- and their pointer codes --
 // are dropped.
+// Strips of up to 12 rows per lane are held to 168 registers (3 CTAs/SM).  Left alone, ptxas spends 176-255 registers
+// on them and the occupancy drops to 2 CTAs/SM for nothing: with the cap the spills are 0-12 bytes.  Measured: -7 %
+// jump time for the cap up to 8 rows, another -8 % up to 12 rows; 128 registers (4 CTAs/SM) gains nothing for 4-6 rows
+// and loses for 8; 16 rows spill 130+ bytes at 168 and stay uncapped.
 template <int KIND, int RT, bool NOBAD>
-// strips of up to 8 rows per lane are held to 168 registers (3 CTAs/SM): left alone, ptxas spends 176-238 registers on
-// the 1-byte kinds there and drops the occupancy to 2 CTAs/SM for nothing (measured: -7 % jump time with the cap)
-#ifndef MB200_X_CAPRT
-#define MB200_X_CAPRT 8
-#endif
-#ifndef MB200_X_CAP4
-#define MB200_X_CAP4 0
-#endif
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_X_CAP4) ? 4 : ((RT <= MB200_X_CAPRT) ? 3 : 1)) dpPairKernel(const DpParams P)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpPairKernel(const DpParams P)
 {
   using KT               = KindTraits<KIND>;
   using PL               = PtrLayout<RT, KT::CELLB>;
