@@ -382,7 +382,7 @@ def main():
                               achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,
                               traffic=(traffic_factor * dom_bytes) if traffic_factor else None, traffic_source=traffic_src,
                               bound_note="HBM is the defined roofline (SURVEY 8d); the kernel itself is integer-ALU-pipe bound "
-                                         "(ncu: alu pipe 75-87% busy, DRAM 13-14%), see profiles/r01_dp_pair_full_v5.txt",
+                                         "(ncu: alu pipe 75-87% busy, DRAM 13-14%), see profiles/r01_dp_pair_full_v6.txt",
                               peak_source=peak_src, algorithmic_bytes_per_launch_set=dom_bytes, kernel_ms_per_step=dom_ms,
                               gcups=tim["indelCells"] / (dom_ms * 1e-3) * 1e-9 if dom_ms > 0 else None),
                 stages=dict(device_ms_per_step=ev_s * 1000.0 / args.steps, asm_ms=stage["asmMs"] / args.steps,
