@@ -376,7 +376,6 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
 {
   __shared__ uint32_t sh[ASM_THREADS < 64 ? 64 : ASM_THREADS];
   __shared__ uint32_t shU[16];
-  __shared__ unsigned long long shBest[2];
 
   const uint32_t tid  = threadIdx.x;
   const uint32_t nt   = blockDim.x;
