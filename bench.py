@@ -375,7 +375,8 @@ def main():
     achieved = dom_bytes / (dom_ms * 1e-3) * 1e-9 if dom_ms > 0 else 0.0
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000.0 * wall / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="int32", data="synthetic", config=config, clocks=clocks,
+                dtype="int32", dtype_note="DP lanes are int16x2 where the host proves that every intermediate fits (results equal the int32 kernel, which the tests also run)",
+                data="synthetic", config=config, clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=launches,
                 roofline=dict(bound="hbm", kernel="dpPairKernel<KIND_INDEL,RT,NOBAD> (large-indel aligner, int16x2, two alignments per warp, 2 B back-pointer per cell; all row classes of one step)",
