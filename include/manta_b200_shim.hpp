@@ -495,6 +495,123 @@ inline std::vector<mb200_small_sv> refineSmallSVs(const Context& ctx, const unsi
   return out;
 }
 
+// ---- SVAlignmentInfo (row a10): host arithmetic on the refined SV records -------------------------------------------
+
+struct known_pos_range2 {  // lib/blt_util/known_pos_range2.hpp (the two members this path uses)
+  int begin = 0, end = 0;
+  int begin_pos() const { return begin; }
+  int end_pos() const { return end; }
+};
+
+namespace detail {
+inline std::string reverseCompCopy(const std::string& s)  // reverseCompCopyStr, lib/blt_util/seq_util.hpp:150-204
+{
+  std::string r(s.rbegin(), s.rend());
+  for (char& c : r) {
+    switch (c) {
+    case 'A': c = 'T'; break;
+    case 'C': c = 'G'; break;
+    case 'G': c = 'C'; break;
+    case 'T': c = 'A'; break;
+    case 'N': break;
+    default: throw GeneralException(MB200_ERR_BAD_BASE, "Invalid base in comp_base");
+    }
+  }
+  return r;
+}
+inline unsigned pathLength(const path_t& p, const bool ofRead, const size_t upTo)
+{
+  unsigned v(0);
+  for (size_t i(0); i < upTo && i < p.size(); ++i) {
+    const unsigned t(p[i].type);
+    const bool     isRead(t == MB200_SEG_MATCH || t == MB200_SEG_INSERT || t == MB200_SEG_SOFT_CLIP || t == MB200_SEG_SEQ_MATCH || t == MB200_SEG_SEQ_MISMATCH);
+    const bool     isRef(t == MB200_SEG_MATCH || t == MB200_SEG_DELETE || t == MB200_SEG_SKIP || t == MB200_SEG_SEQ_MATCH || t == MB200_SEG_SEQ_MISMATCH);
+    if (ofRead ? isRead : isRef) v += p[i].length;
+  }
+  return v;
+}
+}  // namespace detail
+
+/// The mapping from the refined breakends to the assembled contig and the reference windows that split-read scoring
+/// aligns reads against: lib/manta/SVScoreInfo.hpp:35-83, SVScoreInfo.cpp:31-167.  Built from the records the library
+/// returns (mb200_small_sv / mb200_jump_sv are in window coordinates, i.e. the reference's ranges minus get_offset()).
+struct SVAlignmentInfo {
+  /// complex candidate: one kept segment of the selected contig (SVScoreInfo.cpp:109-140)
+  SVAlignmentInfo(const mb200_small_sv& sv, const AlignmentResult<int>& alignment, const std::string& contig, const std::string& bp1Ref)
+    : _isSpanning(false), _bp1ContigReversed(false), _bp2ContigReversed(false)
+  {
+    const path_t&  apath(alignment.align.apath);
+    const unsigned alignRefEnd(alignment.align.beginPos + detail::pathLength(apath, false, apath.size()));
+    // getExtendedContig, lib/alignment/AlignmentUtil.cpp:112-127
+    contigSeq = bp1Ref.substr(0, alignment.align.beginPos) + contig + bp1Ref.substr(alignRefEnd);
+    bp1RefSeq = bp1Ref;
+    const int bp1Hom(sv.bp1End - sv.bp1Begin - 1), bp2Hom(sv.bp2End - sv.bp2Begin - 1);
+    bp1ContigOffset.begin = static_cast<int>(alignment.align.beginPos + detail::pathLength(apath, true, sv.pathFirst)) - 1;
+    bp1ContigOffset.end   = bp1ContigOffset.begin + bp1Hom;
+    bp2ContigOffset.begin = static_cast<int>(alignment.align.beginPos + detail::pathLength(apath, true, sv.pathLast + 1)) - 1;
+    bp2ContigOffset.end   = bp2ContigOffset.begin + bp2Hom;
+    bp1RefOffset = known_pos_range2{sv.bp1Begin, sv.bp1End};
+    bp2RefOffset = known_pos_range2{sv.bp2Begin, sv.bp2End};
+  }
+
+  /// spanning candidate (SVScoreInfo.cpp:47-108); alignRef1 / alignRef2 are the windows align1 / align2 ran against
+  SVAlignmentInfo(const mb200_jump_sv& sv, const JumpAlignmentResult<int>& alignment, const mb200_jump_orient& orient,
+                  const std::string& contig, const std::string& alignRef1, const std::string& alignRef2)
+    : _isSpanning(true), _bp1ContigReversed(orient.isBp1Reversed != 0), _bp2ContigReversed(orient.isBp2Reversed != 0)
+  {
+    const unsigned align2RefEnd(alignment.align2.beginPos + detail::pathLength(alignment.align2.apath, false, alignment.align2.apath.size()));
+    // getExtendedContig, lib/alignment/AlignmentUtil.cpp:97-110
+    contigSeq = alignRef1.substr(0, alignment.align1.beginPos) + contig + alignRef2.substr(align2RefEnd);
+    const int bp1Hom(sv.bp1End - sv.bp1Begin - 1), bp2Hom(sv.bp2End - sv.bp2Begin - 1);
+    const int align1Size(detail::pathLength(alignment.align1.apath, true, alignment.align1.apath.size()));
+    bp1ContigOffset.begin = static_cast<int>(alignment.align1.beginPos) + align1Size - 1;
+    bp2ContigOffset.begin = bp1ContigOffset.begin + static_cast<int>(alignment.jumpInsertSize);
+    if (orient.isBp2AlignedFirst) std::swap(bp1ContigOffset, bp2ContigOffset);
+    bp1ContigOffset.end = bp1ContigOffset.begin + bp1Hom;
+    bp2ContigOffset.end = bp2ContigOffset.begin + bp2Hom;
+    if (_bp1ContigReversed || _bp2ContigReversed) {
+      revContigSeq = detail::reverseCompCopy(contigSeq);
+      const int         revSize(static_cast<int>(contigSeq.size()) - 2);  // -2: the offset jumps to the other side of the breakend
+      known_pos_range2& r(_bp1ContigReversed ? bp1ContigOffset : bp2ContigOffset);
+      const known_pos_range2 tmp(r);
+      r.begin = revSize - tmp.end;
+      r.end   = revSize - tmp.begin;
+    }
+    bp1RefSeq = orient.isBp2AlignedFirst ? alignRef2 : alignRef1;
+    bp2RefSeq = orient.isBp2AlignedFirst ? alignRef1 : alignRef2;
+    bp1RefOffset = known_pos_range2{sv.bp1Begin, sv.bp1Begin + bp1Hom};
+    bp2RefOffset = known_pos_range2{sv.bp2Begin, sv.bp2Begin + bp2Hom};
+  }
+
+  const std::string& bp1ContigSeq() const { return (_bp1ContigReversed ? revContigSeq : contigSeq); }
+  const std::string& bp2ContigSeq() const { return (_bp2ContigReversed ? revContigSeq : contigSeq); }
+  const std::string& bp1ReferenceSeq() const { return bp1RefSeq; }
+  const std::string& bp2ReferenceSeq() const { return (_isSpanning ? bp2RefSeq : bp1RefSeq); }
+  bool               isSpanning() const { return _isSpanning; }
+
+  bool isMinBpEdge(const unsigned minEdge) const  // SVScoreInfo.cpp:142-164
+  {
+    const int iminEdge(minEdge);
+    if ((bp1ContigOffset.begin + 1) < iminEdge) return false;
+    if ((bp2ContigOffset.begin + 1) < iminEdge) return false;
+    if ((bp1RefOffset.begin + 1) < iminEdge) return false;
+    if ((bp2RefOffset.begin + 1) < iminEdge) return false;
+    const int contigBpSize(static_cast<int>(contigSeq.size()) - 1);
+    if ((contigBpSize - bp1ContigOffset.end) < iminEdge) return false;
+    if ((contigBpSize - bp2ContigOffset.end) < iminEdge) return false;
+    if ((static_cast<int>(bp1ReferenceSeq().size()) - 1 - bp1RefOffset.end) < iminEdge) return false;
+    if ((static_cast<int>(bp2ReferenceSeq().size()) - 1 - bp2RefOffset.end) < iminEdge) return false;
+    return true;
+  }
+
+  known_pos_range2 bp1ContigOffset, bp2ContigOffset, bp1RefOffset, bp2RefOffset;
+
+private:
+  std::string contigSeq, revContigSeq, bp1RefSeq, bp2RefSeq;
+  const bool  _isSpanning, _bp1ContigReversed, _bp2ContigReversed;
+};
+
 }  // namespace mb200
+
 
 

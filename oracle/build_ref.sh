@@ -53,6 +53,7 @@ SRCS=(
   "$LIB/blt_util/qscore_cache.cpp"
   "$LIB/common/Exceptions.cpp"
   "$GSC/SplitReadAlignment.cpp"
+  "$LIB/manta/SVScoreInfo.cpp"
   "$OUT/boost_1_58_0/libs/date_time/src/gregorian/greg_month.cpp"
   "$HERE/ref_shim.cpp"
   "$HERE/ref_refiner_shim.cpp"

@@ -25,6 +25,8 @@
 #include "alignment/GlobalLargeIndelAligner.hpp"
 #include "assembly/IterativeAssembler.hpp"
 
+#include "manta/SVScoreInfo.hpp"
+
 #include "manta_b200.h"
 #include "manta_oracle.h"  // checksum terms only (macros); no oracle code is linked here
 
@@ -319,6 +321,88 @@ REF_API int ref_jump_sv_batch(uint32_t nLoci, const uint8_t* isJump, const uint3
     }
     out[li] = v;
   }
+  return MB200_OK;
+}
+
+/// SVAlignmentInfo (lib/manta/SVScoreInfo.cpp:31-140) of one refined SV, flattened: out[0..7] = bp1ContigOffset, bp2ContigOffset,
+/// bp1RefOffset, bp2RefOffset (begin, end each); out[8] = isMinBpEdge(minEdge); the extended contig (getExtendedContig,
+/// lib/alignment/AlignmentUtil.cpp:97-127) and its reverse complement go to contigOut / revOut (NUL-terminated, cap bytes).
+/// Pins the host-side shim class mb200::SVAlignmentInfo (tests/cpp/align_info_test.cpp).
+REF_API int ref_sv_align_info_small(const char* contig, const char* ref1, int32_t beginPos, const uint32_t* path, uint32_t nPath,
+                                    uint32_t segFirst, uint32_t segLast, int32_t bp1Begin, int32_t bp1End, int32_t bp2Begin,
+                                    int32_t bp2End, uint32_t minEdge, int32_t* out, char* contigOut, char* revOut, uint32_t cap)
+{
+  SVCandidate sv;
+  sv.setPrecise();
+  sv.bp1.interval.range.set_range(bp1Begin, bp1End);
+  sv.bp2.interval.range.set_range(bp2Begin, bp2End);
+  sv.assemblyAlignIndex   = 0;
+  sv.assemblySegmentIndex = 0;
+  SVCandidateAssemblyData ad;
+  ad.isSpanning = false;
+  ad.smallSVAlignments.resize(1);
+  ad.smallSVAlignments[0].align.beginPos = beginPos;
+  ad.smallSVAlignments[0].align.apath    = toPath(path, nPath);
+  ad.smallSVSegments.resize(1);
+  ad.smallSVSegments[0].push_back(std::make_pair(segFirst, segLast));
+  ad.extendedContigs.resize(1);
+  ad.bp1ref.seq() = ref1;
+  ad.bp1ref.set_offset(0);
+  getExtendedContig(ad.smallSVAlignments[0], std::string(contig), ad.bp1ref.seq(), ad.extendedContigs[0]);
+  const SVAlignmentInfo ai(sv, ad);
+  out[0] = ai.bp1ContigOffset.begin_pos(); out[1] = ai.bp1ContigOffset.end_pos();
+  out[2] = ai.bp2ContigOffset.begin_pos(); out[3] = ai.bp2ContigOffset.end_pos();
+  out[4] = ai.bp1RefOffset.begin_pos(); out[5] = ai.bp1RefOffset.end_pos();
+  out[6] = ai.bp2RefOffset.begin_pos(); out[7] = ai.bp2RefOffset.end_pos();
+  out[8] = ai.isMinBpEdge(minEdge) ? 1 : 0;
+  const std::string& c(ai.bp1ContigSeq());
+  if (c.size() + 1 > cap) return MB200_ERR_POOL_OVERFLOW;
+  std::memcpy(contigOut, c.c_str(), c.size() + 1);
+  revOut[0] = 0;
+  return MB200_OK;
+}
+
+REF_API int ref_sv_align_info_jump(const char* contig, const char* alignRef1, const char* alignRef2, int32_t score, uint32_t jumpInsertSize,
+                                   uint32_t jumpRange, int32_t beginPos1, const uint32_t* path1, uint32_t nPath1, int32_t beginPos2,
+                                   const uint32_t* path2, uint32_t nPath2, const mb200_jump_orient* orient, int32_t bp1Begin,
+                                   int32_t bp1End, int32_t bp2Begin, int32_t bp2End, uint32_t minEdge, int32_t* out, char* contigOut,
+                                   char* revOut, uint32_t cap)
+{
+  SVCandidate sv;
+  sv.setPrecise();
+  sv.bp1.interval.range.set_range(bp1Begin, bp1End);
+  sv.bp2.interval.range.set_range(bp2Begin, bp2End);
+  sv.assemblyAlignIndex = 0;
+  SVCandidateAssemblyData ad;
+  ad.isSpanning = true;
+  ad.spanningAlignments.resize(1);
+  JumpAlignmentResult<int>& a(ad.spanningAlignments[0]);
+  a.score = score; a.jumpInsertSize = jumpInsertSize; a.jumpRange = jumpRange;
+  a.align1.beginPos = beginPos1; a.align1.apath = toPath(path1, nPath1);
+  a.align2.beginPos = beginPos2; a.align2.apath = toPath(path2, nPath2);
+  ad.bporient.isBp2AlignedFirst = (orient->isBp2AlignedFirst != 0);
+  ad.bporient.isBp1Reversed     = (orient->isBp1Reversed != 0);
+  ad.bporient.isBp2Reversed     = (orient->isBp2Reversed != 0);
+  // align1 ran against bp2's window when bp2 is aligned first (:1544-1547)
+  ad.bp1ref.seq() = orient->isBp2AlignedFirst ? alignRef2 : alignRef1;
+  ad.bp2ref.seq() = orient->isBp2AlignedFirst ? alignRef1 : alignRef2;
+  ad.bp1ref.set_offset(0);
+  ad.bp2ref.set_offset(0);
+  ad.extendedContigs.resize(1);
+  getExtendedContig(a, std::string(contig), std::string(alignRef1), std::string(alignRef2), ad.extendedContigs[0]);
+  const SVAlignmentInfo ai(sv, ad);
+  out[0] = ai.bp1ContigOffset.begin_pos(); out[1] = ai.bp1ContigOffset.end_pos();
+  out[2] = ai.bp2ContigOffset.begin_pos(); out[3] = ai.bp2ContigOffset.end_pos();
+  out[4] = ai.bp1RefOffset.begin_pos(); out[5] = ai.bp1RefOffset.end_pos();
+  out[6] = ai.bp2RefOffset.begin_pos(); out[7] = ai.bp2RefOffset.end_pos();
+  out[8] = ai.isMinBpEdge(minEdge) ? 1 : 0;
+  // the forward contig is the one a non-reversed breakend reads; the reversed one (if any) the other
+  const bool         rev1(orient->isBp1Reversed != 0), rev2(orient->isBp2Reversed != 0);
+  const std::string& fwd(rev1 ? ai.bp2ContigSeq() : ai.bp1ContigSeq());
+  const std::string  rev((rev1 || rev2) ? (rev1 ? ai.bp1ContigSeq() : ai.bp2ContigSeq()) : std::string());
+  if (fwd.size() + 1 > cap || rev.size() + 1 > cap) return MB200_ERR_POOL_OVERFLOW;
+  std::memcpy(contigOut, fwd.c_str(), fwd.size() + 1);
+  std::memcpy(revOut, rev.c_str(), rev.size() + 1);
   return MB200_OK;
 }
 

@@ -32,3 +32,17 @@ def test_shim_known_answers():
     build()
     out = subprocess.check_output([EXE]).decode()
     assert "shim_test ok" in out
+
+
+def test_shim_sv_alignment_info_vs_reference():
+    """mb200::SVAlignmentInfo (host arithmetic of row a10 in the shim) against the reference class through oracle/_ref"""
+    ref = os.path.join(ROOT, "oracle", "_ref", "libmanta_ref.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref is not built here")
+    exe = os.path.join(ROOT, "tests", "cpp", "align_info_test")
+    src = os.path.join(ROOT, "tests", "cpp", "align_info_test.cpp")
+    hdr = os.path.join(ROOT, "include", "manta_b200_shim.hpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-ldl"])
+    assert "align_info_test ok" in subprocess.check_output([exe, ref]).decode()
