@@ -51,10 +51,12 @@ def _load_library() -> C.CDLL:
 class Context(Binding):
     """One device context (mb200_ctx): owns the stream and all device buffers."""
 
-    def __init__(self, device: int = 0, ctas_per_sm: int = 0, scratch_bytes: int = 0, force_int32: bool = False):
+    def __init__(self, device: int = 0, ctas_per_sm: int = 0, scratch_bytes: int = 0, force_int32: bool = False,
+                 max_contig_len: int = 0):
         lib = _load_library()
         cfg = np.zeros(1, dtype=_cabi.CONFIG_DT)
         cfg["ctasPerSm"] = ctas_per_sm
+        cfg["maxContigLen"] = max_contig_len  # assembler workspace cap per contig (0 = library default 2048)
         cfg["scratchBytes"] = scratch_bytes
         cfg["reserved"][0][0] = 1 if force_int32 else 0  # always use the int32 one-alignment-per-warp DP kernel
         handle = C.c_void_p()
