@@ -181,7 +181,9 @@ def _apply_path(rng, path, lead):
     return np.concatenate(contig), np.concatenate(ref)
 
 
-def fuzz_case(seed, n_loci=200):
+def fuzz_case(seed, n_loci=200, exotic=False):
+    """exotic=True sprinkles hard clips at the path ends and reference skips ('N') inside jump-arm paths -- segment
+    types the aligners never emit but the path helpers handle (CPU-only comparisons use it)"""
     rng = np.random.default_rng(seed)
     isJump = (rng.random(n_loci) < 0.4).astype(np.uint8)
     nContigs = rng.integers(0, 6, n_loci).astype(np.uint32)
@@ -214,6 +216,14 @@ def fuzz_case(seed, n_loci=200):
                 s = s0 + k
                 p1 = _rand_path(rng, "none") if rng.random() < 0.9 else []
                 p2 = _rand_path(rng, "none") if rng.random() < 0.9 else []
+                if exotic:
+                    for p in (p1, p2):
+                        if p and rng.random() < 0.5:
+                            p.append((6, int(rng.integers(1, 20))))        # trailing hard clip
+                        if p and rng.random() < 0.5:
+                            p.insert(0, (6, int(rng.integers(1, 20))))     # leading hard clip
+                        if len(p) > 2 and rng.random() < 0.4:
+                            p.insert(len(p) // 2, (4, int(rng.integers(1, 300))))  # skip
                 if rng.random() < 0.3:  # short arm
                     p1 = [(EQ, int(rng.integers(1, 40)))]
                 o1, n1 = put_path(p1)

@@ -193,3 +193,10 @@ def test_jump_sv_fuzz_vs_ref(orc, ref, seed):
     combos = {(int(o["isBp2AlignedFirst"]), int(o["isBp1Reversed"]), int(o["isBp2Reversed"]), int(o["bp1RightOpen"]), int(o["bp2RightOpen"]))
               for o in orient[b["valid"] == 1]}
     assert len(combos) >= 20
+
+
+def test_jump_qc_exotic_segments_vs_ref(orc, ref):
+    """hard clips and reference skips in the jump arms (never emitted by the aligners, handled by the path helpers)"""
+    import qc_cases
+    case = qc_cases.fuzz_case(9, 300, exotic=True)
+    _same_qc(case.run(orc), case.run(ref))
