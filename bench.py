@@ -272,7 +272,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctx = manta_b200.Context(local_rank, max_contig_len=int(os.environ.get("MB200_BENCH_MAX_CONTIG", "0")))
+    ctx = manta_b200.Context(local_rank)
     batch = synth.make_candidate_batch(args.loci, seed=20260923 + rank)
     # every input array lives in pinned host memory, so that the staged upload is asynchronous end to end
     _keep = []
