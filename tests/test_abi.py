@@ -37,15 +37,20 @@ def test_struct_sizes_match_header(tmp_path):
     prog = tmp_path / "sizes.c"
     names = ["mb200_scores", "mb200_seqview", "mb200_aln_result", "mb200_jump_result", "mb200_sr_result",
              "mb200_sr_job", "mb200_qscore_tables", "mb200_asm_opts", "mb200_contig", "mb200_asm_locus",
-             "mb200_config", "mb200_timing"]
+             "mb200_config", "mb200_timing", "mb200_candidate_opts", "mb200_candidate_timing", "mb200_ref_cuts",
+             "mb200_trim_result", "mb200_qc_opts", "mb200_contig_qc", "mb200_small_sv", "mb200_jump_orient", "mb200_jump_sv"]
     prog.write_text('#include <stdio.h>\n#include "manta_b200.h"\nint main(){' +
                     "".join('printf("%%zu\\n", sizeof(%s));' % n for n in names) + "return 0;}")
     exe = tmp_path / "sizes"
-    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
+    # the header is plain C: strict C99 must accept it
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(cb.Scores), cb.SEQVIEW_DT.itemsize, cb.ALN_RESULT_DT.itemsize, cb.JUMP_RESULT_DT.itemsize,
             cb.SR_RESULT_DT.itemsize, cb.SR_JOB_DT.itemsize, cb.QSCORE_TABLES_DT.itemsize, cb.ASM_OPTS_DT.itemsize,
-            cb.CONTIG_DT.itemsize, cb.ASM_LOCUS_DT.itemsize, cb.CONFIG_DT.itemsize, cb.TIMING_DT.itemsize]
+            cb.CONTIG_DT.itemsize, cb.ASM_LOCUS_DT.itemsize, cb.CONFIG_DT.itemsize, cb.TIMING_DT.itemsize,
+            cb.CAND_OPTS_DT.itemsize, cb.CAND_TIMING_DT.itemsize, cb.REF_CUTS_DT.itemsize, cb.TRIM_RESULT_DT.itemsize,
+            cb.QC_OPTS_DT.itemsize, cb.CONTIG_QC_DT.itemsize, cb.SMALL_SV_DT.itemsize, cb.JUMP_ORIENT_DT.itemsize,
+            cb.JUMP_SV_DT.itemsize]
     assert got == want
 
 
