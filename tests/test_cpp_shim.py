@@ -46,3 +46,22 @@ def test_shim_sv_alignment_info_vs_reference():
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.check_call([gxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-ldl"])
     assert "align_info_test ok" in subprocess.check_output([exe, ref]).decode()
+
+
+def test_example_driver_compiles_and_links():
+    """examples/staged_driver.cpp (the INTEGRATION.md call sequence through the C ABI and the shim) builds against the library"""
+    build()
+    src = os.path.join(ROOT, "examples", "staged_driver.cpp")
+    exe = os.path.join(ROOT, "examples", "staged_driver")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([gxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), src, "-o", exe, manta_b200.library_path(),
+                           "-Wl,-rpath," + os.path.dirname(manta_b200.library_path())])
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_example_driver_runs():
+    test_example_driver_compiles_and_links()
+    out = subprocess.check_output([os.path.join(ROOT, "examples", "staged_driver")]).decode()
+    assert "bestAlignmentIndex: 0" in out and "140=120D104= at 560, deletion ref[700,820) cipos [0,0]" in out
+    assert "leftSize 70 rightSize 80 mismatches 0/0" in out
