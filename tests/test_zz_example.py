@@ -4,12 +4,14 @@ import subprocess
 
 import pytest
 
-from test_cpp_shim import ROOT, test_example_driver_compiles_and_links
+import test_cpp_shim
+
+ROOT = test_cpp_shim.ROOT
 
 
 @pytest.mark.gpu
 def test_example_driver_runs():
-    test_example_driver_compiles_and_links()
+    test_cpp_shim.test_example_driver_compiles_and_links()
     out = subprocess.check_output([os.path.join(ROOT, "examples", "staged_driver")]).decode()
     assert "bestAlignmentIndex: 0" in out and "140=120D104= at 560, deletion ref[700,820) cipos [0,0]" in out
     assert "leftSize 70 rightSize 80 mismatches 0/0" in out
