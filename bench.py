@@ -227,7 +227,7 @@ def main():
                           "SVCandidateAssemblyRefiner.cpp:1984-2011), contig QC + bestAlignmentIndex selection (:1364, :2119)"),
                   l2="inputs (~0.9 GB per batch) and back-pointer stream exceed the 126 MB L2; no flush needed",
                   parallelism="loci sharded by rank, no data-path collective" + (
-                      "; one NCCL gather of the per-GPU result buffers" if world > 1 else ""))
+                      "; one NCCL gather per step of the per-GPU candidate results (bestAlignmentIndex + the selected contigs' records)" if world > 1 else ""))
 
     if args.workload == "split":
         return split_microbench(args)
@@ -289,9 +289,15 @@ def main():
             return
         # the single collective of the path: per-GPU result buffers to rank 0 over NVLink
         from manta_b200 import shard
-        parts = [out["aln"], out["jump"]]
         if refine:
-            parts += [out["qc"], out["best"]]
+            # what the merged candidate buffer needs: bestAlignmentIndex of every candidate and the alignment / QC
+            # records of the selected contigs
+            best = out["best"]
+            sel = np.nonzero(best >= 0)[0]
+            slots = sel * int(opts["asmOpts"]["maxAssemblyCount"][0]) + best[sel]
+            parts = [best, out["aln"][slots], out["jump"][slots], out["qc"][slots]]
+        else:
+            parts = [out["aln"], out["jump"]]
         shard.gather_buffers(parts, dst=0, device="cuda:%d" % local_rank, state=gather_state)
 
     def sync_all():
