@@ -33,7 +33,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libmanta_b200.so")
+    # MANTA_B200_LIBRARY: an instrumented build of the same sources (tools/asm_profile.py), never a different backend
+    return os.environ.get("MANTA_B200_LIBRARY") or os.path.join(_HERE, "libmanta_b200.so")
 
 
 def _load_library() -> C.CDLL:
@@ -52,13 +53,15 @@ class Context(Binding):
     """One device context (mb200_ctx): owns the stream and all device buffers."""
 
     def __init__(self, device: int = 0, ctas_per_sm: int = 0, scratch_bytes: int = 0, force_int32: bool = False,
-                 max_contig_len: int = 0):
+                 max_contig_len: int = 0, no_tag_kernel: bool = False):
         lib = _load_library()
         cfg = np.zeros(1, dtype=_cabi.CONFIG_DT)
         cfg["ctasPerSm"] = ctas_per_sm
         cfg["maxContigLen"] = max_contig_len  # assembler workspace cap per contig (0 = library default 2048)
         cfg["scratchBytes"] = scratch_bytes
-        cfg["reserved"][0][0] = 1 if force_int32 else 0  # always use the int32 one-alignment-per-warp DP kernel
+        # bit 0: always use the int32 one-alignment-per-warp DP kernel; bit 1: int16x2 pairs on the predicate/SEL
+        # kernel, never the tagged-score kernel (the default where its score range allows)
+        cfg["reserved"][0][0] = (1 if force_int32 else 0) | (2 if no_tag_kernel else 0)
         handle = C.c_void_p()
         st = lib.mb200_create(C.c_int(device), cfg.ctypes.data_as(C.c_void_p), C.byref(handle))
         if st != _cabi.MB200_OK:

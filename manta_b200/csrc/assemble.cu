@@ -84,6 +84,19 @@ struct AsmParams {
 
 enum { FLAG_UNUSED = 1, FLAG_REPEAT = 2, FLAG_PEELED = 4, FLAG_ONSTACK = 8 };
 
+// -DMB200_ASM_PROFILE: per-phase clock64 totals and event counts of assembleKernel (tools/asm_profile.py); never in
+// the product build
+#ifdef MB200_ASM_PROFILE
+__device__ unsigned long long gAsmProf[32];
+#define PROF_DECL() long long profT = clock64()
+#define PROF_MARK(i) do { const long long _t = clock64(); if (threadIdx.x == 0) atomicAdd(&gAsmProf[i], (unsigned long long)(_t - profT)); profT = _t; } while (0)
+#define PROF_COUNT(i, v) do { if (threadIdx.x == 0) atomicAdd(&gAsmProf[i], (unsigned long long)(v)); } while (0)
+#else
+#define PROF_DECL() do { } while (0)
+#define PROF_MARK(i) do { } while (0)
+#define PROF_COUNT(i, v) do { } while (0)
+#endif
+
 struct CtgMeta {
   uint32_t lo, hi;  // contig == ctgSeq[lo, hi)
   int32_t  consBegin, consEnd;
@@ -433,6 +446,8 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
     __syncthreads();
     if (li >= P.nLoci) break;
 
+    PROF_DECL();
+    PROF_COUNT(19, 1);
     const uint64_t r0              = P.readOff[li];
     const uint32_t normalReadCount = (uint32_t)(P.readOff[li + 1] - r0);
     const uint32_t SW              = (normalReadCount + maxIter + 31) / 32;  // set words of this locus
@@ -471,8 +486,10 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
     uint32_t lastK    = 0;
 
     if (status == MB200_OK) {
+      PROF_MARK(0);
       for (uint32_t k = opt.minWordLength; k <= opt.maxWordLength; k += opt.wordStepSize) {
         lastK = k;
+        PROF_COUNT(16, 1);
         // ============================ buildContigs(k) ============================
         // ---- windows
         if (tid == 0) {
@@ -502,6 +519,8 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
         for (uint32_t i = tid; i < nWin * SW; i += nt) W.bits[i] = 0;
         if (tid == 0) shU[4] = 0;  // nWords
         __syncthreads();
+        PROF_MARK(1);
+        PROF_COUNT(21, nWin);
 
         // ---- getKmerCounts: keys of all N-free windows, then insertion
         for (uint32_t r = warp; r < nReads; r += nt / 32) {
@@ -521,6 +540,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           }
         }
         __syncthreads();
+        PROF_MARK(2);
         for (uint32_t r = warp; r < nReads; r += nt / 32) {
           const uint32_t len = W.readLen[r];
           if (len < k) continue;
@@ -558,6 +578,8 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
         }
         __syncthreads();
         const uint32_t nWords = shU[4];
+        PROF_MARK(3);
+        PROF_COUNT(20, nWords);
 
         // ---- successor / predecessor ids, homopolymer repeats, in-degrees for the trimming pass
         for (uint32_t i = tid; i < nWords * 4; i += nt) {
@@ -574,6 +596,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           }
         }
         __syncthreads();
+        PROF_MARK(4);
 
         // ---- is there any cycle besides homopolymer self loops?  (Kahn trimming, level synchronous)
         {
@@ -608,6 +631,8 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
         }
         const bool hasCycle = (shU[5] != nWords);
         __syncthreads();
+        PROF_MARK(5);
+        PROF_COUNT(22, hasCycle ? 1 : 0);
 
         if (hasCycle) {
           // ================= exact replay of getRepeatKmers (hash-order DFS roots) =================
@@ -722,6 +747,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           __syncthreads();
         }
 
+        PROF_MARK(6);
         // ---- unusedWords = {count >= minCoverage}
         for (uint32_t i = tid; i < nWords; i += nt) {
           const uint32_t id = W.wordList[i];
@@ -787,7 +813,9 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           __syncthreads();
           const uint32_t seed = shU[7];
           __syncthreads();
+          PROF_MARK(7);
           if (seed == NONE32) break;  // unusedWords.empty()
+          PROF_COUNT(17, 1);
 
           // ---------------- walk(seed)  (warp 0; IterativeAssembler.cpp:149-501)
           if (warp == 0) {
@@ -899,6 +927,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                   }
                   __syncwarp();
                   curWord = maxWord;
+                  PROF_COUNT(18, 1);
                 }
                 if (mode == 0) consEnd = (int)conservativeEndOffset;
                 else consBegin = (int)conservativeEndOffset;
@@ -918,6 +947,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
             }
           }
           __syncthreads();
+          PROF_MARK(8);
           if (shU[8]) isAssemblySuccess = false;
           if (shU[9]) status = MB200_ERR_ASM_OVERFLOW;
           nCtg++;
@@ -956,12 +986,14 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           packRead(src, len, pk, mk, nPk, nMk, false, lane);
         }
         __syncthreads();
+        PROF_MARK(9);
         // NB: the pseudo reads must be packed from the contig buffers BEFORE the next buildContigs overwrites
         // them; the copies used for the output (below) are taken from the packed form.
       }
     }
 
     // ================= selectContigs (:722-842) + output (warp 0) =================
+    PROF_MARK(10);
     if (warp == 0) {
       mb200_asm_locus Lo;
       memset(&Lo, 0, sizeof(Lo));
@@ -1071,6 +1103,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
       if (lane == 0) P.loci[li] = Lo;
     }
     __syncthreads();
+    PROF_MARK(11);
   }
 }
 
@@ -1253,6 +1286,18 @@ int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, co
   ctx->timing.launches++;
   return MB200_OK;
 }
+
+#ifdef MB200_ASM_PROFILE
+extern "C" __attribute__((visibility("default"))) int mb200_debug_asm_profile(unsigned long long* out32, int reset)
+{
+  if (cudaMemcpyFromSymbol(out32, gAsmProf, sizeof(unsigned long long) * 32) != cudaSuccess) return 1;
+  if (reset) {
+    unsigned long long z[32] = {0};
+    if (cudaMemcpyToSymbol(gAsmProf, z, sizeof(z)) != cudaSuccess) return 1;
+  }
+  return 0;
+}
+#endif
 
 extern "C" int mb200_assemble_batch(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci,
                                     const uint64_t* readOff, const mb200_seqview* readViews, const uint8_t* pool,

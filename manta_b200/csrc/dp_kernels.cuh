@@ -55,6 +55,8 @@ struct DpPair {
 struct DpParams {
   int match, mismatch, open, extend, offEdge, allowEdgeIns;
   int extra;  // jumpScore (KIND_JUMP) or largeIndelScore (KIND_INDEL)
+  int tagBias, tagBad;  // dpTagKernel: score offset and the sentinel's stand-in, in score units
+  uint32_t one;         // 1, opaque to ptxas: keeps dpTagKernel's re-tagging adds on the FMA pipe as IMADs
   const DpTask*  tasks;
   uint32_t       nTasks;
   const DpPair*  pairs;   // pair kernel: two tasks per warp (int16x2 lanes)
@@ -290,20 +292,51 @@ __device__ void rawLengths(const uint32_t* raw, uint32_t n, uint32_t& readLen, u
 // to S, so lane i speculatively fetches the i-th cell ahead and one ballot finds where the run ends -- one memory
 // round trip per <= 32 path steps instead of one per step.  All lanes keep identical copies of the scalar
 // bookkeeping; only lane 0 writes segments.
-template <int KIND, int RT>
-__device__ __forceinline__ uint32_t loadPtrField(const uint8_t* ptrBuf, size_t passStride, uint32_t q, uint32_t c, uint32_t state)
+// dpTagKernel keeps the cells of the two alignments of a pair interleaved in ONE stream (the packed registers are
+// stored as they are): 2-byte cells as [row][task] 16-bit halves of one 32-bit word per row, 1-byte cells as
+// [task][row parity] bytes of one 32-bit word per two rows.
+template <int RT, int CELLB> struct PairLayout {
+  static constexpr int WORDS            = (CELLB == 2) ? RT : (RT + 1) / 2;  // 32-bit words per thread per step
+  static constexpr int BYTES_PER_THREAD = WORDS * 4;
+  static constexpr int CHUNK_BYTES      = (BYTES_PER_THREAD % 16 == 0) ? 16 : ((BYTES_PER_THREAD % 8 == 0) ? 8 : 4);
+  static constexpr int NCHUNK           = BYTES_PER_THREAD / CHUNK_BYTES;
+  static constexpr int STEP_BYTES       = 32 * BYTES_PER_THREAD;
+  __device__ static __forceinline__ size_t passBytes(uint32_t rtot) { return (size_t)(rtot + 31) * STEP_BYTES; }
+  __device__ static __forceinline__ size_t cellOffset(uint32_t q, uint32_t c, size_t passStride, uint32_t half)
+  {
+    const uint32_t row    = q - 1;
+    const uint32_t pass   = row / (32 * RT);
+    const uint32_t within = row % (32 * RT);
+    const uint32_t lane   = within / RT;
+    const uint32_t rr     = within % RT;
+    const uint32_t t      = c - 1 + lane;
+    const uint32_t boff   = (CELLB == 2) ? (rr * 4 + half * 2) : ((rr >> 1) * 4 + half * 2 + (rr & 1));
+    const uint32_t chunk  = boff / CHUNK_BYTES;
+    const uint32_t inner  = boff % CHUNK_BYTES;
+    return (size_t)pass * passStride + ((size_t)(t * NCHUNK + chunk) * 32 + lane) * CHUNK_BYTES + inner;
+  }
+};
+
+// TAGGED: written by dpTagKernel -- interleaved pair layout (`half` selects the alignment), and the fields hold the
+// winner's tie-break code: state = TOPC - code
+template <int KIND, int RT, bool TAGGED>
+__device__ __forceinline__ uint32_t loadPtrField(const uint8_t* ptrBuf, size_t passStride, uint32_t q, uint32_t c, uint32_t state,
+                                                 uint32_t half)
 {
   using KT = KindTraits<KIND>;
   using PL = PtrLayout<RT, KT::CELLB>;
+  using PP = PairLayout<RT, KT::CELLB>;
+  const size_t off = TAGGED ? PP::cellOffset(q, c, passStride, half) : PL::cellOffset(q, c, passStride);
   uint32_t cell;
-  if (KT::CELLB == 1) cell = ptrBuf[PL::cellOffset(q, c, passStride)];
-  else cell = *reinterpret_cast<const uint16_t*>(ptrBuf + PL::cellOffset(q, c, passStride));
-  return (cell >> (KT::BITS * state)) & ((1u << KT::BITS) - 1);
+  if (KT::CELLB == 1) cell = ptrBuf[off];
+  else cell = *reinterpret_cast<const uint16_t*>(ptrBuf + off);
+  const uint32_t f = (cell >> (KT::BITS * state)) & ((1u << KT::BITS) - 1);
+  return TAGGED ? ((KIND == KIND_INDEL ? 4u : 3u) - f) : f;
 }
 
-template <int KIND, int RT>
+template <int KIND, int RT, bool TAGGED = false>
 __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t* ptrBuf, size_t passStride,
-                           uint32_t* segBuf, long long bestKey, bool stageOk, int lane)
+                           uint32_t* segBuf, long long bestKey, bool stageOk, int lane, uint32_t pairHalf = 0)
 {
   const uint32_t Q = task.Q, R1 = task.R1;
   const uint32_t R2   = (KIND == KIND_JUMP) ? task.R2 : 0u;
@@ -340,7 +373,7 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
       if (state == ST_JUMP) {
         if (psType != MB200_SEG_NONE) {
           // first visit of the jump state: close the open segment (no move)
-          const uint32_t next = loadPtrField<KIND, RT>(ptrBuf, passStride, queryBegin, refBegin, ST_JUMP);
+          const uint32_t next = loadPtrField<KIND, RT, TAGGED>(ptrBuf, passStride, queryBegin, refBegin, ST_JUMP, pairHalf);
           beginPos2 = (int)(refBegin - R1);
           if (psType == MB200_SEG_INSERT) {
             jumpInsertSize += psLen;
@@ -356,7 +389,7 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
         // walking left along the row while the cells keep pointing to JUMP
         const uint32_t avail = refBegin < 32u ? refBegin : 32u;
         uint32_t       nxt   = ST_JUMP;
-        if ((uint32_t)lane < avail) nxt = loadPtrField<KIND, RT>(ptrBuf, passStride, queryBegin, refBegin - lane, ST_JUMP);
+        if ((uint32_t)lane < avail) nxt = loadPtrField<KIND, RT, TAGGED>(ptrBuf, passStride, queryBegin, refBegin - lane, ST_JUMP, pairHalf);
         const uint32_t diff = __ballot_sync(FULL, ((uint32_t)lane < avail) && nxt != ST_JUMP);
         if (diff) {
           const int n = __ffs(diff) - 1;  // cells 0..n-1 moved, cell n leaves the jump state without moving
@@ -377,7 +410,7 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
       if (avail > 32u) avail = 32u;
       uint32_t nxt = state;
       const uint32_t cq = queryBegin - lane * dq, cc = refBegin - lane * dc;
-      if ((uint32_t)lane < avail) nxt = loadPtrField<KIND, RT>(ptrBuf, passStride, cq, cc, state);
+      if ((uint32_t)lane < avail) nxt = loadPtrField<KIND, RT, TAGGED>(ptrBuf, passStride, cq, cc, state, pairHalf);
       const bool valid = (uint32_t)lane < avail;
       // a MATCH step at the first ref2 column that points back to MATCH ends the alignment (isRef2End)
       const bool stop  = valid && (state == ST_MATCH) && (cc == R1 + 1) && (nxt == ST_MATCH);
@@ -462,7 +495,7 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
       const uint32_t cq = queryBegin - lane * dq, cc = refBegin - lane * dc;
       uint32_t       nxt = state;
       if (valid) {
-        if (cq >= 1 && cc >= 1) nxt = loadPtrField<KIND, RT>(ptrBuf, passStride, cq, cc, state);
+        if (cq >= 1 && cc >= 1) nxt = loadPtrField<KIND, RT, TAGGED>(ptrBuf, passStride, cq, cc, state, pairHalf);
         else  // row 0 / column 0 pointers: all MATCH, except the column-0 insert state with edge insertions allowed
           nxt = (cc == 0 && state == ST_INSERT && P.allowEdgeIns) ? (uint32_t)ST_INSERT : (uint32_t)ST_MATCH;
       }
@@ -1328,6 +1361,418 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpPair
 }
 
 // ======================================================================================================
+// Tagged-score pair kernel (the default when its range check holds).
+//
+// Same skewed wavefront, staging, scratch layout and trace-back as dpPairKernel, but the cell update carries the
+// back-pointer INSIDE the score instead of deriving it from compare predicates: every state value is held per 16-bit
+// half as  u = (score + bias) * SC + code(state)  with SC = 8 (5-state kind) or 4, unsigned, and
+// code(MATCH) > code(DELETE) > code(INSERT) > code(JUMP) > code(JUMPINS).  All maxima of the recurrences list their
+// candidates in exactly that state order and keep the first maximum (AlignerBase.hpp:46-59, JumpAlignerBase.hpp:93-111,
+// GlobalLargeIndelAligner.hpp:124-151), so ONE unsigned maximum over the tagged candidates yields both the score and,
+// in its low bits, the code of the first-winning candidate -- i.e. the reference's pointer.  The maxima map to the
+// 3-input / add-fused packed instructions of sm_100a (VIMNMX3.U16x2, VIADDMNMX.U16x2: two alignments per
+// instruction), the tag is split off with one LOP3, and everything else (re-tagging, the substitution score, the
+// pointer-word assembly) is 32-bit integer arithmetic that ptxas can place on the FMA pipe (IMAD) next to the
+// saturated ALU pipe.  Because every per-half value provably stays inside [0, 65535] (host check tagRangeOk), 32-bit
+// modular arithmetic on the packed word is exact for both halves.  Requires the NOBAD regime (the sentinel never wins,
+// so it never has to be an exact -10000: it is any value below every real score).
+// Pointer fields hold the code; trace-back decodes state = TOPC - code.
+// a * b + c on the FMA pipe (IMAD); asm so that the compiler cannot turn it back into ALU-pipe shifts/logic
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+template <int KIND> struct TagTraits {
+  static constexpr int      SH    = (KIND == KIND_INDEL) ? 3 : 2;
+  static constexpr int      SC    = 1 << SH;
+  static constexpr int      TOPC  = (KIND == KIND_INDEL) ? 4 : 3;
+  static constexpr uint32_t MASK2 = (uint32_t)(SC - 1) * 0x00010001u;
+  static constexpr int      UNITS = 65536 / SC;  // representable score span
+};
+
+template <int KIND, int RT>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagKernel(const DpParams P)
+{
+  using KT               = KindTraits<KIND>;
+  using TT               = TagTraits<KIND>;
+  using PP               = PairLayout<RT, KT::CELLB>;
+  constexpr int NS       = KT::NS;
+  constexpr int STRIP    = 32 * RT;
+  constexpr int SH       = TT::SH;
+  constexpr int SC       = TT::SC;
+  constexpr uint32_t CLEAN = ~TT::MASK2;
+  constexpr int cM = TT::TOPC - ST_MATCH, cD = TT::TOPC - ST_DELETE, cI = TT::TOPC - ST_INSERT;
+  constexpr int cJ = TT::TOPC - ST_JUMP;  // code of JUMPINS is 0
+
+  __shared__ __align__(128) uint8_t sRing[WARPS_PER_CTA][2][REF_RING];
+  __shared__ __align__(8) uint64_t sBar[WARPS_PER_CTA][2][2];
+  __shared__ uint32_t sTask[WARPS_PER_CTA];
+  __shared__ uint32_t sCap[WARPS_PER_CTA][32][RT];
+
+  const int      lane    = threadIdx.x & 31;
+  const int      warp    = threadIdx.x >> 5;
+  const uint32_t slot    = blockIdx.x * WARPS_PER_CTA + warp;
+  uint8_t*       ptrBuf  = P.ptrScratch + (size_t)slot * P.ptrStride;  // both alignments, interleaved (PairLayout)
+  uint32_t*      segBufA = P.segScratch + (size_t)slot * 2 * P.segStride;
+  uint32_t*      segBufB = segBufA + P.segStride;
+  int*           bndBuf  = P.bndScratch + (size_t)slot * P.bndStride;
+
+  StageCursor curA, curB;
+  curA.used[0] = curA.used[1] = curB.used[0] = curB.used[1] = 0;
+#if MB200_USE_TMA
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&sBar[warp][h][b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+#endif
+
+  const int      offEdge = P.offEdge;
+  const int      bias    = P.tagBias;
+  const uint32_t ONE = P.one, NEG1 = 0u - P.one;
+  // T(v, code): both halves hold the tagged score v
+  auto T = [bias](int v, int code) -> uint32_t { return (uint32_t)((v + bias) * SC + code) * 0x00010001u; };
+  // per-half two's-complement constants for the packed add-max instructions
+  const uint32_t open16 = pack2(P.open * SC), extra16 = pack2(P.extra * SC), emo16 = pack2((P.extra - P.open) * SC);
+  // 32-bit modular constants: (delta * SC + code) on both halves (exact while every half stays in range)
+  const uint32_t matchC = (uint32_t)(P.match * SC + cM) * 0x00010001u;
+  const uint32_t negDeltaT = (uint32_t)((P.mismatch - P.match) * SC);  // times (nzA + 65536 nzB)
+  const uint32_t extD = (uint32_t)(P.extend * SC + cD) * 0x00010001u;
+  const uint32_t extI = (uint32_t)(P.extend * SC + cI) * 0x00010001u;
+  const uint32_t codeJ2 = (uint32_t)cJ * 0x00010001u;
+  const uint32_t BADT = (uint32_t)(P.tagBad * SC) * 0x00010001u;
+  const bool     allowEdgeIns = (KIND != KIND_JUMP) && P.allowEdgeIns;
+
+  for (;;) {
+    if (lane == 0) sTask[warp] = atomicAdd(P.workCounter, 1u);
+    __syncwarp();
+    const uint32_t pairIdx = sTask[warp];
+    __syncwarp();
+    if (pairIdx >= P.nPairs) break;
+    const DpPair   pr = P.pairs[pairIdx];
+    const DpTask   tA = pr.a, tB = pr.b;
+    const uint32_t QA = tA.Q, QB = tB.Q;
+    const uint32_t Q  = QA > QB ? QA : QB;
+    const uint32_t R1 = tA.R1;
+    const uint32_t R1A = tA.R1, R1B = tB.R1;
+    const uint32_t R2A = (KIND == KIND_JUMP) ? tA.R2 : 0u, R2B = (KIND == KIND_JUMP) ? tB.R2 : 0u;
+    const uint32_t RTA = R1A + R2A, RTB = R1B + R2B;
+    const uint32_t RTOT = RTA > RTB ? RTA : RTB;
+    const size_t   passStride = PP::passBytes(RTOT);
+
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      StageCursor&   cur  = h ? curB : curA;
+      const DpTask&  tk   = h ? tB : tA;
+      RefStage&      st   = cur.st;
+      st.shift1 = (uint32_t)(reinterpret_cast<uintptr_t>(tk.r1) & 15);
+      st.src1   = tk.r1 - st.shift1;
+      st.base2  = (st.shift1 + tk.R1 + 15) & ~15u;
+      if (KIND == KIND_JUMP) {
+        st.shift2 = (uint32_t)(reinterpret_cast<uintptr_t>(tk.r2) & 15);
+        st.src2   = tk.r2 - st.shift2;
+        st.total  = st.base2 + ((st.shift2 + tk.R2 + 15) & ~15u);
+      } else {
+        st.shift2 = 0;
+        st.src2   = st.src1;
+        st.total  = st.base2;
+      }
+      st.ring   = sRing[warp][h];
+      st.bar    = sBar[warp][h];
+      st.nTiles = (st.total + REF_TILE - 1) / REF_TILE;
+    }
+
+    long long bestA = (long long)0x8000000000000000LL, bestB = bestA;
+    bool      stageOk = true;
+    // tagged half -> score
+    auto valLo = [bias](uint32_t x) -> int { return (int)((x & 0xffffu) >> SH) - bias; };
+    auto valHi = [bias](uint32_t x) -> int { return (int)(x >> (16 + SH)) - bias; };
+
+    const uint32_t nPass = (Q + STRIP - 1) / STRIP;
+    for (uint32_t pass = 0; pass < nPass; ++pass) {
+      const uint32_t q0 = pass * STRIP + lane * RT;
+      uint32_t qpair[RT];
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const uint32_t row = q0 + r;
+        const uint32_t ca  = (row < QA) ? (uint32_t)__ldg(tA.q + row) : 0u;
+        const uint32_t cb  = (row < QB) ? (uint32_t)__ldg(tB.q + row) : 0u;
+        qpair[r]           = ca | (cb << 16);
+      }
+      const int rQA = (QA > q0 && QA <= q0 + RT) ? (int)(QA - q0 - 1) : RT;
+      const int rQB = (QB > q0 && QB <= q0 + RT) ? (int)(QB - q0 - 1) : RT;
+
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        StageCursor& cur = h ? curB : curA;
+        stageIssue(cur.st, 0, lane);
+        cur.nextIssue = 1;
+        if (cur.st.nTiles > 1) {
+          stageIssue(cur.st, 1, lane);
+          cur.nextIssue = 2;
+        }
+        cur.waitTile = 0;
+      }
+
+      uint32_t pM[RT], pD[RT], pI[RT], pJ[RT], pK[RT];
+      const uint32_t M0 = T(0, cM);
+      uint32_t lastM = M0, lastD = BADT, lastI = BADT, lastJ = BADT, lastK = BADT;
+      uint32_t dgM = M0, dgD = BADT, dgI = BADT, dgJ = BADT, dgK = BADT;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) { pM[r] = M0; pD[r] = pI[r] = pJ[r] = pK[r] = BADT; }
+
+      const uint32_t nSteps  = RTOT + 31;
+      uint8_t*       passPtr = ptrBuf + (size_t)pass * passStride;
+
+      for (uint32_t t = 0; t < nSteps; ++t) {
+        if ((t & 31u) == 0) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            StageCursor&   cur = h ? curB : curA;
+            const uint32_t rt  = h ? RTB : RTA;
+            const uint32_t r1  = h ? R1B : R1A;
+            const uint32_t cz0 = (t + 31u < rt) ? t + 31u : rt - 1;
+            const uint32_t need = stagedIndex(cur.st, cz0, r1, KIND == KIND_JUMP) / REF_TILE;
+            while (cur.waitTile <= need) stageOk = cursorWait(cur) && stageOk;
+            if (cur.nextIssue < cur.st.nTiles) {
+              uint32_t czT = t >= 31 ? t - 31 : 0;
+              if (czT >= rt) czT = rt - 1;
+              if (stagedIndex(cur.st, czT, r1, KIND == KIND_JUMP) / REF_TILE >= cur.nextIssue - 1) {
+                __syncwarp();
+                stageIssue(cur.st, cur.nextIssue, lane);
+                cur.nextIssue++;
+              }
+            }
+          }
+        }
+
+        uint32_t upM = __shfl_up_sync(0xffffffffu, lastM, 1);
+        uint32_t upD = __shfl_up_sync(0xffffffffu, lastD, 1);
+        uint32_t upI = __shfl_up_sync(0xffffffffu, lastI, 1);
+        uint32_t upJ = (NS >= 4) ? __shfl_up_sync(0xffffffffu, lastJ, 1) : BADT;
+        uint32_t upK = (NS >= 5) ? __shfl_up_sync(0xffffffffu, lastK, 1) : BADT;
+
+        const int  c      = (int)t - lane + 1;
+        const bool active = (c >= 1) && (c <= (int)RTOT);
+        if (lane == 0) {
+          if (pass == 0) {
+            upM = M0;
+            upD = upI = upJ = upK = BADT;
+          } else if (active) {
+            const uint32_t* b = reinterpret_cast<const uint32_t*>(bndBuf) + (size_t)c * 5;
+            upM = b[0]; upD = b[1]; upI = b[2]; upJ = b[3]; upK = b[4];
+          }
+        }
+
+        if (active) {
+          const bool     phase2 = (KIND == KIND_JUMP) && ((uint32_t)c > R1);
+          const uint32_t cz  = (uint32_t)c - 1;
+          const uint32_t czA = cz < RTA ? cz : RTA - 1;
+          const uint32_t czB = cz < RTB ? cz : RTB - 1;
+          const uint32_t refA = curA.st.ring[stagedIndex(curA.st, czA, R1A, KIND == KIND_JUMP) & (REF_RING - 1)];
+          const uint32_t refB = curB.st.ring[stagedIndex(curB.st, czB, R1B, KIND == KIND_JUMP) & (REF_RING - 1)];
+          const uint32_t refpair = refA | (refB << 16);
+
+          if (c == 1) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              const int q = (int)q0 + r + 1;
+              pM[r] = T(q * offEdge, cM);
+              pD[r] = BADT;
+              pI[r] = allowEdgeIns ? T(P.open + q * P.extend, cI) : BADT;
+              pJ[r] = BADT;
+              pK[r] = BADT;
+            }
+            dgM = T((int)q0 * offEdge, cM);
+            dgD = BADT;
+            dgI = allowEdgeIns ? T(P.open + (int)q0 * P.extend, cI) : BADT;
+            dgJ = dgK = BADT;
+          }
+          if (KIND == KIND_JUMP && (uint32_t)c == R1 + 1) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              pM[r] = T(((int)q0 + r + 1) * offEdge, cM);
+              pD[r] = pI[r] = BADT;
+            }
+            dgM = T((int)q0 * offEdge, cM);
+            dgD = dgI = BADT;
+            if (q0 == 0) dgJ = BADT;
+          }
+
+          uint32_t dM = dgM, dD = dgD, dI = dgI, dJ = dgJ, dK = dgK;
+          uint32_t vM = upM, vI = upI, vJ = upJ, vK = upK;
+          uint32_t ptrw[PP::WORDS];  // pointer cells of both alignments, as stored
+
+#pragma unroll
+          for (int r = 0; r < RT; ++r) {
+            // substitution score of both halves with MATCH's code folded in (1 per half where the characters differ)
+            const uint32_t nz = __vminu2(qpair[r] ^ refpair, 0x00010001u);
+            const uint32_t sC = imad(nz, negDeltaT, matchC);
+            const bool     row1 = (r == 0) && (q0 == 0);
+            uint32_t nM, nD, nI, nJ = BADT, nK = BADT;
+            uint32_t w, cl, cell;  // cell = [B cell : A cell], field k at bits k*SH of each half
+            // per state: w = tagged maximum (ALU: packed 3-input / add-fused max), cl = w without its tag (ALU: LOP3);
+            // the tag w - cl goes into the cell and cl is re-tagged with the state's own code by IMADs (FMA pipe)
+#define MB200_FIELD0() do { cl = w & CLEAN; cell = imad(cl, NEG1, w); } while (0)
+#define MB200_FIELD(K) do { cl = w & CLEAN; cell = imad(w, 1u << ((K) * SH), cell); cell = imad(cl, 0u - (1u << ((K) * SH)), cell); } while (0)
+            if (KIND == KIND_GLOBAL) {
+              w = __vimax3_u16x2(dM, dD, dI);
+              MB200_FIELD0(); nM = imad(cl, ONE, sC);
+              w = __vmaxu2(__viaddmax_u16x2(pM[r], open16, pD[r]), pI[r]);
+              MB200_FIELD(1); nD = imad(cl, ONE, extD); if (row1) nD = BADT;
+              w = __viaddmax_u16x2(vM, open16, vI);
+              MB200_FIELD(2); nI = imad(cl, ONE, extI); if (row1) nI = BADT;
+            } else if (KIND == KIND_INDEL) {
+              w = __vimax3_u16x2(__vimax3_u16x2(dM, dD, dI), dJ, dK);
+              MB200_FIELD0(); nM = imad(cl, ONE, sC);
+              w = __vimax3_u16x2(__viaddmax_u16x2(pM[r], open16, pD[r]), pI[r], pK[r]);
+              MB200_FIELD(1); nD = imad(cl, ONE, extD); if (row1) nD = BADT;
+              w = __viaddmax_u16x2(vM, open16, vI);
+              MB200_FIELD(2); nI = imad(cl, ONE, extI); if (row1) nI = BADT;
+              w = __viaddmax_u16x2(pI[r], emo16, __viaddmax_u16x2(__vmaxu2(pM[r], pK[r]), extra16, pJ[r]));
+              MB200_FIELD(3); nJ = imad(cl, ONE, codeJ2); if (row1) nJ = BADT;
+              w = __viaddmax_u16x2(vM, extra16, vK);
+              MB200_FIELD(4); nK = cl; if (row1) nK = BADT;
+            } else {  // KIND_JUMP
+              if (!phase2) {
+                w = __vimax3_u16x2(dM, dD, dI);
+                MB200_FIELD0(); nM = imad(cl, ONE, sC);
+                w = __vmaxu2(__viaddmax_u16x2(pM[r], open16, pD[r]), pI[r]);
+                MB200_FIELD(1); nD = imad(cl, ONE, extD); if (row1) nD = BADT;
+                w = __viaddmax_u16x2(vM, open16, vI);
+                MB200_FIELD(2); nI = imad(cl, ONE, extI); if (row1) nI = BADT;
+                w = __viaddmax_u16x2(__vmaxu2(nM, nI), extra16, pJ[r]);
+                MB200_FIELD(3); nJ = imad(cl, ONE, codeJ2);
+              } else {
+                w = __vmaxu2(__vimax3_u16x2(dM, dD, dI), dJ);
+                MB200_FIELD0(); nM = imad(cl, ONE, sC);
+                w = __vmaxu2(__viaddmax_u16x2(pM[r], open16, pD[r]), pI[r]);
+                MB200_FIELD(1); nD = imad(cl, ONE, extD);
+                w = __vmaxu2(__viaddmax_u16x2(vM, open16, vI), vJ);
+                MB200_FIELD(2); nI = imad(cl, ONE, extI);
+                nJ = pJ[r];  // the JUMP field of a ref2 cell is the constant JUMP, code 0
+              }
+            }
+#undef MB200_FIELD0
+#undef MB200_FIELD
+            if (KT::CELLB == 2) ptrw[r] = cell;
+            else if ((r & 1) == 0) ptrw[r / 2] = cell;
+            else ptrw[r / 2] = imad(cell, 256u, ptrw[r / 2]);
+
+            dM = pM[r]; dD = pD[r]; dI = pI[r]; dJ = pJ[r]; dK = pK[r];
+            pM[r] = nM; pD[r] = nD; pI[r] = nI; pJ[r] = nJ; pK[r] = nK;
+            vM = nM; vI = nI; vJ = nJ; vK = nK;
+          }
+
+          // ---- back-trace start candidates (same enumeration as the other kernels)
+          const bool validA = (uint32_t)c <= RTA, validB = (uint32_t)c <= RTB;
+          uint32_t capA = 0, capB = 0;
+          if (rQA < RT || rQB < RT) {
+            uint32_t* cp = sCap[warp][lane];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) cp[r] = pM[r];
+            capA = cp[rQA < RT ? rQA : 0];
+            capB = cp[rQB < RT ? rQB : 0];
+          }
+          if (rQA < RT && validA) {
+            const uint32_t seq = (KIND == KIND_JUMP && phase2) ? (R1 + QA + ((uint32_t)c - R1) - 1) : ((uint32_t)c - 1);
+            const long long k  = makeKey(valLo(capA), seq);
+            bestA              = k > bestA ? k : bestA;
+          }
+          if (rQB < RT && validB) {
+            const uint32_t seq = (KIND == KIND_JUMP && phase2) ? (R1 + QB + ((uint32_t)c - R1) - 1) : ((uint32_t)c - 1);
+            const long long k  = makeKey(valHi(capB), seq);
+            bestB              = k > bestB ? k : bestB;
+          }
+          const bool edge1 = (KIND == KIND_JUMP) && ((uint32_t)c == R1);
+          const bool edgeA = ((uint32_t)c == RTA), edgeB = ((uint32_t)c == RTB);
+          if (edge1 || edgeA || edgeB) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              const uint32_t q = q0 + r + 1;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t Qh = h ? QB : QA;
+                if (q > Qh) continue;
+                const int  m    = h ? valHi(pM[r]) : valLo(pM[r]);
+                const bool edge = h ? edgeB : edgeA;
+                long long& best = h ? bestB : bestA;
+                if (KIND == KIND_JUMP) {
+                  const uint32_t R2h = h ? R2B : R2A;
+                  if (q < Qh) {
+                    if (edge1) { const long long k = makeKey(m + (int)(Qh - q) * offEdge, R1 + q); best = k > best ? k : best; }
+                    if (edge) { const long long k = makeKey(m + (int)(Qh - q) * offEdge, R1 + Qh + R2h + q); best = k > best ? k : best; }
+                  }
+                } else if (edge) {
+                  const uint32_t Rh = h ? R1B : R1A;
+                  if (q == Qh && allowEdgeIns) {
+                    const long long k = makeKey(h ? valHi(pI[r]) : valLo(pI[r]), Rh);
+                    best              = k > best ? k : best;
+                  }
+                  if (q < Qh || KIND == KIND_INDEL) {
+                    const long long k = makeKey(m + (int)(Qh - q) * offEdge, Rh + 1 + q);
+                    best              = k > best ? k : best;
+                  }
+                }
+              }
+            }
+            if (q0 == 0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t Qh = h ? QB : QA;
+                const bool edge = h ? edgeB : edgeA;
+                long long& best = h ? bestB : bestA;
+                if (KIND == KIND_JUMP) {
+                  const uint32_t R2h = h ? R2B : R2A;
+                  if (edge1) { const long long k = makeKey((int)Qh * offEdge, R1); best = k > best ? k : best; }
+                  if (edge) { const long long k = makeKey((int)Qh * offEdge, R1 + Qh + R2h); best = k > best ? k : best; }
+                } else if (edge) {
+                  const long long k = makeKey((int)Qh * offEdge, (h ? R1B : R1A) + 1);
+                  best              = k > best ? k : best;
+                }
+              }
+            }
+          }
+
+          dgM = upM; dgD = upD; dgI = upI; dgJ = upJ; dgK = upK;
+          lastM = vM; lastD = pD[RT - 1]; lastI = vI; lastJ = vJ; lastK = vK;
+
+          storePtrWords<PP, PP::WORDS>(passPtr + (size_t)t * PP::STEP_BYTES, lane, ptrw);
+          if (lane == 31 && pass + 1 < nPass) {
+            uint32_t* b = reinterpret_cast<uint32_t*>(bndBuf) + (size_t)c * 5;
+            b[0] = lastM; b[1] = lastD; b[2] = lastI; b[3] = lastJ; b[4] = lastK;
+          }
+        }
+      }  // steps
+      while (curA.waitTile < curA.nextIssue) stageOk = cursorWait(curA) && stageOk;
+      while (curB.waitTile < curB.nextIssue) stageOk = cursorWait(curB) && stageOk;
+      __syncwarp();
+    }  // passes
+
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const long long oa = __shfl_xor_sync(0xffffffffu, bestA, off);
+      const long long ob = __shfl_xor_sync(0xffffffffu, bestB, off);
+      bestA              = oa > bestA ? oa : bestA;
+      bestB              = ob > bestB ? ob : bestB;
+    }
+    __threadfence_block();
+    __syncwarp();
+    emitResult<KIND, RT, true>(P, tA, ptrBuf, passStride, segBufA, bestA, stageOk, lane, 0);
+    if (!pr.dup) emitResult<KIND, RT, true>(P, tB, ptrBuf, passStride, segBufB, bestB, stageOk, lane, 1);
+    __syncwarp();
+  }
+}
+
+// ======================================================================================================
 // host side
 template <int KIND, int RT> size_t ptrBytesFor(uint32_t Q, uint32_t rtot)
 {
@@ -1386,22 +1831,55 @@ int launchClass(mb200_ctx* ctx, const DpParams& base, const ClassPlan& plan, siz
 }
 
 struct PairPlan {
-  size_t nPairs = 0;
-  size_t maxPtr = 0, maxSeg = 0, maxBnd = 0;
+  size_t   nPairs = 0;
+  size_t   maxPtr = 0, maxSeg = 0, maxBnd = 0;
+  uint32_t maxQ = 0;
+  bool     noBad = false, tag = false;
+  int      tagBias = 0, tagBad = 0;
 };
 
-template <int KIND, int RT, bool NOBAD>
+// can badVal ever win a max?  M[q][c] >= -L*q with L = max(|match|,|mismatch|,|offEdge|) (induction over the
+// recurrences, column 0 and the ref2 re-initialisation included); every max that has badVal as a candidate starts
+// from M + open / M + extra / M + jump, so below this bound the sentinel never compares strictly greater.
+inline bool sentinelNeverWins(const mb200_scores* sc, int extra, uint32_t maxQ)
+{
+  auto ab = [](int v) { return (long long)(v < 0 ? -v : v); };
+  const long long L = std::max(std::max(ab(sc->match), ab(sc->mismatch)), ab(sc->offEdge));
+  return L * (long long)(maxQ + 1) + std::max(ab(sc->open), ab(extra)) + ab(sc->extend) + 8 < 10000;
+}
+
+// dpTagKernel's range: with match >= 0 and every other score <= 0 all real state values lie in
+// [-L*maxQ - G, match*maxQ], G = |open| + |extend| + 2|extra| (a state other than MATCH is at least a MATCH value plus
+// one gap/jump constant, a candidate adds at most one more), and the sentinel's stand-in needs G of room below it and
+// 2G between it and the lowest real candidate.  `units` = 65536 / SC score units fit one 16-bit half.
+inline bool tagRangeOk(const mb200_scores* sc, int extra, uint32_t maxQ, int units, int* bias, int* bad)
+{
+  if (sc->match < 0 || sc->mismatch > 0 || sc->open > 0 || sc->extend > 0 || sc->offEdge > 0 || extra > 0) return false;
+  auto ab = [](int v) { return (long long)(v < 0 ? -v : v); };
+  const long long L = std::max(std::max(ab(sc->match), ab(sc->mismatch)), ab(sc->offEdge));
+  const long long G = ab(sc->open) + ab(sc->extend) + 2 * ab(extra);
+  const long long b = G + 8;
+  const long long off = b + 2 * G + L * (long long)(maxQ + 1) + 16;
+  if (off + (long long)sc->match * (maxQ + 2) + 16 >= units) return false;
+  *bias = (int)off;
+  *bad  = (int)b;
+  return true;
+}
+
+// which kernel runs a class: the tagged-score kernel (TAG), else the predicate/SEL pair kernel with or without the
+// sentinel comparisons (NOBAD)
+template <int KIND, int RT, bool NOBAD, bool TAG>
 int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, size_t pairOffset, uint32_t* dCounter,
                     int cls, int nActive)
 {
   if (plan.nPairs == 0) return MB200_OK;
+  auto kernel = TAG ? dpTagKernel<KIND, RT> : dpPairKernel<KIND, RT, NOBAD>;
   DeviceBuffer& dPtr = ctx->dPtrC[cls];
   DeviceBuffer& dSeg = ctx->dSegC[cls];
   DeviceBuffer& dBnd = ctx->dBndC[cls];
   cudaStream_t  strm = ctx->dpStream[cls];
   int ctasPerSm = 0;
-  MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, dpPairKernel<KIND, RT, NOBAD>,
-                                                                      WARPS_PER_CTA * 32, 0));
+  MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, WARPS_PER_CTA * 32, 0));
   if (ctasPerSm < 1) ctasPerSm = 1;
   if (ctx->cfg.ctasPerSm && (int)ctx->cfg.ctasPerSm < ctasPerSm) ctasPerSm = (int)ctx->cfg.ctasPerSm;
   uint32_t grid = (uint32_t)(ctx->smCount * ctasPerSm);
@@ -1417,6 +1895,8 @@ int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, 
   const size_t bndSlot = (plan.maxBnd + 63) & ~(size_t)63;
   if ((rc = mb200_reserve(ctx, dBnd, nSlots * bndSlot * sizeof(int) + 256)) != MB200_OK) return rc;
   DpParams P    = base;
+  P.tagBias     = plan.tagBias;
+  P.tagBad      = plan.tagBad;
   P.pairs       = reinterpret_cast<const DpPair*>(ctx->dTasksK[KIND].ptr) + pairOffset;
   P.nPairs      = (uint32_t)plan.nPairs;
   P.tasks       = nullptr;
@@ -1430,7 +1910,7 @@ int launchPairClass(mb200_ctx* ctx, const DpParams& base, const PairPlan& plan, 
   P.bndStride   = bndSlot;
   MB200_CUDA_CHECK(ctx, cudaStreamWaitEvent(strm, ctx->dpFork, 0));
   MB200_CUDA_CHECK(ctx, cudaStreamWaitEvent(strm, ctx->copyDone[KIND], 0));
-  dpPairKernel<KIND, RT, NOBAD><<<grid, WARPS_PER_CTA * 32, 0, strm>>>(P);
+  kernel<<<grid, WARPS_PER_CTA * 32, 0, strm>>>(P);
   MB200_CUDA_CHECK(ctx, cudaGetLastError());
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->dpDone[cls], strm));
   MB200_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->dpDone[cls], 0));
@@ -1529,6 +2009,7 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
     const size_t   pb    = nPass * ((size_t)(rtot + 31) * 32 * (size_t)(((RT * KindTraits<KIND>::CELLB + 3) / 4) * 4));  // PtrLayout::STEP_BYTES
     PairPlan&      p     = plans[cls];
     p.nPairs++;
+    p.maxQ   = std::max(p.maxQ, Q);
     p.maxPtr = std::max(p.maxPtr, pb);
     p.maxSeg = std::max(p.maxSeg, 2 * ((size_t)Q + rtot + 8));
     p.maxBnd = std::max(p.maxBnd, (Q > (uint32_t)(32 * RT)) ? ((size_t)rtot + 2) * 5 : (size_t)8);
@@ -1547,29 +2028,29 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
   int nActive = 0;
   for (int c = 0; c < NCLS; ++c) nActive += plans[c].nPairs == 0 ? 0 : 1;
   // every class runs on its own stream with its own scratch, forked from / joined to the ctx stream, so that the
-  // tail of one class overlaps the body of the next (largest strips first)
-  // can badVal ever win a max?  M[q][c] >= -L*q with L = max(|match|,|mismatch|,|offEdge|) (induction over the
-  // recurrences, column 0 and the ref2 re-initialisation included); every max that has badVal as a candidate starts
-  // from M + open / M + extra / M + jump, so below this bound the sentinel never compares strictly greater.
-  uint32_t maxQ = 0;
-  for (const DpTask& t : tasks) maxQ = std::max(maxQ, t.Q);
-  auto ab = [](int v) { return (long long)(v < 0 ? -v : v); };
-  const long long L     = std::max(std::max(ab(scores->match), ab(scores->mismatch)), ab(scores->offEdge));
-  const bool      noBad = (L * (long long)(maxQ + 1) + std::max(ab(scores->open), ab(extra)) + ab(scores->extend) + 8 < 10000);
-#define MB200_LAUNCH_PAIRS(NB)                                                                                       \
+  // tail of one class overlaps the body of the next (largest strips first).  Kernel choice per class, from the
+  // longest query of the class: tagged scores where the range allows, else predicates/SEL with or without the sentinel.
+  for (int c = 0; c < NCLS; ++c) {
+    PairPlan& p = plans[c];
+    p.noBad = sentinelNeverWins(scores, extra, p.maxQ);
+    p.tag   = p.noBad && !ctx->noTagKernel && tagRangeOk(scores, extra, p.maxQ, TagTraits<KIND>::UNITS, &p.tagBias, &p.tagBad);
+  }
+#define MB200_LAUNCH_CLASS(RTV, C)                                                                                   \
   do {                                                                                                               \
-    if ((rc = launchPairClass<KIND, 16, NB>(ctx, base, plans[6], offsets[6], dWorkCounters + 6, 6, nActive)) != MB200_OK) return rc; \
-    if ((rc = launchPairClass<KIND, 12, NB>(ctx, base, plans[5], offsets[5], dWorkCounters + 5, 5, nActive)) != MB200_OK) return rc; \
-    if ((rc = launchPairClass<KIND, 10, NB>(ctx, base, plans[4], offsets[4], dWorkCounters + 4, 4, nActive)) != MB200_OK) return rc; \
-    if ((rc = launchPairClass<KIND, 9, NB>(ctx, base, plans[3], offsets[3], dWorkCounters + 3, 3, nActive)) != MB200_OK) return rc; \
-    if ((rc = launchPairClass<KIND, 8, NB>(ctx, base, plans[2], offsets[2], dWorkCounters + 2, 2, nActive)) != MB200_OK) return rc; \
-    if ((rc = launchPairClass<KIND, 6, NB>(ctx, base, plans[1], offsets[1], dWorkCounters + 1, 1, nActive)) != MB200_OK) return rc; \
-    if ((rc = launchPairClass<KIND, 4, NB>(ctx, base, plans[0], offsets[0], dWorkCounters + 0, 0, nActive)) != MB200_OK) return rc; \
+    if (plans[C].tag) rc = launchPairClass<KIND, RTV, true, true>(ctx, base, plans[C], offsets[C], dWorkCounters + C, C, nActive); \
+    else if (plans[C].noBad) rc = launchPairClass<KIND, RTV, true, false>(ctx, base, plans[C], offsets[C], dWorkCounters + C, C, nActive); \
+    else rc = launchPairClass<KIND, RTV, false, false>(ctx, base, plans[C], offsets[C], dWorkCounters + C, C, nActive); \
+    if (rc != MB200_OK) return rc;                                                                                   \
   } while (0)
   MB200_CUDA_CHECK(ctx, cudaEventRecord(ctx->dpFork, ctx->stream));
-  if (noBad) MB200_LAUNCH_PAIRS(true);
-  else MB200_LAUNCH_PAIRS(false);
-#undef MB200_LAUNCH_PAIRS
+  MB200_LAUNCH_CLASS(16, 6);
+  MB200_LAUNCH_CLASS(12, 5);
+  MB200_LAUNCH_CLASS(10, 4);
+  MB200_LAUNCH_CLASS(9, 3);
+  MB200_LAUNCH_CLASS(8, 2);
+  MB200_LAUNCH_CLASS(6, 1);
+  MB200_LAUNCH_CLASS(4, 0);
+#undef MB200_LAUNCH_CLASS
   return MB200_OK;
 }
 
@@ -1582,6 +2063,7 @@ int dpRunKind(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vector
   memset(&P, 0, sizeof(P));
   P.match = scores->match; P.mismatch = scores->mismatch; P.open = scores->open; P.extend = scores->extend;
   P.offEdge = scores->offEdge; P.allowEdgeIns = scores->isAllowEdgeInsertion ? 1 : 0; P.extra = extra;
+  P.one       = 1;
   P.results   = dResults;
   P.cigarPool = dCigar;
   P.cigarCap  = cigarCap;

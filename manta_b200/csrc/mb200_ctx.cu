@@ -76,6 +76,7 @@ int mb200_create(int device, const mb200_config* cfg, mb200_ctx** out)
   ctx->smCount   = prop.multiProcessorCount;
   if (cfg) ctx->cfg = *cfg;
   ctx->forceInt32 = (ctx->cfg.reserved[0] & 1u) != 0;
+  ctx->noTagKernel = (ctx->cfg.reserved[0] & 2u) != 0;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return MB200_ERR_CUDA;

@@ -37,6 +37,7 @@ struct mb200_ctx {
   mb200_timing timing     = {};
   std::string  lastError;
   bool         forceInt32 = false;  // cfg.reserved[0] & 1: always use the int32 one-alignment-per-warp DP kernel
+  bool         noTagKernel = false;  // cfg.reserved[0] & 2: int16x2 pairs on the predicate/SEL kernel, never the tagged-score one
   // growable device buffers, reused across calls (library owns device memory)
   DeviceBuffer dPool, dTasks, dResults, dCigar, dPtrScratch, dSegScratch, dBndScratch, dMisc, dJobs, dTables;
   DeviceBuffer dAsmWork, dAsmOut0, dAsmOut1, dAsmOut2, dAsmOut3, dAsmOut4, dViews, dReadOff;

@@ -57,3 +57,13 @@ def gpu32():
     ctx = manta_b200.Context(0, force_int32=True)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="session")
+def gpusel():
+    """same library, int16x2 pairs forced onto the predicate/SEL pair kernel (the default is the tagged-score kernel
+    where the score range allows it)"""
+    import manta_b200
+    ctx = manta_b200.Context(0, no_tag_kernel=True)
+    yield ctx
+    ctx.close()

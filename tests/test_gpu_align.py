@@ -15,9 +15,9 @@ SCORE_SETS = [((2, -4, -5, -1, -1, 0), -3), ((2, -8, -12, -1, -1, 0), -100), ((2
               ((2, -8, -18, 0, -1, 1), -50), ((1, -4, -5, -1, -2, 1), -10)]
 
 
-@pytest.fixture(params=["pair16", "int32"])
-def dev(request, gpu, gpu32):
-    return gpu if request.param == "pair16" else gpu32
+@pytest.fixture(params=["tag16", "pair16", "int32"])
+def dev(request, gpu, gpusel, gpu32):
+    return {"tag16": gpu, "pair16": gpusel, "int32": gpu32}[request.param]
 
 
 def test_alignment_golden_gpu(dev):
