@@ -425,6 +425,11 @@ MB200_API int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* o
                                    mb200_jump_result* jumpResults, uint32_t* cigarPool, uint64_t cigarCap,
                                    uint64_t* cigarUsed, mb200_trim_result* trim, mb200_contig_qc* qc, int32_t* best);
 MB200_API int mb200_candidates_timing(const mb200_ctx* ctx, mb200_candidate_timing* out);
+/* shape of the batch the NEXT mb200_candidates_run will work on (the oldest staged one, else the one consumed last):
+ * the record arrays of that run must hold nLoci (loci, best), nLoci*maxAssemblyCount (contigs, alnResults,
+ * jumpResults, trim, qc) and 2*nLoci*maxAssemblyCount (pseudoReads) entries.  With uploads pipelined ahead of runs
+ * the newest upload is NOT the batch the next run consumes.  MB200_ERR_BAD_ARG when nothing is staged. */
+MB200_API int mb200_candidates_pending(mb200_ctx* ctx, uint32_t* nLoci, uint64_t* nReads, uint64_t* poolBytes);
 /* refined small SVs (mb200_small_sv_batch) of the batch the last mb200_candidates_run with qc/best worked on, computed
  * on the still-resident alignments */
 MB200_API int mb200_candidates_small_svs(mb200_ctx* ctx, uint32_t* svFirst, mb200_small_sv* svs, uint64_t svCap,
@@ -432,6 +437,20 @@ MB200_API int mb200_candidates_small_svs(mb200_ctx* ctx, uint32_t* svFirst, mb20
 /* refined spanning breakends (mb200_jump_sv_batch) of the same run; orient[nLoci] (entries of complex candidates are
  * ignored), out[nLoci] */
 MB200_API int mb200_candidates_jump_svs(mb200_ctx* ctx, const mb200_jump_orient* orient, mb200_jump_sv* out);
+
+/* ---- row a1: the per-bin edge partition (host arithmetic, no device, no ctx) ---------------------------------------
+ * GSC/EdgeRetrieverBin.cpp:43-235 on a flattened SVLocusSet (include/manta_b200_graph.hpp: mb200::FlatLocusGraph, filled on
+ * the reference side by mb200::flattenLocusSet): locusNodeOff[nLoci+1], nodeEdgeOff[nNodes+1], and per out-edge its target
+ * node index inside the locus (ascending per node, the std::map order) and its directed observation count.  Writes the
+ * edges of bin `binIndex` of `binCount` in the retriever's order; *nEdges is the number the bin holds (MB200_ERR_POOL_OVERFLOW
+ * when that exceeds edgeCap: nothing beyond edgeCap is written).  graphNodeMaxEdgeCount 0 = no noisy-node filter. */
+typedef struct mb200_edge_info {
+  uint32_t locusIndex, nodeIndex1, nodeIndex2; /* lib/svgraph/EdgeInfo.hpp:30-39 */
+} mb200_edge_info;
+MB200_API int mb200_edge_bin_enumerate(uint32_t nLoci, const uint32_t* locusNodeOff, const uint64_t* nodeEdgeOff,
+                                       const uint32_t* edgeTo, const uint32_t* edgeCount, uint32_t graphNodeMaxEdgeCount,
+                                       uint32_t binCount, uint32_t binIndex, mb200_edge_info* edges, uint64_t edgeCap,
+                                       uint64_t* nEdges);
 
 #ifdef __cplusplus
 }

@@ -470,14 +470,24 @@ class Binding:
             self._raise(st)
         # the copy is asynchronous: keep the host arrays alive until the consuming run has returned
         self._cand_keep = getattr(self, "_cand_keep", [])[-2:] + [(batch, cuts)]
-        self._cand_shape = (batch.nLoci, int(batch.readViews["len"].sum()), batch.readsPerLocus)
+        # staged batches are consumed first-in first-out: the shape of the NEWEST upload is not the shape of the next run
+        self._cand_fifo = getattr(self, "_cand_fifo", []) + [(batch.nLoci, int(batch.readViews["len"].sum()), batch.readsPerLocus)]
 
     def candidates_run(self, opts: np.ndarray, out: Optional[dict] = None, select: bool = False, zeros=np.zeros) -> dict:
         """run on the staged batch; `out` (from a previous call) is reused to avoid re-allocating host buffers.
         select=True also returns the per-contig trim / QC records and the per-locus bestAlignmentIndex.
         `zeros(n, dtype=...)` allocates the host result buffers (pass a pinned-memory allocator for faster copies)."""
+        # the batch this run consumes: the oldest staged one, else the one consumed last (repeat on resident inputs)
+        if getattr(self, "_cand_fifo", None):
+            self._cand_shape = self._cand_fifo.pop(0)
         nLoci, totalBases, rpl = self._cand_shape
+        pend = C.c_uint32(0)
+        if self._call("candidates_pending", C.byref(pend), None, None) != MB200_OK or pend.value != nLoci:
+            raise Mb200Error(MB200_ERR_BAD_ARG, "staged-batch bookkeeping out of step with the library")
         A = int(opts["asmOpts"]["maxAssemblyCount"][0])
+        if out is not None and (len(out["loci"]) < nLoci or len(out["contigs"]) < nLoci * A or
+                                ("qc" in out and len(out["qc"]) < nLoci * A)):
+            out = None  # buffers of a smaller batch: the library writes nLoci*A records, never reuse them
         if out is None:
             out = dict(loci=zeros(nLoci, dtype=ASM_LOCUS_DT), contigs=zeros(nLoci * A, dtype=CONTIG_DT),
                        pseudo=zeros(nLoci * 2 * A, dtype=SEQVIEW_DT),

@@ -149,6 +149,7 @@ int mb200_candidates_run(mb200_ctx* ctx, const mb200_candidate_opts* opts, mb200
   if (!c.scan.valid || c.scan.minWordLength != opts->asmOpts.minWordLength) {
     // first word length differs from the one the batch was scanned for: fetch the views back and scan again
     std::vector<mb200_seqview> hv(c.nReads ? c.nReads : 1);
+    MB200_CUDA_CHECK(ctx, cudaEventSynchronize(c.upEnd));  // the views are uploaded on uploadStream, not the legacy stream
     MB200_CUDA_CHECK(ctx, cudaMemcpy(hv.data(), c.dViews.ptr, sizeof(mb200_seqview) * (size_t)c.nReads, cudaMemcpyDeviceToHost));
     if ((rc = mb200_asm_scan(ctx, opts->asmOpts.minWordLength, nLoci, c.readOff.data(), hv.data(), c.poolBytes, &c.scan)) != MB200_OK) return rc;
     C.scanWordLength = opts->asmOpts.minWordLength;
@@ -384,6 +385,18 @@ int mb200_candidates_jump_svs(mb200_ctx* ctx, const mb200_jump_orient* orient, m
   if (rc != MB200_OK) return rc;
   MB200_CUDA_CHECK(ctx, cudaMemcpyAsync(out, ctx->dSvs.ptr, sizeof(mb200_jump_sv) * (size_t)nLoci, cudaMemcpyDeviceToHost, ctx->stream));
   MB200_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MB200_OK;
+}
+
+int mb200_candidates_pending(mb200_ctx* ctx, uint32_t* nLoci, uint64_t* nReads, uint64_t* poolBytes)
+{
+  if (!ctx) return MB200_ERR_BAD_ARG;
+  const auto& C   = ctx->cand;
+  const int   idx = C.nQueued > 0 ? C.queue[0] : C.cur;
+  if (idx < 0) return mb200_fail(ctx, MB200_ERR_BAD_ARG, "no staged batch (call mb200_candidates_upload first)");
+  if (nLoci) *nLoci = C.slot[idx].nLoci;
+  if (nReads) *nReads = C.slot[idx].nReads;
+  if (poolBytes) *poolBytes = C.slot[idx].poolBytes;
   return MB200_OK;
 }
 

@@ -939,7 +939,8 @@ __device__ __forceinline__ void vmaxp(uint32_t code, uint32_t& m, uint32_t v, ui
 struct StageCursor {
   RefStage st;
   uint32_t nextIssue, waitTile;
-  uint32_t used[2];
+  uint32_t used0, used1;  // completed uses of ring slot 0 / 1 (mbarrier parity); two scalars: an indexed array would
+                          // push the whole cursor into local memory
 };
 
 __device__ __forceinline__ uint32_t stagedIndex(const RefStage& st, uint32_t cz, uint32_t R1, bool isJump)
@@ -950,8 +951,9 @@ __device__ __forceinline__ uint32_t stagedIndex(const RefStage& st, uint32_t cz,
 __device__ __forceinline__ bool cursorWait(StageCursor& cur)
 {
 #if MB200_USE_TMA
-  const uint32_t barAddr = smemAddr(&cur.st.bar[cur.waitTile & 1]);
-  const uint32_t parity  = cur.used[cur.waitTile & 1] & 1;
+  const bool     odd     = (cur.waitTile & 1) != 0;
+  const uint32_t barAddr = smemAddr(cur.st.bar) + (odd ? 8u : 0u);
+  const uint32_t parity  = (odd ? cur.used1 : cur.used0) & 1;
   uint32_t       ok      = 0;
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     asm volatile(
@@ -961,7 +963,7 @@ __device__ __forceinline__ bool cursorWait(StageCursor& cur)
         : "memory");
     if (ok) break;
   }
-  cur.used[cur.waitTile & 1]++;
+  if (odd) cur.used1++; else cur.used0++;
   cur.waitTile++;
   return ok != 0;
 #else
@@ -1017,7 +1019,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpPair
   int*           bndBuf  = P.bndScratch + (size_t)slot * P.bndStride;
 
   StageCursor curA, curB;
-  curA.used[0] = curA.used[1] = curB.used[0] = curB.used[1] = 0;
+  curA.used0 = curA.used1 = curB.used0 = curB.used1 = 0;
 #if MB200_USE_TMA
   if (lane == 0) {
 #pragma unroll
@@ -1421,7 +1423,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagK
   int*           bndBuf  = P.bndScratch + (size_t)slot * P.bndStride;
 
   StageCursor curA, curB;
-  curA.used[0] = curA.used[1] = curB.used[0] = curB.used[1] = 0;
+  curA.used0 = curA.used1 = curB.used0 = curB.used1 = 0;
 #if MB200_USE_TMA
   if (lane == 0) {
 #pragma unroll
@@ -1496,6 +1498,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagK
     auto valHi = [bias](uint32_t x) -> int { return (int)(x >> (16 + SH)) - bias; };
 
     const uint32_t nPass = (Q + STRIP - 1) / STRIP;
+    uint8_t* const ringA = sRing[warp][0];
+    uint8_t* const ringB = sRing[warp][1];
+    // staged coordinate of column c (0-based cz) = cz + off1 in ref1, cz + off2 in ref2 (jump pairs share R1)
+    const uint32_t off1A = curA.st.shift1, off1B = curB.st.shift1;
+    const uint32_t off2A = curA.st.base2 + curA.st.shift2 - R1A, off2B = curB.st.base2 + curB.st.shift2 - R1B;
     for (uint32_t pass = 0; pass < nPass; ++pass) {
       const uint32_t q0 = pass * STRIP + lane * RT;
       uint32_t qpair[RT];
@@ -1506,8 +1513,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagK
         const uint32_t cb  = (row < QB) ? (uint32_t)__ldg(tB.q + row) : 0u;
         qpair[r]           = ca | (cb << 16);
       }
-      const int rQA = (QA > q0 && QA <= q0 + RT) ? (int)(QA - q0 - 1) : RT;
-      const int rQB = (QB > q0 && QB <= q0 + RT) ? (int)(QB - q0 - 1) : RT;
+      const int  rQA = (QA > q0 && QA <= q0 + RT) ? (int)(QA - q0 - 1) : RT;
+      const int  rQB = (QB > q0 && QB <= q0 + RT) ? (int)(QB - q0 - 1) : RT;
+      const bool ownsQ = (rQA < RT) || (rQB < RT);
+      // running maxima of the last query row over the columns: (tagged M << 16) | (0xffff - column), so that the unsigned
+      // maximum keeps the first (lowest-column) maximum -- the start candidates enumerate in column order in both
+      // phases.  Turned into the 64-bit (score, -sequence) key once per pass.
+      uint32_t keyA = 0, keyB = 0;
 
       __syncwarp();
 #pragma unroll
@@ -1522,17 +1534,28 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagK
         cur.waitTile = 0;
       }
 
+      // column 0 of my rows (a lane's registers are first touched at its column 1, step t == lane)
       uint32_t pM[RT], pD[RT], pI[RT], pJ[RT], pK[RT];
       const uint32_t M0 = T(0, cM);
-      uint32_t lastM = M0, lastD = BADT, lastI = BADT, lastJ = BADT, lastK = BADT;
-      uint32_t dgM = M0, dgD = BADT, dgI = BADT, dgJ = BADT, dgK = BADT;
 #pragma unroll
-      for (int r = 0; r < RT; ++r) { pM[r] = M0; pD[r] = pI[r] = pJ[r] = pK[r] = BADT; }
+      for (int r = 0; r < RT; ++r) {
+        const int q = (int)q0 + r + 1;
+        pM[r] = T(q * offEdge, cM);
+        pD[r] = BADT;
+        pI[r] = allowEdgeIns ? T(P.open + q * P.extend, cI) : BADT;
+        pJ[r] = BADT;
+        pK[r] = BADT;
+      }
+      uint32_t lastM = M0, lastD = BADT, lastI = BADT, lastJ = BADT, lastK = BADT;
+      uint32_t dgM = T((int)q0 * offEdge, cM), dgD = BADT, dgI = allowEdgeIns ? T(P.open + (int)q0 * P.extend, cI) : BADT;
+      uint32_t dgJ = BADT, dgK = BADT;
 
-      const uint32_t nSteps  = RTOT + 31;
-      uint8_t*       passPtr = ptrBuf + (size_t)pass * passStride;
+      const uint32_t nSteps = RTOT + 31;
+      const bool     isTop  = (lane == 0) && (pass == 0);
+      uint8_t*       stp    = ptrBuf + (size_t)pass * passStride + (size_t)lane * PP::CHUNK_BYTES;  // my chunk 0 of step t
+      uint32_t       cdn    = 0xffffu + (uint32_t)lane;                                              // 0xffff - c + 1 at step 0
 
-      for (uint32_t t = 0; t < nSteps; ++t) {
+      for (uint32_t t = 0; t < nSteps; ++t, stp += PP::STEP_BYTES) {
         if ((t & 31u) == 0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -1559,44 +1582,28 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagK
         uint32_t upI = __shfl_up_sync(0xffffffffu, lastI, 1);
         uint32_t upJ = (NS >= 4) ? __shfl_up_sync(0xffffffffu, lastJ, 1) : BADT;
         uint32_t upK = (NS >= 5) ? __shfl_up_sync(0xffffffffu, lastK, 1) : BADT;
-
-        const int  c      = (int)t - lane + 1;
-        const bool active = (c >= 1) && (c <= (int)RTOT);
-        if (lane == 0) {
-          if (pass == 0) {
-            upM = M0;
-            upD = upI = upJ = upK = BADT;
-          } else if (active) {
-            const uint32_t* b = reinterpret_cast<const uint32_t*>(bndBuf) + (size_t)c * 5;
-            upM = b[0]; upD = b[1]; upI = b[2]; upJ = b[3]; upK = b[4];
-          }
+        if (isTop) {  // row 0 of every column
+          upM = M0;
+          upD = upI = upJ = upK = BADT;
+        }
+        cdn--;
+        const uint32_t cz     = t - (uint32_t)lane;  // 0-based column; wraps for lanes that have not started
+        const bool     active = cz < RTOT;
+        if (pass != 0 && lane == 0 && active) {
+          const uint32_t* b = reinterpret_cast<const uint32_t*>(bndBuf) + (size_t)(cz + 1) * 5;
+          upM = b[0]; upD = b[1]; upI = b[2]; upJ = b[3]; upK = b[4];
         }
 
         if (active) {
-          const bool     phase2 = (KIND == KIND_JUMP) && ((uint32_t)c > R1);
-          const uint32_t cz  = (uint32_t)c - 1;
-          const uint32_t czA = cz < RTA ? cz : RTA - 1;
-          const uint32_t czB = cz < RTB ? cz : RTB - 1;
-          const uint32_t refA = curA.st.ring[stagedIndex(curA.st, czA, R1A, KIND == KIND_JUMP) & (REF_RING - 1)];
-          const uint32_t refB = curB.st.ring[stagedIndex(curB.st, czB, R1B, KIND == KIND_JUMP) & (REF_RING - 1)];
+          const uint32_t c      = cz + 1;
+          const bool     phase2 = (KIND == KIND_JUMP) && (cz >= R1);
+          // reference characters of this column.  A column past the shorter alignment's own end reads whatever the ring
+          // holds there: those cells are never used (no start candidate, no trace-back), and the halves do not interact.
+          const uint32_t refA = ringA[(cz + (phase2 ? off2A : off1A)) & (REF_RING - 1)];
+          const uint32_t refB = ringB[(cz + (phase2 ? off2B : off1B)) & (REF_RING - 1)];
           const uint32_t refpair = refA | (refB << 16);
 
-          if (c == 1) {
-#pragma unroll
-            for (int r = 0; r < RT; ++r) {
-              const int q = (int)q0 + r + 1;
-              pM[r] = T(q * offEdge, cM);
-              pD[r] = BADT;
-              pI[r] = allowEdgeIns ? T(P.open + q * P.extend, cI) : BADT;
-              pJ[r] = BADT;
-              pK[r] = BADT;
-            }
-            dgM = T((int)q0 * offEdge, cM);
-            dgD = BADT;
-            dgI = allowEdgeIns ? T(P.open + (int)q0 * P.extend, cI) : BADT;
-            dgJ = dgK = BADT;
-          }
-          if (KIND == KIND_JUMP && (uint32_t)c == R1 + 1) {
+          if (KIND == KIND_JUMP && cz == R1) {
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
               pM[r] = T(((int)q0 + r + 1) * offEdge, cM);
@@ -1672,28 +1679,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagK
             vM = nM; vI = nI; vJ = nJ; vK = nK;
           }
 
-          // ---- back-trace start candidates (same enumeration as the other kernels)
-          const bool validA = (uint32_t)c <= RTA, validB = (uint32_t)c <= RTB;
-          uint32_t capA = 0, capB = 0;
-          if (rQA < RT || rQB < RT) {
+          // ---- back-trace start candidates: the last query row of A / B in this lane
+          if (ownsQ) {
             uint32_t* cp = sCap[warp][lane];
 #pragma unroll
             for (int r = 0; r < RT; ++r) cp[r] = pM[r];
-            capA = cp[rQA < RT ? rQA : 0];
-            capB = cp[rQB < RT ? rQB : 0];
+            if (rQA < RT && c <= RTA) {
+              const uint32_t k = (cp[rQA] << 16) | cdn;
+              keyA             = k > keyA ? k : keyA;
+            }
+            if (rQB < RT && c <= RTB) {
+              const uint32_t k = (cp[rQB] & 0xffff0000u) | cdn;
+              keyB             = k > keyB ? k : keyB;
+            }
           }
-          if (rQA < RT && validA) {
-            const uint32_t seq = (KIND == KIND_JUMP && phase2) ? (R1 + QA + ((uint32_t)c - R1) - 1) : ((uint32_t)c - 1);
-            const long long k  = makeKey(valLo(capA), seq);
-            bestA              = k > bestA ? k : bestA;
-          }
-          if (rQB < RT && validB) {
-            const uint32_t seq = (KIND == KIND_JUMP && phase2) ? (R1 + QB + ((uint32_t)c - R1) - 1) : ((uint32_t)c - 1);
-            const long long k  = makeKey(valHi(capB), seq);
-            bestB              = k > bestB ? k : bestB;
-          }
-          const bool edge1 = (KIND == KIND_JUMP) && ((uint32_t)c == R1);
-          const bool edgeA = ((uint32_t)c == RTA), edgeB = ((uint32_t)c == RTB);
+          const bool edge1 = (KIND == KIND_JUMP) && (c == R1);
+          const bool edgeA = (c == RTA), edgeB = (c == RTB);
           if (edge1 || edgeA || edgeB) {
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
@@ -1745,13 +1746,36 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagK
           dgM = upM; dgD = upD; dgI = upI; dgJ = upJ; dgK = upK;
           lastM = vM; lastD = pD[RT - 1]; lastI = vI; lastJ = vJ; lastK = vK;
 
-          storePtrWords<PP, PP::WORDS>(passPtr + (size_t)t * PP::STEP_BYTES, lane, ptrw);
+          // ---- back-pointers: chunk ch of this step at stp + ch * 32 * CHUNK (one contiguous line per warp and chunk)
+          {
+            constexpr int CW = PP::CHUNK_BYTES / 4;
+#pragma unroll
+            for (int ch = 0; ch < PP::NCHUNK; ++ch) {
+              uint8_t* dst = stp + (size_t)ch * 32 * PP::CHUNK_BYTES;
+              if (CW == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(ptrw[ch * 4], ptrw[ch * 4 + 1], ptrw[ch * 4 + 2], ptrw[ch * 4 + 3]);
+              else if (CW == 2) *reinterpret_cast<uint2*>(dst) = make_uint2(ptrw[ch * 2], ptrw[ch * 2 + 1]);
+              else *reinterpret_cast<uint32_t*>(dst) = ptrw[ch];
+            }
+          }
           if (lane == 31 && pass + 1 < nPass) {
             uint32_t* b = reinterpret_cast<uint32_t*>(bndBuf) + (size_t)c * 5;
             b[0] = lastM; b[1] = lastD; b[2] = lastI; b[3] = lastJ; b[4] = lastK;
           }
         }
       }  // steps
+      // this pass's best last-row cells as (score, -sequence) keys
+      if (keyA) {
+        const uint32_t c   = 0xffffu - (keyA & 0xffffu);
+        const uint32_t seq = (KIND == KIND_JUMP && c > R1) ? (R1 + QA + (c - R1) - 1) : (c - 1);
+        const long long k  = makeKey((int)(keyA >> (16 + SH)) - bias, seq);
+        bestA              = k > bestA ? k : bestA;
+      }
+      if (keyB) {
+        const uint32_t c   = 0xffffu - (keyB & 0xffffu);
+        const uint32_t seq = (KIND == KIND_JUMP && c > R1) ? (R1 + QB + (c - R1) - 1) : (c - 1);
+        const long long k  = makeKey((int)(keyB >> (16 + SH)) - bias, seq);
+        bestB              = k > bestB ? k : bestB;
+      }
       while (curA.waitTile < curA.nextIssue) stageOk = cursorWait(curA) && stageOk;
       while (curB.waitTile < curB.nextIssue) stageOk = cursorWait(curB) && stageOk;
       __syncwarp();
@@ -1833,7 +1857,7 @@ int launchClass(mb200_ctx* ctx, const DpParams& base, const ClassPlan& plan, siz
 struct PairPlan {
   size_t   nPairs = 0;
   size_t   maxPtr = 0, maxSeg = 0, maxBnd = 0;
-  uint32_t maxQ = 0;
+  uint32_t maxQ = 0, maxR = 0;
   bool     noBad = false, tag = false;
   int      tagBias = 0, tagBad = 0;
 };
@@ -2010,6 +2034,7 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
     PairPlan&      p     = plans[cls];
     p.nPairs++;
     p.maxQ   = std::max(p.maxQ, Q);
+    p.maxR   = std::max(p.maxR, rtot);
     p.maxPtr = std::max(p.maxPtr, pb);
     p.maxSeg = std::max(p.maxSeg, 2 * ((size_t)Q + rtot + 8));
     p.maxBnd = std::max(p.maxBnd, (Q > (uint32_t)(32 * RT)) ? ((size_t)rtot + 2) * 5 : (size_t)8);
@@ -2033,7 +2058,7 @@ int dpRunPairs(mb200_ctx* ctx, const mb200_scores* scores, int extra, std::vecto
   for (int c = 0; c < NCLS; ++c) {
     PairPlan& p = plans[c];
     p.noBad = sentinelNeverWins(scores, extra, p.maxQ);
-    p.tag   = p.noBad && !ctx->noTagKernel && tagRangeOk(scores, extra, p.maxQ, TagTraits<KIND>::UNITS, &p.tagBias, &p.tagBad);
+    p.tag   = p.noBad && !ctx->noTagKernel && p.maxR < 65535u /* 16-bit column in the start-candidate keys */ && tagRangeOk(scores, extra, p.maxQ, TagTraits<KIND>::UNITS, &p.tagBias, &p.tagBad);
   }
 #define MB200_LAUNCH_CLASS(RTV, C)                                                                                   \
   do {                                                                                                               \

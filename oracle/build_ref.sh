@@ -24,6 +24,11 @@ if [ ! -d "$OUT/boost_1_58_0/boost" ]; then
   echo "[build_ref] unpacking boost headers"
   tar -xjf "$REF/redist/boost_1_58_0.tar.bz2" -C "$OUT" boost_1_58_0/boost boost_1_58_0/libs/date_time/src
 fi
+if [ ! -d "$OUT/boost_1_58_0/libs/serialization/src" ]; then
+  # SVLocusSet.cpp instantiates boost::archive (graph save/load): the serialization library itself is compiled too
+  echo "[build_ref] unpacking boost.serialization sources"
+  tar -xjf "$REF/redist/boost_1_58_0.tar.bz2" -C "$OUT" boost_1_58_0/libs/serialization/src
+fi
 if [ ! -d "$OUT/htslib-1.9/htslib" ]; then
   echo "[build_ref] unpacking htslib headers"
   tar -xjf "$REF/redist/htslib-1.9.tar.bz2" -C "$OUT" htslib-1.9/htslib
@@ -57,14 +62,31 @@ SRCS=(
   "$OUT/boost_1_58_0/libs/date_time/src/gregorian/greg_month.cpp"
   "$HERE/ref_shim.cpp"
   "$HERE/ref_refiner_shim.cpp"
+  # the SV locus graph and the per-bin edge retriever (row a1)
+  "$LIB/svgraph/SVLocusSet.cpp"
+  "$LIB/svgraph/SVLocus.cpp"
+  "$LIB/svgraph/SVLocusNode.cpp"
+  "$LIB/svgraph/GenomeInterval.cpp"
+  "$LIB/svgraph/EdgeInfo.cpp"
+  "$LIB/svgraph/SVLocusSampleCounts.cpp"
+  "$GSC/EdgeRetrieverBin.cpp"
+  "$HERE/ref_graph_shim.cpp"
 )
+# boost.serialization (narrow-character archives only)
+for f in "$OUT"/boost_1_58_0/libs/serialization/src/*.cpp; do
+  case "$(basename "$f" .cpp)" in
+    *w*archive*|*wi*|*wo*|xml_w*|text_w*|basic_xml_grammar|xml_grammar|xml_wgrammar|codecvt_null|utf8_codecvt_facet|shared_ptr_helper) continue ;;
+  esac
+  SRCS+=("$f")
+done
 
 OBJS=()
 pids=()
 for src in "${SRCS[@]}"; do
   obj="$OUT/obj/$(basename "${src%.cpp}").o"
   OBJS+=("$obj")
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/../include/manta_b200.h" -nt "$obj" ] || [ "$HERE/manta_oracle.h" -nt "$obj" ]; then
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$HERE/../include/manta_b200.h" -nt "$obj" ] || [ "$HERE/manta_oracle.h" -nt "$obj" ] ||
+     { [ "$(basename "$src")" = ref_graph_shim.cpp ] && [ "$HERE/../include/manta_b200_graph.hpp" -nt "$obj" ]; }; then
     $CXX $CXXFLAGS -c "$src" -o "$obj" &
     pids+=($!)
   fi

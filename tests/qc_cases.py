@@ -83,6 +83,7 @@ def pipeline_case(binding, batch, opts, cuts=None):
         cigs.append(cig)
     cigar = np.concatenate(cigs) if cigs else np.zeros(1, dtype=np.uint32)
     case = QcCase(batch.isJump.copy(), slotFirst, nContigs, aln, jump, cigar, pool, contigSeq, batch.ref1.copy(), support)
+    case.asm = (loci, contigs, pseudo, cpool, spool)  # the assembler's own outputs, for tests that compare them too
     return case, trims
 
 

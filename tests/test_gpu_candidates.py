@@ -137,11 +137,14 @@ def test_candidates_staging_queue(gpu, orc):
     gpu.candidates_upload(b2)
     with pytest.raises(cb.Mb200Error):
         gpu.candidates_upload(b1)
-    gpu._cand_shape = (b1.nLoci, int(b1.readViews["len"].sum()), b1.readsPerLocus)
-    assert decode_candidates(b1, opts, gpu.candidates_run(opts)) == w1
+    # the binding sizes the host arrays from the batch the run CONSUMES (b1: 16 loci), not from the newest upload
+    # (b2: 20 loci), and a reused `out` of a smaller batch is replaced instead of being overrun
+    out1 = gpu.candidates_run(opts)
+    assert len(out1["loci"]) == b1.nLoci
+    assert decode_candidates(b1, opts, out1) == w1
     gpu.candidates_upload(b1)  # overwrites the slot of the batch just consumed while b2 is still staged
-    gpu._cand_shape = (b2.nLoci, int(b2.readViews["len"].sum()), b2.readsPerLocus)
-    assert decode_candidates(b2, opts, gpu.candidates_run(opts)) == w2
-    gpu._cand_shape = (b1.nLoci, int(b1.readViews["len"].sum()), b1.readsPerLocus)
+    out2 = gpu.candidates_run(opts, out=out1)
+    assert len(out2["loci"]) == b2.nLoci
+    assert decode_candidates(b2, opts, out2) == w2
     assert decode_candidates(b1, opts, gpu.candidates_run(opts)) == w1
     assert decode_candidates(b1, opts, gpu.candidates_run(opts)) == w1  # nothing staged: repeat on the resident batch

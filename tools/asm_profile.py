@@ -12,7 +12,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PROF = os.path.join(ROOT, "build", "prof", "libmanta_b200_prof.so")
+PROF = os.path.join(ROOT, "tools", "_prof", "libmanta_b200_prof.so")  # build/ does not travel to the GPU box
 ap = argparse.ArgumentParser()
 ap.add_argument("--build", action="store_true")
 ap.add_argument("--loci", type=int, default=6000)
@@ -27,7 +27,7 @@ if args.build:
     for s in srcs:
         o = os.path.join(ROOT, "build", "obj", os.path.basename(s)[:-3] + ".o")
         if os.path.basename(s) == "assemble.cu":
-            o = os.path.join(ROOT, "build", "prof", "assemble_prof.o")
+            o = os.path.join(ROOT, "tools", "_prof", "assemble_prof.o")
             subprocess.check_call(["nvcc"] + [f for f in g.NVCC_FLAGS if f != "-shared"] + ["-DMB200_ASM_PROFILE", "-c", s, "-o", o])
         objs.append(o)
     subprocess.check_call(["nvcc", "-shared", "-o", PROF] + objs)
