@@ -282,13 +282,21 @@ def main():
         _keep.append(t)
     cuts = cb.default_ref_cuts(batch.nLoci) if refine else None
 
-    gather_state = {}
+    gatherer = None
+    if dist is not None:
+        # the single collective of the path, through the library's C ABI (mb200_gather_results: its own NCCL communicator,
+        # lengths all-gathered, ncclSend/ncclRecv into the merged buffer); torch.distributed only carries the 128-byte id
+        from manta_b200 import shard
+
+        def bcast_id(uid):
+            box = [uid]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        gatherer = shard.NcclGather(ctx, rank, world, "cuda:%d" % local_rank, bcast_id)
 
     def gather_results(out):
         if dist is None:
             return
-        # the single collective of the path: per-GPU result buffers to rank 0 over NVLink
-        from manta_b200 import shard
         if refine:
             # what the merged candidate buffer needs: bestAlignmentIndex of every candidate and the alignment / QC
             # records of the selected contigs
@@ -298,7 +306,7 @@ def main():
             parts = [best, out["aln"][slots], out["jump"][slots], out["qc"][slots]]
         else:
             parts = [out["aln"], out["jump"]]
-        shard.gather_buffers(parts, dst=0, device="cuda:%d" % local_rank, state=gather_state)
+        gatherer.gather(parts, dst=0)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -404,6 +412,7 @@ def main():
         line["cpu_baseline"] = cpu
     if dist is not None:
         dist.barrier()
+        gatherer.close()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))

@@ -438,6 +438,21 @@ MB200_API int mb200_candidates_small_svs(mb200_ctx* ctx, uint32_t* svFirst, mb20
  * ignored), out[nLoci] */
 MB200_API int mb200_candidates_jump_svs(mb200_ctx* ctx, const mb200_jump_orient* orient, mb200_jump_sv* out);
 
+/* ---- row (e): the one collective of the path -- merge the per-rank result buffers on `root` over NCCL ------------------
+ * Loci shard across the GPUs of a box with no data-path collective; this gather of the per-rank candidate /
+ * result buffers is the only exchange.  `ncclComm` is an ncclComm_t (the host's own, or one made with the two helpers
+ * below when the host has no NCCL bootstrap of its own: rank 0 calls mb200_nccl_unique_id and hands the 128 bytes to the
+ * other ranks by any means, then every rank calls mb200_nccl_comm_init).  localDev / rootDev are DEVICE pointers;
+ * rankBytes[nRanks] receives every rank's byte count on every rank; on `root` the merged buffer is the concatenation in
+ * rank order.  Collective: every rank of the communicator must call it; it returns after the transfer has completed on
+ * the ctx stream.  MB200_ERR_POOL_OVERFLOW (on every rank alike) when the merged size exceeds rootCap.  NCCL is loaded on
+ * first use (dlopen libnccl.so.2): MB200_ERR_UNSUPPORTED when it is not installed. */
+MB200_API int mb200_gather_results(mb200_ctx* ctx, void* ncclComm, int root, const void* localDev, uint64_t localBytes,
+                                   void* rootDev, uint64_t rootCap, uint64_t* rankBytes);
+MB200_API int mb200_nccl_unique_id(uint8_t id[128]);
+MB200_API int mb200_nccl_comm_init(mb200_ctx* ctx, int nRanks, const uint8_t id[128], int rank, void** ncclComm);
+MB200_API int mb200_nccl_comm_destroy(void* ncclComm);
+
 /* ---- row a1: the per-bin edge partition (host arithmetic, no device, no ctx) ---------------------------------------
  * GSC/EdgeRetrieverBin.cpp:43-235 on a flattened SVLocusSet (include/manta_b200_graph.hpp: mb200::FlatLocusGraph, filled on
  * the reference side by mb200::flattenLocusSet): locusNodeOff[nLoci+1], nodeEdgeOff[nNodes+1], and per out-edge its target

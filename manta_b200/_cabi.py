@@ -532,6 +532,34 @@ class Binding:
             self._raise(st)
         return int(nc.value), int(cells.value), int(ssum.value), int(qsum.value)
 
+    # -- the one collective of the path (product library only) --------------------------------
+    def nccl_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self.lib.mb200_nccl_unique_id.restype = C.c_int
+        st = self.lib.mb200_nccl_unique_id(buf)
+        if st != MB200_OK:
+            raise Mb200Error(st, "mb200_nccl_unique_id failed (status %d): libnccl.so.2 not available?" % st)
+        return bytes(buf)
+
+    def nccl_comm_init(self, n_ranks: int, unique_id: bytes, rank: int) -> C.c_void_p:
+        comm = C.c_void_p()
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        st = self._call("nccl_comm_init", C.c_int(n_ranks), idbuf, C.c_int(rank), C.byref(comm))
+        if st != MB200_OK:
+            self._raise(st)
+        return comm
+
+    def nccl_comm_destroy(self, comm) -> None:
+        self.lib.mb200_nccl_comm_destroy(comm)
+
+    def gather_results(self, comm, root: int, local_dev_ptr: int, local_bytes: int, root_dev_ptr: int, root_cap: int,
+                       n_ranks: int):
+        """mb200_gather_results on device pointers; returns (status, bytes per rank)"""
+        sizes = (C.c_uint64 * n_ranks)()
+        st = self._call("gather_results", comm, C.c_int(root), C.c_void_p(local_dev_ptr), C.c_uint64(local_bytes),
+                        C.c_void_p(root_dev_ptr), C.c_uint64(root_cap), sizes)
+        return st, [int(x) for x in sizes]
+
     def candidates_timing(self) -> dict:
         t = np.zeros(1, dtype=CAND_TIMING_DT)
         self._call("candidates_timing", _ptr(t))

@@ -15,10 +15,12 @@ import numpy as np
 
 
 def bin_bounds(total_observations: int, bin_count: int, bin_index: int) -> Tuple[int, int]:
-    """[begin, end) of cumulative observation count owned by one bin (EdgeRetrieverBin.cpp:38-61)"""
+    """(begin, end] of the running observation total owned by one bin: floor(T*i/B) computed in double like
+    getBoundaryCount (GSC/EdgeRetrieverBin.cpp:38-41)"""
     assert 0 <= bin_index < bin_count
-    begin = (total_observations * bin_index) // bin_count
-    end = (total_observations * (bin_index + 1)) // bin_count
+    import math
+    begin = int(math.floor((float(total_observations) * float(bin_index)) / float(bin_count)))
+    end = int(math.floor((float(total_observations) * float(bin_index + 1)) / float(bin_count)))
     return begin, end
 
 
@@ -26,17 +28,57 @@ def bins_for_rank(bin_count: int, rank: int, world: int) -> List[int]:
     return [b for b in range(bin_count) if b % world == rank]
 
 
+class FlatLocusGraph:
+    """CSR copy of an SVLocusSet (include/manta_b200_graph.hpp mb200::FlatLocusGraph)"""
+
+    def __init__(self, locusNodeOff, nodeEdgeOff, edgeTo, edgeCount):
+        self.locusNodeOff = np.ascontiguousarray(locusNodeOff, dtype=np.uint32)
+        self.nodeEdgeOff = np.ascontiguousarray(nodeEdgeOff, dtype=np.uint64)
+        self.edgeTo = np.ascontiguousarray(edgeTo, dtype=np.uint32)
+        self.edgeCount = np.ascontiguousarray(edgeCount, dtype=np.uint32)
+
+    @classmethod
+    def from_pair_counts(cls, observation_counts: Sequence[int]) -> "FlatLocusGraph":
+        """one two-node locus per candidate, all observations on the node0 -> node1 edge (what a graph of isolated
+        breakend pairs looks like)"""
+        c = np.asarray(observation_counts, dtype=np.uint32)
+        n = len(c)
+        edge_to = np.tile(np.array([1, 0], dtype=np.uint32), n)
+        edge_count = np.zeros(2 * n, dtype=np.uint32)
+        edge_count[0::2] = c
+        return cls(np.arange(n + 1, dtype=np.uint32) * 2, np.arange(2 * n + 1, dtype=np.uint64), edge_to, edge_count)
+
+    @property
+    def n_loci(self) -> int:
+        return len(self.locusNodeOff) - 1
+
+
+EDGE_INFO_DT = np.dtype([("locusIndex", "<u4"), ("nodeIndex1", "<u4"), ("nodeIndex2", "<u4")])
+
+
+def enumerate_bin(graph: FlatLocusGraph, bin_count: int, bin_index: int, graph_node_max_edge_count: int = 0) -> np.ndarray:
+    """the edges of one bin, through the library's mb200_edge_bin_enumerate (== the reference's EdgeRetrieverBin,
+    tests/test_edge_bins.py); host arithmetic, no GPU needed"""
+    import ctypes as C
+    from . import library_path
+    lib = C.CDLL(library_path())
+    cap = max(16, len(graph.edgeTo))
+    out = np.zeros(cap, dtype=EDGE_INFO_DT)
+    n = C.c_uint64(0)
+    st = lib.mb200_edge_bin_enumerate(C.c_uint32(graph.n_loci), graph.locusNodeOff.ctypes, graph.nodeEdgeOff.ctypes,
+                                      graph.edgeTo.ctypes, graph.edgeCount.ctypes, C.c_uint32(graph_node_max_edge_count),
+                                      C.c_uint32(bin_count), C.c_uint32(bin_index), out.ctypes, C.c_uint64(cap), C.byref(n))
+    if st != 0:
+        raise RuntimeError("mb200_edge_bin_enumerate failed with status %d" % st)
+    return out[:n.value]
+
+
 def assign_edges(observation_counts: Sequence[int], bin_count: int, rank: int, world: int) -> np.ndarray:
-    """indices of the edges this rank processes: edge e belongs to the bin containing the cumulative count at which
-    the edge starts (edges are never split, like EdgeRetrieverBin::jumpToFirstEdge / next)"""
-    counts = np.asarray(observation_counts, dtype=np.int64)
-    starts = np.concatenate([[0], np.cumsum(counts)[:-1]]) if len(counts) else np.zeros(0, dtype=np.int64)
-    total = int(counts.sum())
-    mine = np.zeros(len(counts), dtype=bool)
-    for b in bins_for_rank(bin_count, rank, world):
-        lo, hi = bin_bounds(total, bin_count, b)
-        mine |= (starts >= lo) & (starts < hi) & (counts > 0)
-    return np.nonzero(mine)[0]
+    """indices of the candidates (one two-node locus each) this rank processes: the bins {b : b mod world == rank} of a
+    `bin_count`-bin split, enumerated by the library's EdgeRetrieverBin"""
+    g = FlatLocusGraph.from_pair_counts(observation_counts)
+    mine = [enumerate_bin(g, bin_count, b)["locusIndex"] for b in bins_for_rank(bin_count, rank, world)]
+    return np.sort(np.concatenate(mine)) if mine else np.zeros(0, dtype=np.uint32)
 
 
 def gather_buffers(buf, dst: int = 0, device: Optional[str] = None, state: Optional[dict] = None):
@@ -90,3 +132,69 @@ def gather_buffers(buf, dst: int = 0, device: Optional[str] = None, state: Optio
     if on_gpu:
         torch.cuda.current_stream(dev).synchronize()
     return [host[i, :sizes[i]].numpy() for i in range(world)]
+
+
+class NcclGather:
+    """The path's one collective through the library's C ABI (mb200_gather_results: lengths all-gathered, then ncclSend /
+    ncclRecv straight into the merged buffer on the root).  The communicator is the library's own: rank 0 draws the NCCL
+    unique id and `bootstrap_broadcast` (any transport: here torch.distributed, gloo or nccl) hands it to the others.
+    torch only provides the device / pinned staging memory."""
+
+    def __init__(self, ctx, rank: int, world: int, device: str, bootstrap_broadcast):
+        import torch
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.torch, self.dev = torch, torch.device(device)
+        uid = bootstrap_broadcast(ctx.nccl_unique_id() if rank == 0 else None)
+        self.comm = ctx.nccl_comm_init(world, uid, rank)
+        self.cap = 0
+        self.stage = self.recv = self.host = None
+
+    def close(self):
+        if self.comm is not None:
+            self.ctx.nccl_comm_destroy(self.comm)
+            self.comm = None
+
+    def gather(self, buf, dst: int = 0):
+        """`buf`: one array or a sequence of arrays (this rank's result buffer).  Returns on `dst` one uint8 array per rank
+        (views into a pinned buffer that the next call overwrites), None elsewhere."""
+        torch = self.torch
+        parts = [buf] if isinstance(buf, np.ndarray) else list(buf)
+        flats = [np.ascontiguousarray(p).view(np.uint8).reshape(-1) for p in parts]
+        total = int(sum(f.size for f in flats))
+        if self.stage is None or self.stage.numel() < total:
+            self.stage = torch.empty(total + total // 8 + 64, dtype=torch.uint8, device=self.dev)
+        o = 0
+        for f in flats:
+            if f.size:
+                self.stage[o:o + f.size].copy_(torch.from_numpy(f), non_blocking=True)
+                o += f.size
+        torch.cuda.current_stream(self.dev).synchronize()  # the library gathers on its own stream
+        for _ in range(2):
+            if self.rank == dst and self.recv is None:
+                self.cap = max(self.cap, 1 << 16)
+                self.recv = torch.empty(self.cap, dtype=torch.uint8, device=self.dev)
+                self.host = torch.empty(self.cap, dtype=torch.uint8, pin_memory=True)
+            st, sizes = self.ctx.gather_results(self.comm, dst, self.stage.data_ptr(), total,
+                                                self.recv.data_ptr() if self.rank == dst else 0,
+                                                self.cap if self.rank == dst else 0, self.world)
+            if st == 0:
+                break
+            from ._cabi import MB200_ERR_POOL_OVERFLOW
+            if st != MB200_ERR_POOL_OVERFLOW:
+                self.ctx._raise(st)
+            # every rank got the same sizes and the same status: the root grows its buffer, everybody calls again
+            self.cap = int(sum(sizes) * 1.25) + 64
+            self.recv = None
+        else:
+            raise RuntimeError("gather_results: merged buffer still too small")
+        if self.rank != dst:
+            return None
+        n = int(sum(sizes))
+        self.host[:n].copy_(self.recv[:n], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        out, o = [], 0
+        h = self.host.numpy()
+        for s_ in sizes:
+            out.append(h[o:o + s_])
+            o += s_
+        return out

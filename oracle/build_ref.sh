@@ -70,6 +70,7 @@ SRCS=(
   "$LIB/svgraph/EdgeInfo.cpp"
   "$LIB/svgraph/SVLocusSampleCounts.cpp"
   "$GSC/EdgeRetrieverBin.cpp"
+  "$LIB/htsapi/bam_header_info.cpp"
   "$HERE/ref_graph_shim.cpp"
 )
 # boost.serialization (narrow-character archives only)

@@ -5,6 +5,8 @@
 // optional mergeSelfOverlap, SVLocusSet::merge), export it through the product's reference-side binding
 // mb200::flattenLocusSet, and list the edges the reference retriever returns for one bin.
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -44,6 +46,9 @@ REF_API int ref_graph_build(uint32_t nSpecs, const uint32_t* nodeOff, const int3
     G->flat = mb200::flattenLocusSet(G->set);
     *handle = G;
     return 0;
+  } catch (const std::exception& e) {
+    if (getenv("REF_GRAPH_VERBOSE")) fprintf(stderr, "ref_graph_build: %s\n", e.what());
+    return 1;
   } catch (...) {
     return 1;
   }

@@ -44,10 +44,20 @@ def _worker(rank, world, port, counts, ret):
 
 def test_bins_partition_edges():
     rng = np.random.default_rng(1)
-    counts = rng.integers(0, 50, 1000)
+    counts = rng.integers(1, 50, 1000)
     for world in (1, 2, 4, 8):
-        seen = np.concatenate([shard.assign_edges(counts, 32, r, world) for r in range(world)])
-        assert sorted(seen.tolist()) == np.nonzero(counts > 0)[0].tolist()  # every edge exactly once
+        seen = np.concatenate([shard.assign_edges(counts, 16 * world, r, world) for r in range(world)])
+        assert sorted(seen.tolist()) == list(range(len(counts)))  # every edge exactly once
+    # bin i owns the edges whose running total ends in (begin_i, end_i] (GSC/EdgeRetrieverBin.cpp: jumpToFirstEdge / next)
+    ends = np.cumsum(counts)
+    g = shard.FlatLocusGraph.from_pair_counts(counts)
+    for b in range(32):
+        lo, hi = shard.bin_bounds(int(counts.sum()), 32, b)
+        want = np.nonzero((ends > lo) & (ends <= hi))[0]
+        assert shard.enumerate_bin(g, 32, b)["locusIndex"].tolist() == want.tolist()
+    # the example of the round-1 review: counts [3,4,3], two bins -> {e0}, {e1, e2}
+    g = shard.FlatLocusGraph.from_pair_counts([3, 4, 3])
+    assert [shard.enumerate_bin(g, 2, b)["locusIndex"].tolist() for b in range(2)] == [[0], [1, 2]]
     # bins carry (nearly) equal observation mass
     total = int(counts.sum())
     for b in range(32):
@@ -56,7 +66,7 @@ def test_bins_partition_edges():
 
 
 def test_gather_world2_gloo():
-    counts = np.random.default_rng(2).integers(0, 20, 300)
+    counts = np.random.default_rng(2).integers(1, 20, 300)
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = _free_port()
@@ -67,6 +77,6 @@ def test_gather_world2_gloo():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert sorted(out[0] + out[1]) == np.nonzero(counts > 0)[0].tolist()
+    assert sorted(out[0] + out[1]) == list(range(len(counts)))
     assert out[0] == shard.assign_edges(counts, 8, 0, 2).tolist()
     assert out[1] == shard.assign_edges(counts, 8, 1, 2).tolist()
