@@ -208,6 +208,9 @@ def main():
     ap.add_argument("--impl", default="manta_b200", choices=["manta_b200", "reference"])
     ap.add_argument("--loci", type=int, default=50000, help="candidate loci per GPU per step (BASELINE configs[1]: 50000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the headline): --loci candidates PER GPU.  strong: ONE fixed list of --loci candidates "
+                         "with observation counts, split over the GPUs by the reference's bins (EdgeRetrieverBin, 16 bins per GPU)")
     ap.add_argument("--no-refine", action="store_true",
                     help="leave out the refiner's 10-mer window trim and contig QC / selection (assemble + align only)")
     ap.add_argument("--workload", default="candidates", choices=["candidates", "split"],
@@ -273,7 +276,17 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = manta_b200.Context(local_rank)
-    batch = synth.make_candidate_batch(args.loci, seed=20260923 + rank)
+    strong = None
+    if args.scaling == "strong":
+        # one fixed, observation-weighted candidate list; rank r takes the bins {b : b mod G == r} of a 16*G-bin split
+        # (GSC/EdgeRetrieverBin.cpp through mb200_edge_bin_enumerate).  Bins balance OBSERVATIONS, not run time.
+        from manta_b200 import shard
+        obs = np.clip(np.random.default_rng(20260923).lognormal(2.5, 1.0, args.loci), 1, 2000).astype(np.uint32)
+        mine = shard.assign_edges(obs, 16 * world, rank, world)
+        batch = synth.make_candidate_batch(0, seed=20260923, locus_ids=mine)
+        strong = dict(total_loci=args.loci, bins=16 * world, my_ids=mine)
+    else:
+        batch = synth.make_candidate_batch(args.loci, seed=20260923 + rank)
     # every input array lives in pinned host memory, so that the staged upload is asynchronous end to end
     _keep = []
     for name in ("pool", "readViews", "readOff", "ref1", "ref2", "isJump"):
@@ -307,6 +320,21 @@ def main():
         else:
             parts = [out["aln"], out["jump"]]
         gatherer.gather(parts, dst=0)
+
+    def merged_checksum(out):
+        """order-independent checksum of what a merged candidate buffer holds (strong scaling: equal for every GPU count):
+        per candidate its global id, bestAlignmentIndex and the selected contig's score, summed over all ranks"""
+        best = out["best"].astype(np.int64)
+        ids = strong["my_ids"].astype(np.int64)
+        A = int(opts["asmOpts"]["maxAssemblyCount"][0])
+        sel = np.nonzero(best >= 0)[0]
+        slots = sel * A + best[sel]
+        score = np.where(batch.isJump[sel] != 0, out["jump"]["score"][slots], out["aln"]["score"][slots]).astype(np.int64)
+        h = int(((ids + 1) * 1000003 * (best + 2)).sum() % (1 << 61)) + int(((ids[sel] + 7) * 8191 * (score + 100000)).sum() % (1 << 61))
+        t = torch.tensor([h % (1 << 61), len(ids)], dtype=torch.int64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t)
+        return int(t[0].item() % (1 << 61)), int(t[1].item())
 
     def sync_all():
         torch.cuda.synchronize()
@@ -370,7 +398,7 @@ def main():
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     wall, wall_e2e, ev_s = [float(x) for x in times.cpu()]
-    total_candidates = args.loci * world * args.steps
+    total_candidates = (args.loci if strong else args.loci * world) * args.steps
     value = total_candidates / wall
     e2e_value = total_candidates / wall_e2e
 
@@ -388,7 +416,7 @@ def main():
     dom_bytes = tim["indelBytes"]
     achieved = dom_bytes / (dom_ms * 1e-3) * 1e-9 if dom_ms > 0 else 0.0
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1000.0 * wall / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step=1000.0 * wall / args.steps, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                 dtype="int32", dtype_note="DP lanes are int16x2 where the host proves that every intermediate fits (results equal the int32 kernel, which the tests also run)",
                 data="synthetic", config=config, clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
@@ -407,6 +435,17 @@ def main():
                             indel_cells=tim["indelCells"], jump_cells=tim["jumpCells"],
                             jump_gcups=(tim["jumpCells"] / (stage["jumpMs"] / args.steps * 1e-3) * 1e-9) if stage["jumpMs"] > 0 else None,
                             jump_gbs=(tim["jumpBytes"] / (stage["jumpMs"] / args.steps * 1e-3) * 1e-9) if stage["jumpMs"] > 0 else None))
+    if strong:
+        csum, n_all = merged_checksum(out)
+        per = torch.zeros(world, 2, dtype=torch.float64, device="cuda")
+        per[rank, 0], per[rank, 1] = batch.nLoci, ev_ms / args.steps
+        if dist is not None:
+            dist.all_reduce(per)
+        per = per.cpu().numpy()
+        line["strong"] = dict(total_loci=args.loci, bins=strong["bins"], loci_per_rank=[int(x) for x in per[:, 0]],
+                              device_ms_per_rank=[round(float(x), 2) for x in per[:, 1]],
+                              imbalance=float(per[:, 1].max() / per[:, 1].mean()), merged_checksum=csum, candidates_seen=n_all)
+        line["config"]["workload"] += "; STRONG scaling: one list of %d candidates split by observation-weighted bins" % args.loci
     if rank == 0 and not args.no_cpu_baseline:
         cpu, _, _ = cpu_baseline(batch, opts, cuts, refine)
         line["cpu_baseline"] = cpu

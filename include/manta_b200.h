@@ -350,6 +350,61 @@ MB200_API int mb200_small_sv_batch(mb200_ctx* ctx, uint32_t minCandidateVariantS
                                    const mb200_seqview* contigSeq, const mb200_seqview* ref1, uint32_t* svFirst,
                                    mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed);
 
+/* ---- large insertions with an incompletely assembled insert (rest of row a9) ------------------------------------------
+ * getSmallSVAssembly tests every contig alignment of a complex candidate as the LEFT or RIGHT side of a large insertion
+ * (GSC/SVCandidateAssemblyRefiner.cpp:2079-2112: isLargeInsertAlignment :611 on the alignment limited to the contig's
+ * conservative range and on the whole alignment, scored with largeInsertEdgeAlignScores), and processLargeInsertion
+ * (:833-1007) pairs a left with a right candidate (all against all, nearest breakpoints first, then best score), joins
+ * the two contigs around 100 'N's, aligns the joined contig with GlobalAligner<int>(largeInsertCompleteAlignScores)
+ * against the window inside the ORIGINAL leading/trailing cuts, and accepts it if the alignment shows one insertion
+ * covering the N block with two well-scoring flanks (getLargestInsertSegment :230, isFinishedLargeInsertAlignment :642,
+ * getInsertTrim :801); the accepted pair becomes a refined SV by setSmallCandSV (:720) unless a fully assembled
+ * insertion already starts at the same position. */
+typedef struct mb200_large_insert_info { /* LargeInsertionInfo  lib/manta/SVCandidateAssemblyData.hpp:60-78 (zeros: no candidate) */
+  uint8_t  isLeftCandidate, isRightCandidate, reserved[2];
+  uint32_t contigOffset;
+  uint32_t refOffset;
+  int32_t  score;
+} mb200_large_insert_info;
+
+enum { /* mb200_large_insertion.status: where processLargeInsertion left */
+  MB200_LI_NONE        = 0, /* no left/right pair within maxBreakDist (:916) */
+  MB200_LI_SEGMENT_QC  = 1, /* joined contig aligned, but not exactly one insert segment >= 100 (:950) */
+  MB200_LI_FLANK_QC    = 2, /* isFinishedLargeInsertAlignment failed (:955) */
+  MB200_LI_TRIM_QC     = 3, /* partial insert sequences shorter than 40 (:966-973) */
+  MB200_LI_RANGE_ERROR = 4, /* setSmallCandSV throws here: cipos does not start at 0 (:768) */
+  MB200_LI_DUPLICATE   = 5, /* a fully assembled insertion of the selected contig starts at the same position (:991) */
+  MB200_LI_ACCEPTED    = 6
+};
+typedef struct mb200_large_insertion {
+  int32_t  status;
+  uint32_t leftContig, rightContig; /* contig indices inside the candidate (status >= 1) */
+  int32_t  breakDist, breakScore;
+  int32_t  score, beginPos;         /* alignment of left + 100 N + right; beginPos in the UNcut window (:941) */
+  uint32_t cigarLen;
+  uint64_t cigarOff;                /* into the call's output cigar pool */
+  uint32_t segFirst, segLast;       /* the insert segment (status >= 2) */
+  int32_t  insertTrimBegin, insertTrimEnd; /* getInsertTrim (status >= 3) */
+  int32_t  refBegin, refEnd, readBegin, readEnd, ciposBegin, ciposEnd; /* as mb200_small_sv (status >= 4) */
+  int32_t  bp1Begin, bp1End, bp2Begin, bp2End;                         /* status >= 5 */
+  uint32_t leftSeqBegin;  /* unknownSizeInsertionLeftSeq  = leftContig[leftSeqBegin, end)   (status == ACCEPTED) */
+  uint32_t rightSeqLen;   /* unknownSizeInsertionRightSeq = rightContig[0, rightSeqLen) */
+} mb200_large_insertion;
+
+/* Layout as mb200_select_contigs_batch.  aln[] are the large-indel alignments of the contigs (beginPos in the uncut window),
+ * consRange[2*slot .. ] = AssembledContig::conservativeRange (begin, end), cuts may be NULL (no cut), svFirst/svs = the
+ * refined small SVs of the selected contigs (mb200_small_sv_batch; NULL: nothing is excluded).  info[nSlots] and
+ * out[nLoci] are written for complex candidates (zeros for spanning ones).  MB200_ERR_POOL_OVERFLOW when outCigarCap is
+ * too small (*outCigarUsed = segments needed). */
+MB200_API int mb200_large_insertion_batch(mb200_ctx* ctx, const mb200_scores* edgeScores, const mb200_scores* completeScores,
+                                          uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst,
+                                          const uint32_t* nContigs, uint32_t nSlots, const mb200_aln_result* aln,
+                                          const uint32_t* cigarPool, uint64_t cigarLen, const uint8_t* pool, uint64_t poolBytes,
+                                          const mb200_seqview* contigSeq, const int32_t* consRange, const mb200_seqview* ref1,
+                                          const mb200_ref_cuts* cuts, const uint32_t* svFirst, const mb200_small_sv* svs,
+                                          mb200_large_insert_info* info, mb200_large_insertion* out, uint32_t* outCigar,
+                                          uint64_t outCigarCap, uint64_t* outCigarUsed);
+
 /* Refined breakends of a spanning candidate from its selected jump alignment: generateRefinedSVCandidateFromJumpAlignment
  * (GSC/SVCandidateAssemblyRefiner.cpp:1190-1223) = adjustAssembledBreakend (:59-86) on both breakends.  What the
  * refiner knows about the candidate besides the alignment: */

@@ -104,6 +104,17 @@ SMALL_SV_DT = np.dtype([("locus", "<u4"), ("contig", "<u4"), ("segment", "<u4"),
                         ("ciposBegin", "<i4"), ("ciposEnd", "<i4"), ("bp1Begin", "<i4"), ("bp1End", "<i4"), ("bp2Begin", "<i4"),
                         ("bp2End", "<i4")], align=True)
 assert SMALL_SV_DT.itemsize == 64
+LARGE_INSERT_INFO_DT = np.dtype([("isLeftCandidate", "u1"), ("isRightCandidate", "u1"), ("reserved", "u1", (2,)),
+                                 ("contigOffset", "<u4"), ("refOffset", "<u4"), ("score", "<i4")], align=True)
+LARGE_INSERTION_DT = np.dtype([("status", "<i4"), ("leftContig", "<u4"), ("rightContig", "<u4"), ("breakDist", "<i4"),
+                               ("breakScore", "<i4"), ("score", "<i4"), ("beginPos", "<i4"), ("cigarLen", "<u4"),
+                               ("cigarOff", "<u8"), ("segFirst", "<u4"), ("segLast", "<u4"), ("insertTrimBegin", "<i4"),
+                               ("insertTrimEnd", "<i4"), ("refBegin", "<i4"), ("refEnd", "<i4"), ("readBegin", "<i4"),
+                               ("readEnd", "<i4"), ("ciposBegin", "<i4"), ("ciposEnd", "<i4"), ("bp1Begin", "<i4"),
+                               ("bp1End", "<i4"), ("bp2Begin", "<i4"), ("bp2End", "<i4"), ("leftSeqBegin", "<u4"),
+                               ("rightSeqLen", "<u4")], align=True)
+assert LARGE_INSERT_INFO_DT.itemsize == 16 and LARGE_INSERTION_DT.itemsize == 104
+LI_NONE, LI_SEGMENT_QC, LI_FLANK_QC, LI_TRIM_QC, LI_RANGE_ERROR, LI_DUPLICATE, LI_ACCEPTED = range(7)
 CAND_OPTS_DT = np.dtype([("asmOpts", ASM_OPTS_DT), ("indelScores", "<i4", (6,)), ("largeIndelScore", "<i4"),
                          ("jumpScores", "<i4", (6,)), ("jumpScore", "<i4"), ("qcOpts", QC_OPTS_DT)], align=True)
 CAND_TIMING_DT = np.dtype([("h2dMs", "<f4"), ("asmMs", "<f4"), ("indelMs", "<f4"), ("jumpMs", "<f4"), ("d2hMs", "<f4"),
@@ -422,6 +433,40 @@ class Binding:
                 self._raise(st)
             return svFirst, svs[:int(used.value)]
         raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "small SV record overflow")
+
+    def large_insertion_raw(self, edgeScores, completeScores, isJump: np.ndarray, slotFirst: np.ndarray, nContigs: np.ndarray,
+                            aln: np.ndarray, cigar: np.ndarray, pool: np.ndarray, contigSeq: np.ndarray,
+                            consRange: np.ndarray, ref1: np.ndarray, cuts: Optional[np.ndarray] = None,
+                            svFirst: Optional[np.ndarray] = None, svs: Optional[np.ndarray] = None):
+        """large insertions with an incompletely assembled insert (GSC/SVCandidateAssemblyRefiner.cpp:2079-2112, :833-1007);
+        returns (info[nSlots], records[nLoci], cigar pool of the joined-contig alignments)"""
+        nLoci, nSlots = len(isJump), len(contigSeq)
+        info = np.zeros(max(1, nSlots), dtype=LARGE_INSERT_INFO_DT)
+        out = np.zeros(max(1, nLoci), dtype=LARGE_INSERTION_DT)
+        es, cs = Scores(*edgeScores), Scores(*completeScores)
+        consRange = np.ascontiguousarray(consRange, dtype=np.int32)
+        cap = 256
+        for _ in range(4):
+            oc = np.zeros(cap, dtype=np.uint32)
+            used = C.c_uint64(0)
+            args = [C.byref(es), C.byref(cs), C.c_uint32(nLoci), _ptr(isJump), _ptr(slotFirst), _ptr(nContigs), C.c_uint32(nSlots),
+                    _ptr(aln), _ptr(cigar)]
+            if self.ctx is not None:
+                args.append(C.c_uint64(cigar.size))
+            args.append(_ptr(pool))
+            if self.ctx is not None:
+                args.append(C.c_uint64(pool.size))
+            st = self._call("large_insertion_batch", *args, _ptr(contigSeq), _ptr(consRange), _ptr(ref1),
+                            _ptr(cuts) if cuts is not None else None, _ptr(svFirst) if svFirst is not None else None,
+                            _ptr(svs) if svs is not None and len(svs) else None, _ptr(info), _ptr(out), _ptr(oc),
+                            C.c_uint64(cap), C.byref(used))
+            if st == MB200_ERR_POOL_OVERFLOW:
+                cap = int(used.value) + 64
+                continue
+            if st != MB200_OK:
+                self._raise(st)
+            return info[:nSlots], out[:nLoci], oc[:int(used.value)]
+        raise Mb200Error(MB200_ERR_POOL_OVERFLOW, "large insertion cigar overflow")
 
     def jump_sv_raw(self, isJump: np.ndarray, slotFirst: np.ndarray, nSlots: int, best: np.ndarray, jump: np.ndarray,
                     cigar: np.ndarray, ref1: np.ndarray, ref2: np.ndarray, orient: np.ndarray) -> np.ndarray:

@@ -763,33 +763,15 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           unsigned long long bestCnt = 0;  // (count << 32) | has
           Key                bestKey = {~0ull, ~0ull, ~0ull};
           uint32_t           bestId  = NONE32;
-          // four words per lane and round: the id, flag and count loads of a round are independent and issued together
-          // (the scan is a chain of dependent loads otherwise); a word's key is only fetched when its count can still win.
-          // (count desc, key asc) is a strict total order over distinct words, so the scan order does not matter.
-          for (uint32_t i0 = tid; i0 < nWords; i0 += 4 * nt) {
-            uint32_t ids[4], cn[4];
-            uint8_t  fl[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const uint32_t i = i0 + (uint32_t)u * nt;
-              ids[u]           = (i < nWords) ? W.wordList[i] : NONE32;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              fl[u] = (ids[u] != NONE32) ? W.flags[ids[u]] : (uint8_t)0;
-              cn[u] = (ids[u] != NONE32) ? W.count[ids[u]] : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (!(fl[u] & FLAG_UNUSED)) continue;
-              const uint32_t c = cn[u];
-              if (bestId != NONE32 && c < (uint32_t)bestCnt) continue;
-              const Key key = loadKey(W, ids[u]);
-              if (bestId == NONE32 || c > (uint32_t)bestCnt || keyLess(key, bestKey)) {
-                bestCnt = c;
-                bestKey = key;
-                bestId  = ids[u];
-              }
+          for (uint32_t i = tid; i < nWords; i += nt) {
+            const uint32_t id = W.wordList[i];
+            if (!(W.flags[id] & FLAG_UNUSED)) continue;
+            const uint32_t c   = W.count[id];
+            const Key      key = loadKey(W, id);
+            if (bestId == NONE32 || c > (uint32_t)bestCnt || (c == (uint32_t)bestCnt && keyLess(key, bestKey))) {
+              bestCnt = c;
+              bestKey = key;
+              bestId  = id;
             }
           }
           // warp reduce then block reduce (4 warps)
@@ -881,42 +863,6 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                   const uint32_t cand[4] = {cand4.x, cand4.y, cand4.z, cand4.w};
                   uint32_t maxBaseCount = 0, maxCnt = 0, maxBase = 0, maxWord = NONE32;
                   uint32_t maxW = 0, maxCW = 0, sup2Remove = 0, rej2Add = 0;
-                  const int nCand = (cand[0] != NONE32) + (cand[1] != NONE32) + (cand[2] != NONE32) + (cand[3] != NONE32);
-                  if (nCand == 0) break;  // no extension: maxBaseCount stays 0 < minCoverage (minCoverage >= 1)
-                  if (nCand == 1) {
-                    // ---- the usual step, one possible extension: everything the step needs from that word is independent
-                    // of everything else, so all of it is fetched in ONE memory round trip (the walk is a chain of
-                    // dependent loads; the general code below needs five round trips per step)
-                    const int      s0 = cand[0] != NONE32 ? 0 : (cand[1] != NONE32 ? 1 : (cand[2] != NONE32 ? 2 : 3));
-                    const uint32_t id = cand[s0];
-                    const uint32_t cw     = (lane < SW) ? W.bits[(size_t)id * SW + lane] : 0u;
-                    const uint32_t cnt    = W.count[id];
-                    const uint8_t  inCtg  = W.inContig[id];
-                    const uint4    alt4   = *reinterpret_cast<const uint4*>((isEnd ? W.pred : W.succ) + (size_t)id * 4);
-                    const uint32_t contigWord = support & cw;
-                    if (!__any_sync(0xffffffffu, contigWord != 0)) break;  // no shared read: maxBaseCount == 0
-                    maxW = cw; maxCW = contigWord; maxBaseCount = cnt; maxBase = (uint32_t)s0; maxWord = id;
-                    if (maxBaseCount < opt.minCoverage) break;
-                    if (inCtg == (uint8_t)serial) {
-                      isRepeatFound = true;
-                      break;
-                    }
-                    // walk backwards one step at the branching point (:375-427): the words that also lead into maxWord
-                    const uint32_t alt[4] = {alt4.x, alt4.y, alt4.z, alt4.w};
-                    uint32_t       back[4];
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                      const uint32_t aid = alt[s];
-                      const bool     use = (aid != NONE32) && (aid != maxWord) && (aid != curWord);
-                      back[s] = (use && lane < SW) ? W.bits[(size_t)aid * SW + lane] : 0u;
-                    }
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                      const uint32_t toUpdate = back[s] & ~(maxCW & back[s]);
-                      rej2Add |= toUpdate;
-                      sup2Remove |= toUpdate;
-                    }
-                  } else {
 #pragma unroll
                   for (int s = 0; s < 4; ++s) {
                     const uint32_t id = cand[s];
@@ -960,7 +906,6 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                       rej2Add |= toUpdate;
                       sup2Remove |= toUpdate;
                     }
-                  }
                   }
                   // contig.seq = addBase(contig.seq, maxBase, isEnd)
                   if (hi - lo + 1 > P.maxContigLen || lo == 0 || hi + 1 >= ctgBuf) {

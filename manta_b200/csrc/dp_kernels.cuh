@@ -1395,8 +1395,11 @@ template <int KIND> struct TagTraits {
   static constexpr int      UNITS = 65536 / SC;  // representable score span
 };
 
+#ifndef MB200_TAG_OCC4_MAXRT
+#define MB200_TAG_OCC4_MAXRT 0  // strips up to this many rows per lane are held to 128 registers (4 CTAs/SM)
+#endif
 template <int KIND, int RT>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= 12) ? 3 : 1) dpTagKernel(const DpParams P)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXRT) ? 4 : ((RT <= 12) ? 3 : 1)) dpTagKernel(const DpParams P)
 {
   using KT               = KindTraits<KIND>;
   using TT               = TagTraits<KIND>;

@@ -170,6 +170,8 @@ void mb200_destroy(mb200_ctx* ctx)
                           &ctx->dQcViews, &ctx->dQcRef, &ctx->dQcCuts, &ctx->dQcTrim, &ctx->dQcIsJump, &ctx->dQc, &ctx->dQcBest, &ctx->dSvFirst, &ctx->dSvs};
   for (DeviceBuffer* b : bufs)
     if (b->ptr) cudaFree(b->ptr);
+  for (DeviceBuffer& b : ctx->dLi)
+    if (b.ptr) cudaFree(b.ptr);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   for (int i = 0; i < 4; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

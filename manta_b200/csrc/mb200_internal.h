@@ -40,6 +40,7 @@ struct mb200_ctx {
   bool         noTagKernel = false;  // cfg.reserved[0] & 2: int16x2 pairs on the predicate/SEL kernel, never the tagged-score one
   // growable device buffers, reused across calls (library owns device memory)
   DeviceBuffer dPool, dTasks, dResults, dCigar, dPtrScratch, dSegScratch, dBndScratch, dMisc, dJobs, dTables;
+  DeviceBuffer dLi[14];  // large_insert.cu
   DeviceBuffer dAsmWork, dAsmOut0, dAsmOut1, dAsmOut2, dAsmOut3, dAsmOut4, dViews, dReadOff;
   // pinned staging
   void*  hPinned      = nullptr;

@@ -173,7 +173,7 @@ class CandidateBatch:
 
 
 def make_candidate_batch(n_loci: int, seed: int = 20260923, reads_per_locus: int = 64, read_len: int = 150,
-                         window: int = 5000, seqview_dtype=None) -> CandidateBatch:
+                         window: int = 5000, seqview_dtype=None, locus_ids=None) -> CandidateBatch:
     """SURVEY.md 8(d) config 2.  Per locus: a `window`-bp iid reference; an SV at a breakpoint
     (40 % deletion 50-2000 bp, 20 % novel insertion 50-300 bp, 20 % inversion, 20 % translocation to a second
     window); 48 reads from the alt haplotype tiling the breakpoint (start in [bp-140, bp-10]) + 16 from the
@@ -181,8 +181,14 @@ def make_candidate_batch(n_loci: int, seed: int = 20260923, reads_per_locus: int
     10 % of loci carry a tandem repeat (period 2-30, >= 100 bp) at the breakpoint.
     Deletion/insertion loci are 'complex' candidates aligned with the large-indel aligner against the whole
     window; inversion/translocation loci are 'spanning' candidates aligned with the jump aligner against two
-    window/2 references (R1 + R2 = window)."""
+    window/2 references (R1 + R2 = window).
+
+    `locus_ids` (strong-scaling bench): generate exactly the loci with these GLOBAL indices of one fixed candidate list,
+    each from its own stream default_rng([seed, id]) -- any rank can build any subset of the same list (n_loci is then
+    len(locus_ids))."""
     from ._cabi import SEQVIEW_DT
+    if locus_ids is not None:
+        n_loci = len(locus_ids)
     rng = np.random.default_rng(seed)
     n_alt = reads_per_locus * 3 // 4
     read_stride = read_len
@@ -204,6 +210,8 @@ def make_candidate_batch(n_loci: int, seed: int = 20260923, reads_per_locus: int
     col = np.arange(read_len)
     ref_base = reads_bytes_al
     for li in range(n_loci):
+        if locus_ids is not None:
+            rng = np.random.default_rng([seed, int(locus_ids[li])])
         w1 = ACGT[rng.integers(0, 4, window)]
         kind = rng.random()
         bp = int(rng.integers(window // 5, window // 2))
@@ -251,6 +259,54 @@ def make_candidate_batch(n_loci: int, seed: int = 20260923, reads_per_locus: int
         else:
             pool[rb:rb + window] = w1
             ref1["off"][li], ref1["len"][li] = rb, window
+    return CandidateBatch(n_loci, reads_per_locus, read_len, pool, readOff, readViews, isJump, ref1, ref2)
+
+
+def make_large_insertion_batch(n_loci: int, seed: int = 7, reads_per_locus: int = 64, read_len: int = 150, window: int = 3000,
+                               min_insert: int = 400, max_insert: int = 900) -> CandidateBatch:
+    """Complex candidates whose novel insertion is too long to assemble through (GSC/SVCandidateAssemblyRefiner.cpp
+    processLargeInsertion :833): reads cover the left edge (reference flank + start of the insert), the right edge (end
+    of the insert + reference flank) and the reference allele, so the assembler returns a left and a right contig.
+    A fifth of the loci carry a short (assemblable) insertion instead, a tenth a second copy of the left edge shifted by a
+    few bases (competing left candidates).  Same layout as make_candidate_batch."""
+    from ._cabi import SEQVIEW_DT
+    rng = np.random.default_rng(seed)
+    read_stride = read_len
+    reads_bytes_al = (n_loci * reads_per_locus * read_stride + 15) // 16 * 16
+    ref_stride = (window + 15) // 16 * 16
+    pool = np.zeros(reads_bytes_al + n_loci * ref_stride + 64, dtype=np.uint8)
+    readViews = np.zeros(n_loci * reads_per_locus, dtype=SEQVIEW_DT)
+    readViews["off"] = np.arange(n_loci * reads_per_locus, dtype=np.uint64) * read_stride
+    readViews["len"] = read_len
+    readOff = np.arange(n_loci + 1, dtype=np.uint64) * reads_per_locus
+    isJump = np.zeros(n_loci, dtype=np.uint8)
+    ref1 = np.zeros(n_loci, dtype=SEQVIEW_DT)
+    ref2 = np.zeros(n_loci, dtype=SEQVIEW_DT)
+    col = np.arange(read_len)
+    third = reads_per_locus // 3
+    for li in range(n_loci):
+        w1 = ACGT[rng.integers(0, 4, window)]
+        bp = int(rng.integers(window // 3, 2 * window // 3))
+        il = int(rng.integers(60, 200)) if rng.random() < 0.2 else int(rng.integers(min_insert, max_insert + 1))
+        alt = np.concatenate([w1[:bp], ACGT[rng.integers(0, 4, il)], w1[bp:]])
+        st_left = rng.integers(bp - 140, bp - 9, third)
+        st_right = rng.integers(bp + il - 140, bp + il - 9, third)
+        if rng.random() < 0.1:
+            st_left[::2] += int(rng.integers(3, 12))
+        st_ref = rng.integers(bp - 140, bp - 9, reads_per_locus - 2 * third)
+        rd = np.empty((reads_per_locus, read_len), dtype=np.uint8)
+        rd[:third] = alt[st_left[:, None] + col[None, :]]
+        rd[third:2 * third] = alt[st_right[:, None] + col[None, :]]
+        rd[2 * third:] = w1[st_ref[:, None] + col[None, :]]
+        u = rng.random((reads_per_locus, read_len))
+        sub = u < 0.004
+        rd[sub] = ACGT[rng.integers(0, 4, int(sub.sum()))]
+        rd[(u >= 0.004) & (u < 0.014)] = ord("N")
+        o = li * reads_per_locus * read_stride
+        pool[o:o + reads_per_locus * read_len] = rd.reshape(-1)
+        rb = reads_bytes_al + li * ref_stride
+        pool[rb:rb + window] = w1
+        ref1["off"][li], ref1["len"][li] = rb, window
     return CandidateBatch(n_loci, reads_per_locus, read_len, pool, readOff, readViews, isJump, ref1, ref2)
 
 

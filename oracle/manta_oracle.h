@@ -68,6 +68,14 @@ ORC_API int orc_small_sv_batch(uint32_t minCandidateVariantSize, uint32_t nLoci,
                                const mb200_seqview* contigSeq, const mb200_seqview* ref1, uint32_t* svFirst,
                                mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed);
 
+ORC_API int orc_large_insertion_batch(const mb200_scores* edgeScores, const mb200_scores* completeScores, uint32_t nLoci,
+                                      const uint8_t* isJump, const uint32_t* slotFirst, const uint32_t* nContigs,
+                                      uint32_t nSlots, const mb200_aln_result* aln, const uint32_t* cigarPool,
+                                      const uint8_t* pool, const mb200_seqview* contigSeq, const int32_t* consRange,
+                                      const mb200_seqview* ref1, const mb200_ref_cuts* cuts, const uint32_t* svFirst,
+                                      const mb200_small_sv* svs, mb200_large_insert_info* info, mb200_large_insertion* out,
+                                      uint32_t* outCigar, uint64_t outCigarCap, uint64_t* outCigarUsed);
+
 ORC_API int orc_jump_sv_batch(uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst, uint32_t nSlots,
                               const int32_t* best, const mb200_jump_result* jump, const uint32_t* cigarPool,
                               const mb200_seqview* ref1, const mb200_seqview* ref2, const mb200_jump_orient* orient,

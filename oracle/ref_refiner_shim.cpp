@@ -274,6 +274,168 @@ REF_API int ref_small_sv_batch(uint32_t minCandidateVariantSize, uint32_t nLoci,
   return used > svCap ? MB200_ERR_POOL_OVERFLOW : MB200_OK;
 }
 
+/// Large insertions with an incompletely assembled insert, through the reference's own statics: the per-contig
+/// candidate test of getSmallSVAssembly (:2079-2112, restated here around isLargeInsertAlignment :612 because the loop is
+/// inline in a member function that needs BAM/FASTA files) and processLargeInsertion (:833-1007) itself on an
+/// SVCandidateAssemblyData filled from the flat arrays.  The set of excluded positions is the rule of :2253-2256
+/// (getExtendedSVType == INSERT) applied to the refined small SVs.  Where processLargeInsertion returns early the exit is
+/// recovered from what it leaves behind; the two QC exits at :955 and :966-973 leave the same state, so they are
+/// reported as MB200_LI_FLANK_QC both.
+REF_API int ref_large_insertion_batch(const mb200_scores* edgeScores, const mb200_scores* completeScores, uint32_t nLoci,
+                                      const uint8_t* isJump, const uint32_t* slotFirst, const uint32_t* nContigs,
+                                      uint32_t nSlots, const mb200_aln_result* aln, const uint32_t* cigarPool,
+                                      const uint8_t* pool, const mb200_seqview* contigSeq, const int32_t* consRange,
+                                      const mb200_seqview* ref1, const mb200_ref_cuts* cuts, const uint32_t* svFirst,
+                                      const mb200_small_sv* svs, mb200_large_insert_info* info, mb200_large_insertion* out,
+                                      uint32_t* outCigar, uint64_t outCigarCap, uint64_t* outCigarUsed)
+{
+  const GlobalAligner<int> edgeAligner(toScores2(edgeScores));
+  const GlobalAligner<int> completeAligner(toScores2(completeScores));
+  GSCOptions               opt;
+  uint64_t                 used(0);
+  bool                     overflow(false);
+  std::memset(info, 0, sizeof(*info) * nSlots);
+  std::memset(out, 0, sizeof(*out) * nLoci);
+  for (uint32_t li(0); li < nLoci; ++li) {
+    if (isJump[li]) continue;
+    const uint32_t          s0(slotFirst[li]), nc(nContigs[li]);
+    SVCandidateAssemblyData ad;
+    ad.isSpanning = false;
+    ad.bp1ref.seq() = std::string(reinterpret_cast<const char*>(pool + ref1[li].off), ref1[li].len);
+    ad.bp1ref.set_offset(0);
+    ad.contigs.resize(nc);
+    ad.smallSVAlignments.resize(nc);
+    ad.smallSVSegments.resize(nc);
+    ad.largeInsertInfo.resize(nc);
+    ad.extendedContigs.resize(nc);
+    std::vector<unsigned> candidateIndex;
+    for (uint32_t k(0); k < nc; ++k) {
+      const uint32_t s(s0 + k);
+      ad.contigs[k].seq = std::string(reinterpret_cast<const char*>(pool + contigSeq[s].off), contigSeq[s].len);
+      ad.contigs[k].conservativeRange.set_range(consRange[2 * s], consRange[2 * s + 1]);
+      ad.smallSVAlignments[k].score          = aln[s].score;
+      ad.smallSVAlignments[k].align.beginPos = aln[s].beginPos;
+      ad.smallSVAlignments[k].align.apath    = toPath(cigarPool + aln[s].cigarOff, aln[s].cigarLen);
+      // ---- :2079-2112
+      LargeInsertionInfo& candidateInsertInfo(ad.largeInsertInfo[k]);
+      candidateInsertInfo.clear();
+      LargeInsertionInfo insertInfo;
+      ALIGNPATH::path_t  apath_conservative(ad.smallSVAlignments[k].align.apath);
+      apath_limit_read_length(ad.contigs[k].conservativeRange, apath_conservative);
+      bool isCandidate(isLargeInsertAlignment(edgeAligner, apath_conservative, insertInfo));
+      if (isCandidate) {
+        LargeInsertionInfo insertInfo2;
+        isCandidate = isLargeInsertAlignment(edgeAligner, ad.smallSVAlignments[k].align.apath, insertInfo2);
+        if ((insertInfo.isLeftCandidate != insertInfo2.isLeftCandidate) ||
+            (insertInfo.isRightCandidate != insertInfo2.isRightCandidate)) {
+          isCandidate = false;
+        }
+        insertInfo.contigOffset = insertInfo2.contigOffset;
+        insertInfo.refOffset    = insertInfo2.refOffset;
+      }
+      if (isCandidate) {
+        candidateInsertInfo = insertInfo;
+        candidateIndex.push_back(k);
+        info[s].isLeftCandidate  = insertInfo.isLeftCandidate ? 1 : 0;
+        info[s].isRightCandidate = insertInfo.isRightCandidate ? 1 : 0;
+        info[s].contigOffset     = insertInfo.contigOffset;
+        info[s].refOffset        = insertInfo.refOffset;
+        info[s].score            = insertInfo.score;
+      }
+    }
+    std::set<pos_t> excludedPos;
+    if (svFirst && svs) {
+      for (uint32_t v(svFirst[li]); v < svFirst[li + 1]; ++v) {
+        if (svs[v].status != 0) continue;
+        const unsigned deleteSize(svs[v].bp2Begin - svs[v].bp1Begin);
+        const unsigned insertSize(svs[v].readEnd - svs[v].readBegin);
+        if (deleteSize < insertSize) excludedPos.insert(svs[v].bp1Begin);
+      }
+    }
+    SVCandidate sv;
+    const pos_t leadingCut(cuts ? cuts[li].leadingCut : 0), trailingCut(cuts ? cuts[li].trailingCut : 0);
+    mb200_large_insertion& o(out[li]);
+    bool                   threw(false);
+    try {
+      processLargeInsertion(sv, leadingCut, trailingCut, completeAligner, candidateIndex, excludedPos, ad, opt);
+    } catch (const illumina::common::GeneralException&) {
+      threw = true;
+    }
+    if (ad.contigs.size() == nc) continue;  // no pair: MB200_LI_NONE
+    // which pair was joined: the joined contig is left + 100 N + right
+    const std::string& fake(ad.contigs[nc].seq);
+    bool               found(false);
+    for (uint32_t a(0); a < nc && !found; ++a) {
+      for (uint32_t b(0); b < nc && !found; ++b) {
+        if (a == b || !(ad.largeInsertInfo[a].isLeftCandidate && ad.largeInsertInfo[b].isRightCandidate)) continue;
+        if (fake == ad.contigs[a].seq + std::string(100, 'N') + ad.contigs[b].seq) {
+          // several pairs can spell the same joined contig only if two contigs are equal, which the assembler never returns
+          o.leftContig = a; o.rightContig = b;
+          found = true;
+        }
+      }
+    }
+    if (!found) return MB200_ERR_BAD_ARG;
+    {
+      const LargeInsertionInfo& i1(ad.largeInsertInfo[o.leftContig]);
+      const LargeInsertionInfo& i2(ad.largeInsertInfo[o.rightContig]);
+      o.breakDist  = std::abs(static_cast<long>(aln[s0 + o.leftContig].beginPos + i1.refOffset) -
+                              static_cast<long>(aln[s0 + o.rightContig].beginPos + i2.refOffset));
+      o.breakScore = i1.score + i2.score;
+    }
+    const SVCandidateAssemblyData::SmallAlignmentResultType& fa(ad.smallSVAlignments[nc]);
+    o.score = fa.score; o.beginPos = fa.align.beginPos; o.cigarLen = fa.align.apath.size(); o.cigarOff = used;
+    for (const ALIGNPATH::path_segment& ps : fa.align.apath) {
+      if (used < outCigarCap) outCigar[used] = MB200_SEG_MAKE(ps.length, static_cast<uint32_t>(ps.type));
+      else overflow = true;
+      ++used;
+    }
+    o.status = MB200_LI_SEGMENT_QC;
+    const std::vector<std::pair<unsigned, unsigned>>& segs(ad.smallSVSegments[nc]);
+    if ((1 != segs.size()) || (segs[0].second < segs[0].first)) continue;
+    o.segFirst = segs[0].first; o.segLast = segs[0].second;
+    o.status   = MB200_LI_FLANK_QC;
+    if (threw) {
+      o.status = MB200_LI_RANGE_ERROR;
+    } else if (ad.extendedContigs[nc].empty()) {
+      continue;  // :955 or :966-973
+    } else if (ad.svs.empty()) {
+      o.status = MB200_LI_DUPLICATE;
+    } else {
+      o.status = MB200_LI_ACCEPTED;
+    }
+    const known_pos_range2 trim(getInsertTrim(fa.align.apath, segs[0]));
+    o.insertTrimBegin = trim.begin_pos(); o.insertTrimEnd = trim.end_pos();
+    {
+      pos_t readPos(0), refPos(fa.align.beginPos);
+      for (unsigned i(0); i < fa.align.apath.size(); ++i) {
+        const ALIGNPATH::path_segment& ps(fa.align.apath[i]);
+        if (i == segs[0].first) { o.refBegin = refPos; o.readBegin = readPos; }
+        if (is_segment_type_ref_length(ps.type)) refPos += ps.length;
+        if (is_segment_type_read_length(ps.type)) readPos += ps.length;
+        if (i == segs[0].second) { o.refEnd = refPos; o.readEnd = readPos; }
+      }
+    }
+    const known_pos_range2 cipos(getVariantRange(ad.bp1ref.seq(), known_pos_range2(o.refBegin, o.refEnd), fake,
+                                                 known_pos_range2(o.readBegin, o.readEnd)));
+    o.ciposBegin = cipos.begin_pos(); o.ciposEnd = cipos.end_pos();
+    if (o.status == MB200_LI_RANGE_ERROR) continue;
+    if (o.status == MB200_LI_ACCEPTED) {
+      const SVCandidate& nsv(ad.svs.back());
+      o.bp1Begin = nsv.bp1.interval.range.begin_pos(); o.bp1End = nsv.bp1.interval.range.end_pos();
+      o.bp2Begin = nsv.bp2.interval.range.begin_pos(); o.bp2End = nsv.bp2.interval.range.end_pos();
+      o.leftSeqBegin = ad.contigs[o.leftContig].seq.size() - nsv.unknownSizeInsertionLeftSeq.size();
+      o.rightSeqLen  = nsv.unknownSizeInsertionRightSeq.size();
+      if (!nsv.isUnknownSizeInsertion) return MB200_ERR_BAD_ARG;
+    } else {  // duplicate: the breakends the static computed before it gave up (same formula as setSmallCandSV)
+      o.bp1Begin = o.refBegin - 1; o.bp1End = o.bp1Begin + o.ciposEnd + 1;
+      o.bp2Begin = o.refEnd; o.bp2End = o.bp2Begin + o.ciposEnd + 1;
+    }
+  }
+  *outCigarUsed = used;
+  return overflow ? MB200_ERR_POOL_OVERFLOW : MB200_OK;
+}
+
 /// Refined spanning breakends through the reference's own generateRefinedSVCandidateFromJumpAlignment (:1190), which
 /// applies adjustAssembledBreakend (:59) to both breakends; only the window sizes of bp1ref / bp2ref matter to it.
 REF_API int ref_jump_sv_batch(uint32_t nLoci, const uint8_t* isJump, const uint32_t* slotFirst, uint32_t /*nSlots*/,
