@@ -252,6 +252,57 @@ MB200_API int mb200_split_align_batch(mb200_ctx* ctx, const mb200_qscore_tables*
                                       uint32_t flankScoreSize, uint32_t n, const uint8_t* pool,
                                       uint64_t poolBytes, const mb200_sr_job* jobs, mb200_sr_result* results);
 
+/* ---- split-read scoring of a candidate's reads (row a11) --------------------------------------------------------------
+ * getReadSplitScore (GSC/SVScorerSplit.cpp:131-267): every read near a breakend is realigned to the four targets of the
+ * candidate's SVAlignmentInfo (lib/manta/SVScoreInfo.cpp:31-167, mb200::SVAlignmentInfo in the C++ shim) -- alt contig at
+ * bp1 and bp2 with dopt.altQ, reference at bp1 and bp2 with dopt.refQ -- and incrementSplitReadEvidence (:88-128) turns the
+ * four SRAlignmentInfo into the read's SVFragmentEvidence entries and the sample's allele counts.  DNA only (the RNA branch
+ * :216-221 reads the BAM alignment instead).  A fragment's read is evaluated once per candidate (isSplitEvaluated, :150-153):
+ * later occurrences of the same (fragment, isRead1) get status MB200_SPLIT_DUPLICATE and change nothing. */
+typedef struct mb200_split_target {
+  mb200_seqview seq;              /* bp?ContigSeq() / bp?ReferenceSeq() in the pool */
+  int32_t       bpBegin, bpEnd;   /* bp?ContigOffset / bp?RefOffset */
+} mb200_split_target;
+typedef struct mb200_split_candidate {
+  mb200_split_target altBp1, altBp2, refBp1, refBp2;
+} mb200_split_candidate;
+typedef struct mb200_split_read {
+  mb200_seqview seq;      /* read bases as splitReadAligner gets them (already reverse-complemented for a reversed shadow) */
+  uint64_t      qualOff;
+  uint32_t      fragment; /* index of the read's fragment (qname) inside the candidate */
+  uint8_t       isRead1;
+  uint8_t       mapq;
+  uint8_t       reserved[2];
+} mb200_split_read;
+#define MB200_SPLIT_DUPLICATE 1
+typedef struct mb200_split_read_evidence {
+  int32_t status;                      /* 0, MB200_SPLIT_DUPLICATE, or the error status of a splitReadAligner call */
+  uint8_t isAnchored, isTier2Anchored; /* setReadEvidence  GSC/SVScorerShared.cpp:26-42 */
+  uint8_t countedRef, countedAlt;      /* the read was added to sample.ref / sample.alt (incrementAlleleEvidence :70) */
+  float   splitLnLhood[4];             /* [altBp1, altBp2, refBp1, refBp2] SVFragmentEvidenceAlleleBreakendPerRead::splitLnLhood */
+  float   splitEvidence[4];
+  uint8_t isSplitSupport[4];
+  uint8_t isTier2SplitSupport[4];
+  float   refEvidence, altEvidence;    /* what was added to the allele's splitReadEvidence */
+} mb200_split_read_evidence;
+typedef struct mb200_split_allele_counts { /* SVSampleAlleleInfo  lib/manta/SVScoreInfo.hpp:83-123 (split-read part) */
+  uint32_t splitReadCount;
+  float    splitReadEvidence; /* accumulated in read order, like the reference */
+  float    splitReadMapQ;
+  uint32_t reserved;
+} mb200_split_allele_counts;
+typedef struct mb200_split_sample_counts {
+  mb200_split_allele_counts ref, alt;
+} mb200_split_sample_counts;
+
+/* reads of candidate i: reads[readFirst[i] .. readFirst[i+1]) in the order the reference meets them (bp1's region, then
+ * bp2's).  sr[4 * r + k]: the four alignments of read r in call order (altBp1, altBp2, refBp1, refBp2); ev[r]; counts[i]. */
+MB200_API int mb200_split_score_batch(mb200_ctx* ctx, const mb200_qscore_tables* tables, uint32_t flankScoreSize,
+                                      uint32_t minMapQ, uint32_t minTier2MapQ, uint32_t nCandidates,
+                                      const mb200_split_candidate* candidates, const uint32_t* readFirst,
+                                      const mb200_split_read* reads, const uint8_t* pool, uint64_t poolBytes,
+                                      mb200_sr_result* sr, mb200_split_read_evidence* ev, mb200_split_sample_counts* counts);
+
 /* ---- assembler ------------------------------------------------------------------------------
  * nLoci independent read sets.  reads of locus i are readViews[readOff[i] .. readOff[i+1]).
  * Outputs: loci[nLoci]; contigs[contigCap]; pseudoReads[pseudoCap] (views into contigPool);

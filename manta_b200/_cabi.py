@@ -70,6 +70,21 @@ SR_RESULT_DT = np.dtype([("alignPos", "<u4"), ("leftSize", "<u4"), ("homSize", "
 SR_JOB_DT = np.dtype([("q_off", "<u8"), ("q_len", "<u4"), ("q_res", "<u4"), ("qualOff", "<u8"),
                       ("t_off", "<u8"), ("t_len", "<u4"), ("t_res", "<u4"), ("bpBegin", "<i4"),
                       ("bpEnd", "<i4"), ("table", "<u4"), ("reserved", "<u4")], align=True)
+SPLIT_TARGET_DT = np.dtype([("off", "<u8"), ("len", "<u4"), ("res", "<u4"), ("bpBegin", "<i4"), ("bpEnd", "<i4")], align=True)
+SPLIT_CAND_DT = np.dtype([("altBp1", SPLIT_TARGET_DT), ("altBp2", SPLIT_TARGET_DT), ("refBp1", SPLIT_TARGET_DT),
+                          ("refBp2", SPLIT_TARGET_DT)], align=True)
+SPLIT_READ_DT = np.dtype([("off", "<u8"), ("len", "<u4"), ("res", "<u4"), ("qualOff", "<u8"), ("fragment", "<u4"),
+                          ("isRead1", "u1"), ("mapq", "u1"), ("reserved", "u1", (2,))], align=True)
+SPLIT_EVIDENCE_DT = np.dtype([("status", "<i4"), ("isAnchored", "u1"), ("isTier2Anchored", "u1"), ("countedRef", "u1"),
+                              ("countedAlt", "u1"), ("splitLnLhood", "<f4", (4,)), ("splitEvidence", "<f4", (4,)),
+                              ("isSplitSupport", "u1", (4,)), ("isTier2SplitSupport", "u1", (4,)), ("refEvidence", "<f4"),
+                              ("altEvidence", "<f4")], align=True)
+SPLIT_ALLELE_DT = np.dtype([("splitReadCount", "<u4"), ("splitReadEvidence", "<f4"), ("splitReadMapQ", "<f4"),
+                            ("reserved", "<u4")], align=True)
+SPLIT_COUNTS_DT = np.dtype([("ref", SPLIT_ALLELE_DT), ("alt", SPLIT_ALLELE_DT)], align=True)
+assert SPLIT_TARGET_DT.itemsize == 24 and SPLIT_CAND_DT.itemsize == 96 and SPLIT_READ_DT.itemsize == 32
+assert SPLIT_EVIDENCE_DT.itemsize == 56 and SPLIT_COUNTS_DT.itemsize == 32
+MB200_SPLIT_DUPLICATE = 1
 ASM_OPTS_DT = np.dtype([("minWordLength", "<u4"), ("maxWordLength", "<u4"), ("wordStepSize", "<u4"),
                         ("minCoverage", "<u4"), ("minConservativeCoverage", "<u4"),
                         ("maxAssemblyCount", "<u4"), ("minUnusedReads", "<u4"), ("minSupportReads", "<u4")],
@@ -346,6 +361,22 @@ class Binding:
         if st != MB200_OK:
             self._raise(st)
         return res
+
+    def split_score_raw(self, tables: np.ndarray, flank: int, minMapQ: int, minTier2MapQ: int, cands: np.ndarray,
+                        readFirst: np.ndarray, reads: np.ndarray, pool: np.ndarray):
+        """getReadSplitScore for every read of every candidate (row a11); returns (sr[4 per read], evidence, counts)"""
+        nC, nR = len(cands), len(reads)
+        sr = np.zeros(max(1, 4 * nR), dtype=SR_RESULT_DT)
+        ev = np.zeros(max(1, nR), dtype=SPLIT_EVIDENCE_DT)
+        counts = np.zeros(max(1, nC), dtype=SPLIT_COUNTS_DT)
+        args = [_ptr(tables), C.c_uint32(flank), C.c_uint32(minMapQ), C.c_uint32(minTier2MapQ), C.c_uint32(nC), _ptr(cands),
+                _ptr(readFirst), _ptr(reads), _ptr(pool)]
+        if self.ctx is not None:
+            args.append(C.c_uint64(pool.size))
+        st = self._call("split_score_batch", *args, _ptr(sr), _ptr(ev), _ptr(counts))
+        if st != MB200_OK:
+            self._raise(st)
+        return sr[:4 * nR], ev[:nR], counts[:nC]
 
     # -- assembler ----------------------------------------------------------------------------
     def assemble_raw(self, opts: np.ndarray, readOff: np.ndarray, views: np.ndarray, pool: np.ndarray):

@@ -368,3 +368,59 @@ def make_split_batch(n_reads: int, seed: int = 5, n_contigs: int = 1000, contig_
     jobs["bpEnd"] = b4 - 1 + h4
     jobs["table"] = np.array([1, 1, 0, 0], dtype=np.uint32)[which]  # alt alleles: snpPrior 0, ref alleles: 1e-3
     return pool, jobs
+
+
+def make_split_candidates(n_cand: int, reads_per_cand: int = 40, seed: int = 11, contig_len: int = 900, read_len: int = 150):
+    """Row a11 inputs: per candidate the four targets of its SVAlignmentInfo (alt contig with the bp1 / bp2 offset ranges,
+    reference windows at bp1 / bp2) and the reads the scorer would meet around the two breakends: reads from the alt
+    allele across bp1 or bp2, reads from either reference window, flank-only reads; 1 % substitutions, a few N, qualities
+    20-40 with 2 % at Q2, MAPQ 0-60; every eighth read is met a second time (same fragment and read number).
+    Returns (pool, candidates, readFirst, reads)."""
+    from ._cabi import SPLIT_CAND_DT, SPLIT_READ_DT
+    rng = np.random.default_rng(seed)
+    stride = (contig_len + 15) // 16 * 16
+    n_reads = n_cand * reads_per_cand
+    tbytes = n_cand * 3 * stride
+    pool = np.zeros(tbytes + 2 * n_reads * read_len + 64, dtype=np.uint8)
+    cands = np.zeros(n_cand, dtype=SPLIT_CAND_DT)
+    reads = np.zeros(n_reads, dtype=SPLIT_READ_DT)
+    readFirst = np.arange(n_cand + 1, dtype=np.uint32) * reads_per_cand
+    rbase, qbase = tbytes, tbytes + n_reads * read_len
+    for c in range(n_cand):
+        alt = ACGT[rng.integers(0, 4, contig_len)]
+        bp1 = int(rng.integers(300, 400))
+        ins = int(rng.integers(0, 120))          # inserted sequence between the two breakpoints on the contig
+        bp2 = bp1 + ins
+        hom = int(rng.integers(0, 9))
+        ref1 = ACGT[rng.integers(0, 4, contig_len)]
+        ref2 = ACGT[rng.integers(0, 4, contig_len)]
+        ref1[:bp1 + hom] = alt[:bp1 + hom]          # reference at bp1 agrees with the contig left of the breakpoint
+        ref2[bp2:] = alt[bp2:]                      # reference at bp2 agrees right of it
+        o = c * 3 * stride
+        pool[o:o + contig_len] = alt
+        pool[o + stride:o + stride + contig_len] = ref1
+        pool[o + 2 * stride:o + 2 * stride + contig_len] = ref2
+        for name, off, b in (("altBp1", o, bp1), ("altBp2", o, bp2), ("refBp1", o + stride, bp1), ("refBp2", o + 2 * stride, bp2)):
+            cands[name]["off"][c], cands[name]["len"][c] = off, contig_len
+            cands[name]["bpBegin"][c], cands[name]["bpEnd"][c] = b - 1, b - 1 + hom
+        for k in range(reads_per_cand):
+            r = c * reads_per_cand + k
+            if k % 8 == 7:   # the same read met again from the other breakend's region
+                reads[r] = reads[r - 3]
+                continue
+            kind = rng.random()
+            src = alt if kind < 0.5 else (ref1 if kind < 0.7 else (ref2 if kind < 0.9 else alt))
+            center = bp1 if (kind < 0.25 or 0.5 <= kind < 0.7) else bp2
+            start = center - int(rng.integers(10, read_len - 10)) if kind < 0.9 else center + int(rng.integers(20, 200))
+            start = int(np.clip(start, 0, contig_len - read_len - 1))
+            rd = src[start:start + read_len].copy()
+            u = rng.random(read_len)
+            rd[u < 0.01] = ACGT[rng.integers(0, 4, int((u < 0.01).sum()))]
+            rd[(u >= 0.01) & (u < 0.013)] = ord("N")
+            q = rng.integers(20, 41, read_len).astype(np.uint8)
+            q[rng.random(read_len) < 0.02] = 2
+            pool[rbase + r * read_len:rbase + (r + 1) * read_len] = rd
+            pool[qbase + r * read_len:qbase + (r + 1) * read_len] = q
+            reads["off"][r], reads["len"][r], reads["qualOff"][r] = rbase + r * read_len, read_len, qbase + r * read_len
+            reads["fragment"][r], reads["isRead1"][r], reads["mapq"][r] = k // 2, k % 2, int(rng.integers(0, 61))
+    return pool, cands, readFirst, reads

@@ -72,6 +72,8 @@ SRCS=(
   "$GSC/EdgeRetrieverBin.cpp"
   "$LIB/htsapi/bam_header_info.cpp"
   "$HERE/ref_graph_shim.cpp"
+  "$HERE/ref_split_shim.cpp"
+  "$GSC/SVScorerShared.cpp"
 )
 # boost.serialization (narrow-character archives only)
 for f in "$OUT"/boost_1_58_0/libs/serialization/src/*.cpp; do

@@ -68,6 +68,12 @@ ORC_API int orc_small_sv_batch(uint32_t minCandidateVariantSize, uint32_t nLoci,
                                const mb200_seqview* contigSeq, const mb200_seqview* ref1, uint32_t* svFirst,
                                mb200_small_sv* svs, uint64_t svCap, uint64_t* svUsed);
 
+/* getReadSplitScore + incrementSplitReadEvidence (GSC/SVScorerSplit.cpp:42-267) on top of orc_split_align_batch */
+ORC_API int orc_split_score_batch(const mb200_qscore_tables* tables, uint32_t flankScoreSize, uint32_t minMapQ,
+                                  uint32_t minTier2MapQ, uint32_t nCandidates, const mb200_split_candidate* candidates,
+                                  const uint32_t* readFirst, const mb200_split_read* reads, const uint8_t* pool,
+                                  mb200_sr_result* sr, mb200_split_read_evidence* ev, mb200_split_sample_counts* counts);
+
 ORC_API int orc_large_insertion_batch(const mb200_scores* edgeScores, const mb200_scores* completeScores, uint32_t nLoci,
                                       const uint8_t* isJump, const uint32_t* slotFirst, const uint32_t* nContigs,
                                       uint32_t nSlots, const mb200_aln_result* aln, const uint32_t* cigarPool,

@@ -162,3 +162,75 @@ int orc_split_align_batch(const mb200_qscore_tables* tables, uint32_t flankScore
   }
   return MB200_OK;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * getReadSplitScore (GSC/SVScorerSplit.cpp:131-267, DNA branch) with incrementSplitReadEvidence (:88-128) and
+ * incrementAlleleEvidence (:42-86); setReadEvidence GSC/SVScorerShared.cpp:26-42.
+ * ------------------------------------------------------------------------------------------------------------- */
+#include <stdlib.h>
+
+static void allele_evidence(const mb200_sr_result* bp1, const mb200_sr_result* bp2, unsigned mapq, float evidence,
+                            mb200_split_allele_counts* allele, mb200_split_read_evidence* e, int k1, int k2, uint8_t* counted,
+                            float* added)
+{
+  if (bp1->isEvidence) { e->isSplitSupport[k1] = 1; e->splitEvidence[k1] = bp1->evidence; }
+  if (bp1->isTier2Evidence) e->isTier2SplitSupport[k1] = 1;
+  if (bp2->isEvidence) { e->isSplitSupport[k2] = 1; e->splitEvidence[k2] = bp2->evidence; }
+  if (bp2->isTier2Evidence) e->isTier2SplitSupport[k2] = 1;
+  if (bp1->isEvidence || bp2->isEvidence) {
+    allele->splitReadCount++;
+    allele->splitReadEvidence += evidence;
+    allele->splitReadMapQ += mapq * mapq; /* unsigned product, then float += (:72) */
+    *counted = 1;
+    *added   = evidence;
+  }
+}
+
+int orc_split_score_batch(const mb200_qscore_tables* tables, uint32_t flankScoreSize, uint32_t minMapQ, uint32_t minTier2MapQ,
+                          uint32_t nCandidates, const mb200_split_candidate* candidates, const uint32_t* readFirst,
+                          const mb200_split_read* reads, const uint8_t* pool, mb200_sr_result* sr,
+                          mb200_split_read_evidence* ev, mb200_split_sample_counts* counts)
+{
+  for (uint32_t c = 0; c < nCandidates; ++c) {
+    memset(&counts[c], 0, sizeof(counts[c]));
+    const uint32_t r0 = readFirst[c], r1 = readFirst[c + 1];
+    for (uint32_t r = r0; r < r1; ++r) {
+      mb200_split_read_evidence* e = &ev[r];
+      memset(e, 0, sizeof(*e));
+      memset(&sr[4 * (size_t)r], 0, 4 * sizeof(mb200_sr_result));
+      /* isSplitEvaluated (:150-159): one evaluation per (fragment, read number) and candidate */
+      int dup = 0;
+      for (uint32_t p = r0; p < r && !dup; ++p)
+        if (reads[p].fragment == reads[r].fragment && (reads[p].isRead1 != 0) == (reads[r].isRead1 != 0)) dup = 1;
+      if (dup) { e->status = MB200_SPLIT_DUPLICATE; continue; }
+      e->isAnchored      = reads[r].mapq >= minMapQ;
+      e->isTier2Anchored = reads[r].mapq >= minTier2MapQ;
+      const mb200_split_target* tg[4] = {&candidates[c].altBp1, &candidates[c].altBp2, &candidates[c].refBp1, &candidates[c].refBp2};
+      mb200_sr_job jobs[4];
+      for (int k = 0; k < 4; ++k) {
+        memset(&jobs[k], 0, sizeof(jobs[k]));
+        jobs[k].query = reads[r].seq; jobs[k].qualOff = reads[r].qualOff; jobs[k].target = tg[k]->seq;
+        jobs[k].bpBegin = tg[k]->bpBegin; jobs[k].bpEnd = tg[k]->bpEnd;
+        jobs[k].table = k < 2 ? 1u : 0u; /* dopt.altQ for the alt contig, dopt.refQ for the reference (:190-214) */
+      }
+      mb200_sr_result* a = &sr[4 * (size_t)r];
+      orc_split_align_batch(tables, flankScoreSize, 4, pool, jobs, a);
+      for (int k = 0; k < 4; ++k)
+        if (a[k].status != MB200_OK && e->status == 0) e->status = a[k].status;
+      if (e->status != 0) continue; /* the reference throws out of the candidate here */
+      /* incrementSplitReadEvidence :88-128 (isRNA == false) */
+      for (int k = 0; k < 4; ++k) e->splitLnLhood[k] = a[k].alignLnLhood;
+      const float altLlh = a[0].alignLnLhood > a[1].alignLnLhood ? a[0].alignLnLhood : a[1].alignLnLhood; /* std::max */
+      const float refLlh = a[2].alignLnLhood > a[3].alignLnLhood ? a[2].alignLnLhood : a[3].alignLnLhood;
+      if (refLlh > altLlh) {
+        const float e1 = a[2].isEvidence ? a[2].evidence : 0, e2 = a[3].isEvidence ? a[3].evidence : 0;
+        allele_evidence(&a[2], &a[3], reads[r].mapq, e1 > e2 ? e1 : e2, &counts[c].ref, e, 2, 3, &e->countedRef, &e->refEvidence);
+      }
+      if (altLlh > refLlh) {
+        const float e1 = a[0].isEvidence ? a[0].evidence : 0, e2 = a[1].isEvidence ? a[1].evidence : 0;
+        allele_evidence(&a[0], &a[1], reads[r].mapq, e1 > e2 ? e1 : e2, &counts[c].alt, e, 0, 1, &e->countedAlt, &e->altEvidence);
+      }
+    }
+  }
+  return MB200_OK;
+}
