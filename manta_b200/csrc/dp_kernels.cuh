@@ -226,9 +226,12 @@ __device__ __forceinline__ bool segIsReadLen(uint32_t t)
 }
 __device__ __forceinline__ bool segIsRefLen(uint32_t t) { return t == MB200_SEG_MATCH || t == MB200_SEG_DELETE; }
 
-// Expand a raw path (given in REVERSE order in raw[first..first+n)) into the final '='/'X' form
-// (apath_add_seqmatch).  If out == nullptr only counts.  q/r point at the first query/ref base the path covers.
-__device__ uint32_t expandPath(const uint32_t* raw, uint32_t n, const uint8_t* q, const uint8_t* r, uint32_t* out)
+// Expand a raw path (given in REVERSE order in raw[0..n)) into the final '='/'X' form (apath_add_seqmatch,
+// lib/blt_util/align_path_impl.hpp:33-75).  If out == nullptr only counts.  q/r point at the first query/ref base the path
+// covers.  By the whole warp: the lanes compare 32 bases of a match run at once and every lane folds the ballot into the
+// run-length state (identical in all lanes); lane 0 writes.  (Round 1 did this on one lane: ~ 1 000 dependent loads per
+// alignment.)
+__device__ uint32_t expandPathWarp(const uint32_t* raw, uint32_t n, const uint8_t* q, const uint8_t* r, uint32_t* out, int lane)
 {
   uint32_t count = 0;
   uint32_t curT = MB200_SEG_NONE, curL = 0;
@@ -237,38 +240,52 @@ __device__ uint32_t expandPath(const uint32_t* raw, uint32_t n, const uint8_t* q
     const uint32_t type = MB200_SEG_TYPE(seg);
     const uint32_t len  = MB200_SEG_LEN(seg);
     if (type == MB200_SEG_MATCH) {
-      for (uint32_t i = 0; i < len; ++i) {
-        const uint8_t qc = q[i], rc = r[i];
-        const bool isMatch = (qc == rc) && (qc != 'N') && (rc != 'N');
-        const uint32_t t   = isMatch ? MB200_SEG_SEQ_MATCH : MB200_SEG_SEQ_MISMATCH;
-        if (t == curT) {
-          curL++;
-        } else {
-          if (curT != MB200_SEG_NONE) {
-            if (out) out[count] = MB200_SEG_MAKE(curL, curT);
-            count++;
+      for (uint32_t base = 0; base < len; base += 32) {
+        const uint32_t i  = base + (uint32_t)lane;
+        bool           m  = false;
+        if (i < len) {
+          const uint8_t qc = q[i], rc = r[i];
+          m = (qc == rc) && (qc != 'N') && (rc != 'N');
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, m);
+        const uint32_t nb   = (len - base) < 32u ? (len - base) : 32u;
+        uint32_t       pos  = 0;
+        while (pos < nb) {
+          const uint32_t bit = (bits >> pos) & 1u;
+          const uint32_t t   = bit ? MB200_SEG_SEQ_MATCH : MB200_SEG_SEQ_MISMATCH;
+          const uint32_t x   = (bit ? ~bits : bits) >> pos;  // first set bit: where the run of equal bits ends
+          uint32_t       run = x ? (uint32_t)(__ffs(x) - 1) : (32u - pos);
+          if (run > nb - pos) run = nb - pos;
+          if (t == curT) {
+            curL += run;
+          } else {
+            if (curT != MB200_SEG_NONE) {
+              if (out && lane == 0) out[count] = MB200_SEG_MAKE(curL, curT);
+              count++;
+            }
+            curT = t;
+            curL = run;
           }
-          curT = t;
-          curL = 1;
+          pos += run;
         }
       }
       q += len;
       r += len;
     } else {
       if (curT != MB200_SEG_NONE) {
-        if (out) out[count] = MB200_SEG_MAKE(curL, curT);
+        if (out && lane == 0) out[count] = MB200_SEG_MAKE(curL, curT);
         count++;
         curT = MB200_SEG_NONE;
         curL = 0;
       }
-      if (out) out[count] = seg;
+      if (out && lane == 0) out[count] = seg;
       count++;
       if (segIsReadLen(type)) q += len;
       if (segIsRefLen(type)) r += len;
     }
   }
   if (curT != MB200_SEG_NONE) {
-    if (out) out[count] = MB200_SEG_MAKE(curL, curT);
+    if (out && lane == 0) out[count] = MB200_SEG_MAKE(curL, curT);
     count++;
   }
   return count;
@@ -438,7 +455,8 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
 #undef PUSH_TO
 #undef UPDATE_PATH
     __syncwarp();
-    if (lane == 0) {
+    {
+      // every lane keeps the same scalars; the '='/'X' expansion is warp-parallel, lane 0 writes
       uint32_t read1, refl1, read2, refl2;
       rawLengths(segBuf, n1, read1, refl1);
       rawLengths(segBuf + half, n2, read2, refl2);
@@ -462,18 +480,22 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
         }
       }
       const uint8_t* q2 = qSeq + read1 + jumpInsertSize;
-      const uint32_t c1 = expandPath(segBuf, n1, qSeq, ref1 + beginPos1, nullptr);
-      const uint32_t c2 = expandPath(segBuf + half, n2, q2, ref2 + beginPos2, nullptr);
-      const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)(c1 + c2));
+      const uint32_t c1 = expandPathWarp(segBuf, n1, qSeq, ref1 + beginPos1, nullptr, lane);
+      const uint32_t c2 = expandPathWarp(segBuf + half, n2, q2, ref2 + beginPos2, nullptr, lane);
+      unsigned long long off = 0;
+      if (lane == 0) off = atomicAdd(P.cigarUsed, (unsigned long long)(c1 + c2));
+      off = __shfl_sync(FULL, off, 0);
       if (off + c1 + c2 <= P.cigarCap) {
-        expandPath(segBuf, n1, qSeq, ref1 + beginPos1, P.cigarPool + off);
-        expandPath(segBuf + half, n2, q2, ref2 + beginPos2, P.cigarPool + off + c1);
+        expandPathWarp(segBuf, n1, qSeq, ref1 + beginPos1, P.cigarPool + off, lane);
+        expandPathWarp(segBuf + half, n2, q2, ref2 + beginPos2, P.cigarPool + off + c1, lane);
       }
-      mb200_jump_result* o = reinterpret_cast<mb200_jump_result*>(P.results) + task.outIndex;
-      o->score = bestVal; o->jumpInsertSize = jumpInsertSize; o->jumpRange = jumpRange;
-      o->beginPos1 = beginPos1; o->beginPos2 = beginPos2;
-      o->cigarLen1 = c1; o->cigarLen2 = c2; o->reserved = 0;
-      o->cigarOff1 = off; o->cigarOff2 = off + c1;
+      if (lane == 0) {
+        mb200_jump_result* o = reinterpret_cast<mb200_jump_result*>(P.results) + task.outIndex;
+        o->score = bestVal; o->jumpInsertSize = jumpInsertSize; o->jumpRange = jumpRange;
+        o->beginPos1 = beginPos1; o->beginPos2 = beginPos2;
+        o->cigarLen1 = c1; o->cigarLen2 = c2; o->reserved = 0;
+        o->cigarOff1 = off; o->cigarOff2 = off + c1;
+      }
     }
   } else {
     // ---------------- SingleRefAlignerBase::backTraceAlignment (SingleRefAlignerSharedImpl.hpp:75-168)
@@ -521,13 +543,17 @@ __device__ void emitResult(const DpParams& P, const DpTask& task, const uint8_t*
     if (psType != MB200_SEG_NONE) { if (lane == 0) segBuf[n] = MB200_SEG_MAKE(psLen, psType); n++; }
     if (queryBegin != 0) { if (lane == 0) segBuf[n] = MB200_SEG_MAKE(queryBegin, MB200_SEG_SOFT_CLIP); n++; }
     __syncwarp();
-    if (lane == 0) {
-      const int      beginPos = (int)refBegin;
-      const uint32_t cnt      = expandPath(segBuf, n, qSeq, ref1 + beginPos, nullptr);
-      const unsigned long long off = atomicAdd(P.cigarUsed, (unsigned long long)cnt);
-      if (off + cnt <= P.cigarCap) expandPath(segBuf, n, qSeq, ref1 + beginPos, P.cigarPool + off);
-      mb200_aln_result* o = reinterpret_cast<mb200_aln_result*>(P.results) + task.outIndex;
-      o->score = bestVal; o->beginPos = beginPos; o->isJumped = isJumped; o->cigarLen = cnt; o->cigarOff = off;
+    {
+      const int          beginPos = (int)refBegin;
+      const uint32_t     cnt      = expandPathWarp(segBuf, n, qSeq, ref1 + beginPos, nullptr, lane);
+      unsigned long long off      = 0;
+      if (lane == 0) off = atomicAdd(P.cigarUsed, (unsigned long long)cnt);
+      off = __shfl_sync(FULL, off, 0);
+      if (off + cnt <= P.cigarCap) expandPathWarp(segBuf, n, qSeq, ref1 + beginPos, P.cigarPool + off, lane);
+      if (lane == 0) {
+        mb200_aln_result* o = reinterpret_cast<mb200_aln_result*>(P.results) + task.outIndex;
+        o->score = bestVal; o->beginPos = beginPos; o->isJumped = isJumped; o->cigarLen = cnt; o->cigarOff = off;
+      }
     }
   }
   __syncwarp();
