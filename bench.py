@@ -403,11 +403,12 @@ def main():
     e2e_value = total_candidates / wall_e2e
 
     peak, peak_src = load_peaks()
-    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/r01_dp_traffic.json), scaled from
+    # DRAM traffic of the dominant kernel from the newest committed ncu capture (profiles/rNN_dp_traffic.json), scaled from
     # the captured launch set to this one by the algorithmic bytes (same kernels, same strip-padding statistics)
     traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dp_traffic.json")))
+        import glob
+        tj = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dp_traffic.json")))[-1]))
         traffic_factor = float(tj["traffic_per_algorithmic_byte"])
         traffic_src = tj["source"]
     except Exception:
@@ -421,11 +422,11 @@ def main():
                 data="synthetic", config=config, clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=launches,
-                roofline=dict(bound="hbm", kernel="dpPairKernel<KIND_INDEL,RT,NOBAD> (large-indel aligner, int16x2, two alignments per warp, 2 B back-pointer per cell; all row classes of one step)",
+                roofline=dict(bound="hbm", kernel="dpTagKernel<KIND_INDEL,RT> (large-indel aligner: two alignments per warp in the halves of 32-bit lanes, score and back-pointer state in one tagged 16-bit value, packed VIMNMX3/VIADDMNMX, 2 B back-pointer per cell; all row classes of one step)",
                               achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,
                               traffic=(traffic_factor * dom_bytes) if traffic_factor else None, traffic_source=traffic_src,
-                              bound_note="HBM is the defined roofline (SURVEY 8d); the kernel itself is integer-ALU-pipe bound "
-                                         "(ncu: alu pipe 75-87% busy, DRAM 13-14%), see profiles/r01_dp_pair_full_v6.txt",
+                              bound_note="HBM is the defined roofline (SURVEY 8d); the kernel itself is issue/latency bound on integer work "
+                                         "(ncu, dominant class <INDEL,RT=9> at 50k loci: issue slots 73% busy, IPC 2.94 of 4, ALU pipe 65%, DRAM 31% = 2.5 TB/s; 12 warps/SM at 166 registers), see profiles/r02_dp_tag_sections.txt, r02_sass_dp_tag_indel12.txt and r02_pipe_probe.txt",
                               peak_source=peak_src, algorithmic_bytes_per_launch_set=dom_bytes, kernel_ms_per_step=dom_ms,
                               gcups=tim["indelCells"] / (dom_ms * 1e-3) * 1e-9 if dom_ms > 0 else None),
                 stages=dict(device_ms_per_step=ev_s * 1000.0 / args.steps, asm_ms=stage["asmMs"] / args.steps,

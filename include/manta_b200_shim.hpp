@@ -8,10 +8,12 @@
 //   mb200::splitReadAligner                     <- GSC/SplitReadAlignment.hpp:63-70
 //   mb200::runIterativeAssembler                <- lib/assembly/IterativeAssembler.hpp:43-47
 //
-// The shim is deliberately free of reference headers: result types are minimal look-alikes (same member names) so
-// that this file compiles on its own; INTEGRATION.md shows the three-line conversions to the reference's own
-// ALIGNPATH::path_t / AssembledContig types.  Errors of the C ABI are thrown as mb200::GeneralException, which
-// the integration maps onto illumina::common::GeneralException (same what() text as the reference).
+// The shim is deliberately free of reference headers: it ships minimal look-alike result types (same member names)
+// so that this file compiles on its own, and every entry point is a template over the result / option / contig type,
+// so the reference's own AlignmentResult<int>, JumpAlignmentResult<int>, SRAlignmentInfo, AssembledContig,
+// IterativeAssemblerOptions ... pass straight through (integration/manta_b200.patch does exactly that; the patched
+// GenerateSVCandidates reproduces the reference's demo VCFs, tests/test_vcf_demo.py).  Errors of the C ABI are thrown as
+// mb200::GeneralException, which the integration maps onto illumina::common::GeneralException (same what() text).
 //
 // Batch size is 1 per call here (drop-in semantics); the staged driver described in INTEGRATION.md calls the
 // batched C entry points directly.
@@ -55,6 +57,14 @@ private:
   mb200_ctx* _ctx = nullptr;
 };
 
+/// the calling thread's context, created on first use.  Aligners built without an explicit Context use it at CALL time,
+/// so objects constructed on one thread and used by a worker (the refiner's const aligner members) stay race-free.
+inline const Context& threadContext()
+{
+  static thread_local Context ctx(0);
+  return ctx;
+}
+
 // ---- ALIGNPATH look-alikes (lib/blt_util/align_path.hpp:34-60) ----------------------------------
 struct path_segment {
   unsigned type;  // ALIGNPATH::align_t value
@@ -84,6 +94,12 @@ struct AlignmentScores {  // lib/alignment/AlignmentScores.hpp:23-57
   }
   const ScoreType match, mismatch, open, extend, offEdge;
   const bool      isAllowEdgeInsertion;
+  /// from any type with the reference's member names (lib/alignment/AlignmentScores.hpp)
+  template <typename S>
+  explicit AlignmentScores(const S& s)
+    : match(s.match), mismatch(s.mismatch), open(s.open), extend(s.extend), offEdge(s.offEdge), isAllowEdgeInsertion(s.isAllowEdgeInsertion)
+  {
+  }
   mb200_scores    c() const { return mb200_scores{match, mismatch, open, extend, offEdge, isAllowEdgeInsertion ? 1 : 0}; }
 };
 
@@ -118,19 +134,37 @@ inline mb200_seqview append(std::vector<uint8_t>& pool, SymIter b, SymIter e)
   while (pool.size() % 16) pool.push_back(0);
   return v;
 }
+/// fill any path type whose segments have the reference's {type, length} members (ALIGNPATH::path_t, mb200::path_t)
+template <typename PathT>
+inline void fillPath(PathT& path, const uint32_t* segs, const uint64_t off, const uint32_t n)
+{
+  typedef typename PathT::value_type Seg;
+  path.clear();
+  path.reserve(n);
+  for (uint32_t i(0); i < n; ++i) {
+    Seg s;
+    s.type   = static_cast<decltype(s.type)>(MB200_SEG_TYPE(segs[off + i]));
+    s.length = MB200_SEG_LEN(segs[off + i]);
+    path.push_back(s);
+  }
+}
 }  // namespace detail
 
-/// GlobalJumpAligner<int>::align  lib/alignment/GlobalJumpAligner.hpp:45-53 (throws on empty inputs, Impl:50-58)
+/// GlobalJumpAligner<int>::align  lib/alignment/GlobalJumpAligner.hpp:45-53 (throws on empty inputs, Impl:50-58).
+/// `ResultT` is any type with JumpAlignmentResult's members (the reference's own or the look-alike above).
 template <typename ScoreType>
 struct GlobalJumpAligner {
   GlobalJumpAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores, const ScoreType jumpScore)
-    : _ctx(ctx), _scores(scores), _jumpScore(jumpScore)
+    : _ctx(&ctx), _scores(scores), _jumpScore(jumpScore)
   {
   }
-  template <typename SymIter>
+  /// uses threadContext() of the calling thread
+  GlobalJumpAligner(const AlignmentScores<ScoreType>& scores, const ScoreType jumpScore) : _ctx(nullptr), _scores(scores), _jumpScore(jumpScore) {}
+  template <typename SymIter, typename ResultT>
   void align(const SymIter queryBegin, const SymIter queryEnd, const SymIter ref1Begin, const SymIter ref1End,
-             const SymIter ref2Begin, const SymIter ref2End, JumpAlignmentResult<ScoreType>& result) const
+             const SymIter ref2Begin, const SymIter ref2End, ResultT& result) const
   {
+    const Context&       ctx(_ctx ? *_ctx : threadContext());
     std::vector<uint8_t> pool;
     const mb200_seqview  q(detail::append(pool, queryBegin, queryEnd));
     const mb200_seqview  r1(detail::append(pool, ref1Begin, ref1End));
@@ -139,21 +173,22 @@ struct GlobalJumpAligner {
     mb200_jump_result     res;
     uint64_t              used(0);
     const mb200_scores    sc(_scores.c());
-    _ctx.check(mb200_jump_align_batch(_ctx.get(), &sc, _jumpScore, 1, pool.data(), pool.size(), &q, &r1, &r2, &res,
-                                      cigar.data(), cigar.size(), &used));
-    result                 = JumpAlignmentResult<ScoreType>();
+    ctx.check(mb200_jump_align_batch(ctx.get(), &sc, _jumpScore, 1, pool.data(), pool.size(), &q, &r1, &r2, &res,
+                                     cigar.data(), cigar.size(), &used));
+    result                 = ResultT();
     result.score           = static_cast<ScoreType>(res.score);
     result.jumpInsertSize  = res.jumpInsertSize;
     result.jumpRange       = res.jumpRange;
     result.align1.beginPos = res.beginPos1;
     result.align2.beginPos = res.beginPos2;
-    result.align1.apath    = detail::toPath(cigar.data(), res.cigarOff1, res.cigarLen1);
-    result.align2.apath    = detail::toPath(cigar.data(), res.cigarOff2, res.cigarLen2);
+    detail::fillPath(result.align1.apath, cigar.data(), res.cigarOff1, res.cigarLen1);
+    detail::fillPath(result.align2.apath, cigar.data(), res.cigarOff2, res.cigarLen2);
   }
-  const ScoreType& getJumpScore() const { return _jumpScore; }
+  const ScoreType&                  getJumpScore() const { return _jumpScore; }
+  const AlignmentScores<ScoreType>& getScores() const { return _scores; }
 
 private:
-  const Context&                   _ctx;
+  const Context*                   _ctx;
   const AlignmentScores<ScoreType> _scores;
   const ScoreType                  _jumpScore;
 };
@@ -162,15 +197,15 @@ private:
 /// largeIndelScore, GlobalAligner<int>::align (lib/alignment/GlobalAligner.hpp) otherwise
 template <typename ScoreType>
 struct SingleRefAligner {
-  SingleRefAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores) : _ctx(ctx), _scores(scores), _isIndel(false), _L(0) {}
-  SingleRefAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores, const ScoreType largeIndelScore)
+  SingleRefAligner(const Context* ctx, const AlignmentScores<ScoreType>& scores) : _ctx(ctx), _scores(scores), _isIndel(false), _L(0) {}
+  SingleRefAligner(const Context* ctx, const AlignmentScores<ScoreType>& scores, const ScoreType largeIndelScore)
     : _ctx(ctx), _scores(scores), _isIndel(true), _L(largeIndelScore)
   {
   }
-  template <typename SymIter>
-  void align(const SymIter queryBegin, const SymIter queryEnd, const SymIter refBegin, const SymIter refEnd,
-             AlignmentResult<ScoreType>& result) const
+  template <typename SymIter, typename ResultT>
+  void align(const SymIter queryBegin, const SymIter queryEnd, const SymIter refBegin, const SymIter refEnd, ResultT& result) const
   {
+    const Context&        ctx(_ctx ? *_ctx : threadContext());
     std::vector<uint8_t>  pool;
     const mb200_seqview   q(detail::append(pool, queryBegin, queryEnd));
     const mb200_seqview   r(detail::append(pool, refBegin, refEnd));
@@ -179,18 +214,19 @@ struct SingleRefAligner {
     uint64_t              used(0);
     const mb200_scores    sc(_scores.c());
     if (_isIndel)
-      _ctx.check(mb200_indel_align_batch(_ctx.get(), &sc, _L, 1, pool.data(), pool.size(), &q, &r, &res, cigar.data(), cigar.size(), &used));
+      ctx.check(mb200_indel_align_batch(ctx.get(), &sc, _L, 1, pool.data(), pool.size(), &q, &r, &res, cigar.data(), cigar.size(), &used));
     else
-      _ctx.check(mb200_global_align_batch(_ctx.get(), &sc, 1, pool.data(), pool.size(), &q, &r, &res, cigar.data(), cigar.size(), &used));
-    result                = AlignmentResult<ScoreType>();
+      ctx.check(mb200_global_align_batch(ctx.get(), &sc, 1, pool.data(), pool.size(), &q, &r, &res, cigar.data(), cigar.size(), &used));
+    result                = ResultT();
     result.score          = static_cast<ScoreType>(res.score);
     result.isJumped       = (res.isJumped != 0);
     result.align.beginPos = res.beginPos;
-    result.align.apath    = detail::toPath(cigar.data(), res.cigarOff, res.cigarLen);
+    detail::fillPath(result.align.apath, cigar.data(), res.cigarOff, res.cigarLen);
   }
+  const AlignmentScores<ScoreType>& getScores() const { return _scores; }
 
 private:
-  const Context&                   _ctx;
+  const Context*                   _ctx;
   const AlignmentScores<ScoreType> _scores;
   const bool                       _isIndel;
   const ScoreType                  _L;
@@ -198,13 +234,18 @@ private:
 template <typename ScoreType>
 struct GlobalLargeIndelAligner : public SingleRefAligner<ScoreType> {
   GlobalLargeIndelAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores, const ScoreType largeIndelScore)
-    : SingleRefAligner<ScoreType>(ctx, scores, largeIndelScore)
+    : SingleRefAligner<ScoreType>(&ctx, scores, largeIndelScore)
+  {
+  }
+  GlobalLargeIndelAligner(const AlignmentScores<ScoreType>& scores, const ScoreType largeIndelScore)
+    : SingleRefAligner<ScoreType>(nullptr, scores, largeIndelScore)
   {
   }
 };
 template <typename ScoreType>
 struct GlobalAligner : public SingleRefAligner<ScoreType> {
-  GlobalAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores) : SingleRefAligner<ScoreType>(ctx, scores) {}
+  GlobalAligner(const Context& ctx, const AlignmentScores<ScoreType>& scores) : SingleRefAligner<ScoreType>(&ctx, scores) {}
+  explicit GlobalAligner(const AlignmentScores<ScoreType>& scores) : SingleRefAligner<ScoreType>(nullptr, scores) {}
 };
 
 // ---- split-read scan --------------------------------------------------------------------------------
@@ -219,10 +260,11 @@ struct SRAlignmentInfo {  // GSC/SplitReadAlignment.hpp:35-49
 /// splitReadAligner  GSC/SplitReadAlignment.hpp:63-70.  `lnComp`/`lnErr` are the 71-entry tables of the caller's
 /// qscore_snp (qphred_to_ln_comp_error_prob / qphred_to_ln_error_prob, lib/blt_util/qscore_snp.hpp:43-53);
 /// targetBpBegin/End are targetBpOffsetRange.begin_pos()/end_pos().
+template <typename SRAlignmentInfoT>
 inline void splitReadAligner(const Context& ctx, const unsigned flankScoreSize, const std::string& querySeq,
                              const double* lnComp, const double* lnErr, const uint8_t* queryQual,
                              const std::string& targetSeq, const int targetBpBegin, const int targetBpEnd,
-                             SRAlignmentInfo& alignment)
+                             SRAlignmentInfoT& alignment)
 {
   std::vector<uint8_t> pool;
   mb200_sr_job         job;
@@ -249,6 +291,23 @@ inline void splitReadAligner(const Context& ctx, const unsigned flankScoreSize, 
   alignment.isEvidence = (r.isEvidence != 0); alignment.isTier2Evidence = (r.isTier2Evidence != 0); alignment.evidence = r.evidence;
 }
 
+/// The reference's own argument list (GSC/SplitReadAlignment.hpp:63-70): `qualConvert` is the caller's qscore_snp (any
+/// type with qphred_to_ln_comp_error_prob / qphred_to_ln_error_prob), `targetBpOffsetRange` its known_pos_range2.
+/// Runs on the calling thread's context.
+template <typename QscoreSnpT, typename PosRangeT, typename SRAlignmentInfoT>
+inline void splitReadAligner(const unsigned flankScoreSize, const std::string& querySeq, const QscoreSnpT& qualConvert,
+                             const uint8_t* queryQual, const std::string& targetSeq, const PosRangeT& targetBpOffsetRange,
+                             SRAlignmentInfoT& alignment)
+{
+  double lnComp[71], lnErr[71];
+  for (int q(0); q <= 70; ++q) {
+    lnComp[q] = qualConvert.qphred_to_ln_comp_error_prob(q);
+    lnErr[q]  = qualConvert.qphred_to_ln_error_prob(q);
+  }
+  splitReadAligner(threadContext(), flankScoreSize, querySeq, lnComp, lnErr, queryQual, targetSeq,
+                   static_cast<int>(targetBpOffsetRange.begin_pos()), static_cast<int>(targetBpOffsetRange.end_pos()), alignment);
+}
+
 // ---- assembler ----------------------------------------------------------------------------------------
 struct IterativeAssemblerOptions {  // lib/options/IterativeAssemblerOptions.hpp:26-59
   unsigned minWordLength = 41, maxWordLength = 76, wordStepSize = 5, minCoverage = 1, minConservativeCoverage = 2;
@@ -270,9 +329,30 @@ typedef std::vector<AssembledContig>  Assembly;
 
 /// runIterativeAssembler  lib/assembly/IterativeAssembler.hpp:43-47: `reads` is mutated (pseudo reads appended),
 /// `readInfo` and `contigs` are filled exactly as the reference leaves them.
-inline void runIterativeAssembler(const Context& ctx, const IterativeAssemblerOptions& opt, AssemblyReadInput& reads,
-                                  AssemblyReadOutput& readInfo, Assembly& contigs)
+namespace detail {
+// AssembledContig::conservativeRange is a known_pos_range2 in the reference (lib/assembly/AssembledContig.hpp:49) and
+// two ints in the look-alike above
+template <typename ContigT>
+inline auto setConservativeRange(ContigT& c, const int b, const int e, int) -> decltype(c.conservativeRange.set_range(b, e), void())
 {
+  c.conservativeRange.set_range(b, e);
+}
+template <typename ContigT>
+inline void setConservativeRange(ContigT& c, const int b, const int e, long)
+{
+  c.conservativeRangeBegin = b;
+  c.conservativeRangeEnd   = e;
+}
+}  // namespace detail
+
+/// `OptionsT`, the element of `ReadInfoVecT` and the element of `AssemblyT` are the reference's
+/// IterativeAssemblerOptions / AssemblyReadInfo / AssembledContig or the look-alikes above.
+template <typename OptionsT, typename ReadInfoVecT, typename AssemblyT>
+inline void runIterativeAssembler(const Context& ctx, const OptionsT& opt, AssemblyReadInput& reads, ReadInfoVecT& readInfo,
+                                  AssemblyT& contigs)
+{
+  typedef typename ReadInfoVecT::value_type AssemblyReadInfoT;
+  typedef typename AssemblyT::value_type    AssembledContigT;
   std::vector<uint8_t>       pool;
   std::vector<mb200_seqview> views;
   for (const std::string& r : reads) views.push_back(detail::append(pool, r.begin(), r.end()));
@@ -303,15 +383,14 @@ inline void runIterativeAssembler(const Context& ctx, const IterativeAssemblerOp
   const unsigned normalReadCount(reads.size());
   for (uint32_t p(0); p < L.nPseudo; ++p)
     reads.emplace_back(reinterpret_cast<const char*>(cpool.data() + ps[L.firstPseudo + p].off), ps[L.firstPseudo + p].len);
-  readInfo.assign(reads.size(), AssemblyReadInfo());
+  readInfo.assign(reads.size(), AssemblyReadInfoT());
   for (unsigned r(normalReadCount); r < reads.size(); ++r) readInfo[r].isPseudo = true;
   contigs.clear();
   for (uint32_t c(0); c < L.nContigs; ++c) {
     const mb200_contig& m(cs[L.firstContig + c]);
-    AssembledContig     ac;
+    AssembledContigT    ac;
     ac.seq.assign(reinterpret_cast<const char*>(cpool.data() + m.seqOff), m.seqLen);
-    ac.conservativeRangeBegin = m.conservativeBegin;
-    ac.conservativeRangeEnd   = m.conservativeEnd;
+    detail::setConservativeRange(ac, m.conservativeBegin, m.conservativeEnd, 0);
     for (uint32_t w(0); w < L.setWords; ++w) {
       for (uint32_t b(0); b < 32; ++b) {
         if (spool[m.supportOff + w] & (1u << b)) ac.supportReads.insert(w * 32 + b);
@@ -498,6 +577,8 @@ inline std::vector<mb200_small_sv> refineSmallSVs(const Context& ctx, const unsi
 // ---- SVAlignmentInfo (row a10): host arithmetic on the refined SV records -------------------------------------------
 
 struct known_pos_range2 {  // lib/blt_util/known_pos_range2.hpp (the two members this path uses)
+  known_pos_range2() {}
+  known_pos_range2(const int b, const int e) : begin(b), end(e) {}  // (C++11: no aggregate init with member initializers)
   int begin = 0, end = 0;
   int begin_pos() const { return begin; }
   int end_pos() const { return end; }
