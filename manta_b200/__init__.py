@@ -53,7 +53,7 @@ class Context(Binding):
     """One device context (mb200_ctx): owns the stream and all device buffers."""
 
     def __init__(self, device: int = 0, ctas_per_sm: int = 0, scratch_bytes: int = 0, force_int32: bool = False,
-                 max_contig_len: int = 0, no_tag_kernel: bool = False):
+                 max_contig_len: int = 0, no_tag_kernel: bool = False, assembler: str = "auto"):
         lib = _load_library()
         cfg = np.zeros(1, dtype=_cabi.CONFIG_DT)
         cfg["ctasPerSm"] = ctas_per_sm
@@ -61,7 +61,12 @@ class Context(Binding):
         cfg["scratchBytes"] = scratch_bytes
         # bit 0: always use the int32 one-alignment-per-warp DP kernel; bit 1: int16x2 pairs on the predicate/SEL
         # kernel, never the tagged-score kernel (the default where its score range allows)
-        cfg["reserved"][0][0] = (1 if force_int32 else 0) | (2 if no_tag_kernel else 0)
+        # bits 2/3: assembler kernel -- "global" (window-indexed tables in HBM, 32 loci per SM: throughput), "onchip" (dense
+        # tables in shared memory, 3 loci per SM: latency); "auto" takes the on-chip kernel for batches of up to 3 loci per SM
+        if assembler not in ("auto", "global", "onchip"):
+            raise ValueError("assembler must be 'auto', 'global' or 'onchip'")
+        cfg["reserved"][0][0] = ((1 if force_int32 else 0) | (2 if no_tag_kernel else 0) |
+                                 (4 if assembler == "global" else 0) | (8 if assembler == "onchip" else 0))
         handle = C.c_void_p()
         st = lib.mb200_create(C.c_int(device), cfg.ctypes.data_as(C.c_void_p), C.byref(handle))
         if st != _cabi.MB200_OK:

@@ -28,6 +28,8 @@
 // at most 1024 - 2*maxAssemblyCount reads per locus, word lengths 2..96, contigs up to cfg.maxContigLen.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -80,9 +82,12 @@ struct AsmParams {
   unsigned long long   setPoolCap;
   unsigned long long*  setPoolUsed;
   int*                 errFlag;
+  // list mode (second pass over the loci the on-chip kernel could not hold): process lociList[0 .. *lociListCount)
+  const uint32_t*      lociList;
+  const uint32_t*      lociListCount;
 };
 
-enum { FLAG_UNUSED = 1, FLAG_REPEAT = 2, FLAG_PEELED = 4, FLAG_ONSTACK = 8 };
+enum { FLAG_UNUSED = 1, FLAG_REPEAT = 2, FLAG_PEELED = 4, FLAG_ONSTACK = 8, FLAG_ONE_PRED = 16, FLAG_ONE_SUCC = 32 };  // the last two: on-chip kernel only
 
 // -DMB200_ASM_PROFILE: per-phase clock64 totals and event counts of assembleKernel (tools/asm_profile.py); never in
 // the product build
@@ -439,12 +444,16 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
   const uint32_t       maxIter = 2 * opt.maxAssemblyCount;  // contigs per word length
   const uint32_t       ctgBuf  = 2 * P.maxContigLen;        // bytes per contig buffer
 
+  const uint32_t lociTotal = P.lociListCount ? *P.lociListCount : P.nLoci;
   for (;;) {
-    if (tid == 0) shU[0] = atomicAdd(P.lociCounter, 1u);
+    if (tid == 0) {
+      const uint32_t idx = atomicAdd(P.lociCounter, 1u);
+      shU[0]             = (idx < lociTotal) ? (P.lociList ? P.lociList[idx] : idx) : NONE32;
+    }
     __syncthreads();
     const uint32_t li = shU[0];
     __syncthreads();
-    if (li >= P.nLoci) break;
+    if (li == NONE32) break;
 
     PROF_DECL();
     PROF_COUNT(19, 1);
@@ -1107,6 +1116,918 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
   }
 }
 
+// ======================================================================================================
+// On-chip assembler (round 2).  Same algorithm and results as assembleKernel above, different residence of the data:
+//   * one CTA of CHIP_THREADS threads per locus; every per-word table the hot phases touch lives in SHARED memory under
+//     DENSE word ids (16 bit): slot table, read-support bitsets, successor / predecessor ids, count, flags, in-degrees;
+//   * words are not stored at all: a word is the (read, offset) of one of its windows (4 bytes) and its key is cut out
+//     of the packed reads on demand (the packed normal reads sit in shared memory too when they fit);
+//   * count and first read are derived from the bitset (count = normal reads + minCoverage * pseudo reads that contain
+//     the word, IterativeAssembler.cpp:524-541), so insertion needs one shared atomicOr per window and nothing else;
+//   * global memory keeps only what is streamed (window -> slot map, contig buffers) or rare (the arrays of the exact
+//     unordered_map replay, now sized by the word capacity instead of the window count).
+// A locus that does not fit (more than Wc distinct words at some word length, more than 32*SWc reads incl. pseudo
+// reads, a read longer than 65535) is appended to a retry list and assembled by assembleKernel afterwards.
+constexpr int      CHIP_THREADS = 128;
+constexpr uint32_t NONE16       = 0xffffu;
+
+struct ChipLayout {
+  size_t   packed, nmask, winSlot, hashv, hash2, seqA, arr, pos, bktHead, bktMin, bktCnt, chainNext, gs, orderA, tmpA, idx, low,
+           wstack, frame, ctgSeq, ctgSets, ctgMeta, total;
+  uint32_t maxReads, nWinMax, packWords, maskWords, bktMax;
+  uint32_t Wc, SWc, SL, SPK;  // word capacity, set words per word, slots (power of two, >= Wc + CHIP_THREADS + 1), shared pack words
+  uint32_t smemBytes;
+};
+
+struct ChipParams {
+  AsmParams  A;  // opt, inputs, outputs, counters (work / L unused)
+  ChipLayout C;
+  uint8_t*   work;
+  uint32_t*  retryList;
+  uint32_t*  retryCount;
+};
+
+struct Chip {  // shared-memory view
+  uint32_t *slot, *ref, *bits;
+  uint16_t *succ, *pred, *count, *queue;
+  uint8_t * flags, *inC, *indeg;
+  uint32_t *len, *packOff, *maskOff, *winStart;
+  uint64_t*       spk;
+  const uint64_t* gPacked;
+  uint32_t        nShared;  // reads [0, nShared) have their packed words in spk
+  uint32_t        SWc;
+};
+
+__device__ __forceinline__ const uint64_t* packOf(const Chip& S, uint32_t r) { return (r < S.nShared ? S.spk : S.gPacked) + S.packOff[r]; }
+__device__ __forceinline__ Key keyOfRef(const Chip& S, uint32_t ref, uint32_t k) { return extractKey(packOf(S, ref >> 16), ref & 0xffffu, k); }
+
+__device__ uint32_t findWordChip(const Chip& S, const Key& key, uint32_t k, uint32_t slotMask)
+{
+  const uint32_t h32 = hashKey(key), tag = h32 >> 27;
+  uint32_t       h   = h32 & slotMask;
+  for (;;) {
+    const uint32_t v = S.slot[h];
+    if (v == 0) return NONE16;
+    if ((v >> 27) == tag) {
+      const uint32_t id = (v & 0x7ffffffu) - 1;
+      if (keyEq(keyOfRef(S, S.ref[id], k), key)) return id;
+    }
+    h = (h + 1) & slotMask;
+  }
+}
+
+// first read of a word / its count, from the bitset
+__device__ __forceinline__ uint32_t firstReadOf(const Chip& S, uint32_t id, uint32_t SW)
+{
+  for (uint32_t w = 0; w < SW; ++w) {
+    const uint32_t b = S.bits[id * S.SWc + w];
+    if (b) return w * 32 + (uint32_t)__ffs((int)b) - 1;
+  }
+  return NONE32;
+}
+
+__global__ void __launch_bounds__(CHIP_THREADS) assembleChipKernel(const ChipParams P)
+{
+  extern __shared__ __align__(16) uint8_t smemRaw[];
+  __shared__ uint32_t sh[CHIP_THREADS];
+  __shared__ uint32_t shU[20];
+
+  const uint32_t tid  = threadIdx.x;
+  const uint32_t nt   = blockDim.x;
+  const uint32_t lane = tid & 31;
+  const uint32_t warp = tid >> 5;
+  const uint32_t Wc = P.C.Wc, SWc = P.C.SWc, SL = P.C.SL, RC = SWc * 32;
+
+  Chip S;
+  {
+    uint8_t* q = smemRaw;
+    S.spk      = reinterpret_cast<uint64_t*>(q); q += 8 * (size_t)P.C.SPK;
+    S.slot     = reinterpret_cast<uint32_t*>(q); q += 4 * (size_t)SL;
+    S.ref      = reinterpret_cast<uint32_t*>(q); q += 4 * (size_t)Wc;
+    S.bits     = reinterpret_cast<uint32_t*>(q); q += 4 * (size_t)Wc * SWc;
+    S.len      = reinterpret_cast<uint32_t*>(q); q += 4 * (size_t)RC;
+    S.packOff  = reinterpret_cast<uint32_t*>(q); q += 4 * (size_t)RC;
+    S.maskOff  = reinterpret_cast<uint32_t*>(q); q += 4 * (size_t)RC;
+    S.winStart = reinterpret_cast<uint32_t*>(q); q += 4 * (size_t)(RC + 4);
+    S.succ     = reinterpret_cast<uint16_t*>(q); q += 8 * (size_t)Wc;
+    S.pred     = reinterpret_cast<uint16_t*>(q); q += 8 * (size_t)Wc;
+    S.count    = reinterpret_cast<uint16_t*>(q); q += 2 * (size_t)Wc;
+    S.queue    = reinterpret_cast<uint16_t*>(q); q += 2 * (size_t)Wc;
+    S.flags    = q; q += Wc;
+    S.inC      = q; q += Wc;
+    S.indeg    = q; q += Wc;
+    S.SWc      = SWc;
+  }
+  uint8_t*  base    = P.work + (size_t)blockIdx.x * P.C.total;
+  uint64_t* gPacked = reinterpret_cast<uint64_t*>(base + P.C.packed);
+  uint64_t* gMask   = reinterpret_cast<uint64_t*>(base + P.C.nmask);
+  uint16_t* winSlot = reinterpret_cast<uint16_t*>(base + P.C.winSlot);
+  S.gPacked         = gPacked;
+  Work W;  // the arrays of the unordered_map replay (global, sized by Wc)
+  W.hashv     = reinterpret_cast<uint64_t*>(base + P.C.hashv);
+  uint64_t* hash2 = reinterpret_cast<uint64_t*>(base + P.C.hash2);
+  W.seqA      = reinterpret_cast<uint32_t*>(base + P.C.seqA);
+  W.arr       = reinterpret_cast<uint32_t*>(base + P.C.arr);
+  W.pos       = reinterpret_cast<uint32_t*>(base + P.C.pos);
+  W.bktHead   = reinterpret_cast<uint32_t*>(base + P.C.bktHead);
+  W.bktMin    = reinterpret_cast<uint32_t*>(base + P.C.bktMin);
+  W.bktCnt    = reinterpret_cast<uint32_t*>(base + P.C.bktCnt);
+  W.chainNext = reinterpret_cast<uint32_t*>(base + P.C.chainNext);
+  W.gs        = reinterpret_cast<uint32_t*>(base + P.C.gs);
+  W.orderA    = reinterpret_cast<uint32_t*>(base + P.C.orderA);
+  W.tmpA      = reinterpret_cast<uint32_t*>(base + P.C.tmpA);
+  W.idx       = reinterpret_cast<uint32_t*>(base + P.C.idx);
+  W.low       = reinterpret_cast<uint32_t*>(base + P.C.low);
+  W.wstack    = reinterpret_cast<uint32_t*>(base + P.C.wstack);
+  W.frame     = reinterpret_cast<uint32_t*>(base + P.C.frame);
+  W.ctgSeq    = base + P.C.ctgSeq;
+  W.ctgSets   = reinterpret_cast<uint32_t*>(base + P.C.ctgSets);
+  W.ctgMeta   = reinterpret_cast<CtgMeta*>(base + P.C.ctgMeta);
+
+  const mb200_asm_opts opt     = P.A.opt;
+  const uint32_t       maxIter = 2 * opt.maxAssemblyCount;
+  const uint32_t       ctgBuf  = 2 * P.A.maxContigLen;
+  const uint32_t       slotMask = SL - 1;
+
+  for (;;) {
+    if (tid == 0) shU[0] = atomicAdd(P.A.lociCounter, 1u);
+    __syncthreads();
+    const uint32_t li = shU[0];
+    __syncthreads();
+    if (li >= P.A.nLoci) break;
+
+    PROF_DECL();
+    PROF_COUNT(19, 1);
+    const uint64_t r0              = P.A.readOff[li];
+    const uint32_t normalReadCount = (uint32_t)(P.A.readOff[li + 1] - r0);
+    const uint32_t SW              = (normalReadCount + maxIter + 31) / 32;
+    int            status          = MB200_OK;
+    bool           retry           = (SW > SWc);  // does not fit: legacy kernel
+
+    // ---------------- pack the normal reads
+    if (!retry) {
+      if (tid == 0) {
+        uint32_t po = 0, mo = 0, tooLong = 0;
+        for (uint32_t r = 0; r < normalReadCount; ++r) {
+          const uint32_t len = P.A.views[r0 + r].len;
+          S.len[r]     = len;
+          S.packOff[r] = po;
+          S.maskOff[r] = mo;
+          if (len > 0xffffu) tooLong = 1;
+          po += (len + 31) / 32 + 4;
+          mo += (len + 63) / 64 + 3;
+        }
+        shU[1] = po;
+        shU[2] = mo;
+        shU[11] = tooLong;
+      }
+      __syncthreads();
+      if (shU[11]) retry = true;
+    }
+    const uint32_t normPackWords = shU[1], normMaskWords = shU[2];
+    if (!retry) {
+      bool badBase = false;
+      for (uint32_t r = warp; r < normalReadCount; r += nt / 32) {
+        const uint8_t* src = P.A.pool + P.A.views[r0 + r].off;
+        const uint32_t len = S.len[r];
+        const uint32_t nPk = (len + 31) / 32 + 4, nMk = (len + 63) / 64 + 3;
+        if (packRead(src, len, gPacked + S.packOff[r], gMask + S.maskOff[r], nPk, nMk, true, lane)) badBase = true;
+      }
+      if (__syncthreads_or(badBase ? 1 : 0)) status = MB200_ERR_BAD_BASE;
+      // packed normal reads to shared memory (they are read once per window and per key comparison)
+      S.nShared = 0;
+      if (normPackWords <= P.C.SPK) {
+        for (uint32_t i = tid; i < normPackWords; i += nt) S.spk[i] = gPacked[i];
+        S.nShared = normalReadCount;
+      }
+      __syncthreads();
+    }
+
+    uint32_t nReads = normalReadCount;
+    uint32_t nCtg   = 0;
+    uint32_t lastK  = 0;
+
+    if (!retry && status == MB200_OK) {
+      PROF_MARK(0);
+      for (uint32_t k = opt.minWordLength; k <= opt.maxWordLength; k += opt.wordStepSize) {
+        lastK = k;
+        PROF_COUNT(16, 1);
+        // ---- windows
+        if (tid == 0) {
+          uint32_t acc = 0;
+          for (uint32_t r = 0; r < nReads; ++r) {
+            S.winStart[r] = acc;
+            const uint32_t len = S.len[r];
+            if (len >= k) acc += len - k + 1;
+          }
+          S.winStart[nReads] = acc;
+          shU[3] = acc;
+          shU[4] = 0;   // claimed slots
+          shU[12] = 0;  // overflow
+          shU[13] = 0;  // dense ids handed out
+        }
+        for (uint32_t i = tid; i < SL; i += nt) S.slot[i] = 0;
+        __syncthreads();
+        PROF_MARK(1);
+        PROF_COUNT(21, shU[3]);
+
+        // ---- pass A: every N-free window claims or finds the slot of its word
+        for (uint32_t r = warp; r < nReads; r += nt / 32) {
+          const uint32_t len = S.len[r];
+          if (len < k) continue;
+          const uint64_t* pk = packOf(S, r);
+          const uint64_t* mk = gMask + S.maskOff[r];
+          const uint32_t  ws = S.winStart[r];
+          for (uint32_t j = lane; j + k <= len; j += 32) {
+            bool hasN = getBits(mk, j, k < 64 ? k : 64) != 0;
+            if (k > 64) hasN = hasN || (getBits(mk, j + 64, k - 64) != 0);
+            uint32_t found = NONE16;
+            if (!hasN) {
+              const Key      key = extractKey(pk, j, k);
+              const uint32_t h32 = hashKey(key), tag = h32 >> 27;
+              const uint32_t val = (tag << 27) | (((r << 16) | j) + 1);
+              uint32_t       h   = h32 & slotMask;
+              for (;;) {
+                uint32_t cur = S.slot[h];
+                if (cur == 0) {
+                  if (*reinterpret_cast<volatile uint32_t*>(&shU[12])) break;  // capacity exceeded: stop claiming
+                  cur = atomicCAS(&S.slot[h], 0u, val);
+                  if (cur == 0) {
+                    if (atomicAdd(&shU[4], 1u) >= Wc) shU[12] = 1;
+                    found = h;
+                    break;
+                  }
+                }
+                if ((cur >> 27) == tag && keyEq(keyOfRef(S, (cur & 0x7ffffffu) - 1, k), key)) {
+                  found = h;
+                  break;
+                }
+                h = (h + 1) & slotMask;
+              }
+            }
+            winSlot[ws + j] = (uint16_t)found;
+          }
+        }
+        __syncthreads();
+        if (shU[12]) {  // more distinct words than the shared tables hold
+          retry = true;
+          break;
+        }
+        PROF_MARK(2);
+        // ---- pass B: dense ids
+        for (uint32_t h = tid; h < SL; h += nt) {
+          const uint32_t v = S.slot[h];
+          if (v == 0) continue;
+          const uint32_t id = atomicAdd(&shU[13], 1u);
+          S.ref[id]   = (v & 0x7ffffffu) - 1;
+          S.slot[h]   = (v & 0xf8000000u) | (id + 1);
+          S.flags[id] = 0;
+          S.inC[id]   = 0;
+          S.indeg[id] = 0;
+          for (uint32_t w = 0; w < SW; ++w) S.bits[id * SWc + w] = 0;
+        }
+        __syncthreads();
+        const uint32_t nWords = shU[13];
+        // ---- pass C: read-support bits (std::set<std::string> readWords: a word repeated inside a read counts once)
+        for (uint32_t r = warp; r < nReads; r += nt / 32) {
+          const uint32_t len = S.len[r];
+          if (len < k) continue;
+          const uint32_t ws  = S.winStart[r];
+          const uint32_t bit = 1u << (r & 31);
+          for (uint32_t j = lane; j + k <= len; j += 32) {
+            const uint32_t hs = winSlot[ws + j];
+            if (hs == NONE16) continue;
+            const uint32_t id = (S.slot[hs] & 0x7ffffffu) - 1;
+            atomicOr(&S.bits[id * SWc + (r >> 5)], bit);
+          }
+        }
+        __syncthreads();
+        // ---- counts: 1 per normal read, minCoverage per pseudo read (:541)
+        for (uint32_t id = tid; id < nWords; id += nt) {
+          uint32_t c = 0;
+          for (uint32_t w = 0; w < SW; ++w) {
+            const uint32_t b  = S.bits[id * SWc + w];
+            const uint32_t lo = w * 32;
+            uint32_t       pm;  // pseudo-read mask of this set word
+            if (normalReadCount <= lo) pm = 0xffffffffu;
+            else if (normalReadCount >= lo + 32) pm = 0;
+            else pm = ~((1u << (normalReadCount - lo)) - 1);
+            c += (uint32_t)__popc(b & ~pm) + opt.minCoverage * (uint32_t)__popc(b & pm);
+          }
+          S.count[id] = (uint16_t)(c > 0xffffu ? 0xffffu : c);
+        }
+        __syncthreads();
+        PROF_MARK(3);
+        PROF_COUNT(20, nWords);
+
+        // ---- successor / predecessor ids, homopolymer repeats, in-degrees
+        for (uint32_t i = tid; i < nWords * 4; i += nt) {
+          const uint32_t id  = i >> 2;
+          const uint32_t sym = i & 3;
+          const Key      key = keyOfRef(S, S.ref[id], k);
+          const uint32_t s   = findWordChip(S, succKey(key, sym, k), k, slotMask);
+          S.succ[id * 4 + sym] = (uint16_t)s;
+          if (s == id) {
+            atomicOr(reinterpret_cast<unsigned int*>(S.flags + (id & ~3u)), (unsigned)FLAG_REPEAT << (8 * (id & 3)));
+          } else if (s != NONE16) {
+            atomicAdd(reinterpret_cast<unsigned int*>(S.indeg + (s & ~3u)), 1u << (8 * (s & 3)));
+          }
+        }
+        __syncthreads();
+        PROF_MARK(4);
+
+        // ---- Kahn trimming: any cycle besides homopolymer self loops?
+        {
+          if (tid == 0) shU[5] = 0;
+          __syncthreads();
+          for (uint32_t id = tid; id < nWords; id += nt)
+            if (S.indeg[id] == 0) S.queue[atomicAdd(&shU[5], 1u)] = (uint16_t)id;
+          __syncthreads();
+          uint32_t head = 0;
+          for (;;) {
+            const uint32_t tail = shU[5];
+            if (head == tail) break;
+            __syncthreads();
+            for (uint32_t i = head + tid; i < tail; i += nt) {
+              const uint32_t id = S.queue[i];
+              const uint2    sc = *reinterpret_cast<const uint2*>(S.succ + id * 4);
+              const uint32_t ss[4] = {sc.x & 0xffffu, sc.x >> 16, sc.y & 0xffffu, sc.y >> 16};
+#pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                const uint32_t nx = ss[s];
+                if (nx == NONE16 || nx == id) continue;
+                const uint32_t shf = 8 * (nx & 3);
+                const uint32_t old = atomicSub(reinterpret_cast<unsigned int*>(S.indeg + (nx & ~3u)), 1u << shf);
+                if (((old >> shf) & 0xffu) == 1u) S.queue[atomicAdd(&shU[5], 1u)] = (uint16_t)nx;
+              }
+            }
+            head = tail;
+            __syncthreads();
+          }
+        }
+        const bool hasCycle = (shU[5] != nWords);
+        __syncthreads();
+        PROF_MARK(5);
+        PROF_COUNT(22, hasCycle ? 1 : 0);
+
+        if (hasCycle) {
+          // ================= exact replay of getRepeatKmers (hash-order DFS roots), see assembleKernel =================
+          uint32_t* bucketStart = W.tmpA;
+          uint32_t* members     = W.orderA;
+          uint32_t* firstRead   = W.idx;  // until the DFS needs idx
+          for (uint32_t r = tid; r <= nReads; r += nt) W.gs[r] = 0;
+          __syncthreads();
+          for (uint32_t id = tid; id < nWords; id += nt) {
+            const uint32_t fr = firstReadOf(S, id, SW);
+            firstRead[id]     = fr;
+            atomicAdd(&W.gs[fr], 1u);
+          }
+          __syncthreads();
+          if (tid == 0) {
+            uint32_t acc = 0;
+            for (uint32_t r = 0; r < nReads; ++r) {
+              bucketStart[r] = acc;
+              acc += W.gs[r];
+              W.gs[r] = 0;
+            }
+            bucketStart[nReads] = acc;
+          }
+          __syncthreads();
+          for (uint32_t id = tid; id < nWords; id += nt) {
+            const uint32_t r = firstRead[id];
+            members[bucketStart[r] + atomicAdd(&W.gs[r], 1u)] = id;
+          }
+          __syncthreads();
+          for (uint32_t id = tid; id < nWords; id += nt) {
+            const uint32_t r   = firstRead[id];
+            const Key      key = keyOfRef(S, S.ref[id], k);
+            uint32_t       rank = 0;
+            for (uint32_t m = bucketStart[r]; m < bucketStart[r + 1]; ++m)
+              if (keyLess(keyOfRef(S, S.ref[members[m]], k), key)) rank++;
+            const uint32_t p = bucketStart[r] + rank;
+            W.seqA[p]        = id;
+            W.hashv[p]       = stlHashWord(key, k);
+          }
+          __syncthreads();
+          uint32_t* order1 = W.low;  // order1 and order2 must survive until chainNext is built
+          unorderedOrder(W, W.hashv, nWords, order1, sh);
+          for (uint32_t i = tid; i < nWords; i += nt) hash2[i] = W.hashv[order1[i]];
+          __syncthreads();
+          uint32_t* order2 = W.wstack;
+          unorderedOrder(W, hash2, nWords, order2, sh);
+          for (uint32_t i = tid; i < nWords; i += nt) W.frame[i] = W.seqA[order1[order2[i]]];  // root sequence
+          __syncthreads();
+          for (uint32_t i = tid; i < nWords; i += nt) W.chainNext[i] = W.frame[i];
+          __syncthreads();
+          PROF_MARK(12);
+          // the DFS state lives in shared memory: idx on the (finished) Kahn queue, low on inC+indeg (contiguous, both
+          // dead here), the two stacks on the predecessor table, which is only filled afterwards
+          uint16_t* dIdx   = S.queue;
+          uint16_t* dLow   = reinterpret_cast<uint16_t*>(S.inC);
+          uint16_t* dStack = S.pred;
+          uint16_t* dFrame = S.pred + Wc;      // (word << 3) | next symbol needs 14 bits
+          for (uint32_t id = tid; id < nWords; id += nt) {
+            dIdx[id] = 0;
+            dLow[id] = 0;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            const uint32_t* roots  = W.chainNext;
+            uint32_t        index  = 1;
+            uint32_t        nStack = 0;
+            for (uint32_t ri = 0; ri < nWords; ++ri) {
+              const uint32_t root = roots[ri];
+              if (dIdx[root] != 0) continue;
+              uint32_t depth = 1;
+              dFrame[0]      = (uint16_t)(root << 3);
+              dIdx[root] = dLow[root] = (uint16_t)index++;
+              dStack[nStack++]        = (uint16_t)root;
+              S.flags[root] |= FLAG_ONSTACK;
+              while (depth) {
+                const uint32_t fr  = dFrame[depth - 1];
+                const uint32_t w   = fr >> 3;
+                const uint32_t sym = fr & 7;
+                if (sym < 4) {
+                  dFrame[depth - 1] = (uint16_t)(fr + 1);
+                  const uint32_t nw = S.succ[w * 4 + sym];
+                  if (nw == w) continue;
+                  if (nw == NONE16) continue;
+                  if (dIdx[nw] == 0) {
+                    dFrame[depth++] = (uint16_t)(nw << 3);
+                    dIdx[nw] = dLow[nw] = (uint16_t)index++;
+                    dStack[nStack++]    = (uint16_t)nw;
+                    S.flags[nw] |= FLAG_ONSTACK;
+                  } else if (S.flags[nw] & FLAG_ONSTACK) {
+                    if (dIdx[nw] < dLow[w]) dLow[w] = dIdx[nw];
+                  }
+                } else {
+                  if (dLow[w] == dIdx[w]) {
+                    const uint32_t lastWord = dStack[nStack - 1];
+                    if (lastWord == w) {
+                      nStack--;
+                      S.flags[w] &= ~FLAG_ONSTACK;
+                    } else {
+                      const bool isSmallCircle = ((uint32_t)dIdx[lastWord] - (uint32_t)dIdx[w]) <= 50;
+                      for (;;) {
+                        const uint32_t rw = dStack[--nStack];
+                        S.flags[rw] &= ~FLAG_ONSTACK;
+                        if (isSmallCircle) S.flags[rw] |= FLAG_REPEAT;
+                        if (rw == w) break;
+                      }
+                    }
+                  }
+                  depth--;
+                  if (depth) {
+                    const uint32_t parent = dFrame[depth - 1] >> 3;
+                    if (dLow[w] < dLow[parent]) dLow[parent] = dLow[w];
+                  }
+                }
+              }
+            }
+          }
+          __syncthreads();
+          for (uint32_t id = tid; id < nWords; id += nt) S.inC[id] = 0;  // was the low-link array
+          __syncthreads();
+          PROF_MARK(13);
+        }
+        PROF_MARK(6);
+
+        // ---- predecessor ids (their table doubled as the DFS stacks), unusedWords = {count >= minCoverage}
+        for (uint32_t i = tid; i < nWords * 4; i += nt) {
+          const uint32_t id  = i >> 2;
+          const uint32_t sym = i & 3;
+          S.pred[id * 4 + sym] = (uint16_t)findWordChip(S, predKey(keyOfRef(S, S.ref[id], k), sym, k), k, slotMask);
+        }
+        __syncthreads();
+        for (uint32_t id = tid; id < nWords; id += nt) {
+          const uint2 sc = *reinterpret_cast<const uint2*>(S.succ + id * 4);
+          const uint2 pc = *reinterpret_cast<const uint2*>(S.pred + id * 4);
+          const int   nS = ((sc.x & 0xffffu) != NONE16) + ((sc.x >> 16) != NONE16) + ((sc.y & 0xffffu) != NONE16) + ((sc.y >> 16) != NONE16);
+          const int   nP = ((pc.x & 0xffffu) != NONE16) + ((pc.x >> 16) != NONE16) + ((pc.y & 0xffffu) != NONE16) + ((pc.y >> 16) != NONE16);
+          uint32_t    f  = S.flags[id];
+          if (S.count[id] >= opt.minCoverage) f |= FLAG_UNUSED;
+          if (nP <= 1) f |= FLAG_ONE_PRED;
+          if (nS <= 1) f |= FLAG_ONE_SUCC;
+          S.flags[id] = (uint8_t)f;
+        }
+        __syncthreads();
+        PROF_MARK(14);
+
+        // ---- contig loop (:685-716)
+        bool isAssemblySuccess = true;
+        nCtg                   = 0;
+        while (nCtg < maxIter) {
+          // seed: max count, ties -> lexicographically smallest word.  Stage 1: the maximum count.
+          uint32_t myMax = 0;
+          bool     any   = false;
+          for (uint32_t id = tid; id < nWords; id += nt) {
+            if (!(S.flags[id] & FLAG_UNUSED)) continue;
+            const uint32_t c = S.count[id];
+            if (!any || c > myMax) myMax = c;
+            any = true;
+          }
+          uint32_t enc = any ? (myMax + 1) : 0;  // 0 = nothing unused
+          enc          = __reduce_max_sync(0xffffffffu, enc);
+          if (lane == 0) sh[warp] = enc;
+          __syncthreads();
+          uint32_t encAll = 0;
+          for (uint32_t w = 0; w < nt / 32; ++w) encAll = max(encAll, sh[w]);
+          __syncthreads();
+          if (encAll == 0) {
+            PROF_MARK(7);
+            break;  // unusedWords.empty()
+          }
+          const uint32_t cMax = encAll - 1;
+          // stage 2: the smallest word among those with that count
+          Key      bestKey = {~0ull, ~0ull, ~0ull};
+          uint32_t bestId  = NONE32;
+          for (uint32_t id = tid; id < nWords; id += nt) {
+            if (!(S.flags[id] & FLAG_UNUSED) || S.count[id] != cMax) continue;
+            const Key key = keyOfRef(S, S.ref[id], k);
+            if (bestId == NONE32 || keyLess(key, bestKey)) {
+              bestKey = key;
+              bestId  = id;
+            }
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const uint32_t oid = __shfl_xor_sync(0xffffffffu, bestId, off);
+            Key            ok;
+            ok.k0 = __shfl_xor_sync(0xffffffffu, bestKey.k0, off);
+            ok.k1 = __shfl_xor_sync(0xffffffffu, bestKey.k1, off);
+            ok.k2 = __shfl_xor_sync(0xffffffffu, bestKey.k2, off);
+            if (oid != NONE32 && (bestId == NONE32 || keyLess(ok, bestKey))) {
+              bestKey = ok;
+              bestId  = oid;
+            }
+          }
+          if (lane == 0) sh[warp] = bestId;
+          __syncthreads();
+          if (tid == 0) {
+            uint32_t bid = NONE32;
+            Key      bk  = {0, 0, 0};
+            for (uint32_t w = 0; w < nt / 32; ++w) {
+              const uint32_t id = sh[w];
+              if (id == NONE32) continue;
+              const Key kk = keyOfRef(S, S.ref[id], k);
+              if (bid == NONE32 || keyLess(kk, bk)) {
+                bid = id;
+                bk  = kk;
+              }
+            }
+            shU[7] = bid;
+          }
+          __syncthreads();
+          const uint32_t seed = shU[7];
+          __syncthreads();
+          PROF_MARK(7);
+          PROF_COUNT(17, 1);
+
+          // ---------------- walk(seed)  (warp 0; IterativeAssembler.cpp:149-501)
+          if (warp == 0) {
+            uint8_t*       seq     = W.ctgSeq + (size_t)nCtg * ctgBuf;
+            uint32_t*      sets    = W.ctgSets + (size_t)nCtg * 2 * MAX_SETW;
+            const uint32_t serial  = nCtg + 1;
+            const Key      seedKey = keyOfRef(S, S.ref[seed], k);
+            uint32_t       lo = P.A.maxContigLen - k / 2, hi;
+            hi = lo + k;
+            for (uint32_t i = lane; i < k; i += 32) seq[lo + i] = "ACGT"[baseAt(seedKey, i, k)];
+            uint32_t support = (lane < SW) ? S.bits[seed * SWc + lane] : 0u;
+            uint32_t reject  = 0;
+            const bool seedIsRepeat = (S.flags[seed] & FLAG_REPEAT) != 0;
+            __syncwarp();
+            if (lane == 0) S.flags[seed] &= ~FLAG_UNUSED;
+            int  consBegin = 0, consEnd = 0;
+            bool isRepeatFound = false;
+            bool overflow      = false;
+            if (seedIsRepeat) {
+              consBegin     = 0;
+              consEnd       = (int)k;
+              isRepeatFound = true;
+            } else {
+              if (lane == 0) S.inC[seed] = (uint8_t)serial;
+              {  // rejecting reads from the seed's sibling words (same k-1 prefix)  :185-210
+                const uint32_t lastSym = (uint32_t)seedKey.k0 & 3u;
+                Key            trunkK  = seedKey;
+                trunkK.k0 &= ~3ull;
+                for (uint32_t s = 0; s < 4; ++s) {
+                  if (s == lastSym) continue;
+                  Key kk = trunkK;
+                  kk.k0 |= s;
+                  const uint32_t id = findWordChip(S, kk, k, slotMask);
+                  if (id == NONE16) continue;
+                  if (lane < SW) reject |= S.bits[id * SWc + lane];
+                }
+              }
+              __syncwarp();
+              uint32_t curWord = seed;
+              for (int mode = 0; mode < 2; ++mode) {
+                const bool      isEnd = (mode == 0);
+                const uint16_t* fwd   = isEnd ? S.succ : S.pred;
+                const uint16_t* bwd   = isEnd ? S.pred : S.succ;
+                uint32_t        conservativeEndOffset = 0;
+                curWord = seed;
+                const uint32_t oneBack = isEnd ? (uint32_t)FLAG_ONE_PRED : (uint32_t)FLAG_ONE_SUCC;
+                for (;;) {
+                  const uint2    c2 = *reinterpret_cast<const uint2*>(fwd + curWord * 4);
+                  const uint32_t cand[4] = {c2.x & 0xffffu, c2.x >> 16, c2.y & 0xffffu, c2.y >> 16};
+                  const uint32_t vmask = (cand[0] != NONE16 ? 1u : 0u) | (cand[1] != NONE16 ? 2u : 0u) | (cand[2] != NONE16 ? 4u : 0u) |
+                                         (cand[3] != NONE16 ? 8u : 0u);
+                  if (vmask == 0) break;  // nothing to extend with: maxBaseCount stays 0 < minCoverage
+                  if ((vmask & (vmask - 1)) == 0) {
+                    // ---- one candidate (most steps): the general step below with everything about "the other candidates" gone
+                    const uint32_t sym = (uint32_t)__ffs((int)vmask) - 1;
+                    const uint32_t id  = ((sym & 2u) ? c2.y : c2.x) >> (16 * (sym & 1u)) & 0xffffu;
+                    const uint32_t cw1 = (lane < SW) ? S.bits[id * SWc + lane] : 0u;
+                    const uint32_t cn1 = S.count[id];
+                    const uint32_t in1 = S.inC[id];
+                    const uint32_t fl1 = S.flags[id];
+                    const uint32_t contig1 = support & cw1;
+                    if (__reduce_add_sync(0xffffffffu, (uint32_t)__popc(contig1)) == 0) break;
+                    if (cn1 < opt.minCoverage) break;
+                    if (in1 == serial) {
+                      isRepeatFound = true;
+                      break;
+                    }
+                    uint32_t upd = 0;
+                    if (!(fl1 & oneBack)) {  // the chosen word has other neighbours on the side we come from (:375-427)
+                      const uint2    a2 = *reinterpret_cast<const uint2*>(bwd + id * 4);
+                      const uint32_t alt[4] = {a2.x & 0xffffu, a2.x >> 16, a2.y & 0xffffu, a2.y >> 16};
+#pragma unroll
+                      for (int t = 0; t < 4; ++t) {
+                        const uint32_t o = alt[t];
+                        if (o == NONE16 || o == id || o == curWord) continue;
+                        const uint32_t back = (lane < SW) ? S.bits[o * SWc + lane] : 0u;
+                        upd |= back & ~(contig1 & back);
+                      }
+                    }
+                    if (hi - lo + 1 > P.A.maxContigLen || lo == 0 || hi + 1 >= ctgBuf) {
+                      overflow = true;
+                      break;
+                    }
+                    if (lane == 0) seq[isEnd ? hi : lo - 1] = (uint8_t)(0x54474341u >> (8 * sym));  // "ACGT"[sym]
+                    if (isEnd) hi++; else lo--;
+                    if ((conservativeEndOffset != 0) || (cn1 < opt.minConservativeCoverage)) conservativeEndOffset += 1;
+                    reject |= upd;
+                    support |= cw1 & ~reject;
+                    support &= ~upd;
+                    __syncwarp();
+                    if (lane == 0) {
+                      S.flags[id] = (uint8_t)(fl1 & ~(uint32_t)FLAG_UNUSED);
+                      S.inC[id]   = (uint8_t)serial;
+                    }
+                    __syncwarp();
+                    curWord = id;
+                    PROF_COUNT(18, 1);
+                    continue;
+                  }
+                  // everything the step can need of the (usually one) candidates, loaded before any of it is used
+                  uint32_t cw[4], cnt[4], cc[4], inc[4], flg[4];
+                  uint2    bw[4];
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) {
+                    const uint32_t id = cand[s];
+                    const bool     v  = (id != NONE16);
+                    cw[s]  = (v && lane < SW) ? S.bits[id * SWc + lane] : 0u;
+                    cnt[s] = v ? (uint32_t)S.count[id] : 0u;
+                    inc[s] = v ? (uint32_t)S.inC[id] : 0u;
+                    flg[s] = v ? (uint32_t)S.flags[id] : 0u;
+                    bw[s]  = v ? *reinterpret_cast<const uint2*>(bwd + id * 4) : make_uint2(0xffffffffu, 0xffffffffu);
+                  }
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) cc[s] = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(support & cw[s]));
+                  uint32_t maxBaseCount = 0, maxCnt = 0, maxBase = 0, maxWord = NONE16, maxInc = 0, maxFlg = 0;
+                  uint32_t maxW = 0, maxCW = 0, sup2Remove = 0, rej2Add = 0;
+                  uint2    maxBw = make_uint2(0xffffffffu, 0xffffffffu);
+#pragma unroll
+                  for (int s = 0; s < 4; ++s) {
+                    if (cc[s] == 0) continue;  // not a word, or no read of the contig supports it
+                    const uint32_t contigWord = support & cw[s];
+                    const uint32_t shared     = maxCW & cw[s];
+                    if (cc[s] > maxCnt) {
+                      sup2Remove |= maxCW & ~shared;
+                      rej2Add |= maxW & ~shared;
+                      maxW         = cw[s];
+                      maxCnt       = cc[s];
+                      maxCW        = contigWord;
+                      maxBaseCount = cnt[s];
+                      maxBase      = (uint32_t)s;
+                      maxWord      = cand[s];
+                      maxInc       = inc[s];
+                      maxFlg       = flg[s];
+                      maxBw        = bw[s];
+                    } else {
+                      sup2Remove |= contigWord & ~shared;
+                      rej2Add |= cw[s] & ~shared;
+                    }
+                  }
+                  if (maxBaseCount < opt.minCoverage) break;
+                  if (maxInc == serial) {
+                    isRepeatFound = true;
+                    break;
+                  }
+                  {  // walk backwards one step at the branching point (:375-427): the other neighbours of the chosen word
+                    const uint32_t alt[4] = {maxBw.x & 0xffffu, maxBw.x >> 16, maxBw.y & 0xffffu, maxBw.y >> 16};
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                      const uint32_t id = alt[s];
+                      if (id == NONE16 || id == maxWord || id == curWord) continue;
+                      const uint32_t back     = (lane < SW) ? S.bits[id * SWc + lane] : 0u;
+                      const uint32_t toUpdate = back & ~(maxCW & back);
+                      rej2Add |= toUpdate;
+                      sup2Remove |= toUpdate;
+                    }
+                  }
+                  if (hi - lo + 1 > P.A.maxContigLen || lo == 0 || hi + 1 >= ctgBuf) {
+                    overflow = true;
+                    break;
+                  }
+                  if (lane == 0) seq[isEnd ? hi : lo - 1] = (uint8_t)(0x54474341u >> (8 * maxBase));  // "ACGT"[maxBase]
+                  if (isEnd) hi++; else lo--;
+                  if ((conservativeEndOffset != 0) || (maxBaseCount < opt.minConservativeCoverage)) conservativeEndOffset += 1;
+                  reject |= rej2Add;
+                  support |= maxW & ~reject;
+                  support &= ~sup2Remove;
+                  __syncwarp();
+                  if (lane == 0) {
+                    S.flags[maxWord] = (uint8_t)(maxFlg & ~(uint32_t)FLAG_UNUSED);
+                    S.inC[maxWord]   = (uint8_t)serial;
+                  }
+                  __syncwarp();
+                  curWord = maxWord;
+                  PROF_COUNT(18, 1);
+                }
+                if (mode == 0) consEnd = (int)conservativeEndOffset;
+                else consBegin = (int)conservativeEndOffset;
+              }
+              consEnd = (int)(hi - lo) - consEnd;
+            }
+            if (lane < MAX_SETW) {
+              sets[lane]            = support;
+              sets[MAX_SETW + lane] = reject;
+            }
+            if (lane == 0) {
+              CtgMeta m;
+              m.lo = lo; m.hi = hi; m.consBegin = consBegin; m.consEnd = consEnd;
+              W.ctgMeta[nCtg] = m;
+              shU[8]          = isRepeatFound ? 1u : 0u;
+              shU[9]          = overflow ? 1u : 0u;
+            }
+          }
+          __syncthreads();
+          PROF_MARK(8);
+          if (shU[8]) isAssemblySuccess = false;
+          if (shU[9]) status = MB200_ERR_ASM_OVERFLOW;
+          nCtg++;
+          __syncthreads();
+          if (status != MB200_OK) break;
+        }
+        if (status != MB200_OK) break;
+        if (isAssemblySuccess) break;
+
+        // ---- pseudo reads for the next word length (:882-910)
+        if (tid == 0) {
+          uint32_t po = normPackWords, mo = normMaskWords, nr = normalReadCount;
+          for (uint32_t c = 0; c < nCtg; ++c) {
+            const uint32_t len = W.ctgMeta[c].hi - W.ctgMeta[c].lo;
+            if (len > k + opt.wordStepSize) {
+              S.len[nr]     = len;
+              S.packOff[nr] = po;
+              S.maskOff[nr] = mo;
+              W.tmpA[nr]    = c;
+              po += (len + 31) / 32 + 4;
+              mo += (len + 63) / 64 + 3;
+              nr++;
+            }
+          }
+          shU[10] = nr;
+        }
+        __syncthreads();
+        nReads = shU[10];
+        for (uint32_t r = normalReadCount + warp; r < nReads; r += nt / 32) {
+          const uint32_t c   = W.tmpA[r];
+          const uint8_t* src = W.ctgSeq + (size_t)c * ctgBuf + W.ctgMeta[c].lo;
+          const uint32_t len = S.len[r];
+          const uint32_t nPk = (len + 31) / 32 + 4, nMk = (len + 63) / 64 + 3;
+          packRead(src, len, gPacked + S.packOff[r], gMask + S.maskOff[r], nPk, nMk, false, lane);
+        }
+        __syncthreads();
+        PROF_MARK(9);
+      }
+    }
+
+    if (retry) {  // uniform across the CTA
+      if (tid == 0) P.retryList[atomicAdd(P.retryCount, 1u)] = li;
+      __syncthreads();
+      continue;
+    }
+
+    // ================= selectContigs (:722-842) + output (warp 0) =================
+    PROF_MARK(10);
+    if (warp == 0) {
+      mb200_asm_locus Lo;
+      memset(&Lo, 0, sizeof(Lo));
+      Lo.firstContig    = li * opt.maxAssemblyCount;
+      Lo.firstPseudo    = li * maxIter;
+      Lo.setWords       = SW;
+      Lo.lastWordLength = lastK;
+      Lo.status         = status;
+      if (status == MB200_OK) {
+        uint32_t usedReads = 0, usedPseudo = 0;
+        uint32_t aliveMask = (nCtg >= 32) ? 0xffffffffu : ((1u << nCtg) - 1);
+        uint32_t nSel      = 0;
+        uint32_t pseudoMask;
+        {
+          const uint32_t lo = lane * 32;
+          if (normalReadCount <= lo) pseudoMask = 0xffffffffu;
+          else if (normalReadCount >= lo + 32) pseudoMask = 0;
+          else pseudoMask = ~((1u << (normalReadCount - lo)) - 1);
+        }
+        while (aliveMask && nSel < opt.maxAssemblyCount) {
+          const uint32_t usedNormal   = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(usedReads)) -
+                                      __reduce_add_sync(0xffffffffu, (uint32_t)__popc(usedPseudo));
+          const uint32_t unusedNormal = normalReadCount - usedNormal;
+          if (unusedNormal < opt.minUnusedReads) break;
+          int      sel = -1;
+          uint32_t maxSupport = 0, maxLength = 0, removeMask = 0;
+          for (uint32_t c = 0; c < nCtg; ++c) {
+            if (!((aliveMask >> c) & 1)) continue;
+            const uint32_t sup    = W.ctgSets[(size_t)c * 2 * MAX_SETW + lane];
+            const uint32_t newSup = sup & ~usedReads;
+            const uint32_t newNormal = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(newSup & ~pseudoMask));
+            if (newNormal < opt.minSupportReads) {
+              removeMask |= 1u << c;
+              continue;
+            }
+            const uint32_t curSup = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(newSup));
+            const uint32_t curLen = W.ctgMeta[c].hi - W.ctgMeta[c].lo;
+            if (curSup > maxSupport || (curSup == maxSupport && curLen > maxLength)) {
+              sel        = (int)c;
+              maxSupport = curSup;
+              maxLength  = curLen;
+            }
+          }
+          if (maxSupport == 0) break;
+          {
+            const uint32_t c   = (uint32_t)sel;
+            const CtgMeta  m   = W.ctgMeta[c];
+            const uint32_t len = m.hi - m.lo;
+            unsigned long long off = 0, soff = 0;
+            if (lane == 0) {
+              off  = atomicAdd(P.A.contigPoolUsed, (unsigned long long)len);
+              soff = atomicAdd(P.A.setPoolUsed, (unsigned long long)(2 * SW));
+            }
+            off  = __shfl_sync(0xffffffffu, off, 0);
+            soff = __shfl_sync(0xffffffffu, soff, 0);
+            const uint8_t* src = W.ctgSeq + (size_t)c * ctgBuf + m.lo;
+            if (off + len <= P.A.contigPoolCap)
+              for (uint32_t i = lane; i < len; i += 32) P.A.contigPool[off + i] = src[i];
+            if (soff + 2 * SW <= P.A.setPoolCap && lane < SW) {
+              P.A.setPool[soff + lane]      = W.ctgSets[(size_t)c * 2 * MAX_SETW + lane];
+              P.A.setPool[soff + SW + lane] = W.ctgSets[(size_t)c * 2 * MAX_SETW + MAX_SETW + lane];
+            }
+            if (lane == 0) {
+              mb200_contig o;
+              o.seqOff = off; o.seqLen = len; o.seedReadCount = 0;
+              o.conservativeBegin = m.consBegin; o.conservativeEnd = m.consEnd;
+              o.supportOff = soff; o.rejectOff = soff + SW;
+              P.A.contigs[(size_t)Lo.firstContig + nSel] = o;
+            }
+            const uint32_t sup = W.ctgSets[(size_t)c * 2 * MAX_SETW + lane];
+            usedReads |= sup;
+            usedPseudo |= sup & pseudoMask;
+            removeMask |= 1u << c;
+          }
+          aliveMask &= ~removeMask;
+          nSel++;
+        }
+        Lo.nContigs = nSel;
+        Lo.nPseudo  = nReads - normalReadCount;
+        for (uint32_t r = normalReadCount; r < nReads; ++r) {
+          const uint32_t     len = S.len[r];
+          unsigned long long off = 0;
+          if (lane == 0) off = atomicAdd(P.A.contigPoolUsed, (unsigned long long)len);
+          off = __shfl_sync(0xffffffffu, off, 0);
+          const uint64_t* pk = gPacked + S.packOff[r];
+          if (off + len <= P.A.contigPoolCap)
+            for (uint32_t i = lane; i < len; i += 32)
+              P.A.contigPool[off + i] = "ACGT"[(pk[i >> 5] >> (62 - 2 * (i & 31))) & 3];
+          if (lane == 0) {
+            mb200_seqview v;
+            v.off = off; v.len = len; v.reserved = 0;
+            P.A.pseudo[(size_t)Lo.firstPseudo + (r - normalReadCount)] = v;
+          }
+        }
+      } else if (lane == 0) {
+        atomicCAS(P.A.errFlag, 0, status);
+      }
+      if (lane == 0) P.A.loci[li] = Lo;
+    }
+    __syncthreads();
+    PROF_MARK(11);
+  }
+}
+
 size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -1259,9 +2180,16 @@ int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, co
   const size_t budget = ctx->cfg.scratchBytes ? (size_t)ctx->cfg.scratchBytes : ((size_t)48 << 30);
   while (grid > 1 && (size_t)grid * L.total > budget) grid = (grid + 1) / 2;
   int rc;
-  if ((rc = mb200_reserve(ctx, ctx->dAsmWork, (size_t)grid * L.total)) != MB200_OK) return rc;
+  // On-chip kernel: 3 loci per SM at a sixth of the per-locus latency of the global-memory kernel (32 loci per SM).  It
+  // wins while the batch is small (a few waves of the on-chip grid: the per-call shim, the reference's per-candidate
+  // call pattern), the global-memory kernel wins on throughput for large batches.
+  const uint32_t chipMaxLoci = ctx->asmChipMaxLoci ? ctx->asmChipMaxLoci : (uint32_t)ctx->smCount * 3;
+  const bool wantChip = !ctx->legacyAssembler && (ctx->forceChipAssembler || nLoci <= chipMaxLoci) &&
+                        (uint64_t)opts->minCoverage * (2 * A) + 128 <= 0xffffu;
+  if (!wantChip && (rc = mb200_reserve(ctx, ctx->dAsmWork, (size_t)grid * L.total)) != MB200_OK) return rc;
 
   AsmParams P;
+  memset(&P, 0, sizeof(P));
   P.opt            = *opts;
   P.pool           = dPool;
   P.readOff        = dReadOff;
@@ -1281,6 +2209,114 @@ int mb200_asm_run(mb200_ctx* ctx, const mb200_asm_opts* opts, uint32_t nLoci, co
   P.contigPoolCap  = contigPoolCap;
   P.setPool        = dSetPool;
   P.setPoolCap     = setPoolCap;
+  // ---- on-chip kernel first (every locus that fits), then the kernel above over the retry list
+  if (wantChip && nLoci > 0) {
+    ChipLayout C;
+    memset(&C, 0, sizeof(C));
+    int maxSmem = 0, smemPerSm = 0;
+    MB200_CUDA_CHECK(ctx, cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    MB200_CUDA_CHECK(ctx, cudaDeviceGetAttribute(&smemPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    uint32_t chipCtas = 4;
+    if (const char* e = getenv("MB200_ASM_CHIP_CTAS")) chipCtas = (uint32_t)std::max(1, atoi(e));
+    C.SWc = (uint32_t)std::min<uint64_t>(4, std::max<uint64_t>(1, (st->maxReads + 2 * A + 31) / 32));
+    const uint32_t RC = C.SWc * 32;
+    C.SPK = (uint32_t)std::min<uint64_t>(640, (st->maxPackWords + 7) / 8 * 8);
+    C.SL  = 2048;
+    const size_t budgetSmem = std::min<size_t>((size_t)maxSmem, (size_t)smemPerSm / chipCtas - 1024) - 64;
+    const size_t fixedSmem  = 8 * (size_t)C.SPK + 4 * (size_t)C.SL + 4 * (size_t)RC * 3 + 4 * (size_t)(RC + 4);
+    const size_t perWord    = 4 + 4 * (size_t)C.SWc + 8 + 8 + 2 + 2 + 3;
+    uint32_t     Wc         = fixedSmem < budgetSmem ? (uint32_t)((budgetSmem - fixedSmem) / perWord) : 0;
+    if (const char* e = getenv("MB200_ASM_CHIP_WC")) Wc = (uint32_t)atoi(e);
+    Wc &= ~7u;
+    if (Wc + CHIP_THREADS + 1 > C.SL) Wc = (C.SL - CHIP_THREADS - 1) & ~7u;
+    C.Wc        = Wc;
+    C.smemBytes = (uint32_t)(fixedSmem + perWord * Wc);
+    if (Wc >= 64 && C.smemBytes <= (uint32_t)maxSmem) {
+      C.maxReads  = L.maxReads;
+      C.nWinMax   = L.nWinMax;
+      C.packWords = L.packWords;
+      C.maskWords = L.maskWords;
+      C.bktMax    = 64;
+      for (int lv = 0; lv < 22; ++lv) {
+        static const uint32_t stl[22] = {13, 29, 59, 127, 257, 541, 1109, 2357, 5087, 10273, 20753, 42043, 85229, 172933, 351061, 712697,
+                                         1447153, 2938679, 5967347, 12117689, 24607243, 49969847};
+        C.bktMax = stl[lv] + 64;
+        if (stl[lv] >= Wc) break;
+      }
+      size_t o2 = 0;
+      auto   put2 = [&](size_t& field, size_t bytes) {
+        field = o2;
+        o2    = alignUp(o2 + bytes, 256);
+      };
+      const size_t WW = (size_t)Wc + C.maxReads + 8;
+      put2(C.packed, 8 * (size_t)C.packWords);
+      put2(C.nmask, 8 * (size_t)C.maskWords);
+      put2(C.winSlot, 2 * (size_t)C.nWinMax + 64);
+      put2(C.hashv, 8 * WW);
+      put2(C.hash2, 8 * WW);
+      put2(C.seqA, 4 * WW);
+      put2(C.arr, 4 * WW);
+      put2(C.pos, 4 * WW);
+      put2(C.bktHead, 4 * (size_t)C.bktMax);
+      put2(C.bktMin, 4 * (size_t)C.bktMax);
+      put2(C.bktCnt, 4 * (size_t)C.bktMax);
+      put2(C.chainNext, 4 * WW);
+      put2(C.gs, 4 * WW);
+      put2(C.orderA, 4 * WW);
+      put2(C.tmpA, 4 * WW);
+      put2(C.idx, 4 * WW);
+      put2(C.low, 4 * WW);
+      put2(C.wstack, 4 * WW);
+      put2(C.frame, 4 * WW);
+      put2(C.ctgSeq, (size_t)2 * A * 2 * maxContigLen);
+      put2(C.ctgSets, 4 * (size_t)2 * A * 2 * MAX_SETW);
+      put2(C.ctgMeta, sizeof(CtgMeta) * (size_t)2 * A);
+      C.total = alignUp(o2, 256);
+
+      MB200_CUDA_CHECK(ctx, cudaFuncSetAttribute(assembleChipKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C.smemBytes));
+      int chipPerSm = 0;
+      MB200_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&chipPerSm, assembleChipKernel, CHIP_THREADS, C.smemBytes));
+      if (chipPerSm < 1) chipPerSm = 1;
+      uint32_t chipGrid = (uint32_t)(ctx->smCount * chipPerSm);
+      if (chipGrid > nLoci) chipGrid = nLoci;
+      // the retry pass keeps a small persistent grid (its per-CTA workspace is large)
+      uint32_t retryGrid = std::min<uint32_t>(grid, (uint32_t)ctx->smCount * 8);
+      const size_t chipWork = (size_t)chipGrid * C.total;
+      const size_t listOff  = alignUp(chipWork, 256);
+      const size_t cntOff   = listOff + alignUp(4 * (size_t)nLoci, 256);
+      if ((rc = mb200_reserve(ctx, ctx->dAsmChip, cntOff + 256)) != MB200_OK) return rc;
+      if ((rc = mb200_reserve(ctx, ctx->dAsmWork, (size_t)retryGrid * L.total)) != MB200_OK) return rc;
+      uint8_t*  chipBase = reinterpret_cast<uint8_t*>(ctx->dAsmChip.ptr);
+      uint32_t* counters = reinterpret_cast<uint32_t*>(chipBase + cntOff);  // [0] retry count, [1] retry pass work counter
+      MB200_CUDA_CHECK(ctx, cudaMemsetAsync(counters, 0, 256, ctx->stream));
+      ChipParams Q;
+      memset(&Q, 0, sizeof(Q));
+      Q.A          = P;
+      Q.A.work     = nullptr;
+      Q.C          = C;
+      Q.work       = chipBase;
+      Q.retryList  = reinterpret_cast<uint32_t*>(chipBase + listOff);
+      Q.retryCount = counters;
+      assembleChipKernel<<<chipGrid, CHIP_THREADS, C.smemBytes, ctx->stream>>>(Q);
+      MB200_CUDA_CHECK(ctx, cudaGetLastError());
+      ctx->timing.launches++;
+      P.work          = reinterpret_cast<uint8_t*>(ctx->dAsmWork.ptr);
+      P.lociList      = Q.retryList;
+      P.lociListCount = counters;
+      P.lociCounter   = counters + 1;
+      assembleKernel<<<retryGrid, ASM_THREADS, 0, ctx->stream>>>(P);
+      MB200_CUDA_CHECK(ctx, cudaGetLastError());
+      ctx->timing.launches++;
+      if (getenv("MB200_ASM_DEBUG")) {  // diagnostics only: forces a synchronisation
+        uint32_t hc[2] = {0, 0};
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[mb200 asm] on-chip kernel: grid %u x %d threads, %u B smem (%d CTAs/SM), Wc %u SWc %u; %u of %u loci retried on the global-memory kernel\n",
+                chipGrid, CHIP_THREADS, C.smemBytes, chipPerSm, C.Wc, C.SWc, hc[0], nLoci);
+      }
+      return MB200_OK;
+    }
+  }
   assembleKernel<<<grid, ASM_THREADS, 0, ctx->stream>>>(P);
   MB200_CUDA_CHECK(ctx, cudaGetLastError());
   ctx->timing.launches++;

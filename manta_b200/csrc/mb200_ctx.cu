@@ -2,6 +2,8 @@
 //
 // One ctx == one device + one stream + grow-only device buffers.  There is deliberately no CPU path:
 // if no CUDA device of compute capability 10.x is usable, mb200_create fails (MB200_ERR_NO_DEVICE).
+#include <cstdlib>
+
 #include "mb200_internal.h"
 
 int mb200_fail(mb200_ctx* ctx, int status, const char* msg)
@@ -77,6 +79,12 @@ int mb200_create(int device, const mb200_config* cfg, mb200_ctx** out)
   if (cfg) ctx->cfg = *cfg;
   ctx->forceInt32 = (ctx->cfg.reserved[0] & 1u) != 0;
   ctx->noTagKernel = (ctx->cfg.reserved[0] & 2u) != 0;
+  ctx->legacyAssembler = (ctx->cfg.reserved[0] & 4u) != 0;
+  ctx->forceChipAssembler = (ctx->cfg.reserved[0] & 8u) != 0;
+  if (const char* e = getenv("MB200_ASM_ONCHIP")) {  // A/B switch for measurements: 0 = never, 1 = always
+    ctx->legacyAssembler    = (atoi(e) == 0);
+    ctx->forceChipAssembler = (atoi(e) != 0);
+  }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return MB200_ERR_CUDA;
@@ -164,7 +172,7 @@ void mb200_destroy(mb200_ctx* ctx)
   if (ctx->dpFork) cudaEventDestroy(ctx->dpFork);
   DeviceBuffer* bufs[] = {&ctx->dPool,    &ctx->dTasks,   &ctx->dResults, &ctx->dCigar,   &ctx->dPtrScratch,
                           &ctx->dSegScratch, &ctx->dBndScratch, &ctx->dMisc, &ctx->dJobs, &ctx->dTables,
-                          &ctx->dAsmWork, &ctx->dAsmOut0, &ctx->dAsmOut1, &ctx->dAsmOut2, &ctx->dAsmOut3,
+                          &ctx->dAsmWork, &ctx->dAsmChip, &ctx->dAsmOut0, &ctx->dAsmOut1, &ctx->dAsmOut2, &ctx->dAsmOut3,
                           &ctx->dAsmOut4, &ctx->dViews,   &ctx->dReadOff, &ctx->dAln, &ctx->dJump,
                           &ctx->dQcScratch, &ctx->dQcSupport, &ctx->dQcSlotLocus, &ctx->dQcSlotFirst, &ctx->dQcNContigs,
                           &ctx->dQcViews, &ctx->dQcRef, &ctx->dQcCuts, &ctx->dQcTrim, &ctx->dQcIsJump, &ctx->dQc, &ctx->dQcBest, &ctx->dSvFirst, &ctx->dSvs};

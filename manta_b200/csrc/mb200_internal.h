@@ -41,6 +41,10 @@ struct mb200_ctx {
   // growable device buffers, reused across calls (library owns device memory)
   DeviceBuffer dPool, dTasks, dResults, dCigar, dPtrScratch, dSegScratch, dBndScratch, dMisc, dJobs, dTables;
   DeviceBuffer dLi[14];  // large_insert.cu
+  bool         legacyAssembler = false;  // cfg.reserved[0] & 4: window-indexed global-memory assembler only (no on-chip kernel)
+  bool         forceChipAssembler = false;  // cfg.reserved[0] & 8: on-chip assembler for every batch size
+  uint32_t     asmChipMaxLoci = 0;       // batches up to this many loci take the on-chip kernel (0 = default, 3 per SM: one wave of the on-chip grid)
+  DeviceBuffer dAsmChip;  // on-chip assembler: per-CTA global workspace + retry list + counters
   DeviceBuffer dAsmWork, dAsmOut0, dAsmOut1, dAsmOut2, dAsmOut3, dAsmOut4, dViews, dReadOff;
   // pinned staging
   void*  hPinned      = nullptr;

@@ -103,6 +103,7 @@ LINK_LIBS="$OUT/libmanta_all.a $OUT/libboost_min.a $OUT/htslib-1.9/libhts.a -lz 
 for a in $APPS; do
   $CXX -o "$OUT/bin/$a" "$OUT"/obj/app/$a/*.o -Wl,--start-group $LINK_LIBS -Wl,--end-group
 done
+strip "$OUT"/bin/* 2>/dev/null || true   # the binaries travel to the GPU box with every gpurun snapshot
 echo "[full] built $(ls "$OUT/bin" | tr '\n' ' ')"
 
 # --- demo inputs (data, not sources) next to the binaries so that they travel to the GPU box --------------------
@@ -130,5 +131,6 @@ if [ "$WITH_B200" = 1 ]; then
   # the patched assembler object must win over the archive member: objects first, archive after
   $CXX -o "$OUT/bin/GenerateSVCandidates_b200" "$OUT"/obj/b200/*.o -Wl,--start-group $LINK_LIBS -Wl,--end-group \
     -L"$HERE/../manta_b200" -lmanta_b200 -Wl,-rpath,'$ORIGIN/../../../../manta_b200'
+  strip "$OUT/bin/GenerateSVCandidates_b200" 2>/dev/null || true
   echo "[full] built GenerateSVCandidates_b200"
 fi

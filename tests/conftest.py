@@ -67,3 +67,14 @@ def gpusel():
     ctx = manta_b200.Context(0, no_tag_kernel=True)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(scope="session", params=["global", "onchip"])
+def gpuasm(request):
+    """same library with the assembler pinned to one of its two kernels: "global" (window-indexed tables in HBM, the
+    throughput kernel of large batches) or "onchip" (dense tables in shared memory, the low-latency kernel the default
+    takes for small batches; loci it cannot hold are retried on the other one)"""
+    import manta_b200
+    ctx = manta_b200.Context(0, assembler=request.param)
+    yield ctx
+    ctx.close()

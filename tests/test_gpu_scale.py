@@ -33,7 +33,8 @@ def _cig(pool, off, n):
     return pool[int(off):int(off) + int(n)].tolist()
 
 
-def test_full_records_at_config_size(gpu, orc):
+def test_full_records_at_config_size(gpuasm, orc):
+    gpu = gpuasm  # once per assembler kernel (2 048 loci: the default would take the global-memory kernel)
     batch = synth.make_candidate_batch(N_LOCI, seed=20260923)   # the bench's generator and seed, 5 kb windows
     opts = cb.default_candidate_opts()
     cuts = cb.default_ref_cuts(batch.nLoci)

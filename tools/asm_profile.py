@@ -44,7 +44,7 @@ batch = synth.make_candidate_batch(args.loci, seed=args.seed)
 opts = cb.default_candidate_opts()
 cuts = cb.default_ref_cuts(batch.nLoci)
 NAMES = ["pack reads", "windows+init", "key extract", "insert", "succ/pred", "kahn", "cycle replay", "seed select", "walk",
-         "pseudo reads", "(loop exit)", "select+output"]
+         "pseudo reads", "(loop exit)", "select+output", "replay: order", "replay: DFS", "pred+unused"]
 with manta_b200.Context(0) as ctx:
     lib = ctx.lib
     buf = (C.c_ulonglong * 32)()
@@ -56,7 +56,7 @@ with manta_b200.Context(0) as ctx:
     t = ctx.candidates_timing()
     lib.mb200_debug_asm_profile(buf, 0)
 v = np.array(list(buf), dtype=np.float64)
-tot = v[:12].sum()
+tot = v[:15].sum()
 print("asm_ms", t["asmMs"], "loci", int(v[19]))
 for i, n in enumerate(NAMES):
     print("%-14s %6.2f %%   %10.0f cycles/locus" % (n, 100 * v[i] / tot, v[i] / v[19]))
