@@ -276,7 +276,7 @@ __device__ bool packRead(const uint8_t* src, uint32_t len, uint64_t* pk, uint64_
 struct Work {
   uint32_t *readLen, *readPackOff, *readMaskOff, *winStart;
   uint64_t *packed, *nmask;
-  uint64_t *key0, *key1, *key2;
+  uint64_t *key0, *key1, *key2;  // key of a word, at the index of the window that claimed its slot
   uint32_t *count, *firstRead, *bits, *slot, *wordList, *succ, *pred, *indeg;
   uint8_t * flags, *inContig;
   uint64_t* hashv;
@@ -287,7 +287,7 @@ struct Work {
   CtgMeta*  ctgMeta;
 };
 
-__device__ __forceinline__ Key loadKey(const Work& W, uint32_t id)
+__device__ __forceinline__ Key loadKey(const Work& W, uint32_t id, uint32_t /*k*/)
 {
   Key k;
   k.k0 = W.key0[id];
@@ -296,13 +296,13 @@ __device__ __forceinline__ Key loadKey(const Work& W, uint32_t id)
   return k;
 }
 
-__device__ uint32_t findWord(const Work& W, const Key& key, uint32_t slotMask)
+__device__ uint32_t findWord(const Work& W, const Key& key, uint32_t k, uint32_t slotMask)
 {
   uint32_t h = hashKey(key) & slotMask;
   for (;;) {
     const uint32_t cur = W.slot[h];
     if (cur == 0) return NONE32;
-    if (keyEq(loadKey(W, cur - 1), key)) return cur - 1;
+    if (keyEq(loadKey(W, cur - 1, k), key)) return cur - 1;
     h = (h + 1) & slotMask;
   }
 }
@@ -523,7 +523,6 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           W.flags[i]     = 0;
           W.inContig[i]  = 0;
           W.indeg[i]     = 0;
-          W.key2[i]      = ~0ull;  // invalid window marker (a valid word has key2 < 2^62)
         }
         for (uint32_t i = tid; i < nWin * SW; i += nt) W.bits[i] = 0;
         if (tid == 0) shU[4] = 0;  // nWords
@@ -531,39 +530,35 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
         PROF_MARK(1);
         PROF_COUNT(21, nWin);
 
-        // ---- getKmerCounts: keys of all N-free windows, then insertion
+        // ---- getKmerCounts: every N-free window claims or finds the slot of its word and sets its read's support bit
+        // (std::set<std::string> readWords: a word repeated inside a read counts once, :524-535)
+        PROF_MARK(2);
         for (uint32_t r = warp; r < nReads; r += nt / 32) {
           const uint32_t len = W.readLen[r];
           if (len < k) continue;
           const uint64_t* pk = W.packed + W.readPackOff[r];
           const uint64_t* mk = W.nmask + W.readMaskOff[r];
           const uint32_t  ws = W.winStart[r];
+          const uint32_t  bit = 1u << (r & 31);
           for (uint32_t j = lane; j + k <= len; j += 32) {
+            const uint32_t w = ws + j;
             bool hasN = getBits(mk, j, k < 64 ? k : 64) != 0;
             if (k > 64) hasN = hasN || (getBits(mk, j + 64, k - 64) != 0);
             if (hasN) continue;
-            const Key key    = extractKey(pk, j, k);
-            W.key0[ws + j]   = key.k0;
-            W.key1[ws + j]   = key.k1;
-            W.key2[ws + j]   = key.k2;
-          }
-        }
-        __syncthreads();
-        PROF_MARK(2);
-        for (uint32_t r = warp; r < nReads; r += nt / 32) {
-          const uint32_t len = W.readLen[r];
-          if (len < k) continue;
-          const uint32_t ws  = W.winStart[r];
-          const uint32_t add = (r >= normalReadCount) ? opt.minCoverage : 1u;  // pseudo reads count minCoverage (:541)
-          for (uint32_t j = lane; j + k <= len; j += 32) {
-            const uint32_t w = ws + j;
-            if (W.key2[w] == ~0ull) continue;
-            const Key key = loadKey(W, w);
+            const Key key = extractKey(pk, j, k);
             uint32_t  h   = hashKey(key) & slotMask;
             uint32_t  owner;
+            bool      stored = false;
             for (;;) {
               uint32_t cur = W.slot[h];
               if (cur == 0) {
+                if (!stored) {  // only a window that may become the word's name stores its key (before the slot is published)
+                  W.key0[w] = key.k0;
+                  W.key1[w] = key.k1;
+                  W.key2[w] = key.k2;
+                  __threadfence_block();
+                  stored = true;
+                }
                 cur = atomicCAS(&W.slot[h], 0u, w + 1);
                 if (cur == 0) {
                   owner = w;
@@ -571,22 +566,35 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                   break;
                 }
               }
-              if (keyEq(loadKey(W, cur - 1), key)) {
+              if (keyEq(loadKey(W, cur - 1, k), key)) {
                 owner = cur - 1;
                 break;
               }
               h = (h + 1) & slotMask;
             }
-            const uint32_t bit = 1u << (r & 31);
-            const uint32_t old = atomicOr(&W.bits[(size_t)owner * SW + (r >> 5)], bit);
-            if (!(old & bit)) {
-              atomicAdd(&W.count[owner], add);
-              atomicMin(&W.firstRead[owner], r);
-            }
+            atomicOr(&W.bits[(size_t)owner * SW + (r >> 5)], bit);
           }
         }
         __syncthreads();
         const uint32_t nWords = shU[4];
+        // counts (1 per normal read, minCoverage per pseudo read, :541) and first reads, from the bitsets
+        for (uint32_t i = tid; i < nWords; i += nt) {
+          const uint32_t id = W.wordList[i];
+          uint32_t       c = 0, first = NONE32;
+          for (uint32_t sw = 0; sw < SW; ++sw) {
+            const uint32_t b2  = W.bits[(size_t)id * SW + sw];
+            const uint32_t lo2 = sw * 32;
+            uint32_t       pm;  // pseudo-read mask of this set word
+            if (normalReadCount <= lo2) pm = 0xffffffffu;
+            else if (normalReadCount >= lo2 + 32) pm = 0;
+            else pm = ~((1u << (normalReadCount - lo2)) - 1);
+            c += (uint32_t)__popc(b2 & ~pm) + opt.minCoverage * (uint32_t)__popc(b2 & pm);
+            if (b2 && first == NONE32) first = lo2 + (uint32_t)__ffs((int)b2) - 1;
+          }
+          W.count[id]     = c;
+          W.firstRead[id] = first;
+        }
+        __syncthreads();
         PROF_MARK(3);
         PROF_COUNT(20, nWords);
 
@@ -594,10 +602,10 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
         for (uint32_t i = tid; i < nWords * 4; i += nt) {
           const uint32_t id  = W.wordList[i >> 2];
           const uint32_t sym = i & 3;
-          const Key      key = loadKey(W, id);
-          const uint32_t s   = findWord(W, succKey(key, sym, k), slotMask);
+          const Key      key = loadKey(W, id, k);
+          const uint32_t s   = findWord(W, succKey(key, sym, k), k, slotMask);
           W.succ[(size_t)id * 4 + sym] = s;
-          W.pred[(size_t)id * 4 + sym] = findWord(W, predKey(key, sym, k), slotMask);
+          W.pred[(size_t)id * 4 + sym] = findWord(W, predKey(key, sym, k), k, slotMask);
           if (s == id) {
             atomicOr(reinterpret_cast<unsigned int*>(W.flags + (id & ~3u)), (unsigned)FLAG_REPEAT << (8 * (id & 3)));
           } else if (s != NONE32) {
@@ -671,10 +679,10 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           for (uint32_t i = tid; i < nWords; i += nt) {
             const uint32_t id  = W.wordList[i];
             const uint32_t r   = W.firstRead[id];
-            const Key      key = loadKey(W, id);
+            const Key      key = loadKey(W, id, k);
             uint32_t       rank = 0;
             for (uint32_t m = bucketStart[r]; m < bucketStart[r + 1]; ++m)
-              if (keyLess(loadKey(W, members[m]), key)) rank++;
+              if (keyLess(loadKey(W, members[m], k), key)) rank++;
             const uint32_t p = bucketStart[r] + rank;
             W.seqA[p]        = id;                 // insertion sequence of wordCount
             W.hashv[p]       = stlHashWord(key, k);
@@ -683,8 +691,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
           // (b) iteration order of wordCount, then of wordIndices (filled while iterating wordCount)
           uint32_t* order1 = W.idx;  // temporarily
           unorderedOrder(W, W.hashv, nWords, order1, sh);
-          uint64_t* hash2 = reinterpret_cast<uint64_t*>(W.key0) + 0;  // cannot alias keys: use frame+wstack area
-          hash2           = reinterpret_cast<uint64_t*>(W.wstack);     // wstack+frame are contiguous uint32[nWin] x2
+          uint64_t* hash2 = reinterpret_cast<uint64_t*>(W.wstack);  // wstack+frame are contiguous uint32[nWin] x2
           for (uint32_t i = tid; i < nWords; i += nt) hash2[i] = W.hashv[order1[i]];
           __syncthreads();
           uint32_t* order2 = W.low;
@@ -768,52 +775,60 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
         bool isAssemblySuccess = true;
         nCtg                   = 0;
         while (nCtg < maxIter) {
-          // seed: max count, ties -> lexicographically smallest word (first in the std::set scan, :686-696)
-          unsigned long long bestCnt = 0;  // (count << 32) | has
-          Key                bestKey = {~0ull, ~0ull, ~0ull};
-          uint32_t           bestId  = NONE32;
+          // seed: max count, ties -> lexicographically smallest word (first in the std::set scan, :686-696).
+          // Stage 1: the maximum count; stage 2: keys only of the words that have it.
+          uint32_t enc = 0;  // count + 1 of the best unused word seen, 0 = none
           for (uint32_t i = tid; i < nWords; i += nt) {
             const uint32_t id = W.wordList[i];
             if (!(W.flags[id] & FLAG_UNUSED)) continue;
-            const uint32_t c   = W.count[id];
-            const Key      key = loadKey(W, id);
-            if (bestId == NONE32 || c > (uint32_t)bestCnt || (c == (uint32_t)bestCnt && keyLess(key, bestKey))) {
-              bestCnt = c;
-              bestKey = key;
-              bestId  = id;
+            const uint32_t c = W.count[id];
+            const uint32_t e = c >= 0xfffffffeu ? 0xffffffffu : c + 1;
+            if (e > enc) enc = e;
+          }
+          enc = __reduce_max_sync(0xffffffffu, enc);
+          if (lane == 0) sh[warp] = enc;
+          __syncthreads();
+          uint32_t encAll = 0;
+          for (uint32_t w = 0; w < nt / 32; ++w) encAll = max(encAll, sh[w]);
+          __syncthreads();
+          Key      bestKey = {~0ull, ~0ull, ~0ull};
+          uint32_t bestId  = NONE32;
+          if (encAll != 0) {
+            for (uint32_t i = tid; i < nWords; i += nt) {
+              const uint32_t id = W.wordList[i];
+              if (!(W.flags[id] & FLAG_UNUSED)) continue;
+              const uint32_t c = W.count[id];
+              if ((c >= 0xfffffffeu ? 0xffffffffu : c + 1) != encAll) continue;
+              const Key key = loadKey(W, id, k);
+              if (bestId == NONE32 || keyLess(key, bestKey)) {
+                bestKey = key;
+                bestId  = id;
+              }
             }
           }
-          // warp reduce then block reduce (4 warps)
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) {
-            const uint32_t oc  = __shfl_xor_sync(0xffffffffu, (uint32_t)bestCnt, off);
             const uint32_t oid = __shfl_xor_sync(0xffffffffu, bestId, off);
             Key            ok;
             ok.k0 = __shfl_xor_sync(0xffffffffu, bestKey.k0, off);
             ok.k1 = __shfl_xor_sync(0xffffffffu, bestKey.k1, off);
             ok.k2 = __shfl_xor_sync(0xffffffffu, bestKey.k2, off);
-            if (oid != NONE32 && (bestId == NONE32 || oc > (uint32_t)bestCnt || (oc == (uint32_t)bestCnt && keyLess(ok, bestKey)))) {
-              bestCnt = oc;
+            if (oid != NONE32 && (bestId == NONE32 || keyLess(ok, bestKey))) {
               bestKey = ok;
               bestId  = oid;
             }
           }
-          if (lane == 0) {
-            sh[warp * 8 + 0] = bestId;
-            sh[warp * 8 + 1] = (uint32_t)bestCnt;
-          }
+          if (lane == 0) sh[warp * 8 + 0] = bestId;
           __syncthreads();
           if (tid == 0) {
-            uint32_t bid = NONE32, bc = 0;
+            uint32_t bid = NONE32;
             Key      bk  = {0, 0, 0};
             for (uint32_t w = 0; w < nt / 32; ++w) {
               const uint32_t id = sh[w * 8 + 0];
               if (id == NONE32) continue;
-              const uint32_t c  = sh[w * 8 + 1];
-              const Key      kk = loadKey(W, id);
-              if (bid == NONE32 || c > bc || (c == bc && keyLess(kk, bk))) {
+              const Key kk = loadKey(W, id, k);
+              if (bid == NONE32 || keyLess(kk, bk)) {
                 bid = id;
-                bc  = c;
                 bk  = kk;
               }
             }
@@ -831,7 +846,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
             uint8_t*       seq     = W.ctgSeq + (size_t)nCtg * ctgBuf;
             uint32_t*      sets    = W.ctgSets + (size_t)nCtg * 2 * MAX_SETW;
             const uint32_t serial  = nCtg + 1;
-            const Key      seedKey = loadKey(W, seed);
+            const Key      seedKey = loadKey(W, seed, k);
             uint32_t       lo = P.maxContigLen - k / 2, hi;
             hi = lo + k;
             for (uint32_t i = lane; i < k; i += 32) seq[lo + i] = "ACGT"[baseAt(seedKey, i, k)];
@@ -856,7 +871,7 @@ __global__ void __launch_bounds__(ASM_THREADS, 32) assembleKernel(const AsmParam
                   if (s == lastSym) continue;
                   Key kk = trunkK;
                   kk.k0 |= s;
-                  const uint32_t id = findWord(W, kk, slotMask);
+                  const uint32_t id = findWord(W, kk, k, slotMask);
                   if (id == NONE32) continue;
                   if (lane < SW) reject |= W.bits[(size_t)id * SW + lane];
                 }
