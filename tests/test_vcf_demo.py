@@ -84,3 +84,17 @@ def test_b200_backed_reference_relaxed_thresholds(tmp_path):
     _run(b200, B200, phase1=stock, **relaxed)
     for v in VCFS:
         assert _records(os.path.join(b200, v + ".vcf")) == _records(os.path.join(stock, v + ".vcf")), v
+
+
+@pytest.mark.gpu
+def test_b200_backed_reference_worker_threads(tmp_path):
+    """--threads 4: every worker thread of the reference's edge pool gets its own library context
+    (mb200::threadContext()); the records must not depend on the thread count (the reference sorts them afterwards,
+    so they are compared as sets here)"""
+    if not (os.path.exists(STOCK) and os.path.exists(B200)):
+        pytest.fail("oracle/_ref/full/bin is missing: run __graft_entry__.build() where /root/reference exists")
+    stock, b200 = str(tmp_path / "stock"), str(tmp_path / "b200")
+    _run(stock, STOCK)
+    _run(b200, B200, phase1=stock, THREADS=4)
+    for v in VCFS:
+        assert sorted(_records(os.path.join(b200, v + ".vcf"))) == sorted(_records(os.path.join(stock, v + ".vcf"))), v
