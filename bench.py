@@ -164,17 +164,32 @@ def pinned_zeros(n, dtype=np.uint8):
 def split_microbench(args):
     """BASELINE configs[4]: reads x (alt bp1, alt bp2, ref bp1, ref bp2) ungapped likelihood scans"""
     import manta_b200
-    pool, jobs = synth.make_split_batch(args.reads)
+    # the batch is generated and submitted in chunks of 2 M reads (host memory of the generator); one step = all chunks
+    CH = 2000000
+    chunks_in = []
+    left, seed = args.reads, 5
+    while left > 0:
+        chunks_in.append(synth.make_split_batch(min(CH, left), seed=seed))
+        left -= CH
+        seed += 1
+    pool, jobs = chunks_in[0]
+    n_jobs = sum(len(j) for _, j in chunks_in)
     tables = manta_b200.qscore_tables(manta_b200.qscore_snp(1e-3), manta_b200.qscore_snp(0.0))
     ctx = manta_b200.Context(int(os.environ.get("LOCAL_RANK", "0")))
     for _ in range(args.warmup):
-        res = ctx.split_align_raw(tables, (1e-3, 0.0), 50, pool, jobs)
-    k_ms = 0.0
+        for pl, jb in chunks_in:
+            res = ctx.split_align_raw(tables, (1e-3, 0.0), 50, pl, jb)
+    k_ms, cells, algo, ok = 0.0, 0, 0, 0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = ctx.split_align_raw(tables, (1e-3, 0.0), 50, pool, jobs)
-        tim = ctx.timing()
-        k_ms += tim["kernelMs"]
+    for st_i in range(args.steps):
+        for pl, jb in chunks_in:
+            res = ctx.split_align_raw(tables, (1e-3, 0.0), 50, pl, jb)
+            tim = ctx.timing()
+            k_ms += tim["kernelMs"]
+            if st_i == 0:
+                cells += tim["cells"]
+                algo += tim["algoBytes"]
+                ok += int((res["status"] == 0).sum())
     wall = time.perf_counter() - t0
     k_ms /= args.steps
     peak, peak_src = load_peaks()
@@ -186,15 +201,16 @@ def split_microbench(args):
         chunks = np.array_split(np.arange(nsample), host_threads() * 4)
         list(ex.map(lambda ix: binding.split_align_raw(tables, (1e-3, 0.0), 50, pool, jobs[ix[0]:ix[-1] + 1]), chunks))
     cpu_dt = time.perf_counter() - t1
-    line = dict(metric="split_read_alignments_per_sec", value=len(jobs) * args.steps / wall, unit="alignments/s",
-                kernel_only=len(jobs) / (k_ms * 1e-3), n_gpus=1, steps=args.steps, warmup=args.warmup, dtype="f32 accumulate of f64 tables",
-                data="synthetic", config=dict(workload="configs[4]: %d reads x 150 bp x 4 targets of 1200 bp (1000 alt contigs)" % args.reads),
+    tim = dict(cells=cells, algoBytes=algo)
+    line = dict(metric="split_read_alignments_per_sec", value=n_jobs * args.steps / wall, unit="alignments/s",
+                kernel_only=n_jobs / (k_ms * 1e-3), n_gpus=1, steps=args.steps, warmup=args.warmup, dtype="f32 accumulate of f64 tables",
+                data="synthetic", config=dict(workload="configs[4]: %d reads x 150 bp x 4 targets of 1200 bp (1000 alt contigs per 2 M-read chunk, %d chunks per step)" % (args.reads, len(chunks_in))),
                 base_compares_per_s=tim["cells"] / (k_ms * 1e-3),
                 roofline=dict(bound="hbm", kernel="splitScanKernel", achieved=tim["algoBytes"] / (k_ms * 1e-3) * 1e-9, peak=peak,
                               unit="GB/s", frac=tim["algoBytes"] / (k_ms * 1e-3) * 1e-9 / peak, traffic=None, peak_source=peak_src),
                 cpu_baseline=dict(value=nsample / cpu_dt, unit="alignments/s", cores=host_threads(), kind=kind,
                                   sample="first %d jobs" % nsample),
-                status_ok=int((res["status"] == 0).sum()))
+                status_ok=ok)
     print(json.dumps(line))
     ctx.close()
     return 0
@@ -203,7 +219,7 @@ def split_microbench(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="manta_b200", choices=["manta_b200", "reference"])
     ap.add_argument("--loci", type=int, default=50000, help="candidate loci per GPU per step (BASELINE configs[1]: 50000)")
@@ -259,7 +275,9 @@ def main():
         value = tot_n / tot_t
         out = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                    ms_per_step=1000.0 * tot_t / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None,
-                   dtype="int32", data="synthetic", config=config,
+                   dtype="int32", data="synthetic",
+                   config=dict(config, reference_sample="each step = the first %d loci of the same generator/seed (a bounded sample "
+                                                        "of the %d-locus workload), %d host threads" % (per_step, args.loci, threads)),
                    cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind=kind,
                                      sample="%d loci per step (first loci of the same generator/seed), %d host threads, %.2f GCUPS"
                                             % (per_step, threads, tot_cells / tot_t * 1e-9)),
@@ -447,6 +465,28 @@ def main():
                               device_ms_per_rank=[round(float(x), 2) for x in per[:, 1]],
                               imbalance=float(per[:, 1].max() / per[:, 1].mean()), merged_checksum=csum, candidates_seen=n_all)
         line["config"]["workload"] += "; STRONG scaling: one list of %d candidates split by observation-weighted bins" % args.loci
+    # ---- parity at the measured size: whole-batch checksums of this run's last result set against the values the compiled
+    # reference AND the oracle port give for the same batch (computed once on the CPU by tools/golden_bench_checksum.py,
+    # ~10 CPU-minutes; committed as tests/golden/bench_config2_checksum.json)
+    parity_ok = True
+    if rank == 0 and refine and not strong:
+        try:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_config2_checksum.json")))
+        except Exception:
+            gold = None
+        if gold and gold["loci"] == args.loci and gold["seed"] == 20260923:
+            A = int(opts["asmOpts"]["maxAssemblyCount"][0])
+            nC = out["loci"]["nContigs"]
+            live = np.arange(A)[None, :] < nC[:, None]
+            score = np.where((batch.isJump != 0)[:, None], out["jump"]["score"].reshape(-1, A), out["aln"]["score"].reshape(-1, A))
+            got = [int(live.sum()), int(tim["indelCells"] + tim["jumpCells"]), int(score[live].sum()),
+                   int(cb.qc_checksum(batch.isJump, nC, A, out["trim"], out["qc"], out["best"], True))]
+            parity_ok = all(got == v for v in gold["results"].values())
+            line["parity"] = dict(checked=True, equal=parity_ok, against=sorted(gold["results"].keys()),
+                                  what="contig count, DP cell count, sum of alignment scores, trim/QC/selection checksum of all %d loci" % args.loci,
+                                  got=got, expected=gold["results"])
+        else:
+            line["parity"] = dict(checked=False, why="no committed checksum for this --loci / seed")
     if rank == 0 and not args.no_cpu_baseline:
         cpu, _, _ = cpu_baseline(batch, opts, cuts, refine)
         line["cpu_baseline"] = cpu
@@ -457,6 +497,9 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     ctx.close()
+    if not parity_ok:
+        print("bench.py: result checksums differ from the reference's -- the number above is void", file=sys.stderr)
+        return 1
     return 0
 
 
