@@ -176,6 +176,12 @@ class qscore_snp:
             self.lnErr.append(math.log(q2p) if q2p > 0 else -math.inf)
 
 
+#: The reference builds its reference-allele table from CallOptionsShared::snpPrior, a FLOAT (options/CallOptionsShared.hpp:30,
+#: SVScorer.hpp:47): qscore_snp(REFERENCE_SNP_PRIOR), not qscore_snp(0.001), reproduces GenerateSVCandidates' split-read
+#: likelihoods to the bit (tests/test_demo_calls.py); the alt-allele table is qscore_snp(0).
+REFERENCE_SNP_PRIOR = float(np.float32(1e-3))
+
+
 def qscore_tables(t0: "qscore_snp", t1: "qscore_snp") -> np.ndarray:
     t = np.zeros(1, dtype=_cabi.QSCORE_TABLES_DT)
     t["lnComp"][0][0], t["lnComp"][0][1] = t0.lnComp, t1.lnComp

@@ -17,7 +17,11 @@ TP="$HERE/_ref"           # boost / htslib unpack dir shared with build_ref.sh
 LIB="$REF/src/c++/lib"
 JOBS="${JOBS:-8}"
 WITH_B200=0
-[ "${1:-}" = "--b200" ] && WITH_B200=1
+WITH_TRACE=0
+for a in "$@"; do
+  [ "$a" = "--b200" ] && WITH_B200=1
+  [ "$a" = "--trace" ] && WITH_TRACE=1
+done
 
 if [ ! -d "$LIB" ]; then
   echo "build_ref_full.sh: reference tree not found at $REF (expected on the build container only)" >&2
@@ -133,4 +137,22 @@ if [ "$WITH_B200" = 1 ]; then
     -L"$HERE/../manta_b200" -lmanta_b200 -Wl,-rpath,'$ORIGIN/../../../../manta_b200'
   strip "$OUT/bin/GenerateSVCandidates_b200" 2>/dev/null || true
   echo "[full] built GenerateSVCandidates_b200"
+fi
+
+# --- the call-recording GenerateSVCandidates (stock algorithms + oracle/ref_trace.hpp at every hot-path call site) ----
+if [ "$WITH_TRACE" = 1 ]; then
+  GSC="$LIB/applications/GenerateSVCandidates"
+  TD="$OUT/traced"
+  rm -rf "$TD"; mkdir -p "$TD/applications/GenerateSVCandidates" "$TD/manta"
+  cp "$GSC"/*.cpp "$GSC"/*.hpp "$TD/applications/GenerateSVCandidates/"
+  cp "$LIB/manta/SVCandidateAssembler.cpp" "$TD/manta/"
+  (cd "$TD" && patch -p1 --quiet < "$HERE/trace_calls.patch")
+  export EXTRA="-I$HERE"
+  { for f in "$TD"/applications/GenerateSVCandidates/*.cpp; do echo "$f $OUT/obj/traced/$(basename "${f%.cpp}").o"; done
+    echo "$TD/manta/SVCandidateAssembler.cpp $OUT/obj/traced/lib_SVCandidateAssembler.o"
+    echo "$REF/src/c++/bin/GenerateSVCandidates.cpp $OUT/obj/traced/main.o"
+  } | compile_list
+  $CXX -o "$OUT/bin/GenerateSVCandidates_trace" "$OUT"/obj/traced/*.o -Wl,--start-group $LINK_LIBS -Wl,--end-group
+  strip "$OUT/bin/GenerateSVCandidates_trace" 2>/dev/null || true
+  echo "[full] built GenerateSVCandidates_trace"
 fi
