@@ -1584,7 +1584,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXR
       uint8_t*       stp    = ptrBuf + (size_t)pass * passStride + (size_t)lane * PP::CHUNK_BYTES;  // my chunk 0 of step t
       uint32_t       cdn    = 0xffffu + (uint32_t)lane;                                              // 0xffff - c + 1 at step 0
 
-      for (uint32_t t = 0; t < nSteps; ++t, stp += PP::STEP_BYTES) {
+      // One anti-diagonal step.  The wavefront is peeled (below): in the long middle of a strip every lane is active and, in a
+      // jump alignment, every lane is on the same side of the jump column, so those steps run a copy of this body in which
+      // the per-lane tests are compile-time constants (ALLACT: cz < RTOT holds; PH = 1 / 2: all lanes in ref1 / ref2 and not
+      // at the jump column; PH = 0: decide per lane).
+      auto step = [&](const uint32_t t, auto actTag, auto phTag) {
+        constexpr bool ALLACT = decltype(actTag)::value;
+        constexpr int  PH     = decltype(phTag)::value;
         if ((t & 31u) == 0) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -1617,7 +1623,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXR
         }
         cdn--;
         const uint32_t cz     = t - (uint32_t)lane;  // 0-based column; wraps for lanes that have not started
-        const bool     active = cz < RTOT;
+        const bool     active = ALLACT || (cz < RTOT);
         if (pass != 0 && lane == 0 && active) {
           const uint32_t* b = reinterpret_cast<const uint32_t*>(bndBuf) + (size_t)(cz + 1) * 5;
           upM = b[0]; upD = b[1]; upI = b[2]; upJ = b[3]; upK = b[4];
@@ -1625,14 +1631,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXR
 
         if (active) {
           const uint32_t c      = cz + 1;
-          const bool     phase2 = (KIND == KIND_JUMP) && (cz >= R1);
+          const bool     phase2 = (KIND == KIND_JUMP) && (PH == 2 || (PH == 0 && cz >= R1));
           // reference characters of this column.  A column past the shorter alignment's own end reads whatever the ring
           // holds there: those cells are never used (no start candidate, no trace-back), and the halves do not interact.
           const uint32_t refA = ringA[(cz + (phase2 ? off2A : off1A)) & (REF_RING - 1)];
           const uint32_t refB = ringB[(cz + (phase2 ? off2B : off1B)) & (REF_RING - 1)];
           const uint32_t refpair = refA | (refB << 16);
 
-          if (KIND == KIND_JUMP && cz == R1) {
+          if (KIND == KIND_JUMP && PH == 0 && cz == R1) {
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
               pM[r] = T(((int)q0 + r + 1) * offEdge, cM);
@@ -1722,7 +1728,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXR
               keyB             = k > keyB ? k : keyB;
             }
           }
-          const bool edge1 = (KIND == KIND_JUMP) && (c == R1);
+          const bool edge1 = (KIND == KIND_JUMP) && PH == 0 && (c == R1);
           const bool edgeA = (c == RTA), edgeB = (c == RTB);
           if (edge1 || edgeA || edgeB) {
 #pragma unroll
@@ -1791,7 +1797,38 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXR
             b[0] = lastM; b[1] = lastD; b[2] = lastI; b[3] = lastJ; b[4] = lastK;
           }
         }
-      }  // steps
+      };  // step
+      {
+        using std::integral_constant;
+        const integral_constant<bool, true>  allAct;
+        const integral_constant<bool, false> perLane;
+        const integral_constant<int, 0>      phAny;
+        const integral_constant<int, 1>      ph1;
+        const integral_constant<int, 2>      ph2;
+        uint32_t t = 0;
+        // all lanes active for t in [31, RTOT); a lane is at the jump column (cz == R1, c == R1 one step earlier) for
+        // t in [R1 - 1, R1 + 31]; before that window every active lane is in ref1, after it in ref2
+        const uint32_t actBegin = 31u < nSteps ? 31u : nSteps, actEnd = RTOT > actBegin ? RTOT : actBegin;
+#ifndef MB200_DP_PEEL_ACT
+#define MB200_DP_PEEL_ACT 1
+#endif
+#if MB200_DP_PEEL_ACT
+        const auto midAct = allAct;
+#else
+        const auto midAct = perLane;
+#endif
+        if (KIND == KIND_JUMP) {
+          for (; t < actBegin; ++t, stp += PP::STEP_BYTES) step(t, perLane, phAny);
+          const uint32_t w0 = (R1 >= 1 ? R1 - 1 : 0u), w1 = R1 + 32u;
+          const uint32_t e1 = w0 < actEnd ? (w0 > t ? w0 : t) : actEnd;
+          for (; t < e1; ++t, stp += PP::STEP_BYTES) step(t, midAct, ph1);
+          const uint32_t e2 = w1 < actEnd ? (w1 > t ? w1 : t) : actEnd;
+          for (; t < e2; ++t, stp += PP::STEP_BYTES) step(t, perLane, phAny);
+          for (; t < actEnd; ++t, stp += PP::STEP_BYTES) step(t, midAct, ph2);
+        }
+        // the kinds with one reference keep ONE copy of the step (peeling them costs more in code than it saves: +4 %)
+        for (; t < nSteps; ++t, stp += PP::STEP_BYTES) step(t, perLane, phAny);
+      }
       // this pass's best last-row cells as (score, -sequence) keys
       if (keyA) {
         const uint32_t c   = 0xffffu - (keyA & 0xffffu);
