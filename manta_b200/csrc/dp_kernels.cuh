@@ -1588,8 +1588,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXR
       // jump alignment, every lane is on the same side of the jump column, so those steps run a copy of this body in which
       // the per-lane tests are compile-time constants (ALLACT: cz < RTOT holds; PH = 1 / 2: all lanes in ref1 / ref2 and not
       // at the jump column; PH = 0: decide per lane).
-      auto step = [&](const uint32_t t, auto actTag, auto phTag) {
-        constexpr bool ALLACT = decltype(actTag)::value;
+      auto step = [&](const uint32_t t, auto hotTag, auto phTag) {
+        constexpr bool HOT    = decltype(hotTag)::value;  // a step of the strip's interior: every lane active, none at an edge
+        constexpr bool ALLACT = HOT;
         constexpr int  PH     = decltype(phTag)::value;
         if ((t & 31u) == 0) {
 #pragma unroll
@@ -1729,7 +1730,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXR
             }
           }
           const bool edge1 = (KIND == KIND_JUMP) && PH == 0 && (c == R1);
-          const bool edgeA = (c == RTA), edgeB = (c == RTB);
+          const bool edgeA = !HOT && (c == RTA), edgeB = !HOT && (c == RTB);
           if (edge1 || edgeA || edgeB) {
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
@@ -1800,34 +1801,43 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (RT <= MB200_TAG_OCC4_MAXR
       };  // step
       {
         using std::integral_constant;
-        const integral_constant<bool, true>  allAct;
-        const integral_constant<bool, false> perLane;
+        const integral_constant<bool, true>  hot;
+        const integral_constant<bool, false> generic;
         const integral_constant<int, 0>      phAny;
         const integral_constant<int, 1>      ph1;
         const integral_constant<int, 2>      ph2;
+        // The wavefront is peeled.  A step is "interior" when all 32 lanes are active (31 <= t < RTOT) and no lane sits at an
+        // event column: the last column of A or B (c == RTA / RTB: t in [RT? - 1, RT? + 31)) or, in a jump alignment, the
+        // jump column (t in [R1 - 1, R1 + 32)).  Interior steps run the specialised copy (per-lane tests and the whole
+        // edge block compiled out; jump: one copy per side of the jump column), everything else the generic copy.
+#ifndef MB200_DP_PEEL_KINDS
+#define MB200_DP_PEEL_KINDS 7  // bit per kind; measured at 50 000 loci: jump 81 -> 54 ms, large-indel 82 -> 78 ms
+#endif
+        constexpr bool PEEL = ((MB200_DP_PEEL_KINDS >> KIND) & 1) != 0;
         uint32_t t = 0;
-        // all lanes active for t in [31, RTOT); a lane is at the jump column (cz == R1, c == R1 one step earlier) for
-        // t in [R1 - 1, R1 + 31]; before that window every active lane is in ref1, after it in ref2
-        const uint32_t actBegin = 31u < nSteps ? 31u : nSteps, actEnd = RTOT > actBegin ? RTOT : actBegin;
-#ifndef MB200_DP_PEEL_ACT
-#define MB200_DP_PEEL_ACT 1
-#endif
-#if MB200_DP_PEEL_ACT
-        const auto midAct = allAct;
-#else
-        const auto midAct = perLane;
-#endif
-        if (KIND == KIND_JUMP) {
-          for (; t < actBegin; ++t, stp += PP::STEP_BYTES) step(t, perLane, phAny);
-          const uint32_t w0 = (R1 >= 1 ? R1 - 1 : 0u), w1 = R1 + 32u;
-          const uint32_t e1 = w0 < actEnd ? (w0 > t ? w0 : t) : actEnd;
-          for (; t < e1; ++t, stp += PP::STEP_BYTES) step(t, midAct, ph1);
-          const uint32_t e2 = w1 < actEnd ? (w1 > t ? w1 : t) : actEnd;
-          for (; t < e2; ++t, stp += PP::STEP_BYTES) step(t, perLane, phAny);
-          for (; t < actEnd; ++t, stp += PP::STEP_BYTES) step(t, midAct, ph2);
+        if (PEEL) {
+          while (t < nSteps) {
+            // boundaries of the event windows, ascending search for the first one beyond t
+            const uint32_t bnd[8] = {31u, RTOT, RTA >= 1 ? RTA - 1 : 0u, RTA + 31u, RTB >= 1 ? RTB - 1 : 0u, RTB + 31u,
+                                     (KIND == KIND_JUMP && R1 >= 1) ? R1 - 1 : 0u, (KIND == KIND_JUMP) ? R1 + 32u : 0u};
+            uint32_t next = nSteps;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (bnd[i] > t && bnd[i] < next) next = bnd[i];
+            const bool inA = (t + 1 >= RTA) && (t < RTA + 31u), inB = (t + 1 >= RTB) && (t < RTB + 31u);
+            const bool inJ = (KIND == KIND_JUMP) && (t + 1 >= R1) && (t < R1 + 32u);
+            const bool interior = (t >= 31u) && (t < RTOT) && !inA && !inB && !inJ;
+            if (!interior) {
+              for (; t < next; ++t, stp += PP::STEP_BYTES) step(t, generic, phAny);
+            } else if (KIND == KIND_JUMP && t >= R1) {
+              for (; t < next; ++t, stp += PP::STEP_BYTES) step(t, hot, ph2);
+            } else {
+              for (; t < next; ++t, stp += PP::STEP_BYTES) step(t, hot, ph1);
+            }
+          }
+        } else {
+          for (; t < nSteps; ++t, stp += PP::STEP_BYTES) step(t, generic, phAny);
         }
-        // the kinds with one reference keep ONE copy of the step (peeling them costs more in code than it saves: +4 %)
-        for (; t < nSteps; ++t, stp += PP::STEP_BYTES) step(t, perLane, phAny);
       }
       // this pass's best last-row cells as (score, -sequence) keys
       if (keyA) {
