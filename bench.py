@@ -440,11 +440,11 @@ def main():
                 data="synthetic", config=config, clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=launches,
-                roofline=dict(bound="hbm", kernel="dpTagKernel<KIND_INDEL,RT> (large-indel aligner: two alignments per warp in the halves of 32-bit lanes, score and back-pointer state in one tagged 16-bit value, packed VIMNMX3/VIADDMNMX, 2 B back-pointer per cell; all row classes of one step)",
+                roofline=dict(bound="hbm", kernel="dpTagKernel<KIND_INDEL,RT> (large-indel aligner: two alignments per warp in the halves of 32-bit lanes, score and back-pointer state in one tagged 16-bit value, packed VIMNMX3/VIADDMNMX, 2 B back-pointer per cell; all row classes of one step; interior steps of the peeled wavefront run a specialised copy)",
                               achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak if peak else None,
                               traffic=(traffic_factor * dom_bytes) if traffic_factor else None, traffic_source=traffic_src,
                               bound_note="HBM is the defined roofline (SURVEY 8d); the kernel itself is issue/latency bound on integer work "
-                                         "(ncu, dominant class <INDEL,RT=9> at 50k loci: issue slots 73% busy, IPC 2.94 of 4, ALU pipe 65%, DRAM 31% = 2.5 TB/s; 12 warps/SM at 166 registers), see profiles/r02_dp_tag_sections.txt, r02_sass_dp_tag_indel12.txt and r02_pipe_probe.txt",
+                                         "(ncu, dominant class <INDEL,RT=9> at 50k loci: issue slots 73% busy, IPC 2.91 of 4, DRAM 34% = 2.8 TB/s; 12 warps/SM at 168 registers), see profiles/r02_dp_tag_sections_v2.txt, r02_sass_dp_tag_indel12.txt and r02_pipe_probe.txt",
                               peak_source=peak_src, algorithmic_bytes_per_launch_set=dom_bytes, kernel_ms_per_step=dom_ms,
                               gcups=tim["indelCells"] / (dom_ms * 1e-3) * 1e-9 if dom_ms > 0 else None),
                 stages=dict(device_ms_per_step=ev_s * 1000.0 / args.steps, asm_ms=stage["asmMs"] / args.steps,
