@@ -75,3 +75,22 @@ def test_gpu_alignments_on_demo_contigs(gpu, gpu32, gpusel, calls):
 @pytest.mark.gpu
 def test_gpu_split_alignments_on_demo_reads(gpu, orc, calls):
     check_splits(gpu, *calls, orc)
+
+
+def test_reference_inputs_stay_inside_the_library_limits(calls):
+    """DESIGN.md 3.3 lists what the library rejects loudly although the reference would accept it (bases outside ACGTN,
+    contigs beyond cfg.maxContigLen = 2048, qualities above 70).  On BAM-decoded data the reference never produces such
+    input -- checked here on everything its own executable fed to the hot path on the demo."""
+    _, by = calls
+    for c in by["asm"]:
+        for r in c["reads"]:
+            assert set(r) <= set("ACGTN")
+        for ctg in c["reference"]["contigs"]:
+            assert len(ctg["seq"]) <= 2048 and set(ctg["seq"]) <= set("ACGT")
+    for kind in ("jump", "indel"):
+        for c in by[kind]:
+            for seq in c["seqs"]:
+                assert set(seq) <= set("ACGTN")
+    for c in by["split"]:
+        assert set(c["query"]) <= set("ACGTN") and set(c["target"]) <= set("ACGTN")
+        assert max(c["qual"]) <= 70
