@@ -4,7 +4,10 @@
 //   getKmerCounts :506-550, getRepeatKmers/searchRepeats :555-642, buildContigs :644-720, walk :149-501,
 //   selectContigs :722-842.
 //
-// Mapping (DESIGN.md "assembler kernel"): one CTA per locus (persistent CTAs, global work counter).
+// Two kernels run the same algorithm: assembleKernel below keeps its tables in global memory (one warp per
+// locus, 32 loci per SM: the throughput kernel of large batches) and assembleChipKernel further down keeps them in shared
+// memory (one 128-thread CTA per locus, 3 loci per SM: a sixth of the latency, taken for batches of up to one wave; what it
+// cannot hold is retried on the first).  Mapping of assembleKernel: one CTA per locus (persistent CTAs, global work counter).
 //   * reads are packed once to 2 bits/base (MSB first, so integer order == lexicographic order A<C<G<T) plus
 //     an N-mask bit plane; a k-mer (k <= 96) is three 64-bit words cut out of the packed stream;
 //   * word table: open addressing keyed by the packed k-mer; the word id is the index of the window that
