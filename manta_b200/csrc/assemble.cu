@@ -11,9 +11,10 @@
 //   * reads are packed once to 2 bits/base (MSB first, so integer order == lexicographic order A<C<G<T) plus
 //     an N-mask bit plane; a k-mer (k <= 96) is three 64-bit words cut out of the packed stream;
 //   * word table: open addressing keyed by the packed k-mer; the word id is the index of the window that
-//     claimed the slot (one atomicCAS, no locks); per word: count, first read, read-support bitset
-//     (<= 32 words of 32 bits == <= 1024 reads incl. pseudo reads), built with atomicOr/atomicAdd so that a
-//     word repeated inside a read counts once (std::set<std::string> readWords, :524-535);
+//     claimed the slot (one atomicCAS, no locks; only a window that tries to claim stores its key); per word a
+//     read-support bitset (<= 32 words of 32 bits == <= 1024 reads incl. pseudo reads) built with one atomicOr per
+//     window, so that a word repeated inside a read counts once (std::set<std::string> readWords, :524-535); count
+//     and first read are derived from the bitset afterwards;
 //   * successor / predecessor word ids are resolved once per word (4 + 4 lookups, all threads) so that the
 //     greedy walk and the cycle search are pure integer graph walks;
 //   * repeat words: homopolymers directly; other cycles are detected by parallel trimming (Kahn).  Only if a
@@ -21,7 +22,7 @@
 //     nested std::unordered_map<std::string,...> is reproduced with a parallel formulation of libstdc++'s
 //     hashtable (per rehash level: groups by bucket, ordered by descending first-arrival, members by descending
 //     arrival), then one thread runs the DFS with the same index/low-link/"small circle <= 50" rules;
-//   * seeds: CTA-wide arg-max (count, then lexicographically smallest word);
+//   * seeds: CTA-wide maximum count, then the lexicographically smallest word among those that have it;
 //   * walk: warp 0, read sets live one 32-bit word per lane, every std::set operation of the reference is a
 //     lane-wise bit operation + warp vote / __reduce_add;
 //   * contigs of a failed word length are re-packed as pseudo reads for the next one; selectContigs runs on
